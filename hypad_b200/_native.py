@@ -1,0 +1,172 @@
+"""ctypes binding of libhypad_b200.so (include/hypad_b200.h).
+
+PyTorch is used for device memory and streams only: tensors are passed as raw `data_ptr()`s, the
+current torch CUDA stream as `cudaStream_t`.  There is no CPU fallback: if the library is missing
+or no CUDA device is present every compute call raises.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhypad_b200.so")
+
+STAGE_ENCODER, STAGE_DECODER, STAGE_MOBIUS_X, STAGE_CRITIC = 1, 2, 4, 8
+STAGE_ALL = 15
+
+COMBINE_MODES = {"mult": 0, "uncertainty": 1, "sum": 2, "critic": 3, "critic_uncertainty": 4, "sum_uncertainty": 5,
+                 "rec": 6, "rec_uncertainty": 7, "euclidean_sum": 8}
+
+c_f32p = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_int = ctypes.c_int
+_vp = ctypes.c_void_p
+
+
+class HypadError(RuntimeError):
+    pass
+
+
+class hypad_weights(ctypes.Structure):
+    _fields_ = [
+        ("signal_shape", ctypes.c_int32), ("latent_dim", ctypes.c_int32), ("hyperbolic", ctypes.c_int32),
+        ("critic_dim", ctypes.c_int32),
+        ("enc_w_ih", _vp * 2), ("enc_b_ih", _vp * 2), ("enc_b_hh", _vp * 2),
+        ("enc_dense_w", _vp), ("enc_dense_b", _vp),
+        ("dec_dense1_w", _vp), ("dec_dense1_b", _vp),
+        ("dec_w_ih", (_vp * 2) * 2), ("dec_b_ih", (_vp * 2) * 2), ("dec_b_hh", (_vp * 2) * 2),
+        ("dec_dense2_w", _vp), ("dec_dense2_b", _vp),
+        ("mobius_w", _vp), ("mobius_b", _vp),
+        ("critic_w", _vp * 5), ("critic_b", _vp * 5),
+    ]
+
+
+class hypad_forward_out(ctypes.Structure):
+    _fields_ = [("z", _vp), ("eucl", _vp), ("hyper", _vp), ("hyper_x", _vp), ("critic", _vp), ("rec", _vp), ("unorm", _vp)]
+
+
+# name -> (restype, argtypes); mirrors include/hypad_b200.h one to one
+_SIGNATURES = {
+    "hypad_abi_version": (_int, []),
+    "hypad_last_error": (ctypes.c_char_p, []),
+    "hypad_ctx_create": (_int, [ctypes.POINTER(_vp), _int]),
+    "hypad_ctx_destroy": (_int, [_vp]),
+    "hypad_pack_weights": (_int, [_vp, ctypes.POINTER(hypad_weights), _vp]),
+    "hypad_forward": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _int, ctypes.POINTER(hypad_forward_out), _vp]),
+    "hypad_mobius_linear": (_int, [_vp, _vp, _i64, _int, _int, _vp, _vp, _int, _vp, _vp]),
+    "hypad_poincare_rowdist": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
+    "hypad_rownorm": (_int, [_vp, _i64, _int, _vp, _vp]),
+    "hypad_window_gather": (_int, [_vp, _i64, _int, _vp, _int, _vp]),
+    "hypad_kde_argmax_overlap": (_int, [_vp, _i64, _i64, _i64, _int, _i64, _i64, _vp, _vp]),
+    "hypad_kde_argmax_overlap_exhaustive": (_int, [_vp, _i64, _i64, _i64, _int, _i64, _i64, _vp, _vp]),
+    "hypad_critic_zscore_smooth": (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "hypad_rolling_mean_centered": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "hypad_zscore_clip": (_int, [_vp, _vp, _int, _i64, _vp, _vp]),
+    "hypad_combine_scores": (_int, [_int, _vp, _vp, _int, _vp, ctypes.c_double, _i64, _vp, _vp]),
+    "hypad_median_overlap": (_int, [_vp, _i64, _int, _vp, _vp]),
+    "hypad_true_from_signal": (_int, [_vp, _int, _i64, _i64, _int, _vp, _vp]),
+    "hypad_dtw_error": (_int, [_vp, _vp, _int, _i64, _int, _vp, _vp]),
+    "hypad_point_error": (_int, [_vp, _vp, _int, _i64, _vp, _vp]),
+    "hypad_area_error": (_int, [_vp, _vp, _int, _i64, _int, _vp, _vp]),
+    "hypad_threshold_windows": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp, _int, _vp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load_library():
+    """dlopen the in-tree library; raises HypadError (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise HypadError(
+                    "hypad_b200: %s is missing -- build it with `python -m hypad_b200.build` "
+                    "(there is no CPU or PyTorch fallback)" % LIB_PATH)
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in _SIGNATURES.items():
+                fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+                fn.restype = res
+                fn.argtypes = args
+            if lib.hypad_abi_version() != 1:
+                raise HypadError("hypad_b200: ABI version mismatch")
+            _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load_library().hypad_last_error()
+        raise HypadError("hypad_b200 error %d: %s" % (rc, msg.decode(errors="replace") if msg else "?"))
+
+
+def require_cuda(t, name="tensor"):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise HypadError("hypad_b200: %s must be a CUDA tensor (the scoring path has no CPU implementation)" % name)
+    return t
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Context:
+    """Owns one hypad_ctx (packed weights + workspace) on one device."""
+
+    def __init__(self, device):
+        self.lib = load_library()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise HypadError("hypad_b200: a CUDA device is required, got %s" % self.device)
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.empty(1, device=self.device)  # make sure the primary context exists
+            h = ctypes.c_void_p()
+            check(self.lib.hypad_ctx_create(ctypes.byref(h), idx))
+        self.handle = h
+        self._keepalive = None
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.hypad_ctx_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stream(self):
+        return stream_ptr(self.device)
+
+    def pack(self, w, keepalive):
+        with torch.cuda.device(self.device):
+            check(self.lib.hypad_pack_weights(self.handle, ctypes.byref(w), self.stream()))
+        self._keepalive = keepalive
+
+
+_default_ctx = {}
+
+
+def default_context(device):
+    """A per-device context for the stateless entry points (workspace only)."""
+    device = torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    ctx = _default_ctx.get(idx)
+    if ctx is None:
+        ctx = _default_ctx[idx] = Context(torch.device("cuda", idx))
+    return ctx

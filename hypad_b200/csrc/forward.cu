@@ -1,0 +1,475 @@
+// Fused TadGAN forward for sm_100a: Encoder -> Decoder -> MobiusLinear (x2) -> row-wise Poincare distance,
+// plus CriticX, over tiles of 64 windows.  Replaces the per-64-window loop of anomaly_detection.py:67-113
+// and the module forwards of models/tadgan.py:23-27, :58-67, :91-106, hyperspace/hyrnn_nets.py:13-35.
+//
+// Every LSTM on this path runs with sequence length 1 and zero state (models/tadgan.py:24), so a
+// layer is   G = x W_ih^T + b_ih + b_hh ;  c = sigmoid(G_i) * tanh(G_g) ;  h = sigmoid(G_o) * tanh(c)
+// and the whole network is a chain of small dense contractions with gate epilogues.
+//
+// Layout.  One CTA = 128 threads = one tile of 64 windows; two CTAs are resident per SM (104-111 KB of
+// shared memory each).  Activations live transposed in shared memory, act[feature][window] (64 floats per
+// feature row), so that the 8 windows a thread owns are two float4 loads and the write of a produced
+// feature row is two float4 stores.  Weights are pre-packed per pass as panels [Kpad][G][64] (G column
+// groups of 64 outputs) and streamed from L2 through a double-buffered cp.async stage of 8 k-rows.
+// A thread owns an 8 (windows) x 4G (outputs) register tile: thread grid 8 x 16, warp = 4 x 8, which
+// keeps the shared-memory traffic at 5 wavefronts per 96 FFMA.  The contraction is fp32 FFMA in
+// ascending-k order (bias added after, as torch's addmm does): score parity with the reference's fp32
+// CPU path (1e-4 after a z-score and an acosh next to 1) rules out TF32 inputs; see DESIGN.md.
+//
+// For an LSTM pass the three column groups are the i, g and o pre-activations of the same 64 hidden
+// units, so the gate epilogue needs no exchange between threads.  The dead forget gate and W_hh are
+// never loaded.
+#include "common.cuh"
+
+namespace hypad {
+
+constexpr int TILE_M = 64;
+constexpr int NTHREADS = 128;
+constexpr int LDM = 64;                    // floats per activation row
+constexpr int KC = 8;                      // k-rows per weight stage
+constexpr int WSTAGE_FLOATS = KC * 3 * 64; // one stage (sized for G = 3)
+constexpr int ACT_ROWS = 128;              // rows of buffers A and B
+
+struct FwdParams {
+    const void* x;
+    const float* z_in;
+    const float* packed;
+    int64_t n;
+    int64_t row_stride;
+    int32_t x_is_f64;
+    int32_t stages;
+    uint32_t pass_mask;      // bit p set: pass p of the layer program runs
+    int32_t need_x;          // the window tile is read
+    int32_t want_rowstats;   // rec and/or unorm are produced
+    hypad_forward_out out;
+    NetProgram prog;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// torch.sigmoid in fp32: 1 / (1 + exp(-x))
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+template <int G>
+__device__ __forceinline__ void stage_chunk(const float* __restrict__ g, float* __restrict__ s, int tid) {
+    // KC*G*64 floats = 128*G float4: G per thread
+#pragma unroll
+    for (int v = 0; v < G; ++v) {
+        int e = (v * NTHREADS + tid) * 4;
+        cp_async16(s + e, g + e);
+    }
+}
+
+// acc[r][4g+j] = sum_k act[k][8tm+r] * W[k][g][4tn+j], ascending k, one FFMA chain per output.
+template <int G>
+__device__ __forceinline__ void gemm_pass(const float* __restrict__ gW, int nchunks, const float* __restrict__ sA,
+                                          float* __restrict__ sW, float (&acc)[8][4 * G], int tid, int tm, int tn) {
+    constexpr int CHUNK = KC * G * 64;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 4 * G; ++c) acc[r][c] = 0.0f;
+
+    stage_chunk<G>(gW, sW, tid);
+    cp_async_commit();
+    for (int c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) {
+            stage_chunk<G>(gW + (size_t)(c + 1) * CHUNK, sW + ((c + 1) & 1) * WSTAGE_FLOATS, tid);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();  // stage c landed for every thread; also orders the producer epilogue before these reads
+        const float* w = sW + (c & 1) * WSTAGE_FLOATS + 4 * tn;
+        const float* a = sA + c * KC * LDM + 8 * tm;
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(a + kk * LDM);
+            const float4 a1 = *reinterpret_cast<const float4*>(a + kk * LDM + 4);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const float4 b = *reinterpret_cast<const float4*>(w + (kk * G + g) * 64);
+                const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[r][4 * g + j] = fmaf(av[r], bv[j], acc[r][4 * g + j]);
+            }
+        }
+        __syncthreads();  // stage (c&1) may be refilled by the next iteration's prefetch
+    }
+}
+
+__device__ __forceinline__ void store_col8(float* dst_row, int tm, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(dst_row + 8 * tm) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(dst_row + 8 * tm + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// Shared-memory float offset of activation buffer `id`: X has x_rows rows, A and B have ACT_ROWS rows.
+// (Offsets from the one `smem` base keep the accesses in the shared address space: LDS/STS, not generic LD/ST.)
+__device__ __forceinline__ int buf_offset(int id, int x_rows) {
+    return id == BUF_X ? 0 : (x_rows + (id - 1) * ACT_ROWS) * LDM;
+}
+
+// One pass of the layer program: contraction + epilogue into the destination activation buffer.
+template <int G>
+__device__ __forceinline__ void run_pass_g(const PassDesc& pd, const float* __restrict__ packed, float* smem, int x_rows,
+                                           float* sW, int tid, int tm, int tn) {
+    float acc[8][4 * G];
+    gemm_pass<G>(packed + pd.w_off, pd.kpad / KC, smem + buf_offset(pd.src, x_rows), sW, acc, tid, tm, tn);
+    const float* __restrict__ b1 = packed + pd.b_off;
+    const float* __restrict__ b2 = b1 + G * 64;
+    float* dst = smem + buf_offset(pd.dst, x_rows) + pd.dst_row * LDM;
+    if constexpr (G == 3) {
+        if (pd.epi == EPI_LSTM) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int u = 4 * tn + j;
+                const float bi1 = b1[u], bg1 = b1[64 + u], bo1 = b1[128 + u];
+                const float bi2 = b2[u], bg2 = b2[64 + u], bo2 = b2[128 + u];
+                float hv[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    // gates = (x W_ih^T + b_ih) + (0 W_hh^T + b_hh)
+                    const float gi = __fadd_rn(__fadd_rn(acc[r][j], bi1), bi2);
+                    const float gg = __fadd_rn(__fadd_rn(acc[r][4 + j], bg1), bg2);
+                    const float go = __fadd_rn(__fadd_rn(acc[r][8 + j], bo1), bo2);
+                    const float c = __fmul_rn(sigmoidf_(gi), tanhf(gg));  // + sigmoid(f) * c0, c0 = 0
+                    hv[r] = __fmul_rn(sigmoidf_(go), tanhf(c));
+                }
+                store_col8(dst + u * LDM, tm, hv);
+            }
+            return;
+        }
+    }
+    // EPI_LINEAR: out = acc + bias, optional activation
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = 64 * g + 4 * tn + j;
+            const float bias = b1[col];
+            float v[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                float t = __fadd_rn(acc[r][4 * g + j], bias);
+                if (pd.act == 1) t = tanhf(t);
+                else if (pd.act == 2) t = t > 0.0f ? t : __fmul_rn(t, 0.2f);  // LeakyReLU(0.2)
+                v[r] = t;
+            }
+            store_col8(dst + col * LDM, tm, v);
+        }
+}
+
+__device__ __forceinline__ void run_pass(const PassDesc& pd, const float* __restrict__ packed, float* smem, int x_rows,
+                                         float* sW, int tid, int tm, int tn) {
+    if (pd.groups == 3) run_pass_g<3>(pd, packed, smem, x_rows, sW, tid, tm, tn);
+    else if (pd.groups == 2) run_pass_g<2>(pd, packed, smem, x_rows, sW, tid, tm, tn);
+    else run_pass_g<1>(pd, packed, smem, x_rows, sW, tid, tm, tn);
+}
+
+// Sum over the two column halves of a row-phase partial (fp64), result identical in both halves.
+template <int NV>
+__device__ __forceinline__ void row_allreduce(double (&v)[NV], double* red, int m, int half) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[(i * 2 + half) * TILE_M + m] = v[i];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = red[(i * 2) * TILE_M + m] + red[(i * 2 + 1) * TILE_M + m];
+    __syncthreads();
+}
+
+// In place: buf[c][m] (= x W^T, hyrnn_nets.py:26) -> project(mobius_add(expmap0(.), bias)) for columns c < S.
+// math_.py:1132-1136 (expmap0), :51-53 (tanh clamp), :536-555 (mobius_add), :340-352 (project, fp32 eps 4e-3), k = -1.
+// Row reductions accumulate the fp32-rounded terms in fp64 and round once (the reference sums them in fp32).
+__device__ void row_mobius(float* buf, const float* __restrict__ bias, float y2, int S, double* red, int tid) {
+    const int m = tid & (TILE_M - 1), half = tid >> 6;
+    double s1[1] = {0.0};
+    for (int c = half; c < S; c += 2) {
+        const float y = buf[c * LDM + m];
+        s1[0] += (double)__fmul_rn(y, y);
+    }
+    row_allreduce<1>(s1, red, m, half);
+    const float n = fmaxf(sqrtf((float)s1[0]), 1e-15f);
+    const float th = (float)tanh((double)fminf(n, 15.0f));
+    double s2[2] = {0.0, 0.0};
+    for (int c = half; c < S; c += 2) {
+        const float p = __fmul_rn(th, __fdiv_rn(buf[c * LDM + m], n));
+        buf[c * LDM + m] = p;
+        s2[0] += (double)__fmul_rn(p, p);
+        s2[1] += (double)__fmul_rn(p, bias[c]);
+    }
+    row_allreduce<2>(s2, red, m, half);
+    const float x2 = (float)s2[0], xy = (float)s2[1];
+    const float one_2xy = __fadd_rn(1.0f, __fmul_rn(2.0f, xy));          // 1 - 2k<x,y>
+    const float ca = __fadd_rn(one_2xy, y2);                            // ... - k|y|^2
+    const float cb = __fsub_rn(1.0f, x2);                               // 1 + k|x|^2
+    const float den = fmaxf(__fadd_rn(one_2xy, __fmul_rn(x2, y2)), 1e-15f);
+    double s3[1] = {0.0};
+    for (int c = half; c < S; c += 2) {
+        const float p = buf[c * LDM + m];
+        const float q = __fdiv_rn(__fadd_rn(__fmul_rn(ca, p), __fmul_rn(cb, bias[c])), den);
+        buf[c * LDM + m] = q;
+        s3[0] += (double)__fmul_rn(q, q);
+    }
+    row_allreduce<1>(s3, red, m, half);
+    const float norm = fmaxf(sqrtf((float)s3[0]), 1e-15f);
+    const float maxnorm = 0.996f;  // (1 - 4e-3) / sqrt(|k| + 1e-15) in fp32
+    if (norm > maxnorm) {
+        for (int c = half; c < S; c += 2) buf[c * LDM + m] = __fmul_rn(__fdiv_rn(buf[c * LDM + m], norm), maxnorm);
+    }
+    __syncthreads();
+}
+
+// Coalesced store of a transposed activation buffer to a row-major (n, ncols) global tensor.
+// Lanes cover 4 windows x 8 consecutive columns: full 32-byte sectors in global, 8-way conflict in smem.
+__device__ void store_rows(const float* buf, float* __restrict__ out, int ncols, int64_t w0, int64_t n, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int mc = lane >> 3, cc = lane & 7;
+    for (int mb = warp * 4; mb < TILE_M; mb += 16) {
+        const int m = mb + mc;
+        if (w0 + m >= n) continue;
+        float* o = out + (w0 + m) * (int64_t)ncols;
+        for (int c = cc; c < ncols; c += 8) o[c] = buf[c * LDM + m];
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void load_x_tile(float* sX, const T* __restrict__ x, int64_t w0, int64_t n, int64_t stride,
+                                            int S, int S8, int tid) {
+    for (int e = tid; e < S8 * TILE_M; e += NTHREADS) {
+        const int k = e >> 6, m = e & 63;
+        float v = 0.0f;
+        if (k < S && w0 + m < n) v = (float)x[(w0 + m) * stride + k];
+        sX[e] = v;
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 2) forward_kernel(const __grid_constant__ FwdParams P) {
+    extern __shared__ __align__(16) float smem[];
+    const NetProgram& prog = P.prog;
+    const int S = prog.S, S8 = prog.S8;
+    float* sX = smem;
+    float* sA = sX + S8 * LDM;
+    float* sB = sA + ACT_ROWS * LDM;
+    float* sW = sB + ACT_ROWS * LDM;
+    double* red = reinterpret_cast<double*>(sW);  // row phases reuse the (idle) weight stage: 3*2*64 doubles = 3 KB
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int tm = (warp & 1) * 4 + (lane >> 3);
+    const int tn = (warp >> 1) * 8 + (lane & 7);
+    const float* __restrict__ packed = P.packed;
+    const int stages = P.stages;
+    const int64_t ntiles = (P.n + TILE_M - 1) / TILE_M;
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t w0 = tile * TILE_M;
+        if (P.need_x) {
+            if (P.x_is_f64) load_x_tile<double>(sX, (const double*)P.x, w0, P.n, P.row_stride, S, S8, tid);
+            else load_x_tile<float>(sX, (const float*)P.x, w0, P.n, P.row_stride, S, S8, tid);
+        }
+        // The layer program: one call site for the contraction, per-pass actions around it.
+        for (int p = 0; p < P_COUNT; ++p) {
+            if (!((P.pass_mask >> p) & 1u)) continue;
+            if (p == P_D0 && !(stages & HYPAD_STAGE_ENCODER)) {
+                // Decoder.forward on a caller-provided latent: B[c][m] = z_in[w0+m][c], zero padded to 64 rows
+                for (int e = tid; e < 64 * TILE_M; e += NTHREADS) {
+                    const int c = e >> 6, m = e & 63;
+                    float v = 0.0f;
+                    if (c < prog.latent && w0 + m < P.n) v = P.z_in[(w0 + m) * prog.latent + c];
+                    sB[e] = v;
+                }
+            }
+            const PassDesc& pd = prog.pass[p];
+            run_pass(pd, packed, smem, S8, sW, tid, tm, tn);
+            if (p == P_C4) {
+                // CriticX dense5 (20 -> 1) per window
+                __syncthreads();
+                if (tid < TILE_M && w0 + tid < P.n) {
+                    const float* w5 = packed + prog.critic5_off;
+                    const float* h = smem + buf_offset(pd.dst, S8);
+                    float a = 0.0f;
+                    for (int k = 0; k < prog.latent_c; ++k) a = fmaf(h[k * LDM + tid], w5[k], a);
+                    P.out.critic[w0 + tid] = __fadd_rn(a, w5[prog.latent_c]);
+                }
+                __syncthreads();
+            } else if (p == P_Z) {
+                if (P.out.z) {
+                    __syncthreads();
+                    store_rows(sB, P.out.z, prog.latent, w0, P.n, tid);
+                }
+            } else if (p == P_DENSE2) {
+                if (P.out.eucl) {
+                    __syncthreads();
+                    store_rows(sB, P.out.eucl, S, w0, P.n, tid);
+                }
+            } else if (p == P_MOB_R || p == P_MOB_X) {
+                float* buf = smem + buf_offset(pd.dst, S8);
+                float* gout = p == P_MOB_R ? P.out.hyper : P.out.hyper_x;
+                __syncthreads();
+                row_mobius(buf, packed + prog.mob_bias_off, packed[prog.mob_y2_off], S, red, tid);
+                if (gout) store_rows(buf, gout, S, w0, P.n, tid);
+            }
+        }
+        if (P.want_rowstats) {
+            // utils/anomaly_detection_utils.py:58-66 in the reference's fp32 operation order; A = hyper, B = hyper_x
+            const int m = tid & (TILE_M - 1), half = tid >> 6;
+            const bool both = P.out.rec != nullptr;
+            double s[3] = {0.0, 0.0, 0.0};
+            for (int c = half; c < S; c += 2) {
+                const float h = sA[c * LDM + m];
+                s[2] += (double)__fmul_rn(h, h);
+                if (both) {
+                    const float hx = sB[c * LDM + m];
+                    const float d = __fsub_rn(hx, h);
+                    s[0] += (double)__fmul_rn(d, d);
+                    s[1] += (double)__fmul_rn(hx, hx);
+                }
+            }
+            row_allreduce<3>(s, red, m, half);
+            if (half == 0 && w0 + m < P.n) {
+                const float sqdist = (float)s[0], squnorm = (float)s[1], sqvnorm = (float)s[2];
+                if (both) {
+                    const float t = __fdiv_rn(__fmul_rn(2.0f, sqdist),
+                                              __fmul_rn(__fsub_rn(1.0f, squnorm), __fsub_rn(1.0f, sqvnorm)));
+                    const float xt = __fadd_rn(__fadd_rn(1.0f, t), 1e-7f);
+                    P.out.rec[w0 + m] = (float)acosh((double)xt);
+                }
+                if (P.out.unorm) P.out.unorm[w0 + m] = sqrtf(sqvnorm);
+            }
+        }
+        __syncthreads();  // next tile overwrites X / A / B
+    }
+}
+
+// Stand-alone MobiusLinear.forward (hyperspace/hyrnn_nets.py:186-200 -> :13-35) for (n, in) -> (n, out).
+struct MobiusParams {
+    const float* x;
+    const float* panel;  // [in8][G][64]
+    const float* bias;   // [128] on the ball, zero padded
+    const float* y2;     // sum(bias^2)
+    float* out;
+    int64_t n;
+    int32_t in_f, in8, out_f, groups, has_bias;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 2) mobius_kernel(const __grid_constant__ MobiusParams P) {
+    extern __shared__ __align__(16) float smem[];
+    float* sX = smem;
+    float* sB = sX + P.in8 * LDM;
+    float* sW = sB + 3 * 64 * LDM;
+    double* red = reinterpret_cast<double*>(sW);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tm = (warp & 1) * 4 + (lane >> 3), tn = (warp >> 1) * 8 + (lane & 7);
+    PassDesc pd;
+    pd.w_off = 0; pd.b_off = 0; pd.kpad = P.in8; pd.groups = P.groups; pd.src = 0; pd.dst = 1; pd.dst_row = 0;
+    pd.epi = EPI_LINEAR; pd.act = 0;
+    const int64_t ntiles = (P.n + TILE_M - 1) / TILE_M;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t w0 = tile * TILE_M;
+        load_x_tile<float>(sX, P.x, w0, P.n, P.in_f, P.in_f, P.in8, tid);
+        // the panel is followed by 2*G*64 zero floats read as the (absent) Euclidean bias
+        {
+            PassDesc q = pd;
+            q.b_off = P.in8 * P.groups * 64;
+            run_pass(q, P.panel, smem, P.in8, sW, tid, tm, tn);
+        }
+        __syncthreads();
+        if (P.has_bias) {
+            row_mobius(sB, P.bias, *P.y2, P.out_f, red, tid);
+        } else {
+            // no bias: project(expmap0(.)) -- mobius_add is skipped (hyrnn_nets.py:28)
+            row_mobius(sB, P.bias, 0.0f, P.out_f, red, tid);
+        }
+        store_rows(sB, P.out, P.out_f, w0, P.n, tid);
+        __syncthreads();
+    }
+}
+
+int launch_mobius(int device, const float* x, int64_t n, int in_f, int out_f, const float* panel, const float* bias,
+                  const float* y2, int has_bias, float* out, cudaStream_t stream) {
+    MobiusParams P;
+    P.x = x; P.panel = panel; P.bias = bias; P.y2 = y2; P.out = out; P.n = n;
+    P.in_f = in_f; P.in8 = (in_f + 7) / 8 * 8; P.out_f = out_f; P.groups = (out_f + 63) / 64; P.has_bias = has_bias;
+    const size_t smem = (size_t)(P.in8 + 3 * 64) * LDM * sizeof(float) + 2 * WSTAGE_FLOATS * sizeof(float);
+    static thread_local size_t configured = 0;
+    if (configured < smem) {
+        HYPAD_CUDA_TRY(cudaFuncSetAttribute(mobius_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int sms = kNumSMs;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int64_t ntiles = ceil_div(n, TILE_M);
+    const int64_t grid = ntiles < 2 * (int64_t)sms ? ntiles : 2 * (int64_t)sms;
+    mobius_kernel<<<(unsigned)grid, NTHREADS, smem, stream>>>(P);
+    HYPAD_LAUNCH_CHECK();
+    return HYPAD_OK;
+}
+
+size_t forward_smem_bytes(int S8) { return (size_t)(S8 + 2 * ACT_ROWS) * LDM * sizeof(float) + 2 * WSTAGE_FLOATS * sizeof(float); }
+
+int launch_forward(const hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_t row_stride, const float* z_in,
+                   int stages, const hypad_forward_out* out, cudaStream_t stream) {
+    FwdParams P;
+    memset(&P, 0, sizeof(P));
+    P.x = x;
+    P.z_in = z_in;
+    P.packed = ctx->packed;
+    P.n = n;
+    P.row_stride = row_stride;
+    P.x_is_f64 = x_is_f64;
+    P.stages = stages;
+    P.out = *out;
+    P.prog = ctx->prog;
+    const bool hyp = ctx->prog.hyperbolic != 0;
+    uint32_t mask = 0;
+    if (stages & HYPAD_STAGE_CRITIC) mask |= (1u << P_C1) | (1u << P_C2) | (1u << P_C3) | (1u << P_C4);
+    if (stages & HYPAD_STAGE_ENCODER) mask |= (1u << P_ENC0) | (1u << P_ENC1) | (1u << P_Z);
+    if (stages & HYPAD_STAGE_DECODER) {
+        mask |= (1u << P_D0) | (1u << P_L0A) | (1u << P_L0B) | (1u << P_L1A) | (1u << P_L1B) | (1u << P_DENSE2);
+        if (hyp) mask |= (1u << P_MOB_R);
+    }
+    if (hyp && (stages & HYPAD_STAGE_MOBIUS_X)) mask |= (1u << P_MOB_X);
+    P.pass_mask = mask;
+    P.need_x = (stages & (HYPAD_STAGE_ENCODER | HYPAD_STAGE_MOBIUS_X | HYPAD_STAGE_CRITIC)) != 0;
+    if (!(hyp && (stages & HYPAD_STAGE_DECODER))) P.out.unorm = nullptr, P.out.hyper = nullptr;
+    if (!(hyp && (stages & HYPAD_STAGE_DECODER) && (stages & HYPAD_STAGE_MOBIUS_X))) P.out.rec = nullptr;
+    if (!(hyp && (stages & HYPAD_STAGE_MOBIUS_X))) P.out.hyper_x = nullptr;
+    P.want_rowstats = (P.out.rec != nullptr) || (P.out.unorm != nullptr);
+    const size_t smem = forward_smem_bytes(ctx->prog.S8);
+    static thread_local size_t configured = 0;
+    if (configured < smem) {
+        HYPAD_CUDA_TRY(cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HYPAD_CUDA_TRY(cudaFuncSetAttribute(forward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured = smem;
+    }
+    int per_sm = 0;
+    HYPAD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel, NTHREADS, smem));
+    if (per_sm < 1) {
+        set_error("forward_kernel does not fit: %zu bytes of shared memory", smem);
+        return HYPAD_ECUDA;
+    }
+    const int64_t ntiles = ceil_div(n, TILE_M);
+    int sms = kNumSMs;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const int64_t grid = ntiles < (int64_t)sms * per_sm ? ntiles : (int64_t)sms * per_sm;
+    forward_kernel<<<(unsigned)grid, NTHREADS, smem, stream>>>(P);
+    HYPAD_LAUNCH_CHECK();
+    return HYPAD_OK;
+}
+
+}  // namespace hypad

@@ -1,0 +1,287 @@
+// Overlap aggregation of critic scores by Gaussian-KDE arg-max (utils/anomaly_detection_utils.py:372-400,
+// twin at :471-503), float64 like scipy.stats.gaussian_kde which the reference calls once per timestep.
+//
+// Timestep i aggregates the critic value of every window covering it: windows hi = min(i, N-1) down to
+// lo = max(0, i-S+1) (the reference's j loop yields them in that, descending, order), n = hi-lo+1 <= S <= 128.
+//   n == 1                      -> the value itself (np.median of one element)
+//   variance == 0 (LinAlgError) -> np.median of identical values = the value
+//   else                        -> V[argmax_j sum_i w * exp(-(P_i - P_j)^2 / 2) * norm],  P = V / cho,
+//                                  cho = sqrt(var_ddof1) * n^(-1/5), w = 1/n, norm = (2 pi)^(-1/2) / cho,
+//                                  first maximum wins (np.argmax).
+// One warp owns one timestep; lanes hold points j = lane + 32 q.
+//
+// kde_exhaustive_kernel evaluates all n^2 kernel values in fp64, accumulating over i in scipy's order.
+// kde_screened_kernel (the product path) first evaluates all densities in fp32 with ex2.approx on centred,
+// bandwidth-scaled values; every j whose fp32 density is within 1e-3 (relative) of the fp32 maximum is a
+// candidate -- the fp32 error is bounded well below that -- and only candidates are
+// re-evaluated in fp64.  The arg-max is then taken over the fp64 densities of the candidates in ascending j,
+// which equals the arg-max over all j.
+#include "common.cuh"
+
+namespace hypad {
+
+constexpr int KDE_WARPS = 4;
+constexpr int KDE_MAXPTS = 128;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct KdeArgs {
+    const float* critic;
+    int64_t critic_offset, critic_len, n_windows, t0, t_count;
+    double* out;
+    int S;
+};
+
+// Loads the n points of timestep i into v[q] (lane + 32q), returns n.  Points beyond n are left 0.
+__device__ __forceinline__ int load_points(const KdeArgs& a, int64_t i, int lane, double (&v)[4]) {
+    const int64_t hi = i < a.n_windows - 1 ? i : a.n_windows - 1;
+    const int64_t lo = i - a.S + 1 > 0 ? i - a.S + 1 : 0;
+    const int n = (int)(hi - lo + 1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int j = lane + 32 * q;
+        v[q] = j < n ? (double)a.critic[hi - j - a.critic_offset] : 0.0;
+    }
+    return n;
+}
+
+// mean / ddof-1 variance of the warp's points (fp64)
+__device__ __forceinline__ void point_stats(const double (&v)[4], int n, int lane, double& mean, double& var) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s += v[q];  // padded entries are 0
+    mean = warp_sum(s) / (double)n;
+    double ss = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (lane + 32 * q < n) {
+            const double d = v[q] - mean;
+            ss += d * d;
+        }
+    var = warp_sum(ss) / (double)(n - 1);
+}
+
+// (best, j) arg-max across the warp with first-index tie-break; returns the winning j to every lane
+__device__ __forceinline__ int warp_argmax_first(double best, int j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, j, o);
+        if (ob > best || (ob == best && oj < j)) {
+            best = ob;
+            j = oj;
+        }
+    }
+    return j;
+}
+
+__global__ void __launch_bounds__(KDE_WARPS * 32) kde_exhaustive_kernel(const KdeArgs a) {
+    __shared__ double sP[KDE_WARPS][KDE_MAXPTS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* P = sP[warp];
+    const int64_t stride = (int64_t)gridDim.x * KDE_WARPS;
+    for (int64_t it = (int64_t)blockIdx.x * KDE_WARPS + warp; it < a.t_count; it += stride) {
+        const int64_t i = a.t0 + it;
+        double v[4];
+        const int n = load_points(a, i, lane, v);
+        if (n == 1) {
+            if (lane == 0) a.out[it] = v[0];
+            continue;
+        }
+        double mean, var;
+        point_stats(v, n, lane, mean, var);
+        if (!(var > 0.0)) {  // scipy: Cholesky of [[0]] raises LinAlgError -> np.median of identical values
+            if (lane == 0) a.out[it] = v[0];
+            continue;
+        }
+        const double cho = sqrt(var) * pow((double)n, -0.2);
+        const double norm = 0.3989422804014327 / cho;  // (2 pi)^(-1/2) / cho
+        const double w = 1.0 / (double)n;
+        double p[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            p[q] = v[q] / cho;
+            if (lane + 32 * q < n) P[lane + 32 * q] = p[q];
+        }
+        __syncwarp();
+        double est[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int k = 0; k < n; ++k) {
+            const double pk = P[k];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double r = pk - p[q];
+                const double e = __dmul_rn(exp(-__dmul_rn(r, r) / 2.0), norm);
+                est[q] = __dadd_rn(est[q], __dmul_rn(w, e));
+            }
+        }
+        double best = -1.0;
+        int bj = 0x7fffffff;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = lane + 32 * q;
+            if (j < n && est[q] > best) {
+                best = est[q];
+                bj = j;
+            }
+        }
+        bj = warp_argmax_first(best, bj);
+        // the winner's value: lane bj%32 holds it in v[bj/32]
+        double val = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (bj == lane + 32 * q) val = v[q];
+        val = __shfl_sync(0xffffffffu, val, bj & 31);
+        if (lane == 0) a.out[it] = val;
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(KDE_WARPS * 32) kde_screened_kernel(const KdeArgs a) {
+    __shared__ double sP[KDE_WARPS][KDE_MAXPTS];
+    __shared__ float sD[KDE_WARPS][KDE_MAXPTS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* P = sP[warp];
+    float* D = sD[warp];
+    const int64_t stride = (int64_t)gridDim.x * KDE_WARPS;
+    const float kNegHalfLog2e = -0.72134752044448170f;  // -(1/2) log2(e)
+    for (int64_t it = (int64_t)blockIdx.x * KDE_WARPS + warp; it < a.t_count; it += stride) {
+        const int64_t i = a.t0 + it;
+        double v[4];
+        const int n = load_points(a, i, lane, v);
+        if (n == 1) {
+            if (lane == 0) a.out[it] = v[0];
+            continue;
+        }
+        double mean, var;
+        point_stats(v, n, lane, mean, var);
+        if (!(var > 0.0)) {
+            if (lane == 0) a.out[it] = v[0];
+            continue;
+        }
+        const double cho = sqrt(var) * pow((double)n, -0.2);
+        float d[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = lane + 32 * q;
+            d[q] = (float)((v[q] - mean) / cho);
+            if (j < n) {
+                P[j] = v[q] / cho;
+                D[j] = d[q];
+            }
+        }
+        __syncwarp();
+        // ---- fp32 screening: all n^2 kernel values with ex2.approx -------------------------------------
+        float e32[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < n; ++k) {
+            const float dk = D[k];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float r = dk - d[q];
+                e32[q] += ex2_approx(r * r * kNegHalfLog2e);
+            }
+        }
+        float m32 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (lane + 32 * q < n) m32 = fmaxf(m32, e32[q]);
+        m32 = warp_max(m32);
+        const float thr = m32 * (1.0f - 1e-3f);
+        // ---- fp64 re-evaluation of the candidates, ascending j -----------------------------------------
+        const double norm = 0.3989422804014327 / cho;
+        const double w = 1.0 / (double)n;
+        double best = -1.0;
+        int bj = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            unsigned cand = __ballot_sync(0xffffffffu, (lane + 32 * q < n) && e32[q] >= thr);
+            while (cand) {
+                const int src = __ffs(cand) - 1;
+                cand &= cand - 1;
+                const int j = src + 32 * q;
+                const double pj = P[j];
+                double part = 0.0;
+                for (int k = lane; k < n; k += 32) {
+                    const double r = P[k] - pj;
+                    part += w * (exp(-(r * r) / 2.0) * norm);
+                }
+                const double tot = warp_sum(part);  // xor tree: bitwise identical in every lane
+                if (tot > best) {
+                    best = tot;
+                    bj = j;
+                }
+            }
+        }
+        double val = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (bj == lane + 32 * q) val = v[q];
+        val = __shfl_sync(0xffffffffu, val, bj & 31);
+        if (lane == 0) a.out[it] = val;
+        __syncwarp();
+    }
+}
+
+static int check_args(const float* critic, int64_t critic_offset, int64_t critic_len, int64_t n_windows, int S, int64_t t0,
+                      int64_t t_count, double* kmax) {
+    HYPAD_REQUIRE(critic && kmax, "kde: NULL argument");
+    HYPAD_REQUIRE(S >= 1 && S <= KDE_MAXPTS, "kde: S=%d outside 1..%d", S, KDE_MAXPTS);
+    HYPAD_REQUIRE(n_windows >= 1, "kde: n_windows < 1");
+    HYPAD_REQUIRE(t0 >= 0 && t_count >= 0 && t0 + t_count <= n_windows + S - 1, "kde: timestep range outside [0, N+S-1)");
+    if (t_count > 0) {
+        const int64_t first = t0 - S + 1 > 0 ? t0 - S + 1 : 0;
+        const int64_t last = t0 + t_count - 1 < n_windows - 1 ? t0 + t_count - 1 : n_windows - 1;
+        HYPAD_REQUIRE(critic_offset <= first && critic_offset + critic_len > last,
+                      "kde: critic slice [%lld,%lld) does not cover windows [%lld,%lld]", (long long)critic_offset,
+                      (long long)(critic_offset + critic_len), (long long)first, (long long)last);
+    }
+    return HYPAD_OK;
+}
+
+template <typename K>
+static int launch_kde(K kernel, const float* critic, int64_t critic_offset, int64_t critic_len, int64_t n_windows, int S,
+                      int64_t t0, int64_t t_count, double* kmax, cudaStream_t stream) {
+    int rc = check_args(critic, critic_offset, critic_len, n_windows, S, t0, t_count, kmax);
+    if (rc != HYPAD_OK || t_count == 0) return rc;
+    KdeArgs a{critic, critic_offset, critic_len, n_windows, t0, t_count, kmax, S};
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = ceil_div(t_count, KDE_WARPS);
+    const int64_t cap = (int64_t)sms * 8;  // 8 CTAs of 4 warps per SM, grid-stride beyond
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    kernel<<<grid, KDE_WARPS * 32, 0, stream>>>(a);
+    HYPAD_LAUNCH_CHECK();
+    return HYPAD_OK;
+}
+
+}  // namespace hypad
+
+extern "C" {
+
+int hypad_kde_argmax_overlap(const float* critic, int64_t critic_offset, int64_t critic_len, int64_t n_windows, int S,
+                             int64_t t0, int64_t t_count, double* kmax, void* stream) {
+    return hypad::launch_kde(hypad::kde_screened_kernel, critic, critic_offset, critic_len, n_windows, S, t0, t_count, kmax,
+                             (cudaStream_t)stream);
+}
+
+int hypad_kde_argmax_overlap_exhaustive(const float* critic, int64_t critic_offset, int64_t critic_len, int64_t n_windows,
+                                        int S, int64_t t0, int64_t t_count, double* kmax, void* stream) {
+    return hypad::launch_kde(hypad::kde_exhaustive_kernel, critic, critic_offset, critic_len, n_windows, S, t0, t_count, kmax,
+                             (cudaStream_t)stream);
+}
+
+}  // extern "C"

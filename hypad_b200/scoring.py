@@ -1,0 +1,426 @@
+"""Device-side scoring steps and the fused window-scoring pipeline.
+
+Thin Python over the C-ABI (include/hypad_b200.h): every function takes/returns CUDA tensors, allocates its
+output with torch (plumbing) and enqueues hand-written sm_100a kernels on the current torch stream.
+`WindowScorer` chains them into what anomaly_detection.py:67-155 + utils/anomaly_detection_utils.py:21-94 of the
+reference compute for one signal, without ever materialising the (N, S) window matrix for univariate signals.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _native, _weights
+from ._native import HypadError, check, ptr
+
+
+def _ctx(t):
+    return _native.default_context(t.device)
+
+
+def _as_dev(a, dtype, device):
+    """numpy / CPU tensor / CUDA tensor -> contiguous CUDA tensor of `dtype` on `device`."""
+    if isinstance(a, torch.Tensor):
+        t = a.detach()
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(a)))
+    return t.to(device=device, dtype=dtype).contiguous()
+
+
+def cuda_device(device=None):
+    if device is not None:
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise HypadError("hypad_b200: device %s is not a CUDA device (no CPU implementation exists)" % device)
+        return device if device.index is not None else torch.device("cuda", torch.cuda.current_device())
+    if not torch.cuda.is_available():
+        raise HypadError("hypad_b200: no CUDA device available; the scoring path has no CPU implementation")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# single steps
+# ---------------------------------------------------------------------------------------------------------
+
+
+def window_gather(X, window, out_dtype=torch.float64):
+    """rolling_window_sequences(window_size=window, target_size=1, step_size=1): (T,) f64 -> (T-window, window)."""
+    X = _native.require_cuda(X, "X").reshape(-1)
+    if X.dtype != torch.float64:
+        X = X.double()
+    n = X.shape[0] - window
+    if n <= 0:
+        return torch.empty((0, window), dtype=out_dtype, device=X.device)
+    out = torch.empty((n, window), dtype=out_dtype, device=X.device)
+    c = _ctx(X)
+    with torch.cuda.device(X.device):
+        check(c.lib.hypad_window_gather(ptr(X), n, window, ptr(out), int(out_dtype == torch.float64), c.stream()))
+    return out
+
+
+def poincare_rowdist(recons, truth):
+    recons = _native.require_cuda(recons, "recons").float().contiguous()
+    truth = _native.require_cuda(truth, "truth").float().contiguous()
+    n, S = recons.shape
+    out = torch.empty(n, dtype=torch.float32, device=recons.device)
+    c = _ctx(recons)
+    with torch.cuda.device(recons.device):
+        check(c.lib.hypad_poincare_rowdist(ptr(recons), ptr(truth), n, S, ptr(out), c.stream()))
+    return out
+
+
+def rownorm(x):
+    x = _native.require_cuda(x, "x").float().contiguous()
+    n, S = x.shape
+    out = torch.empty(n, dtype=torch.float32, device=x.device)
+    c = _ctx(x)
+    with torch.cuda.device(x.device):
+        check(c.lib.hypad_rownorm(ptr(x), n, S, ptr(out), c.stream()))
+    return out
+
+
+def kde_argmax_overlap(critic, S, n_windows=None, critic_offset=0, t0=0, t_count=None, exhaustive=False):
+    """critic (fp32, one value per window) -> kmax (float64, one value per timestep in [t0, t0+t_count))."""
+    critic = _native.require_cuda(critic, "critic").reshape(-1)
+    if critic.dtype != torch.float32:
+        critic = critic.float()
+    critic = critic.contiguous()
+    n_windows = critic.shape[0] if n_windows is None else n_windows
+    total = n_windows + S - 1
+    t_count = total - t0 if t_count is None else t_count
+    out = torch.empty(t_count, dtype=torch.float64, device=critic.device)
+    c = _ctx(critic)
+    fn = c.lib.hypad_kde_argmax_overlap_exhaustive if exhaustive else c.lib.hypad_kde_argmax_overlap
+    with torch.cuda.device(critic.device):
+        check(fn(ptr(critic), critic_offset, critic.shape[0], n_windows, S, t0, t_count, ptr(out), c.stream()))
+    return out
+
+
+def critic_zscore_smooth(kmax, smooth_window):
+    kmax = _native.require_cuda(kmax, "kmax").double().contiguous()
+    out = torch.empty_like(kmax)
+    c = _ctx(kmax)
+    with torch.cuda.device(kmax.device):
+        check(c.lib.hypad_critic_zscore_smooth(c.handle, ptr(kmax), kmax.shape[0], int(smooth_window), ptr(out), c.stream()))
+    return out
+
+
+def rolling_mean_centered(x, window, min_periods=None):
+    x = _native.require_cuda(x, "x").double().contiguous()
+    out = torch.empty_like(x)
+    mp = window // 2 if min_periods is None else min_periods
+    c = _ctx(x)
+    with torch.cuda.device(x.device):
+        check(c.lib.hypad_rolling_mean_centered(c.handle, ptr(x), x.shape[0], int(window), int(mp), ptr(out), c.stream()))
+    return out
+
+
+def zscore_clip(x):
+    x = _native.require_cuda(x, "x")
+    if x.dtype not in (torch.float32, torch.float64):
+        x = x.double()
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.float64, device=x.device)
+    c = _ctx(x)
+    with torch.cuda.device(x.device):
+        check(c.lib.hypad_zscore_clip(c.handle, ptr(x), int(x.dtype == torch.float32), x.numel(), ptr(out), c.stream()))
+    return out
+
+
+def combine(mode, critic_scores=None, rec=None, unorm=None, n=None, lambda_rec=0.5):
+    ref = next(t for t in (critic_scores, rec, unorm) if t is not None)
+    dev = ref.device
+    n = ref.shape[0] if n is None else n
+    if critic_scores is not None:
+        critic_scores = critic_scores.double().contiguous()
+    rec32 = 0
+    if rec is not None:
+        if rec.dtype == torch.float32:
+            rec32 = 1
+        elif rec.dtype != torch.float64:
+            rec = rec.double()
+        rec = rec.contiguous()
+    if unorm is not None:
+        unorm = unorm.float().contiguous()
+    out = torch.empty(n, dtype=torch.float64, device=dev)
+    c = _native.default_context(dev)
+    with torch.cuda.device(dev):
+        check(c.lib.hypad_combine_scores(_native.COMBINE_MODES[mode], ptr(critic_scores), ptr(rec), rec32, ptr(unorm),
+                                         float(lambda_rec), n, ptr(out), c.stream()))
+    return out
+
+
+def median_overlap(y_hat):
+    y_hat = _native.require_cuda(y_hat, "y_hat").float().contiguous()
+    n, S = y_hat.shape
+    out = torch.empty(n + S - 1, dtype=torch.float32, device=y_hat.device)
+    c = _ctx(y_hat)
+    with torch.cuda.device(y_hat.device):
+        check(c.lib.hypad_median_overlap(ptr(y_hat), n, S, ptr(out), c.stream()))
+    return out
+
+
+def true_from_signal(x, n, row_stride, S):
+    x = _native.require_cuda(x, "x")
+    if x.dtype not in (torch.float32, torch.float64):
+        x = x.double()
+    x = x.contiguous()
+    out = torch.empty(n + S - 1, dtype=torch.float64, device=x.device)
+    c = _ctx(x)
+    with torch.cuda.device(x.device):
+        check(c.lib.hypad_true_from_signal(ptr(x), int(x.dtype == torch.float64), n, row_stride, S, ptr(out), c.stream()))
+    return out
+
+
+def _err_inputs(y, y_hat):
+    y = _native.require_cuda(y, "y").reshape(-1).double().contiguous()
+    y_hat = _native.require_cuda(y_hat, "y_hat").reshape(-1)
+    if y_hat.dtype not in (torch.float32, torch.float64):
+        y_hat = y_hat.double()
+    y_hat = y_hat.contiguous()
+    if y.shape != y_hat.shape:
+        raise HypadError("hypad_b200: y and y_hat differ in length (%d vs %d)" % (y.shape[0], y_hat.shape[0]))
+    return y, y_hat, torch.empty_like(y)
+
+
+def dtw_error(y, y_hat, score_window=10):
+    y, y_hat, out = _err_inputs(y, y_hat)
+    c = _ctx(y)
+    with torch.cuda.device(y.device):
+        check(c.lib.hypad_dtw_error(ptr(y), ptr(y_hat), int(y_hat.dtype == torch.float32), y.shape[0], int(score_window),
+                                    ptr(out), c.stream()))
+    return out
+
+
+def point_error(y, y_hat):
+    y, y_hat, out = _err_inputs(y, y_hat)
+    c = _ctx(y)
+    with torch.cuda.device(y.device):
+        check(c.lib.hypad_point_error(ptr(y), ptr(y_hat), int(y_hat.dtype == torch.float32), y.shape[0], ptr(out), c.stream()))
+    return out
+
+
+def area_error(y, y_hat, score_window=10):
+    y, y_hat, out = _err_inputs(y, y_hat)
+    c = _ctx(y)
+    with torch.cuda.device(y.device):
+        check(c.lib.hypad_area_error(ptr(y), ptr(y_hat), int(y_hat.dtype == torch.float32), y.shape[0], int(score_window),
+                                     ptr(out), c.stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# find_anomalies: device statistics / run extraction + host bookkeeping on a handful of runs
+# ---------------------------------------------------------------------------------------------------------
+
+
+def analysis_windows(n, window_size=None, window_size_portion=None, window_step_size=None, window_step_size_portion=None):
+    """Window size, step and count of utils/anomaly_detection_utils.py:1423-1457."""
+    window_size = window_size or n
+    if window_size_portion:
+        window_size = int(np.ceil(n * window_size_portion))
+    step = window_step_size or window_size
+    if window_step_size_portion:
+        step = int(np.ceil(window_size * window_step_size_portion))
+    count = 1
+    while (count - 1) * step + window_size < n:
+        count += 1
+    return int(window_size), int(step), count
+
+
+def threshold_windows(errors, window_size, step, count, ddof, anomaly_padding, max_runs=256):
+    """Per analysis window: (mean, std, threshold, max_below) and the padded above-threshold runs."""
+    errors = _native.require_cuda(errors, "errors").reshape(-1).double().contiguous()
+    dev = errors.device
+    c = _ctx(errors)
+    while True:
+        stats = torch.empty((count, 4), dtype=torch.float64, device=dev)
+        runs = torch.empty((count, max_runs, 3), dtype=torch.float64, device=dev)
+        n_runs = torch.empty(count, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(c.lib.hypad_threshold_windows(c.handle, ptr(errors), errors.shape[0], window_size, step, count, int(ddof),
+                                                int(anomaly_padding), ptr(stats), ptr(runs), ptr(n_runs), max_runs, c.stream()))
+        nr = n_runs.cpu().numpy()
+        if nr.max(initial=0) <= max_runs:
+            return stats.cpu().numpy(), runs.cpu().numpy(), nr
+        max_runs = int(nr.max()) + 16
+
+
+def intervals_from_runs(stats, runs, n_runs, step, min_percent):
+    """Host tail of find_anomalies on the few runs per window: prune (:1203-1237), score (:1240-1269), merge (:1272-1313)."""
+    sequences = []
+    for k in range(stats.shape[0]):
+        mean, std, thr, max_below = stats[k]
+        rows = [(max_below, -1.0, -1.0)] + [(runs[k, r, 2], runs[k, r, 0], runs[k, r, 1]) for r in range(int(n_runs[k]))]
+        rows.sort(key=lambda t: -t[0])  # descending by max error, stable
+        me = np.array([r[0] for r in rows], dtype=np.float64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            increase = (me[:-1] - me[1:]) / me[:-1]
+        too_small = increase < min_percent
+        last = -1 if too_small.all() else int(np.flatnonzero(~too_small)[-1])
+        denom = mean + std
+        for m, s, e in rows[: last + 1]:
+            sequences.append([s + k * step, e + k * step, (m - thr) / denom])
+    if not sequences:
+        return []
+    sequences.sort(key=lambda s: s[0])
+    merged = [sequences[0]]
+    score, weights = [sequences[0][2]], [sequences[0][1] - sequences[0][0]]
+    for seq in sequences[1:]:
+        prev = merged[-1]
+        if seq[0] <= prev[1] + 1:
+            score.append(seq[2])
+            weights.append(seq[1] - seq[0])
+            merged[-1] = [prev[0], max(prev[1], seq[1]), float(np.average(score, weights=weights))]
+        else:
+            score, weights = [seq[2]], [seq[1] - seq[0]]
+            merged.append(seq)
+    return merged
+
+
+def find_anomaly_intervals(errors, index, window_size_portion=None, window_step_size_portion=None, window_size=None,
+                           window_step_size=None, min_percent=0.1, anomaly_padding=50, ddof=0):
+    """find_anomalies(..., fixed_threshold=True) on a device array; returns (K,3) float64 [index[start], index[end], score]."""
+    n = errors.numel()
+    wsize, step, count = analysis_windows(n, window_size, window_size_portion, window_step_size, window_step_size_portion)
+    stats, runs, n_runs = threshold_windows(errors, wsize, step, count, ddof, anomaly_padding)
+    merged = intervals_from_runs(stats, runs, n_runs, step, min_percent)
+    idx = index.detach().cpu().numpy() if isinstance(index, torch.Tensor) else np.asarray(index)
+    out = [[float(idx[int(s)]), float(idx[int(e)]), float(sc)] for s, e, sc in merged]
+    return np.asarray(out, dtype=np.float64).reshape(-1, 3)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the fused pipeline
+# ---------------------------------------------------------------------------------------------------------
+
+HYPERBOLIC_COMBINATIONS = ("mult", "uncertainty", "sum", "sum_uncertainty", "critic", "critic_uncertainty", "rec", "rec_uncertainty")
+_NEEDS_CRITIC = ("mult", "uncertainty", "sum", "sum_uncertainty", "critic", "critic_uncertainty")
+
+
+class WindowScorer:
+    """Scores every window of a signal with a (random-init or trained) TadGAN / HypAD model on one B200.
+
+    encoder, decoder, critic_x: hypad_b200.models.tadgan modules (or reference modules with the same attribute
+    names) whose parameters live on a CUDA device.
+    """
+
+    def __init__(self, encoder, decoder, critic_x):
+        for m in (encoder, decoder, critic_x):
+            if m.training:
+                raise HypadError("hypad_b200: call .eval() on the modules first (scoring is eval-mode only)")
+        self.encoder, self.decoder, self.critic_x = encoder, decoder, critic_x
+        self.net = _weights.packed_net(encoder, decoder, critic_x)
+        self.device = self.net.device
+        self.S = self.net.S
+        self.hyperbolic = self.net.hyperbolic
+
+    # -- network -------------------------------------------------------------------------------------------
+    def _input(self, x, sliding):
+        x = _native.require_cuda(x, "signal" if sliding else "windows")
+        if x.dtype not in (torch.float32, torch.float64):
+            x = x.double()
+        if sliding:
+            x = x.reshape(-1).contiguous()
+            return x, x.shape[0] - self.S, 1
+        x = x.reshape(x.shape[0], -1).contiguous()
+        if x.shape[1] != self.S:
+            raise HypadError("hypad_b200: windows have %d samples, the model expects %d" % (x.shape[1], self.S))
+        return x, x.shape[0], self.S
+
+    def forward(self, x, sliding, keep=(), first=0, count=None):
+        """Runs the fused network over windows [first, first+count).  Returns dict of device tensors:
+        critic (n,) always; rec, unorm (n,) when hyperbolic; plus any of z/eucl/hyper/hyper_x named in `keep`."""
+        self.net.ensure(self.encoder, self.decoder, self.critic_x)
+        x, n_all, stride = self._input(x, sliding)
+        count = n_all - first if count is None else count
+        if count <= 0:
+            raise HypadError("hypad_b200: no windows to score (signal shorter than the window?)")
+        dev, S = x.device, self.S
+        res = {"critic": torch.empty(count, dtype=torch.float32, device=dev)}
+        if self.hyperbolic:
+            res["rec"] = torch.empty(count, dtype=torch.float32, device=dev)
+            res["unorm"] = torch.empty(count, dtype=torch.float32, device=dev)
+        widths = {"z": self.net.latent, "eucl": S, "hyper": S, "hyper_x": S}
+        for name in keep:
+            if name in ("hyper", "hyper_x") and not self.hyperbolic:
+                continue
+            res[name] = torch.empty((count, widths[name]), dtype=torch.float32, device=dev)
+        out = _native.hypad_forward_out()
+        for name, t in res.items():
+            setattr(out, name, t.data_ptr())
+        stages = _native.STAGE_ENCODER | _native.STAGE_DECODER | _native.STAGE_CRITIC
+        if self.hyperbolic:
+            stages |= _native.STAGE_MOBIUS_X
+        base = x.data_ptr() + first * stride * x.element_size()
+        with torch.cuda.device(dev):
+            check(self.net.ctx.lib.hypad_forward(self.net.ctx.handle, base, int(x.dtype == torch.float64), count, stride, None,
+                                                 stages, out, self.net.ctx.stream()))
+        res["_x"], res["_n"], res["_stride"] = x, n_all, stride
+        return res
+
+    # -- scoring -------------------------------------------------------------------------------------------
+    def critic_scores(self, critic, n_windows):
+        """final_critic_scores (:365-404): KDE arg-max overlap aggregation + quantile-band z-score + smoothing."""
+        kmax = kde_argmax_overlap(critic, self.S)
+        return critic_zscore_smooth(kmax, math.trunc(n_windows * 0.01)), kmax
+
+    def score(self, x, sliding=True, combination="uncertainty", rec_error_type="dtw", index=None, keep=(), multivariate=False,
+              lambda_rec=0.5):
+        """Per-position anomaly scores (+ intervals when `index` is given) for one signal.
+
+        sliding=True : x is the scaled signal (T,), windows are x[n:n+S], n in [0, T-S)   (univariate configs)
+        sliding=False: x is (N, S) materialised windows / multivariate rows.
+        Hyperbolic models return one score per window (N,), Euclidean ones one per timestep (N+S-1,), like the reference.
+        """
+        keep = tuple(keep)
+        need = keep if self.hyperbolic else tuple(set(keep) | {"eucl"})
+        fw = self.forward(x, sliding, need)
+        n, S = fw["critic"].shape[0], self.S
+        out = {k: v for k, v in fw.items() if not k.startswith("_")}
+        if self.hyperbolic:
+            if combination not in HYPERBOLIC_COMBINATIONS:
+                raise ValueError("unknown combination %r" % (combination,))
+            rec = fw["rec"]
+            if multivariate:
+                rec = zscore_clip(rec)  # utils/anomaly_detection_utils.py:177-178
+                out["rec"] = rec
+            cs = None
+            if combination in _NEEDS_CRITIC:
+                cs_full, kmax = self.critic_scores(fw["critic"], n)
+                out["kmax"], out["critic_scores_full"] = kmax, cs_full
+                cs = cs_full[:n]
+            out["critic_scores"] = cs
+            final = combine(combination, cs, rec, fw["unorm"], n=n)
+            ddof = 0 if multivariate else 1  # torch tensor (unbiased) vs ndarray
+        else:
+            if multivariate:
+                raise NotImplementedError("hypad_b200: Euclidean multivariate scoring (utils/anomaly_detection_utils.py:157-161) "
+                                          "is not built yet")
+            mode = {"mult": "mult", "sum": "euclidean_sum", "rec": "rec", "critic": "critic"}.get(combination)
+            if mode is None:
+                raise ValueError('Unknown combination specified {}, use "mult", "sum", or "rec" instead.'.format(combination))
+            cs, kmax = self.critic_scores(fw["critic"], n)
+            true = true_from_signal(fw["_x"], n, fw["_stride"], S)
+            pred = median_overlap(fw["eucl"])
+            kind = rec_error_type.lower()
+            if kind == "dtw":
+                errors = dtw_error(true, pred, 10)
+            elif kind == "point":
+                errors = point_error(true, pred)
+            elif kind == "area":
+                errors = area_error(true, pred, 10)
+            else:
+                raise ValueError("unknown rec_error_type %r" % (rec_error_type,))
+            errors = rolling_mean_centered(errors, math.trunc(n * 0.01))
+            rec = zscore_clip(errors)
+            final = combine(mode, cs, rec, None, n=n + S - 1, lambda_rec=lambda_rec)
+            out.update(kmax=kmax, critic_scores=cs, rec=rec, pred=pred, true=true, errors=errors)
+            ddof = 0
+        out["final"] = final
+        if index is not None:
+            if multivariate:
+                out["intervals"] = find_anomaly_intervals(final, index, 0.2, 0.1, anomaly_padding=200, ddof=ddof)
+            else:
+                out["intervals"] = find_anomaly_intervals(final, index, 0.33, 0.1, anomaly_padding=50, ddof=ddof)
+        return out

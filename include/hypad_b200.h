@@ -1,0 +1,181 @@
+/*
+ * hypad_b200 -- C-ABI of the B200-native HypAD windowed anomaly-scoring hot path.
+ *
+ * The reference (aleflabo/HypAD) is pure Python/PyTorch: it has no FFI/plugin layer, so there is no
+ * existing native interface to mirror.  Each entry point below cites the reference
+ * Python function (file:line under the reference tree) whose arithmetic it replaces; the Python
+ * modules in hypad_b200/{models,hyperspace,utils}/ keep the reference's names and signatures and
+ * marshal into these calls with ctypes (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++/torch types.
+ *   - Every pointer argument is a DEVICE pointer unless its name starts with `h_`.
+ *   - The caller owns every buffer it passes.  The library owns only the opaque hypad_ctx
+ *     (packed weights + a growable device workspace).
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     except where documented.
+ *   - Return value: 0 on success, a negative HYPAD_E* code otherwise; hypad_last_error() returns a
+ *     thread-local human-readable message for the last failure.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef HYPAD_B200_H_
+#define HYPAD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HYPAD_OK 0
+#define HYPAD_EINVAL (-1)   /* bad argument */
+#define HYPAD_ECUDA (-2)    /* CUDA runtime error (message in hypad_last_error) */
+#define HYPAD_ENOMEM (-3)   /* workspace allocation failed */
+#define HYPAD_ESTATE (-4)   /* weights not packed / context misuse */
+
+#define HYPAD_ABI_VERSION 1
+
+typedef struct hypad_ctx hypad_ctx;
+
+/* Raw fp32 parameter tensors of the three modules, row-major as torch stores them
+ * (models/tadgan.py:10-106, hyperspace/hyrnn_nets.py:154-185).  weight_hh_* and the forget-gate rows
+ * exist in the modules but never enter the arithmetic (sequence length 1, zero state)
+ * and are therefore not passed.  Direction index: 0 = forward, 1 = reverse. */
+typedef struct hypad_weights {
+    int32_t signal_shape; /* S: window length / channel count (100, 123, 51 ...) 1..128 */
+    int32_t latent_dim;   /* Encoder/Decoder latent_space_dim: 20 (train.py:413); 1..64 */
+    int32_t hyperbolic;   /* Decoder.hyperbolic */
+    int32_t critic_dim;   /* CriticX latent_space_dim (models/tadgan.py:71): 20; 1..64 */
+    const float* enc_w_ih[2];  /* encoder.lstm.weight_ih_l0{,_reverse}   (200, S)   */
+    const float* enc_b_ih[2];  /* encoder.lstm.bias_ih_l0{,_reverse}     (200,)     */
+    const float* enc_b_hh[2];  /* encoder.lstm.bias_hh_l0{,_reverse}     (200,)     */
+    const float* enc_dense_w;  /* encoder.dense.weight                   (latent, 100) */
+    const float* enc_dense_b;  /* encoder.dense.bias                     (latent,)  */
+    const float* dec_dense1_w; /* decoder.dense1.weight                  (50, latent) */
+    const float* dec_dense1_b; /* decoder.dense1.bias                    (50,)      */
+    const float* dec_w_ih[2][2]; /* decoder.lstm.weight_ih_l{0,1}{,_reverse} (256,50) / (256,128) ; [layer][dir] */
+    const float* dec_b_ih[2][2]; /* (256,) */
+    const float* dec_b_hh[2][2]; /* (256,) */
+    const float* dec_dense2_w; /* decoder.dense2.weight                  (S, 128)   */
+    const float* dec_dense2_b; /* decoder.dense2.bias                    (S,)       */
+    const float* mobius_w;     /* decoder.hyperbolic_linear.weight       (S, S)  ; NULL when !hyperbolic */
+    const float* mobius_b;     /* decoder.hyperbolic_linear.bias         (S,) on the ball ; NULL when !hyperbolic */
+    const float* critic_w[5];  /* critic_x.dense{1..5}.weight  (20,S) (20,20) (20,20) (20,20) (1,20) */
+    const float* critic_b[5];  /* critic_x.dense{1..5}.bias */
+} hypad_weights;
+
+/* Which parts of the fused forward run (bit mask for hypad_forward `stages`). */
+#define HYPAD_STAGE_ENCODER 1   /* x -> z                      models/tadgan.py:23-27  */
+#define HYPAD_STAGE_DECODER 2   /* z -> eucl (-> hyper)        models/tadgan.py:58-67  */
+#define HYPAD_STAGE_MOBIUS_X 4  /* x -> hyper_x                anomaly_detection.py:72-74 */
+#define HYPAD_STAGE_CRITIC 8    /* x -> critic                 models/tadgan.py:91-106 */
+#define HYPAD_STAGE_ALL 15
+
+/* Optional outputs of hypad_forward; any pointer may be NULL (= not stored). */
+typedef struct hypad_forward_out {
+    float* z;        /* (N, latent)   Encoder.forward                                     */
+    float* eucl;     /* (N, S)        Decoder tanh output (= recons_signal when !hyperbolic) */
+    float* hyper;    /* (N, S)        Decoder hyperbolic output (recons_signal)           */
+    float* hyper_x;  /* (N, S)        decoder.hyperbolic_linear(window) (real_hyper)      */
+    float* critic;   /* (N,)          CriticX.forward                                     */
+    float* rec;      /* (N,)  fused row-wise Poincare distance  utils/anomaly_detection_utils.py:58-66 */
+    float* unorm;    /* (N,)  ||hyper||_2 (the "uncertainty")   utils/anomaly_detection_utils.py:341-343 */
+} hypad_forward_out;
+
+int hypad_abi_version(void);
+const char* hypad_last_error(void);
+
+/* Context: packed weights + workspace on `device`. */
+int hypad_ctx_create(hypad_ctx** out, int device);
+int hypad_ctx_destroy(hypad_ctx* ctx);
+/* Re-packs the module parameters into the kernel layout (device-to-device, on `stream`). */
+int hypad_pack_weights(hypad_ctx* ctx, const hypad_weights* w, void* stream);
+
+/* Fused network forward over `n` windows (anomaly_detection.py:67-113 for all batches at once).
+ *   x, x_is_f64 : input samples, fp32 or fp64 (the reference feeds float64 windows and casts with
+ *                 .float() inside forward, models/tadgan.py:24,92).
+ *   row_stride  : window w starts at x + w*row_stride.  1 = overlapping windows of a signal
+ *                 (utils/dataloader.py:139-222 never materialised), S = materialised rows (N,S).
+ *   z_in        : when HYPAD_STAGE_ENCODER is not requested and HYPAD_STAGE_DECODER is, the latent
+ *                 input (N, latent) fp32 of Decoder.forward; else NULL.
+ */
+int hypad_forward(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_t row_stride,
+                  const float* z_in, int stages, const hypad_forward_out* out, void* stream);
+
+/* hyperspace/hyrnn_nets.py:13-35 mobius_linear with hyperbolic_input=False, k=-1:
+ * project(mobius_add(expmap0(x W^T), bias)).  x (n,in) W (out,in) bias (out,) or NULL, out (n,out).
+ * hyperbolic_bias=0 applies expmap0 to the bias first (hyrnn_nets.py:29-30).  in,out <= 128. */
+int hypad_mobius_linear(hypad_ctx* ctx, const float* x, int64_t n, int in_features, int out_features,
+                        const float* weight, const float* bias, int hyperbolic_bias, float* out, void* stream);
+
+/* utils/anomaly_detection_utils.py:58-66: acosh(1 + 2|u-v|^2/((1-|u|^2)(1-|v|^2)) + 1e-7), fp32, per row. */
+int hypad_poincare_rowdist(const float* recons, const float* truth, int64_t n, int S, float* out, void* stream);
+/* np.linalg.norm(x, axis=1) on fp32 rows, utils/anomaly_detection_utils.py:342. */
+int hypad_rownorm(const float* x, int64_t n, int S, float* out, void* stream);
+
+/* utils/dataloader.py:139-222 rolling_window_sequences(window_size=S, target_size=1, step_size=1):
+ * out[w, j] = X[w + j], w in [0, n_windows).  Output fp32 or fp64. */
+int hypad_window_gather(const double* X, int64_t n_windows, int S, void* out, int out_is_f64, void* stream);
+
+/* utils/anomaly_detection_utils.py:372-400 (twin :471-503): overlap aggregation of one critic value per
+ * window into one value per timestep by Gaussian-KDE arg-max, float64.  kmax has n_windows+S-1 entries.
+ * Sharded use: `t0`,`t_count` select the timestep range [t0, t0+t_count) written to kmax[0..t_count);
+ * critic must still hold all n_windows values (or pass the shard's slice through critic_offset):
+ * critic[i] is the value of window critic_offset + i, for i in [0, critic_len). */
+int hypad_kde_argmax_overlap(const float* critic, int64_t critic_offset, int64_t critic_len, int64_t n_windows,
+                             int S, int64_t t0, int64_t t_count, double* kmax, void* stream);
+/* Same result computed by evaluating every density in float64 in scipy's accumulation order (no fp32
+ * screening); slower, kept as the in-library cross-check of the screened kernel. */
+int hypad_kde_argmax_overlap_exhaustive(const float* critic, int64_t critic_offset, int64_t critic_len,
+                                        int64_t n_windows, int S, int64_t t0, int64_t t_count, double* kmax,
+                                        void* stream);
+
+/* utils/anomaly_detection_utils.py:307-333 _compute_critic_score: quantile band mean, std, |z|+1, centred
+ * rolling mean (window = smooth_window, min_periods = smooth_window/2).  len entries in and out. */
+int hypad_critic_zscore_smooth(hypad_ctx* ctx, const double* kmax, int64_t len, int64_t smooth_window, double* out,
+                               void* stream);
+
+/* pandas Series.rolling(window, center=True, min_periods).mean() as used at :326-331 and :954-961. */
+int hypad_rolling_mean_centered(hypad_ctx* ctx, const double* x, int64_t len, int64_t window, int64_t min_periods,
+                                double* out, void* stream);
+
+/* scipy.stats.zscore (ddof=0) then clip(min=0)+1: utils/anomaly_detection_utils.py:523-524, :160-161, :177-178.
+ * Input fp64 or fp32 (x_is_f32), output fp64. */
+int hypad_zscore_clip(hypad_ctx* ctx, const void* x, int x_is_f32, int64_t len, double* out, void* stream);
+
+/* utils/anomaly_detection_utils.py:336-362 combine_scores on device arrays (float64 result of length n).
+ * mode: 0 mult, 1 uncertainty, 2 sum, 3 critic, 4 critic_uncertainty, 5 sum_uncertainty, 6 rec, 7 rec_uncertainty,
+ *       8 euclidean "sum" of score_anomalies (:558, lambda_rec) .  rec may be fp32 (rec_is_f32) or fp64. */
+int hypad_combine_scores(int mode, const double* critic_scores, const void* rec, int rec_is_f32, const float* unorm,
+                         double lambda_rec, int64_t n, double* out, void* stream);
+
+/* utils/anomaly_detection_utils.py:918-923: per-timestep median over the anti-diagonal of y_hat (n,S) fp32.
+ * pred has n+S-1 fp32 entries (np.median of fp32: even count -> fp32 mean of the two middle values). */
+int hypad_median_overlap(const float* y_hat, int64_t n, int S, float* pred, void* stream);
+
+/* utils/anomaly_detection_utils.py:908-910: first sample of every window + tail of the last, as float64. */
+int hypad_true_from_signal(const void* x, int x_is_f64, int64_t n, int64_t row_stride, int S, double* out, void* stream);
+
+/* utils/anomaly_detection_utils.py:815-863 _dtw_error (pyts.metrics.dtw defaults restated, see oracle/):
+ * len entries; y fp64, y_hat fp32 (the medians) or fp64. */
+int hypad_dtw_error(const double* y, const void* y_hat, int y_hat_is_f32, int64_t len, int score_window, double* out,
+                    void* stream);
+/* :761-777 _point_wise_error and :780-812 _area_error. */
+int hypad_point_error(const double* y, const void* y_hat, int y_hat_is_f32, int64_t len, double* out, void* stream);
+int hypad_area_error(const double* y, const void* y_hat, int y_hat_is_f32, int64_t len, int score_window, double* out,
+                     void* stream);
+
+/* Per-analysis-window statistics of find_anomalies (utils/anomaly_detection_utils.py:1363-1472 with
+ * fixed_threshold): for window k covering errors[k*step : k*step+window_size] writes
+ * stats[k*4 + {0,1,2,3}] = mean, std(ddof), threshold = mean + 4 std, max of the errors not inside any
+ * padded above-threshold run (max_below, 0 when every element is inside).  `runs` receives, per window,
+ * up to max_runs (start, end, max_error) triples of the dilated above-threshold runs (window-relative
+ * indices as doubles) and n_runs[k] their count (may exceed max_runs: caller re-runs with more room). */
+int hypad_threshold_windows(hypad_ctx* ctx, const double* errors, int64_t len, int64_t window_size, int64_t step,
+                            int64_t n_analysis, int ddof, int anomaly_padding, double* stats, double* runs,
+                            int32_t* n_runs, int max_runs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYPAD_B200_H_ */
