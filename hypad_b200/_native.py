@@ -51,6 +51,7 @@ class hypad_forward_out(ctypes.Structure):
 _SIGNATURES = {
     "hypad_abi_version": (_int, []),
     "hypad_last_error": (ctypes.c_char_p, []),
+    "hypad_launch_count": (ctypes.c_int64, []),
     "hypad_ctx_create": (_int, [ctypes.POINTER(_vp), _int]),
     "hypad_ctx_destroy": (_int, [_vp]),
     "hypad_pack_weights": (_int, [_vp, ctypes.POINTER(hypad_weights), _vp]),

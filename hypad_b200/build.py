@@ -26,10 +26,11 @@ def _nvcc():
 
 def _fingerprint():
     h = hashlib.sha256()
-    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(HERE, "..", "include", "hypad_b200.h")]
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    files.append(os.path.join(HERE, "..", "include", "hypad_b200.h"))
     for f in files:
         with open(f, "rb") as fh:
-            h.update(f.encode() + b"\0" + fh.read())
+            h.update(os.path.basename(f).encode() + b"\0" + fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
 

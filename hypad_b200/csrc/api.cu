@@ -1,6 +1,7 @@
 // extern "C" surface of libhypad_b200.so: context, weight packing, fused forward, Mobius linear.
 #include <stdarg.h>
 
+#include <atomic>
 #include <vector>
 
 #include "common.cuh"
@@ -8,6 +9,9 @@
 namespace hypad {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -102,6 +106,8 @@ extern "C" {
 int hypad_abi_version(void) { return HYPAD_ABI_VERSION; }
 
 const char* hypad_last_error(void) { return g_err; }
+
+int64_t hypad_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 int hypad_ctx_create(hypad_ctx** out, int device) {
     HYPAD_REQUIRE(out != nullptr, "hypad_ctx_create: out is NULL");

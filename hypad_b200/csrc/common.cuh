@@ -28,8 +28,12 @@ void set_error(const char* fmt, ...);
         }                                    \
     } while (0)
 
+void count_launch();
+
+// placed after every <<<...>>>: counts the launch and surfaces launch-configuration errors
 #define HYPAD_LAUNCH_CHECK()                      \
     do {                                          \
+        ::hypad::count_launch();                  \
         HYPAD_CUDA_TRY(cudaPeekAtLastError());    \
     } while (0)
 

@@ -84,14 +84,14 @@ __device__ __forceinline__ void gemm_pass(const float* __restrict__ gW, int nchu
     stage_chunk<G>(gW, sW, tid);
     cp_async_commit();
     for (int c = 0; c < nchunks; ++c) {
+        cp_async_wait<0>();  // this thread's part of stage c has landed
+        // One barrier per chunk: (1) stage c is visible to every thread, (2) every thread is done reading stage c-1,
+        // whose buffer the prefetch below overwrites, (3) for c == 0, the producer epilogue's writes to sA are visible.
+        __syncthreads();
         if (c + 1 < nchunks) {
             stage_chunk<G>(gW + (size_t)(c + 1) * CHUNK, sW + ((c + 1) & 1) * WSTAGE_FLOATS, tid);
             cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
         }
-        __syncthreads();  // stage c landed for every thread; also orders the producer epilogue before these reads
         const float* w = sW + (c & 1) * WSTAGE_FLOATS + 4 * tn;
         const float* a = sA + c * KC * LDM + 8 * tm;
 #pragma unroll
@@ -109,8 +109,10 @@ __device__ __forceinline__ void gemm_pass(const float* __restrict__ gW, int nchu
                     for (int j = 0; j < 4; ++j) acc[r][4 * g + j] = fmaf(av[r], bv[j], acc[r][4 * g + j]);
             }
         }
-        __syncthreads();  // stage (c&1) may be refilled by the next iteration's prefetch
     }
+    // The first stage of the next pass (or a row phase using the stage as scratch) overwrites buffer 0/1:
+    // wait until every thread has finished reading the last stage.
+    __syncthreads();
 }
 
 __device__ __forceinline__ void store_col8(float* dst_row, int tm, const float (&v)[8]) {

@@ -1,0 +1,96 @@
+"""Sharding of one signal's windows across GPUs: one process per GPU, a single gather at the end.
+
+The scoring path is embarrassingly parallel per window; the only coupling is the overlap aggregation, where
+timestep i needs the critic value of windows i-S+1 .. i.  Rank r therefore
+  * owns the contiguous window range [first, first+count) and the timesteps with the same indices (the last
+    rank also owns the S-1 trailing timesteps),
+  * recomputes the S-1 windows to the left of its range (the "halo": 0.01 % extra work at 1M windows/GPU),
+  * runs the fused network + KDE arg-max on its range with no communication,
+and the per-timestep / per-window arrays (kmax f64, rec f32, unorm f32) are gathered once over NCCL
+(NVLink 5 / NVSwitch; <= 16 B per timestep).  The O(T) finish (quantile band, z-score, smoothing, combine,
+thresholding) is then run redundantly on every rank.  There is no collective inside a kernel.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import scoring
+
+
+def shard_ranges(n_windows, world_size):
+    """Balanced contiguous window ranges: [(first, count)] * world_size (counts differ by at most one)."""
+    base, extra = divmod(n_windows, world_size)
+    out, first = [], 0
+    for r in range(world_size):
+        cnt = base + (1 if r < extra else 0)
+        out.append((first, cnt))
+        first += cnt
+    return out
+
+
+def timestep_range(first, count, n_windows, S, is_last):
+    """Timesteps a rank aggregates: its window indices, plus the S-1 trailing ones on the last rank."""
+    return first, count + (S - 1 if is_last else 0)
+
+
+def halo_first(first, S):
+    return max(0, first - (S - 1))
+
+
+def gather_concat(local, sizes, group=None):
+    """All-gather variable-length 1-D tensors (sizes known on every rank) into one concatenated tensor.
+
+    Works on CUDA tensors with NCCL and on CPU tensors with gloo (used by the world_size-2 CPU tests)."""
+    world = dist.get_world_size(group)
+    width = max(sizes)
+    buf = local.new_zeros(width)
+    buf[: local.shape[0]] = local
+    parts = [local.new_empty(width) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    return torch.cat([p[:s] for p, s in zip(parts, sizes)])
+
+
+class ShardedScorer:
+    """WindowScorer over torch.distributed.  Each rank holds only its slice of the signal (`local_slice`)."""
+
+    def __init__(self, scorer, group=None):
+        self.scorer = scorer
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def plan(self, n_windows):
+        """(first, count, h0, sample_lo, sample_hi): owned windows, first halo window and the sample range
+        [sample_lo, sample_hi) of the signal this rank needs resident (sliding windows)."""
+        S = self.scorer.S
+        first, count = shard_ranges(n_windows, self.world)[self.rank]
+        h0 = halo_first(first, S)
+        # window w reads samples [w, w+S); as in the reference (utils/dataloader.py:200) a signal of L samples
+        # yields L-S windows, so the slice carries one sample beyond the last window.
+        return first, count, h0, h0, first + count + S
+
+    def score_hyperbolic(self, local_slice, n_windows, combination="uncertainty", index=None):
+        """local_slice: samples [sample_lo, sample_hi) of the scaled signal (see plan()), on this rank's GPU.
+        Returns the full-length result on every rank."""
+        sc = self.scorer
+        S = sc.S
+        ranges = shard_ranges(n_windows, self.world)
+        first, count, h0, lo, hi = self.plan(n_windows)
+        if local_slice.numel() != hi - lo:
+            raise ValueError("local slice has %d samples, plan() asks for %d" % (local_slice.numel(), hi - lo))
+        fw = sc.forward(local_slice, True)  # windows h0 .. first+count-1
+        lead = first - h0
+        t0, tc = timestep_range(first, count, n_windows, S, self.rank == self.world - 1)
+        kmax_local = scoring.kde_argmax_overlap(fw["critic"], S, n_windows=n_windows, critic_offset=h0, t0=t0, t_count=tc)
+        counts = [c for _, c in ranges]
+        tcounts = [timestep_range(f, c, n_windows, S, r == self.world - 1)[1] for r, (f, c) in enumerate(ranges)]
+        kmax = gather_concat(kmax_local, tcounts, self.group)
+        rec = gather_concat(fw["rec"][lead:], counts, self.group)
+        unorm = gather_concat(fw["unorm"][lead:], counts, self.group)
+        cs = scoring.critic_zscore_smooth(kmax, math.trunc(n_windows * 0.01))
+        final = scoring.combine(combination, cs[:n_windows], rec, unorm, n=n_windows)
+        out = {"final": final, "kmax": kmax, "rec": rec, "unorm": unorm, "critic_scores": cs[:n_windows]}
+        if index is not None:
+            out["intervals"] = scoring.find_anomaly_intervals(final, index, 0.33, 0.1, anomaly_padding=50, ddof=1)
+        return out

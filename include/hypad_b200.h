@@ -84,6 +84,8 @@ typedef struct hypad_forward_out {
 
 int hypad_abi_version(void);
 const char* hypad_last_error(void);
+/* Number of kernels this library has launched in the calling process so far (all contexts, all streams). */
+int64_t hypad_launch_count(void);
 
 /* Context: packed weights + workspace on `device`. */
 int hypad_ctx_create(hypad_ctx** out, int device);

@@ -1,0 +1,96 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/hypad_b200.h
+declares, the ctypes binding covers exactly those symbols, and the product never routes through the oracle."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "hypad_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hypad_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_is_built_and_exports_the_header():
+    from hypad_b200 import _native
+    from hypad_b200.build import build
+
+    build()  # no-op when the in-tree library is current; nvcc cross-compiles without a GPU
+    assert os.path.exists(_native.LIB_PATH)
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), "library does not export %s" % s
+    assert sorted(_native.EXPORTED_SYMBOLS) == syms, "ctypes binding and header disagree"
+    lib.hypad_abi_version.restype = ctypes.c_int
+    assert lib.hypad_abi_version() == 1
+
+
+def test_ctx_create_fails_loudly_without_cuda():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from hypad_b200 import _native
+
+    lib = _native.load_library()
+    h = ctypes.c_void_p()
+    assert lib.hypad_ctx_create(ctypes.byref(h), 0) != 0
+    assert b"cuda" in lib.hypad_last_error().lower()
+
+
+def test_no_cpu_fallback_in_the_mirror():
+    import numpy as np
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from hypad_b200 import HypadError
+    from hypad_b200.hyperspace.hyrnn_nets import mobius_linear
+    from hypad_b200.models.tadgan import CriticX, Decoder, Encoder
+    from hypad_b200.utils import anomaly_detection_utils as adu
+
+    x = torch.zeros(4, 100, 1, dtype=torch.float64)
+    for m in (Encoder(100, 20).eval(), CriticX(100, 20).eval()):
+        with pytest.raises(HypadError):
+            m(x)
+    with pytest.raises(HypadError):
+        Decoder(100, 20, True).eval()(torch.zeros(1, 4, 20))
+    with pytest.raises(HypadError):
+        mobius_linear(torch.zeros(4, 8), torch.zeros(8, 8), hyperbolic_input=False)
+    with pytest.raises(HypadError):
+        adu.find_anomalies(np.ones(500), np.arange(500), window_size_portion=0.33, window_step_size_portion=0.1, fixed_threshold=True)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "hypad_b200")
+    for dirpath, _dirs, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "/root/reference" not in txt, f
+
+
+def test_reference_init_is_reproduced_by_the_mirror_modules():
+    """torch.manual_seed(0); Encoder, Decoder, CriticX on CPU gives the weights the reference's modules get (the golden
+    weight files were dumped from the reference's own classes)."""
+    import numpy as np
+    import torch
+
+    from conftest import weights
+    from hypad_b200.models.tadgan import CriticX, Decoder, Encoder
+
+    for name, S, hyp in (("weights_hyp_s100.npz", 100, True), ("weights_eucl_s100.npz", 100, False), ("weights_hyp_s123.npz", 123, True)):
+        ref = weights(name)
+        torch.manual_seed(0)
+        mods = {"encoder.": Encoder(S, 20), "decoder.": Decoder(S, 20, hyp), "critic_x.": CriticX(S, 20)}
+        mine = {p + k: v for p, m in mods.items() for k, v in m.state_dict().items()}
+        assert sorted(mine) == sorted(ref)
+        for k in ref:
+            assert np.array_equal(mine[k].numpy(), ref[k].numpy()), k

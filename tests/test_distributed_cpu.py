@@ -1,0 +1,75 @@
+"""World-size-2 gloo test (CPU) of the sharding plumbing: ranges, halos, slices and the variable-length gather."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_windows, S, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hypad_b200 import distributed as hd
+
+    ranges = hd.shard_ranges(n_windows, world)
+    first, count = ranges[rank]
+    t0, tc = hd.timestep_range(first, count, n_windows, S, rank == world - 1)
+    # every rank contributes "its" timesteps / windows of two known global arrays
+    kmax_global = torch.arange(n_windows + S - 1, dtype=torch.float64) * 0.5
+    rec_global = torch.arange(n_windows, dtype=torch.float32) + 7
+    tcounts = [hd.timestep_range(f, c, n_windows, S, r == world - 1)[1] for r, (f, c) in enumerate(ranges)]
+    kmax = hd.gather_concat(kmax_global[t0:t0 + tc].clone(), tcounts)
+    rec = hd.gather_concat(rec_global[first:first + count].clone(), [c for _, c in ranges])
+    ok = torch.equal(kmax, kmax_global) and torch.equal(rec, rec_global)
+
+    class FakeScorer:
+        pass
+
+    fs = FakeScorer()
+    fs.S = S
+    sh = hd.ShardedScorer(fs)
+    f2, c2, h0, lo, hi = sh.plan(n_windows)
+    ok = ok and (f2, c2) == (first, count) and h0 == max(0, first - (S - 1)) and lo == h0 and hi - lo - S == first + count - h0
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_windows,S", [(1001, 100), (64, 100), (999900, 100), (7, 3)])
+def test_shard_gather_world2(n_windows, S):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_windows, S, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_shard_ranges_cover_exactly():
+    from hypad_b200 import distributed as hd
+
+    for n in (1, 2, 7, 100, 8540, 999900):
+        for world in (1, 2, 3, 4, 8):
+            r = hd.shard_ranges(n, world)
+            assert r[0][0] == 0 and sum(c for _, c in r) == n
+            assert all(r[i][0] + r[i][1] == r[i + 1][0] for i in range(world - 1))
+            assert max(c for _, c in r) - min(c for _, c in r) <= 1
+            total_t = sum(hd.timestep_range(f, c, n, 100, i == world - 1)[1] for i, (f, c) in enumerate(r))
+            assert total_t == n + 99

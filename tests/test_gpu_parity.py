@@ -1,0 +1,421 @@
+"""Parity of the sm_100a kernels (called through the C-ABI) with the reference's own outputs (tests/golden) and
+with the CPU oracle on seeded inputs.  Run with `-m gpu` on a B200.
+
+Tolerances (north_star: scores within 1e-4 relative in fp32, identical intervals):
+  * integer / selection work (KDE arg-max, medians, run extraction, DTW recurrence) -- exact;
+  * fp32 network outputs -- a few fp32 ulps of the layer's magnitude (the reference's MKL GEMMs and Sleef
+    transcendentals cannot be reproduced bit for bit; not even the reference is bit-stable across batch sizes);
+  * final scores -- 1e-4 relative.  The hyperbolic reconstruction score is `acosh(1 + eps + 1e-7)` evaluated in
+    fp32 with eps ~ 5e-5, i.e. it is quantised in steps of ~1e-3 relative by the reference itself; a last-bit
+    difference upstream can move a window to the neighbouring step, so for `rec`/`final` the test demands
+    >= 99.5 % of the windows within 1e-4 and every window within one quantisation step, and reports the counts.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import build_modules, full_signal, golden
+from oracle import hypad_oracle as ho
+
+pytestmark = pytest.mark.gpu
+
+HYP_CASES = ["cfg1_hyp_uncertainty.npz", "noisy1500_hyp_uncertainty.npz", "edge_n65_hyp.npz", "edge_n300_hyp.npz",
+             "a1test_hyp_uncertainty.npz"]
+EUCL_CASES = ["cfg2_eucl_dtw_mult.npz", "noisy1500_eucl_dtw_mult.npz", "edge_n65_eucl.npz"]
+
+
+def dev_signal(g, device):
+    return torch.from_numpy(full_signal(g)).to(device)
+
+
+def a1_signal(g):
+    sig = g["signal"].copy()
+    sig[-1] = sig[-2]  # the last sample is in no window
+    return sig
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a, dtype=np.float64) - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def quantised_close(mine, want, frac=0.995, step=4e-3):
+    r = rel(mine, want)
+    ok = np.isfinite(r) | (np.isnan(mine) & np.isnan(want))
+    assert ok.all()
+    r = np.nan_to_num(r)
+    assert (r <= 1e-4).mean() >= frac, "only %.4f of the scores within 1e-4" % (r <= 1e-4).mean()
+    assert r.max() <= step, "max relative difference %.3e exceeds one quantisation step" % r.max()
+    return r
+
+
+@pytest.fixture(scope="module")
+def hyp_scorer(cuda_device):
+    from hypad_b200.scoring import WindowScorer
+
+    enc, dec, cx, _ = build_modules("weights_hyp_s100.npz", 100, True, cuda_device)
+    return WindowScorer(enc, dec, cx)
+
+
+@pytest.fixture(scope="module")
+def eucl_scorer(cuda_device):
+    from hypad_b200.scoring import WindowScorer
+
+    enc, dec, cx, _ = build_modules("weights_eucl_s100.npz", 100, False, cuda_device)
+    return WindowScorer(enc, dec, cx)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# network
+# ------------------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("case", HYP_CASES)
+def test_fused_forward_hyperbolic_vs_reference(case, hyp_scorer, cuda_device):
+    g = golden(case)
+    sig = torch.from_numpy(a1_signal(g) if case.startswith("a1test") else full_signal(g)).to(cuda_device)
+    fw = hyp_scorer.forward(sig, True, keep=("z", "eucl", "hyper", "hyper_x"))
+    n = g["critic"].shape[0]
+    assert fw["critic"].shape[0] == n
+    rows = g["rows"]
+    c = fw["critic"].cpu().numpy()
+    np.testing.assert_allclose(c, g["critic"], rtol=0, atol=1.5e-7)
+    np.testing.assert_allclose(fw["z"].cpu().numpy()[: g["z_head"].shape[0]], g["z_head"], rtol=0, atol=5e-7)
+    np.testing.assert_allclose(fw["eucl"].cpu().numpy()[rows], g["eucl_rows"], rtol=0, atol=2e-7)
+    np.testing.assert_allclose(fw["hyper"].cpu().numpy()[rows], g["recons_rows"], rtol=0, atol=4e-9)
+    np.testing.assert_allclose(fw["hyper_x"].cpu().numpy()[rows], g["hyper_x_rows"], rtol=0, atol=4e-9)
+    np.testing.assert_allclose(fw["unorm"].cpu().numpy(), g["unorm"], rtol=3e-6)
+    r = quantised_close(fw["rec"].cpu().numpy(), g["rec"])
+    print("%s: rec windows off by a quantisation step: %d of %d" % (case, int((r > 1e-4).sum()), n))
+
+
+@pytest.mark.parametrize("case", EUCL_CASES)
+def test_fused_forward_euclidean_vs_reference(case, eucl_scorer, cuda_device):
+    g = golden(case)
+    fw = eucl_scorer.forward(dev_signal(g, cuda_device), True, keep=("z", "eucl"))
+    np.testing.assert_allclose(fw["critic"].cpu().numpy(), g["critic"], rtol=0, atol=1.5e-7)
+    np.testing.assert_allclose(fw["eucl"].cpu().numpy()[g["rows"]], g["recons_rows"], rtol=0, atol=2e-7)
+    assert "rec" not in fw
+
+
+def test_materialised_windows_equal_sliding(hyp_scorer, cuda_device):
+    from hypad_b200 import scoring
+
+    g = golden("noisy1500_hyp_uncertainty.npz")
+    sig = dev_signal(g, cuda_device)
+    a = hyp_scorer.forward(sig, True, keep=("hyper",))
+    W64 = scoring.window_gather(sig, 100, torch.float64)
+    W32 = scoring.window_gather(sig, 100, torch.float32)
+    want = ho.rolling_window_sequences(full_signal(g)[:, None], g["index"], 100)[0][:, :, 0]
+    assert np.array_equal(W64.cpu().numpy(), want)
+    assert np.array_equal(W32.cpu().numpy(), want.astype(np.float32))
+    for W in (W64, W32, W64.reshape(-1, 100, 1)):
+        b = hyp_scorer.forward(W, False, keep=("hyper",))
+        for k in ("critic", "rec", "unorm", "hyper"):
+            assert torch.equal(a[k], b[k]), k
+    # a window range (what a shard computes) equals the same rows of the full run
+    part = hyp_scorer.forward(sig, True, first=333, count=500)
+    assert torch.equal(part["rec"], a["rec"][333:833]) and torch.equal(part["critic"], a["critic"][333:833])
+
+
+def test_module_forwards_match_fused(hyp_scorer, cuda_device):
+    """Encoder / Decoder / CriticX / MobiusLinear called one by one (the reference's per-batch usage,
+    anomaly_detection.py:68-94) give the fused kernel's numbers."""
+    g = golden("edge_n300_hyp.npz")
+    sig = dev_signal(g, cuda_device)
+    fw = hyp_scorer.forward(sig, True, keep=("z", "eucl", "hyper", "hyper_x"))
+    W = torch.from_numpy(ho.rolling_window_sequences(full_signal(g)[:, None], g["index"], 100)[0]).to(cuda_device)  # (N,100,1) f64
+    enc, dec, cx = hyp_scorer.encoder, hyp_scorer.decoder, hyp_scorer.critic_x
+    for lo, hi in ((0, 64), (64, 128), (299, 300)):  # includes a batch of one window
+        sample = W[lo:hi]
+        z = enc(sample.float())
+        assert z.shape == (1, hi - lo, 20) and torch.equal(z[0], fw["z"][lo:hi])
+        hyper, eucl = dec(z)
+        assert hyper.shape == (1, hi - lo, 100) and eucl.shape == (1, hi - lo, 100)
+        assert torch.equal(hyper[0], fw["hyper"][lo:hi]) and torch.equal(eucl[0], fw["eucl"][lo:hi])
+        hx = dec.hyperbolic_linear(sample.view(-1, 100).float())
+        np.testing.assert_allclose(hx.cpu().numpy(), fw["hyper_x"][lo:hi].cpu().numpy(), rtol=0, atol=1e-9)
+        c = cx(sample)
+        assert c.shape == (1, hi - lo, 1) and torch.equal(c.reshape(-1), fw["critic"][lo:hi])
+    enc.train()
+    with pytest.raises(Exception):
+        enc(W[:4].float())
+    enc.eval()
+
+
+def test_mobius_linear_vs_reference_pieces(cuda_device):
+    from hypad_b200.hyperspace.hyrnn_nets import mobius_linear
+
+    p = golden("pieces.npz")
+    x, W, b = (torch.from_numpy(p[k]).to(cuda_device) for k in ("ml_x", "ml_W", "ml_b"))
+    for out, key in ((mobius_linear(x, W, b, hyperbolic_input=False, hyperbolic_bias=True), "ml_hb"),
+                     (mobius_linear(x, W, b, hyperbolic_input=False, hyperbolic_bias=False), "ml_eb"),
+                     (mobius_linear(x, W, None, hyperbolic_input=False), "ml_nb"),
+                     (mobius_linear(x * 40, W, b, hyperbolic_input=False, hyperbolic_bias=True), "ml_big")):
+        np.testing.assert_allclose(out.cpu().numpy(), p[key], rtol=2e-6, atol=1e-8, err_msg=key)
+    with pytest.raises(NotImplementedError):
+        mobius_linear(x, W, b)  # hyperbolic_input=True (Mobius matvec) is not on the path
+
+
+def test_poincare_rowdist_and_rownorm(cuda_device):
+    from hypad_b200 import scoring
+
+    g = golden("noisy1500_hyp_uncertainty.npz")
+    recons = torch.from_numpy(g["recons_rows"]).to(cuda_device)
+    truth = torch.from_numpy(g["hyper_x_rows"]).to(cuda_device)
+    rec = scoring.poincare_rowdist(recons, truth).cpu().numpy()
+    quantised_close(rec, g["rec"][g["rows"]], frac=0.999)
+    np.testing.assert_allclose(scoring.rownorm(recons).cpu().numpy(), g["unorm"][g["rows"]], rtol=2e-7)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# overlap aggregation
+# ------------------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("case", HYP_CASES + EUCL_CASES)
+def test_kde_argmax_exact_vs_reference(case, cuda_device):
+    from hypad_b200 import scoring
+
+    g = golden(case)
+    c = torch.from_numpy(g["critic"]).to(cuda_device)
+    for exhaustive in (False, True):
+        kmax = scoring.kde_argmax_overlap(c, 100, exhaustive=exhaustive).cpu().numpy()
+        assert np.array_equal(kmax, g["kmax"]), "exhaustive=%s" % exhaustive
+
+
+def test_kde_argmax_edge_cases_vs_oracle(cuda_device):
+    from hypad_b200 import scoring
+
+    rng = np.random.default_rng(11)
+    cases = {
+        "constant": np.full(400, -0.25, np.float32),                       # zero variance -> median branch
+        "duplicates": rng.choice(rng.standard_normal(7).astype(np.float32), 500),
+        "short": rng.standard_normal(37).astype(np.float32),               # N < S
+        "one": rng.standard_normal(1).astype(np.float32),
+        "bimodal": np.where(rng.random(3000) < 0.5, 0.1, -0.3).astype(np.float32) + 1e-3 * rng.standard_normal(3000).astype(np.float32),
+        "outliers": np.concatenate([rng.standard_normal(700).astype(np.float32) * 1e-3, [50.0, -80.0], rng.standard_normal(300).astype(np.float32) * 1e-3]).astype(np.float32),
+        "smooth": (np.sin(np.arange(5000) / 17.0) * 0.01 - 0.2).astype(np.float32),
+    }
+    for S in (100, 123, 51, 128, 7):
+        for name, c in cases.items():
+            want = ho.kde_argmax_overlap(c, S)
+            for exhaustive in (False, True):
+                got = scoring.kde_argmax_overlap(torch.from_numpy(c).to(cuda_device), S, exhaustive=exhaustive).cpu().numpy()
+                assert np.array_equal(got, want), (name, S, exhaustive, int((got != want).sum()))
+    # timestep sub-range with a critic slice (what a shard evaluates)
+    c = cases["smooth"]
+    want = ho.kde_argmax_overlap(c, 100)
+    part = scoring.kde_argmax_overlap(torch.from_numpy(c[1901:3000]).to(cuda_device), 100, n_windows=len(c), critic_offset=1901,
+                                      t0=2000, t_count=1000).cpu().numpy()
+    assert np.array_equal(part, want[2000:3000])
+
+
+def test_kde_screened_equals_exhaustive_at_scale(cuda_device):
+    """Size-independent property at BASELINE size: the fp32-screened kernel picks exactly what the all-fp64 one picks."""
+    from hypad_b200 import scoring
+
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    t = torch.arange(999900, dtype=torch.float64)
+    c = (0.01 * torch.sin(t / 23.0) + 0.004 * torch.randn(999900, generator=gen, dtype=torch.float64) - 0.23).float().to(cuda_device)
+    a = scoring.kde_argmax_overlap(c, 100)
+    b = scoring.kde_argmax_overlap(c, 100, exhaustive=True)
+    assert torch.equal(a, b)
+    assert a.shape[0] == 999999
+    # every selected value is one of the window's own critic values
+    assert torch.isin(a.float(), c).all()
+
+
+@pytest.mark.parametrize("case", HYP_CASES + EUCL_CASES)
+def test_critic_zscore_smooth_vs_reference(case, cuda_device):
+    from hypad_b200 import scoring
+
+    g = golden(case)
+    n = g["critic"].shape[0]
+    got = scoring.critic_zscore_smooth(torch.from_numpy(g["kmax"]).to(cuda_device), math.trunc(n * 0.01)).cpu().numpy()
+    np.testing.assert_allclose(got, g["critic_scores"], rtol=1e-11, atol=0, equal_nan=True)
+
+
+def test_critic_score_and_rolling_mean_pieces(cuda_device):
+    from hypad_b200 import scoring
+
+    p = golden("pieces.npz")
+    k = torch.from_numpy(p["ccs_in"]).to(cuda_device)
+    for w in (1, 2, 7, 8, 77):
+        np.testing.assert_allclose(scoring.critic_zscore_smooth(k, w).cpu().numpy(), p["ccs_w%d" % w], rtol=1e-12, equal_nan=True)
+    rng = np.random.default_rng(3)
+    for n, w in ((10, 3), (5000, 50), (5000, 51), (100001, 1000), (4097, 2), (2048, 1), (300, 0)):
+        x = rng.standard_normal(n) + 2
+        got = scoring.rolling_mean_centered(torch.from_numpy(x).to(cuda_device), w).cpu().numpy()
+        want = ho.rolling_mean_centered_restated(x, w)
+        if w > 0:
+            np.testing.assert_allclose(want, ho.rolling_mean_centered(x, w), rtol=1e-9, equal_nan=True)
+            want = ho.rolling_mean_centered(x, w)  # pandas: what the reference runs
+        np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-12, equal_nan=True)
+
+
+def test_median_overlap_exact(cuda_device):
+    from hypad_b200 import scoring
+
+    g = golden("noisy1500_eucl_dtw_mult.npz")
+    got = scoring.median_overlap(torch.from_numpy(g["recons_rows"]).to(cuda_device)).cpu().numpy()
+    assert got.dtype == np.float32 and np.array_equal(got, g["pred"])
+    rng = np.random.default_rng(4)
+    for n, S in ((1, 100), (3, 5), (64, 100), (257, 123), (40, 128), (500, 51)):
+        y = rng.standard_normal((n, S)).astype(np.float32)
+        y[rng.random((n, S)) < 0.2] = 0.5  # ties
+        got = scoring.median_overlap(torch.from_numpy(y).to(cuda_device)).cpu().numpy()
+        assert np.array_equal(got, ho.median_overlap(y)), (n, S)
+
+
+def test_reconstruction_errors_vs_reference(cuda_device):
+    from hypad_b200 import scoring
+
+    g = golden("cfg2_eucl_dtw_mult.npz")
+    true = torch.from_numpy(g["true"]).to(cuda_device)
+    pred = torch.from_numpy(g["pred"]).to(cuda_device)
+    dtw = scoring.dtw_error(true, pred, 10).cpu().numpy()
+    np.testing.assert_allclose(dtw, g["dtw_raw"], rtol=1e-15, atol=0)
+    n = g["critic"].shape[0]
+    for kind, fn in (("point", scoring.point_error), ("area", scoring.area_error), ("dtw", scoring.dtw_error)):
+        e = fn(true, pred)
+        rec = scoring.zscore_clip(scoring.rolling_mean_centered(e, math.trunc(n * 0.01))).cpu().numpy()
+        np.testing.assert_allclose(rec, g["rec_" + kind], rtol=1e-9, atol=1e-12, equal_nan=True)
+    # other window lengths go through the generic kernel
+    rng = np.random.default_rng(8)
+    y, yh = rng.standard_normal(700), rng.standard_normal(700).astype(np.float32)
+    for sw in (2, 4, 10, 11, 20, 64):
+        got = scoring.dtw_error(torch.from_numpy(y).to(cuda_device), torch.from_numpy(yh).to(cuda_device), sw).cpu().numpy()
+        np.testing.assert_allclose(got, ho.dtw_error(y, yh, sw), rtol=1e-15, atol=0)
+    # spot-check the vectorised oracle recurrence against the scalar statement of pyts' algorithm
+    for p0 in (0, 17, 300):
+        a = np.pad(y, (5, 5))[p0:p0 + 11]
+        b = np.pad(yh.astype(np.float64), (5, 5))[p0:p0 + 11]
+        assert ho.dtw_error(y, yh, 10)[p0 + 5] == ho.dtw_distance(a, b)
+
+
+def test_reference_utils_mirror_pieces(cuda_device):
+    """The drop-in functions of hypad_b200.utils.anomaly_detection_utils on numpy inputs, vs the reference's outputs."""
+    from hypad_b200.utils import anomaly_detection_utils as adu
+
+    p = golden("pieces.npz")
+    kw = dict(window_size_portion=0.33, window_step_size_portion=0.1, fixed_threshold=True)
+    for key, errors, extra in (("fa_np_uni", p["fa_errors"], {}), ("fa_t_uni", torch.from_numpy(p["fa_errors"]), {}),
+                               ("fa_np_multi", p["fa_errors"], dict(window_size_portion=0.2, anomaly_padding=200))):
+        iv = adu.find_anomalies(errors, p["fa_index"], **{**kw, **extra})
+        assert iv.shape == p[key].shape, key
+        assert np.array_equal(iv[:, :2], p[key][:, :2]), key
+        np.testing.assert_allclose(iv[:, 2], p[key][:, 2], rtol=1e-9)
+    for kind in ("point", "area", "dtw"):
+        err, _ = adu.reconstruction_errors(p["re_y"], p["re_yhat"], 1, 10, 3, True, kind)
+        np.testing.assert_allclose(err, p["re_" + kind], rtol=1e-10, atol=1e-13, equal_nan=True)
+    np.testing.assert_allclose(adu._compute_critic_score(p["ccs_in"], 7), p["ccs_w7"], rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# end to end
+# ------------------------------------------------------------------------------------------------------------
+
+
+def check_intervals(got, want):
+    assert got.shape == want.shape, (got, want)
+    if len(want):
+        assert np.array_equal(got[:, :2], want[:, :2]), (got, want)
+        np.testing.assert_allclose(got[:, 2], want[:, 2], rtol=2e-3)
+
+
+def selection_aware_close(out, g, n, label):
+    """Final-score parity with attribution.  The KDE arg-max is a discrete selection: when two candidate values have
+    densities closer than the fp32 noise of the critic (~1 ulp; the reference's own critic changes by that much
+    between MKL code paths, tests/test_reference_floor.py), a different -- equally valid -- window value is selected
+    at that timestep, and the centred rolling mean (window w = trunc(0.01 N)) spreads the change over at most w
+    outputs.  Every score outside 1e-4 must be attributable to such a selection (or to one acosh quantisation step)."""
+    final = out["final"].cpu().numpy()
+    r = np.nan_to_num(rel(final, g["final"]))
+    kmax = out["kmax"].cpu().numpy()
+    crit_std = float(np.std(g["critic"]))
+    material = np.flatnonzero(np.abs(kmax - g["kmax"]) > 1e-5 * crit_std)
+    w = max(int(n * 0.01), 1)
+    rec_steps = int((rel(out["rec"].cpu().numpy(), g["rec"]) > 1e-4).sum()) if "rec" in g else 0
+    beyond = np.flatnonzero(r > 1e-4)
+    print("%s: %d windows; kde selections differing materially: %d; rec quantisation steps: %d; final beyond 1e-4: %d (max %.2e)"
+          % (label, n, len(material), rec_steps, len(beyond), r.max()))
+    assert len(material) <= max(3, int(1e-3 * n)), "too many selection differences"
+    assert r.max() <= 4e-3
+    # attribution: each out-of-tolerance output lies within w of a differing selection, or is a rec quantisation step
+    if len(beyond):
+        near = np.zeros(len(final) + 2 * w + 2, dtype=bool)
+        for t in material:
+            near[t: t + 2 * w + 1] = True  # positions t-w .. t+w, shifted by w
+        rec_bad = rel(out["rec"].cpu().numpy(), g["rec"]) > 1e-4 if "rec" in g else np.zeros(len(final), bool)
+        unexplained = [int(b) for b in beyond if not near[b + w] and not rec_bad[b]]
+        assert not unexplained, "scores beyond 1e-4 not attributable to a selection difference: %s" % unexplained[:10]
+    assert len(beyond) <= len(material) * (w + 1) + rec_steps
+    return r
+
+
+@pytest.mark.parametrize("case", HYP_CASES)
+def test_end_to_end_hyperbolic(case, hyp_scorer, cuda_device):
+    g = golden(case)
+    sig = torch.from_numpy(a1_signal(g) if case.startswith("a1test") else full_signal(g)).to(cuda_device)
+    out = hyp_scorer.score(sig, True, "uncertainty", index=g["index"])
+    selection_aware_close(out, g, g["critic"].shape[0], case)
+    check_intervals(out["intervals"], g["intervals"])
+
+
+def test_end_to_end_hyperbolic_mult(hyp_scorer, cuda_device):
+    g = golden("noisy1500_hyp_mult.npz")
+    out = hyp_scorer.score(dev_signal(g, cuda_device), True, "mult", index=g["index"])
+    selection_aware_close(out, g, g["critic"].shape[0], "noisy1500_hyp_mult")
+    check_intervals(out["intervals"], g["intervals"])
+
+
+@pytest.mark.parametrize("case", EUCL_CASES)
+def test_end_to_end_euclidean(case, eucl_scorer, cuda_device):
+    g = golden(case)
+    out = eucl_scorer.score(dev_signal(g, cuda_device), True, "mult", "dtw", index=g["index"])
+    assert np.array_equal(out["true"].cpu().numpy(), g["true"])
+    np.testing.assert_allclose(out["pred"].cpu().numpy(), g["pred"], rtol=0, atol=2e-7)
+    final = out["final"].cpu().numpy()
+    assert final.shape == g["final"].shape  # one score per timestep: N + S - 1
+    assert np.array_equal(np.isnan(final), np.isnan(g["final"]))
+    selection_aware_close(out, {k: v for k, v in g.items() if k != "rec"}, g["critic"].shape[0], case)
+    check_intervals(out["intervals"], g["intervals"])
+
+
+def test_drop_in_univariate_anomaly_detection(tmp_path, hyp_scorer, cuda_device):
+    """utils.anomaly_detection_utils.univariate_anomaly_detection fed with the arrays test_tadgan collects."""
+    import argparse
+
+    import pandas as pd
+
+    from hypad_b200.utils import anomaly_detection_utils as adu
+
+    g = golden("noisy1500_hyp_uncertainty.npz")
+    params = argparse.Namespace(hyperbolic=True, signal_shape=100, load=False, save_result=False, dataset="MSL", signal="x")
+    path = str(tmp_path) + "/"
+    iv = adu.univariate_anomaly_detection(g["recons_rows"], g["hyper_x_rows"], params, "uncertainty", list(g["critic"]), path, "",
+                                          "dtw", torch.from_numpy(g["index"]), None, "x", 100)
+    check_intervals(iv, g["intervals"])
+    csv = pd.read_csv(path + "anomalies.csv").values[:, 1:]
+    check_intervals(np.asarray(csv, dtype=np.float64), g["intervals"])
+
+
+def test_multivariate_shape_s123(cuda_device):
+    """configs/multivariate.yaml: signal_shape 123, every row one sample; GPU vs oracle on seeded rows."""
+    from hypad_b200.scoring import WindowScorer
+
+    enc, dec, cx, w = build_modules("weights_hyp_s123.npz", 123, True, cuda_device)
+    rng = np.random.default_rng(21)
+    rows = rng.uniform(-1, 1, (3000, 123))
+    rows[1500:1510] *= 3
+    index = 1353715200.0 + np.arange(3000)
+    want = ho.multivariate_scores(rows, w, True, "mult", index)
+    out = WindowScorer(enc, dec, cx).score(torch.from_numpy(rows).to(cuda_device), False, "mult", index=index, multivariate=True)
+    np.testing.assert_allclose(out["critic"].cpu().numpy(), want["critic"], rtol=0, atol=3e-7)
+    assert np.array_equal(out["kmax"].cpu().numpy(), ho.kde_argmax_overlap(out["critic"].cpu().numpy(), 123))
+    r = rel(out["final"].cpu().numpy(), want["final"])
+    print("multivariate: final beyond 1e-4: %d of %d, max %.2e" % (int((r > 1e-4).sum()), len(r), r.max()))
+    assert (r <= 1e-4).mean() > 0.99
+    check_intervals(out["intervals"], want["intervals"])

@@ -1,0 +1,58 @@
+"""Host-side logic of the product (window bookkeeping of find_anomalies, shard planning), CPU only."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import hypad_oracle as ho
+
+
+def numpy_threshold_windows(errors, wsize, step, count, ddof, pad):
+    """What csrc/finish.cu threshold_windows_kernel computes, in numpy, to drive the host tail without a GPU."""
+    stats = np.zeros((count, 4))
+    runs, n_runs = [], []
+    for k in range(count):
+        w = errors[k * step:k * step + wsize]
+        mean, std = w.mean(), w.std(ddof=ddof)
+        thr = mean + 4 * std
+        seqs, max_below = ho._find_sequences(w, thr, pad)
+        stats[k] = (mean, std, thr, max_below)
+        runs.append([(s, e, w[s:e + 1].max()) for s, e in seqs])
+        n_runs.append(len(seqs))
+    width = max(n_runs + [1])
+    arr = np.zeros((count, width, 3))
+    for k, r in enumerate(runs):
+        for i, (s, e, m) in enumerate(r):
+            arr[k, i] = (s, e, m)
+    return stats, arr, np.asarray(n_runs)
+
+
+@pytest.mark.parametrize("ddof,portion,pad", [(0, 0.33, 50), (1, 0.33, 50), (0, 0.2, 200)])
+def test_interval_bookkeeping_matches_oracle(ddof, portion, pad):
+    from hypad_b200 import scoring
+
+    p = golden("pieces.npz")
+    e, idx = p["fa_errors"], p["fa_index"]
+    wsize, step, count = scoring.analysis_windows(len(e), None, portion, None, 0.1)
+    stats, runs, n_runs = numpy_threshold_windows(e, wsize, step, count, ddof, pad)
+    merged = scoring.intervals_from_runs(stats, runs, n_runs, step, 0.1)
+    mine = np.asarray([[idx[int(s)], idx[int(t)], sc] for s, t, sc in merged], dtype=np.float64).reshape(-1, 3)
+    want = ho.find_anomalies(e, idx, portion, 0.1, anomaly_padding=pad, ddof=ddof)
+    assert mine.shape == want.shape and len(want) > 0
+    assert np.array_equal(mine[:, :2], want[:, :2])
+    np.testing.assert_allclose(mine[:, 2], want[:, 2], rtol=1e-12)
+
+
+def test_analysis_window_count_matches_reference_loop():
+    from hypad_b200 import scoring
+
+    for n in (1, 7, 99, 100, 8540, 8639, 999900):
+        wsize, step, count = scoring.analysis_windows(n, None, 0.33, None, 0.1)
+        # the reference's loop (utils/anomaly_detection_utils.py:1431-1457)
+        start = end = 0
+        k = 0
+        while end < n:
+            end = start + wsize
+            k += 1
+            start += step
+        assert count == k, n
+        assert (count - 1) * step < n
