@@ -324,120 +324,200 @@ __global__ void combine_kernel(int mode, const double* __restrict__ c, const TR*
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// find_anomalies: per analysis window mean / std / threshold, dilated above-threshold runs, max_below
+// find_anomalies: per analysis window mean / std / threshold, dilated above-threshold runs, max_below.
+// Everything is tile-parallel: two-stage sums for the statistics, then one pass that classifies every element
+// (above threshold -> inside a padded run or not) from a bit-packed flag window in shared memory and emits the run
+// starts / ends as unordered events; a second pass attributes every above-threshold value to its run
+// (the run with the largest start <= its position) for the run maximum; a tiny per-window kernel orders the few runs.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int TW_THREADS = 1024;
+constexpr int TW_CHUNK = 4096;   // elements per CTA of the two-stage sums
+constexpr int TW_TILE = 1024;    // elements per CTA of the event pass
 constexpr int TW_MAXPAD = 512;
 
-__device__ __forceinline__ unsigned long long dmax_key(double x) { return dkey(x); }
+struct TwArgs {
+    const double* errors;
+    int64_t len, window_size, step;
+    int n_analysis, ddof, pad, max_runs, n_slices;
+    double* stats;          // [n_analysis][4]
+    double* runs;           // [n_analysis][max_runs][3]
+    int32_t* n_runs;        // [n_analysis]
+    // workspace
+    double* partial;        // [n_analysis][n_slices]
+    double* mean;           // [n_analysis]
+    int* cnt;               // [n_analysis][2] starts, ends
+    unsigned long long* below;  // [n_analysis]
+    long long* starts;      // [n_analysis][max_runs]
+    long long* ends;        // [n_analysis][max_runs]
+    unsigned long long* rmax;   // [n_analysis][max_runs]
+};
 
-__global__ void __launch_bounds__(TW_THREADS) threshold_windows_kernel(const double* __restrict__ errors, int64_t len,
-                                                                       int64_t window_size, int64_t step, int ddof, int pad,
-                                                                       double* __restrict__ stats, double* __restrict__ runs,
-                                                                       int32_t* __restrict__ n_runs, int max_runs,
-                                                                       unsigned long long* __restrict__ run_max_keys) {
+__device__ __forceinline__ void tw_window(const TwArgs& a, int k, const double*& e, int64_t& n) {
+    const int64_t w0 = (int64_t)k * a.step;
+    const int64_t w1 = w0 + a.window_size < a.len ? w0 + a.window_size : a.len;
+    e = a.errors + w0;
+    n = w1 - w0;
+}
+
+// mode 0: partial sums of x ; mode 1: partial sums of (x - mean)^2
+__global__ void __launch_bounds__(256) tw_partial_kernel(const TwArgs a, int mode) {
     __shared__ double sh[32];
-    __shared__ int s_flags[TW_THREADS + 2 * TW_MAXPAD];
-    __shared__ int s_scan[TW_THREADS];
-    __shared__ int s_carry[2];  // [0] runs opened so far, [1] dil flag of the element before the tile
+    const int k = blockIdx.y, s = blockIdx.x;
+    const double* e;
+    int64_t n;
+    tw_window(a, k, e, n);
+    const int64_t b0 = (int64_t)s * TW_CHUNK, b1 = b0 + TW_CHUNK < n ? b0 + TW_CHUNK : n;
+    const double m = mode ? a.mean[k] : 0.0;
+    double acc = 0.0;
+    for (int64_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) {
+        const double d = e[i] - m;
+        acc += mode ? d * d : d;
+    }
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) a.partial[(size_t)k * a.n_slices + s] = acc;
+}
+
+// mode 0: mean ; mode 1: std, threshold, and reset of the event state
+__global__ void __launch_bounds__(32) tw_final_kernel(const TwArgs a, int mode) {
+    const int k = blockIdx.x, lane = threadIdx.x;
+    const double* e;
+    int64_t n;
+    tw_window(a, k, e, n);
+    double acc = 0.0;
+    for (int s = lane; s < a.n_slices; s += 32) acc += a.partial[(size_t)k * a.n_slices + s];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (mode == 0) {
+        if (lane == 0) a.mean[k] = acc / (double)n;
+    } else {
+        if (lane == 0) {
+            const double mean = a.mean[k];
+            const double sd = sqrt(acc / (double)(n - a.ddof));
+            a.stats[k * 4 + 0] = mean;
+            a.stats[k * 4 + 1] = sd;
+            a.stats[k * 4 + 2] = mean + 4.0 * sd;  // _fixed_threshold, k = 4 (:1098-1114)
+            a.cnt[k * 2] = 0;
+            a.cnt[k * 2 + 1] = 0;
+            a.below[k] = 0ull;
+        }
+        for (int r = lane; r < a.max_runs; r += 32) a.rmax[(size_t)k * a.max_runs + r] = 0ull;
+    }
+}
+
+// any flag bit set in [lo, hi] of the packed window
+__device__ __forceinline__ bool any_bits(const unsigned* w, int lo, int hi) {
+    const int w0 = lo >> 5, w1 = hi >> 5;
+    const unsigned m0 = 0xffffffffu << (lo & 31), m1 = 0xffffffffu >> (31 - (hi & 31));
+    if (w0 == w1) return (w[w0] & m0 & m1) != 0u;
+    unsigned acc = (w[w0] & m0) | (w[w1] & m1);
+    for (int i = w0 + 1; i < w1; ++i) acc |= w[i];
+    return acc != 0u;
+}
+
+__global__ void __launch_bounds__(TW_TILE) tw_events_kernel(const TwArgs a) {
+    constexpr int REGION = TW_TILE + 2 * TW_MAXPAD + 2;
+    __shared__ unsigned s_bits[(REGION + 31) / 32 + 1];
+    __shared__ unsigned char s_dil[TW_TILE + 2];
     __shared__ unsigned long long s_below;
-    const int k = blockIdx.x;
-    const int64_t w0 = (int64_t)k * step;
-    const int64_t w1 = w0 + window_size < len ? w0 + window_size : len;
-    const int64_t n = w1 - w0;
-    const double* e = errors + w0;
-    const int tid = threadIdx.x;
-    // mean, std(ddof), threshold (_fixed_threshold, k = 4)
-    double a = 0.0;
-    for (int64_t i = tid; i < n; i += TW_THREADS) a += e[i];
-    const double mean = block_sum(a, sh) / (double)n;
-    a = 0.0;
-    for (int64_t i = tid; i < n; i += TW_THREADS) {
-        const double d = e[i] - mean;
-        a += d * d;
-    }
-    const double sd = sqrt(block_sum(a, sh) / (double)(n - ddof));
-    const double thr = mean + 4.0 * sd;
-    double* rk = runs + (size_t)k * max_runs * 3;
-    unsigned long long* rmax = run_max_keys + (size_t)k * max_runs;
-    for (int i = tid; i < max_runs; i += TW_THREADS) rmax[i] = 0ull;
-    if (tid == 0) {
-        s_carry[0] = 0;
-        s_carry[1] = 0;
-        s_below = 0ull;
+    const int k = blockIdx.y, tid = threadIdx.x;
+    const double* e;
+    int64_t n;
+    tw_window(a, k, e, n);
+    const int64_t t0 = (int64_t)blockIdx.x * TW_TILE;
+    if (t0 >= n) return;
+    const double thr = a.stats[k * 4 + 2];
+    const int pad = a.pad;
+    const int region = TW_TILE + 2 * pad + 2;       // positions t0-pad-1 .. t0+TILE+pad
+    const int64_t r0 = t0 - pad - 1;
+    if (tid == 0) s_below = 0ull;
+    for (int f = tid; f < ((region + 31) & ~31); f += TW_TILE) {
+        const int64_t q = r0 + f;
+        const bool flag = f < region && q >= 0 && q < n && e[q] > thr;
+        const unsigned word = __ballot_sync(0xffffffffu, flag);
+        if ((tid & 31) == 0) s_bits[f >> 5] = word;
     }
     __syncthreads();
-    bool any_below = false;
+    // dilation of positions t0-1 .. t0+TILE: bit range [j, j+2pad] of the packed window
+    for (int j = tid; j < TW_TILE + 2; j += TW_TILE) {
+        const int64_t p = t0 - 1 + j;
+        s_dil[j] = (p >= 0 && p < n && any_bits(s_bits, j, j + 2 * pad)) ? 1 : 0;
+    }
+    __syncthreads();
+    const int64_t i = t0 + tid;
     unsigned long long below_key = 0ull;
-    for (int64_t t0 = 0; t0 < n; t0 += TW_THREADS) {
-        // flags of [t0 - pad, t0 + TW_THREADS + pad)
-        for (int f = tid; f < TW_THREADS + 2 * pad; f += TW_THREADS) {
-            const int64_t idx = t0 - pad + f;
-            s_flags[f] = (idx >= 0 && idx < n && e[idx] > thr) ? 1 : 0;
-        }
-        __syncthreads();
-        const int64_t i = t0 + tid;
-        int dil = 0;
-        if (i < n) {
-            for (int f = tid; f <= tid + 2 * pad; ++f) dil |= s_flags[f];
-        }
-        const int prev_carry = s_carry[1];
-        __syncthreads();
-        s_flags[tid] = dil;  // reuse: dil flags of the tile (only [0, TW_THREADS) needed from here on)
-        __syncthreads();
-        const int prev = tid == 0 ? prev_carry : s_flags[tid - 1];
-        const int is_start = (i < n && dil && !prev) ? 1 : 0;
-        // inclusive scan of starts
-        s_scan[tid] = is_start;
-        __syncthreads();
-        for (int o = 1; o < TW_THREADS; o <<= 1) {
-            const int v = tid >= o ? s_scan[tid - o] : 0;
-            __syncthreads();
-            s_scan[tid] += v;
-            __syncthreads();
-        }
-        const int base = s_carry[0];
-        if (i < n) {
-            const double v = e[i];
-            if (dil) {
-                const int id = base + s_scan[tid] - 1;  // run index of this element
-                if (id < max_runs) {
-                    if (is_start) rk[id * 3 + 0] = (double)i;
-                    const int next = (i + 1 < n) ? ((tid + 1 < TW_THREADS) ? s_flags[tid + 1] : -1) : 0;
-                    int nd = next;
-                    if (next < 0) {  // first element of the next tile: recompute its dilation
-                        nd = 0;
-                        for (int64_t j = i + 1 - pad; j <= i + 1 + pad; ++j)
-                            if (j >= 0 && j < n && e[j] > thr) nd = 1;
-                    }
-                    if (!nd) rk[id * 3 + 1] = (double)i;
-                    if (v > thr) atomicMax(&rmax[id], dmax_key(v));
-                }
-            } else {
-                any_below = true;
-                const unsigned long long kv = dmax_key(v);
-                below_key = kv > below_key ? kv : below_key;
+    if (i < n) {
+        const bool dil = s_dil[tid + 1] != 0;
+        if (dil) {
+            if (!s_dil[tid]) {  // run start (shift(1).fillna(False), :1151-1160)
+                const int slot = atomicAdd(&a.cnt[k * 2], 1);
+                if (slot < a.max_runs) a.starts[(size_t)k * a.max_runs + slot] = i;
             }
+            if (!s_dil[tid + 2]) {  // run end (the last element closes an open run, :1163-1164)
+                const int slot = atomicAdd(&a.cnt[k * 2 + 1], 1);
+                if (slot < a.max_runs) a.ends[(size_t)k * a.max_runs + slot] = i;
+            }
+        } else {
+            below_key = dkey(e[i]);
         }
-        __syncthreads();
-        if (tid == TW_THREADS - 1) {
-            s_carry[0] = base + s_scan[tid];
-            s_carry[1] = dil;
+    }
+    // block max of the not-in-any-run values -> one atomic per CTA
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long v = __shfl_xor_sync(0xffffffffu, below_key, o);
+        below_key = v > below_key ? v : below_key;
+    }
+    if ((tid & 31) == 0 && below_key) atomicMax(&s_below, below_key);
+    __syncthreads();
+    if (tid == 0 && s_below) atomicMax(&a.below[k], s_below);
+}
+
+// every above-threshold value goes to the run whose start is the largest start <= its position
+__global__ void __launch_bounds__(TW_TILE) tw_runmax_kernel(const TwArgs a) {
+    const int k = blockIdx.y;
+    const double* e;
+    int64_t n;
+    tw_window(a, k, e, n);
+    const int64_t i = (int64_t)blockIdx.x * TW_TILE + threadIdx.x;
+    if (i >= n) return;
+    const double v = e[i];
+    if (!(v > a.stats[k * 4 + 2])) return;
+    const int R = a.cnt[k * 2] < a.max_runs ? a.cnt[k * 2] : a.max_runs;
+    const long long* st = a.starts + (size_t)k * a.max_runs;
+    long long best = -1;
+    int arg = -1;
+    for (int r = 0; r < R; ++r) {
+        const long long s = st[r];
+        if (s <= i && s > best) {
+            best = s;
+            arg = r;
         }
-        __syncthreads();
     }
-    if (any_below) atomicMax(&s_below, below_key);
-    __syncthreads();
-    if (tid == 0) {
-        stats[k * 4 + 0] = mean;
-        stats[k * 4 + 1] = sd;
-        stats[k * 4 + 2] = thr;
-        stats[k * 4 + 3] = s_below ? dunkey(s_below) : 0.0;  // `above.all()` -> max_below = 0 (:1154-1155)
-        n_runs[k] = s_carry[0];
+    if (arg >= 0) atomicMax(&a.rmax[(size_t)k * a.max_runs + arg], dkey(v));
+}
+
+// per window: order the runs by start, pair the r-th start with the r-th end, emit (start, end, max)
+__global__ void __launch_bounds__(256) tw_emit_kernel(const TwArgs a) {
+    const int k = blockIdx.x;
+    const int total = a.cnt[k * 2];
+    const int R = total < a.max_runs ? total : a.max_runs;
+    const long long* st = a.starts + (size_t)k * a.max_runs;
+    const long long* en = a.ends + (size_t)k * a.max_runs;
+    double* out = a.runs + (size_t)k * a.max_runs * 3;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const long long s = st[r], t = en[r];
+        int rank_s = 0, rank_e = 0;
+        for (int q = 0; q < R; ++q) {
+            rank_s += st[q] < s;
+            rank_e += en[q] < t;
+        }
+        out[rank_s * 3 + 0] = (double)s;
+        out[rank_s * 3 + 2] = dunkey(a.rmax[(size_t)k * a.max_runs + r]);
+        out[rank_e * 3 + 1] = (double)t;
     }
-    __syncthreads();
-    const int nr = s_carry[0] < max_runs ? s_carry[0] : max_runs;
-    for (int r = tid; r < nr; r += TW_THREADS) rk[r * 3 + 2] = dunkey(rmax[r]);
+    if (threadIdx.x == 0) {
+        a.n_runs[k] = total;
+        const unsigned long long b = a.below[k];
+        a.stats[k * 4 + 3] = b ? dunkey(b) : 0.0;  // `above.all()` -> max_below = 0 (:1154-1155)
+    }
 }
 
 static unsigned red_grid(int64_t n) {
@@ -588,17 +668,43 @@ int hypad_threshold_windows(hypad_ctx* ctx, const double* errors, int64_t len, i
                             int32_t* n_runs, int max_runs, void* stream_) {
     HYPAD_REQUIRE(ctx && errors && stats && runs && n_runs, "hypad_threshold_windows: NULL argument");
     HYPAD_REQUIRE(len >= 1 && window_size >= 1 && step >= 1 && n_analysis >= 1 && max_runs >= 1, "hypad_threshold_windows: bad shape");
+    HYPAD_REQUIRE(n_analysis <= 65535, "hypad_threshold_windows: more than 65535 analysis windows");
     HYPAD_REQUIRE((n_analysis - 1) * step < len, "hypad_threshold_windows: last window starts beyond the data");
     HYPAD_REQUIRE(anomaly_padding >= 0 && anomaly_padding <= TW_MAXPAD, "hypad_threshold_windows: padding %d outside 0..%d",
                   anomaly_padding, TW_MAXPAD);
     HYPAD_REQUIRE(ddof == 0 || ddof == 1, "hypad_threshold_windows: ddof must be 0 or 1");
     cudaStream_t stream = (cudaStream_t)stream_;
     HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
-    int rc = ensure_workspace(ctx, (size_t)n_analysis * max_runs * 8);
+    const int64_t wlen = window_size < len ? window_size : len;
+    TwArgs a;
+    a.errors = errors; a.len = len; a.window_size = window_size; a.step = step;
+    a.n_analysis = (int)n_analysis; a.ddof = ddof; a.pad = anomaly_padding; a.max_runs = max_runs;
+    a.n_slices = (int)ceil_div(wlen, TW_CHUNK);
+    a.stats = stats; a.runs = runs; a.n_runs = n_runs;
+    const size_t na = (size_t)n_analysis, mr = (size_t)max_runs;
+    const size_t o_partial = 0, o_mean = o_partial + align256(na * a.n_slices * 8), o_cnt = o_mean + align256(na * 8);
+    const size_t o_below = o_cnt + align256(na * 2 * 4), o_starts = o_below + align256(na * 8);
+    const size_t o_ends = o_starts + align256(na * mr * 8), o_rmax = o_ends + align256(na * mr * 8);
+    int rc = ensure_workspace(ctx, o_rmax + align256(na * mr * 8));
     if (rc != HYPAD_OK) return rc;
-    threshold_windows_kernel<<<(unsigned)n_analysis, TW_THREADS, 0, stream>>>(errors, len, window_size, step, ddof, anomaly_padding,
-                                                                              stats, runs, n_runs, max_runs,
-                                                                              (unsigned long long*)ctx->workspace);
+    char* ws = (char*)ctx->workspace;
+    a.partial = (double*)(ws + o_partial); a.mean = (double*)(ws + o_mean); a.cnt = (int*)(ws + o_cnt);
+    a.below = (unsigned long long*)(ws + o_below); a.starts = (long long*)(ws + o_starts);
+    a.ends = (long long*)(ws + o_ends); a.rmax = (unsigned long long*)(ws + o_rmax);
+    const dim3 gsum((unsigned)a.n_slices, (unsigned)n_analysis), gtile((unsigned)ceil_div(wlen, TW_TILE), (unsigned)n_analysis);
+    tw_partial_kernel<<<gsum, 256, 0, stream>>>(a, 0);
+    HYPAD_LAUNCH_CHECK();
+    tw_final_kernel<<<(unsigned)n_analysis, 32, 0, stream>>>(a, 0);
+    HYPAD_LAUNCH_CHECK();
+    tw_partial_kernel<<<gsum, 256, 0, stream>>>(a, 1);
+    HYPAD_LAUNCH_CHECK();
+    tw_final_kernel<<<(unsigned)n_analysis, 32, 0, stream>>>(a, 1);
+    HYPAD_LAUNCH_CHECK();
+    tw_events_kernel<<<gtile, TW_TILE, 0, stream>>>(a);
+    HYPAD_LAUNCH_CHECK();
+    tw_runmax_kernel<<<gtile, TW_TILE, 0, stream>>>(a);
+    HYPAD_LAUNCH_CHECK();
+    tw_emit_kernel<<<(unsigned)n_analysis, 256, 0, stream>>>(a);
     HYPAD_LAUNCH_CHECK();
     return HYPAD_OK;
 }

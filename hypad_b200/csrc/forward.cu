@@ -29,6 +29,12 @@ constexpr int LDM = 64;                    // floats per activation row
 constexpr int KC = 8;                      // k-rows per weight stage
 constexpr int WSTAGE_FLOATS = KC * 3 * 64; // one stage (sized for G = 3)
 constexpr int ACT_ROWS = 128;              // rows of buffers A and B
+constexpr int BIAS_FLOATS = 2 * 3 * 64;    // one staged bias block (b_ih | b_hh for G = 3)
+
+// Activation buffers are XOR-swizzled: element (feature k, window m) lives at k*LDM + (m ^ swz(k)).  swz only touches
+// bits 2..4 of m, so float4 groups stay contiguous and a row is still one 256-byte line; it makes the epilogue's
+// float4 stores (lanes = 8 different features x 4 window groups) hit 8 different bank groups instead of one.
+__device__ __forceinline__ int swz(int k) { return ((k >> 2) & 7) << 2; }
 
 struct FwdParams {
     const void* x;
@@ -59,7 +65,7 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 // torch.sigmoid in fp32: 1 / (1 + exp(-x))
-__device__ __forceinline__ float sigmoidf_(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+__device__ __forceinline__ float sigmoidf_(float x) { return __frcp_rn(__fadd_rn(1.0f, expf(-x))); }
 
 template <int G>
 __device__ __forceinline__ void stage_chunk(const float* __restrict__ g, float* __restrict__ s, int tid) {
@@ -72,9 +78,11 @@ __device__ __forceinline__ void stage_chunk(const float* __restrict__ g, float* 
 }
 
 // acc[r][4g+j] = sum_k act[k][8tm+r] * W[k][g][4tn+j], ascending k, one FFMA chain per output.
+// Also stages the pass's 2*G*64 bias values (they follow the panel in global memory) into sBias.
 template <int G>
-__device__ __forceinline__ void gemm_pass(const float* __restrict__ gW, int nchunks, const float* __restrict__ sA,
-                                          float* __restrict__ sW, float (&acc)[8][4 * G], int tid, int tm, int tn) {
+__device__ __forceinline__ void gemm_pass(const float* __restrict__ gW, const float* __restrict__ gBias, int nchunks,
+                                          const float* __restrict__ sA, float* __restrict__ sW, float* __restrict__ sBias,
+                                          float (&acc)[8][4 * G], int tid, int tm, int tn) {
     constexpr int CHUNK = KC * G * 64;
 #pragma unroll
     for (int r = 0; r < 8; ++r)
@@ -82,6 +90,7 @@ __device__ __forceinline__ void gemm_pass(const float* __restrict__ gW, int nchu
         for (int c = 0; c < 4 * G; ++c) acc[r][c] = 0.0f;
 
     stage_chunk<G>(gW, sW, tid);
+    if (tid < 2 * G * 16) cp_async16(sBias + 4 * tid, gBias + 4 * tid);
     cp_async_commit();
     for (int c = 0; c < nchunks; ++c) {
         cp_async_wait<0>();  // this thread's part of stage c has landed
@@ -93,11 +102,13 @@ __device__ __forceinline__ void gemm_pass(const float* __restrict__ gW, int nchu
             cp_async_commit();
         }
         const float* w = sW + (c & 1) * WSTAGE_FLOATS + 4 * tn;
-        const float* a = sA + c * KC * LDM + 8 * tm;
+        const float* a = sA + c * KC * LDM;
+        const int m_lo = (8 * tm) ^ swz(c * KC), m_hi = (8 * tm) ^ swz(c * KC + 4);  // rows kk<4 / kk>=4 of the chunk
 #pragma unroll
         for (int kk = 0; kk < KC; ++kk) {
-            const float4 a0 = *reinterpret_cast<const float4*>(a + kk * LDM);
-            const float4 a1 = *reinterpret_cast<const float4*>(a + kk * LDM + 4);
+            const int m0 = kk < 4 ? m_lo : m_hi;
+            const float4 a0 = *reinterpret_cast<const float4*>(a + kk * LDM + m0);
+            const float4 a1 = *reinterpret_cast<const float4*>(a + kk * LDM + (m0 ^ 4));
             const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
             for (int g = 0; g < G; ++g) {
@@ -115,9 +126,11 @@ __device__ __forceinline__ void gemm_pass(const float* __restrict__ gW, int nchu
     __syncthreads();
 }
 
-__device__ __forceinline__ void store_col8(float* dst_row, int tm, const float (&v)[8]) {
-    *reinterpret_cast<float4*>(dst_row + 8 * tm) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(dst_row + 8 * tm + 4) = make_float4(v[4], v[5], v[6], v[7]);
+// windows 8tm..8tm+7 of feature row k (buf points at the buffer base)
+__device__ __forceinline__ void store_col8(float* buf, int k, int tm, const float (&v)[8]) {
+    const int m0 = (8 * tm) ^ swz(k);
+    *reinterpret_cast<float4*>(buf + k * LDM + m0) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(buf + k * LDM + (m0 ^ 4)) = make_float4(v[4], v[5], v[6], v[7]);
 }
 
 // Shared-memory float offset of activation buffer `id`: X has x_rows rows, A and B have ACT_ROWS rows.
@@ -129,58 +142,62 @@ __device__ __forceinline__ int buf_offset(int id, int x_rows) {
 // One pass of the layer program: contraction + epilogue into the destination activation buffer.
 template <int G>
 __device__ __forceinline__ void run_pass_g(const PassDesc& pd, const float* __restrict__ packed, float* smem, int x_rows,
-                                           float* sW, int tid, int tm, int tn) {
+                                           float* sW, float* sBias, int tid, int tm, int tn) {
     float acc[8][4 * G];
-    gemm_pass<G>(packed + pd.w_off, pd.kpad / KC, smem + buf_offset(pd.src, x_rows), sW, acc, tid, tm, tn);
-    const float* __restrict__ b1 = packed + pd.b_off;
-    const float* __restrict__ b2 = b1 + G * 64;
-    float* dst = smem + buf_offset(pd.dst, x_rows) + pd.dst_row * LDM;
+    gemm_pass<G>(packed + pd.w_off, packed + pd.b_off, pd.kpad / KC, smem + buf_offset(pd.src, x_rows), sW, sBias, acc, tid,
+                 tm, tn);
+    const float* __restrict__ b1 = sBias;
+    const float* __restrict__ b2 = sBias + G * 64;
+    float* dst = smem + buf_offset(pd.dst, x_rows);
     if constexpr (G == 3) {
-        if (pd.epi == EPI_LSTM) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int u = 4 * tn + j;
-                const float bi1 = b1[u], bg1 = b1[64 + u], bo1 = b1[128 + u];
-                const float bi2 = b2[u], bg2 = b2[64 + u], bo2 = b2[128 + u];
-                float hv[8];
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    // gates = (x W_ih^T + b_ih) + (0 W_hh^T + b_hh)
-                    const float gi = __fadd_rn(__fadd_rn(acc[r][j], bi1), bi2);
-                    const float gg = __fadd_rn(__fadd_rn(acc[r][4 + j], bg1), bg2);
-                    const float go = __fadd_rn(__fadd_rn(acc[r][8 + j], bo1), bo2);
-                    const float c = __fmul_rn(sigmoidf_(gi), tanhf(gg));  // + sigmoid(f) * c0, c0 = 0
-                    hv[r] = __fmul_rn(sigmoidf_(go), tanhf(c));
-                }
-                store_col8(dst + u * LDM, tm, hv);
-            }
-            return;
-        }
-    }
-    // EPI_LINEAR: out = acc + bias, optional activation
-#pragma unroll
-    for (int g = 0; g < G; ++g)
+        // EPI_LSTM (the only use of three column groups): i | g | o pre-activations of the same 64 hidden units
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int col = 64 * g + 4 * tn + j;
-            const float bias = b1[col];
-            float v[8];
+            const int u = 4 * tn + j;
+            const float bi1 = b1[u], bg1 = b1[64 + u], bo1 = b1[128 + u];
+            const float bi2 = b2[u], bg2 = b2[64 + u], bo2 = b2[128 + u];
+            float hv[8];
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                float t = __fadd_rn(acc[r][4 * g + j], bias);
-                if (pd.act == 1) t = tanhf(t);
-                else if (pd.act == 2) t = t > 0.0f ? t : __fmul_rn(t, 0.2f);  // LeakyReLU(0.2)
-                v[r] = t;
+                // gates = (x W_ih^T + b_ih) + (0 W_hh^T + b_hh)
+                const float gi = __fadd_rn(__fadd_rn(acc[r][j], bi1), bi2);
+                const float gg = __fadd_rn(__fadd_rn(acc[r][4 + j], bg1), bg2);
+                const float go = __fadd_rn(__fadd_rn(acc[r][8 + j], bo1), bo2);
+                const float c = __fmul_rn(sigmoidf_(gi), tanhf(gg));  // + sigmoid(f) * c0, c0 = 0
+                hv[r] = __fmul_rn(sigmoidf_(go), tanhf(c));
             }
-            store_col8(dst + col * LDM, tm, v);
+            store_col8(dst, pd.dst_row + u, tm, hv);
         }
+    } else {
+        // EPI_LINEAR: out = acc + bias, activation by pass (G == 2: none | tanh ; G == 1: none | LeakyReLU)
+        const int act = pd.act;
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int col = 64 * g + 4 * tn + j;
+                const float bias = b1[col];
+                float v[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    float t = __fadd_rn(acc[r][4 * g + j], bias);
+                    if constexpr (G == 2) {
+                        if (act == 1) t = tanhf(t);
+                    } else {
+                        if (act == 2) t = t > 0.0f ? t : __fmul_rn(t, 0.2f);  // LeakyReLU(0.2)
+                    }
+                    v[r] = t;
+                }
+                store_col8(dst, pd.dst_row + col, tm, v);
+            }
+    }
 }
 
 __device__ __forceinline__ void run_pass(const PassDesc& pd, const float* __restrict__ packed, float* smem, int x_rows,
-                                         float* sW, int tid, int tm, int tn) {
-    if (pd.groups == 3) run_pass_g<3>(pd, packed, smem, x_rows, sW, tid, tm, tn);
-    else if (pd.groups == 2) run_pass_g<2>(pd, packed, smem, x_rows, sW, tid, tm, tn);
-    else run_pass_g<1>(pd, packed, smem, x_rows, sW, tid, tm, tn);
+                                         float* sW, float* sBias, int tid, int tm, int tn) {
+    if (pd.groups == 3) run_pass_g<3>(pd, packed, smem, x_rows, sW, sBias, tid, tm, tn);
+    else if (pd.groups == 2) run_pass_g<2>(pd, packed, smem, x_rows, sW, sBias, tid, tm, tn);
+    else run_pass_g<1>(pd, packed, smem, x_rows, sW, sBias, tid, tm, tn);
 }
 
 // Sum over the two column halves of a row-phase partial (fp64), result identical in both halves.
@@ -201,7 +218,7 @@ __device__ void row_mobius(float* buf, const float* __restrict__ bias, float y2,
     const int m = tid & (TILE_M - 1), half = tid >> 6;
     double s1[1] = {0.0};
     for (int c = half; c < S; c += 2) {
-        const float y = buf[c * LDM + m];
+        const float y = buf[c * LDM + (m ^ swz(c))];
         s1[0] += (double)__fmul_rn(y, y);
     }
     row_allreduce<1>(s1, red, m, half);
@@ -209,8 +226,9 @@ __device__ void row_mobius(float* buf, const float* __restrict__ bias, float y2,
     const float th = (float)tanh((double)fminf(n, 15.0f));
     double s2[2] = {0.0, 0.0};
     for (int c = half; c < S; c += 2) {
-        const float p = __fmul_rn(th, __fdiv_rn(buf[c * LDM + m], n));
-        buf[c * LDM + m] = p;
+        const int e = c * LDM + (m ^ swz(c));
+        const float p = __fmul_rn(th, __fdiv_rn(buf[e], n));
+        buf[e] = p;
         s2[0] += (double)__fmul_rn(p, p);
         s2[1] += (double)__fmul_rn(p, bias[c]);
     }
@@ -222,16 +240,20 @@ __device__ void row_mobius(float* buf, const float* __restrict__ bias, float y2,
     const float den = fmaxf(__fadd_rn(one_2xy, __fmul_rn(x2, y2)), 1e-15f);
     double s3[1] = {0.0};
     for (int c = half; c < S; c += 2) {
-        const float p = buf[c * LDM + m];
+        const int e = c * LDM + (m ^ swz(c));
+        const float p = buf[e];
         const float q = __fdiv_rn(__fadd_rn(__fmul_rn(ca, p), __fmul_rn(cb, bias[c])), den);
-        buf[c * LDM + m] = q;
+        buf[e] = q;
         s3[0] += (double)__fmul_rn(q, q);
     }
     row_allreduce<1>(s3, red, m, half);
     const float norm = fmaxf(sqrtf((float)s3[0]), 1e-15f);
     const float maxnorm = 0.996f;  // (1 - 4e-3) / sqrt(|k| + 1e-15) in fp32
     if (norm > maxnorm) {
-        for (int c = half; c < S; c += 2) buf[c * LDM + m] = __fmul_rn(__fdiv_rn(buf[c * LDM + m], norm), maxnorm);
+        for (int c = half; c < S; c += 2) {
+            const int e = c * LDM + (m ^ swz(c));
+            buf[e] = __fmul_rn(__fdiv_rn(buf[e], norm), maxnorm);
+        }
     }
     __syncthreads();
 }
@@ -245,7 +267,7 @@ __device__ void store_rows(const float* buf, float* __restrict__ out, int ncols,
         const int m = mb + mc;
         if (w0 + m >= n) continue;
         float* o = out + (w0 + m) * (int64_t)ncols;
-        for (int c = cc; c < ncols; c += 8) o[c] = buf[c * LDM + m];
+        for (int c = cc; c < ncols; c += 8) o[c] = buf[c * LDM + (m ^ swz(c))];
     }
 }
 
@@ -256,7 +278,7 @@ __device__ __forceinline__ void load_x_tile(float* sX, const T* __restrict__ x, 
         const int k = e >> 6, m = e & 63;
         float v = 0.0f;
         if (k < S && w0 + m < n) v = (float)x[(w0 + m) * stride + k];
-        sX[e] = v;
+        sX[k * LDM + (m ^ swz(k))] = v;
     }
 }
 
@@ -268,7 +290,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) forward_kernel(const __grid_const
     float* sA = sX + S8 * LDM;
     float* sB = sA + ACT_ROWS * LDM;
     float* sW = sB + ACT_ROWS * LDM;
+    float* sBias0 = sW + 2 * WSTAGE_FLOATS;       // two bias blocks, alternated per pass (a warp may run one pass ahead)
     double* red = reinterpret_cast<double*>(sW);  // row phases reuse the (idle) weight stage: 3*2*64 doubles = 3 KB
+    int pass_parity = 0;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -293,11 +317,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) forward_kernel(const __grid_const
                     const int c = e >> 6, m = e & 63;
                     float v = 0.0f;
                     if (c < prog.latent && w0 + m < P.n) v = P.z_in[(w0 + m) * prog.latent + c];
-                    sB[e] = v;
+                    sB[c * LDM + (m ^ swz(c))] = v;
                 }
             }
             const PassDesc& pd = prog.pass[p];
-            run_pass(pd, packed, smem, S8, sW, tid, tm, tn);
+            run_pass(pd, packed, smem, S8, sW, sBias0 + pass_parity * BIAS_FLOATS, tid, tm, tn);
+            pass_parity ^= 1;
             if (p == P_C4) {
                 // CriticX dense5 (20 -> 1) per window
                 __syncthreads();
@@ -305,7 +330,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) forward_kernel(const __grid_const
                     const float* w5 = packed + prog.critic5_off;
                     const float* h = smem + buf_offset(pd.dst, S8);
                     float a = 0.0f;
-                    for (int k = 0; k < prog.latent_c; ++k) a = fmaf(h[k * LDM + tid], w5[k], a);
+                    for (int k = 0; k < prog.latent_c; ++k) a = fmaf(h[k * LDM + (tid ^ swz(k))], w5[k], a);
                     P.out.critic[w0 + tid] = __fadd_rn(a, w5[prog.latent_c]);
                 }
                 __syncthreads();
@@ -333,10 +358,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) forward_kernel(const __grid_const
             const bool both = P.out.rec != nullptr;
             double s[3] = {0.0, 0.0, 0.0};
             for (int c = half; c < S; c += 2) {
-                const float h = sA[c * LDM + m];
+                const int e = c * LDM + (m ^ swz(c));
+                const float h = sA[e];
                 s[2] += (double)__fmul_rn(h, h);
                 if (both) {
-                    const float hx = sB[c * LDM + m];
+                    const float hx = sB[e];
                     const float d = __fsub_rn(hx, h);
                     s[0] += (double)__fmul_rn(d, d);
                     s[1] += (double)__fmul_rn(hx, hx);
@@ -374,7 +400,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) mobius_kernel(const __grid_consta
     float* sX = smem;
     float* sB = sX + P.in8 * LDM;
     float* sW = sB + 3 * 64 * LDM;
+    float* sBias0 = sW + 2 * WSTAGE_FLOATS;
     double* red = reinterpret_cast<double*>(sW);
+    int pass_parity = 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tm = (warp & 1) * 4 + (lane >> 3), tn = (warp >> 1) * 8 + (lane & 7);
     PassDesc pd;
@@ -388,7 +416,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) mobius_kernel(const __grid_consta
         {
             PassDesc q = pd;
             q.b_off = P.in8 * P.groups * 64;
-            run_pass(q, P.panel, smem, P.in8, sW, tid, tm, tn);
+            run_pass(q, P.panel, smem, P.in8, sW, sBias0 + pass_parity * BIAS_FLOATS, tid, tm, tn);
+            pass_parity ^= 1;
         }
         __syncthreads();
         if (P.has_bias) {
@@ -407,7 +436,7 @@ int launch_mobius(int device, const float* x, int64_t n, int in_f, int out_f, co
     MobiusParams P;
     P.x = x; P.panel = panel; P.bias = bias; P.y2 = y2; P.out = out; P.n = n;
     P.in_f = in_f; P.in8 = (in_f + 7) / 8 * 8; P.out_f = out_f; P.groups = (out_f + 63) / 64; P.has_bias = has_bias;
-    const size_t smem = (size_t)(P.in8 + 3 * 64) * LDM * sizeof(float) + 2 * WSTAGE_FLOATS * sizeof(float);
+    const size_t smem = (size_t)(P.in8 + 3 * 64) * LDM * sizeof(float) + (2 * WSTAGE_FLOATS + 2 * BIAS_FLOATS) * sizeof(float);
     static thread_local size_t configured = 0;
     if (configured < smem) {
         HYPAD_CUDA_TRY(cudaFuncSetAttribute(mobius_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -422,7 +451,9 @@ int launch_mobius(int device, const float* x, int64_t n, int in_f, int out_f, co
     return HYPAD_OK;
 }
 
-size_t forward_smem_bytes(int S8) { return (size_t)(S8 + 2 * ACT_ROWS) * LDM * sizeof(float) + 2 * WSTAGE_FLOATS * sizeof(float); }
+size_t forward_smem_bytes(int S8) {
+    return (size_t)(S8 + 2 * ACT_ROWS) * LDM * sizeof(float) + (2 * WSTAGE_FLOATS + 2 * BIAS_FLOATS) * sizeof(float);
+}
 
 int launch_forward(const hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_t row_stride, const float* z_in,
                    int stages, const hypad_forward_out* out, cudaStream_t stream) {

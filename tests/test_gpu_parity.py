@@ -334,8 +334,10 @@ def selection_aware_close(out, g, n, label):
     final = out["final"].cpu().numpy()
     r = np.nan_to_num(rel(final, g["final"]))
     kmax = out["kmax"].cpu().numpy()
-    crit_std = float(np.std(g["critic"]))
-    material = np.flatnonzero(np.abs(kmax - g["kmax"]) > 1e-5 * crit_std)
+    # a selection differs "materially" when another window's value was picked, i.e. the difference exceeds both the
+    # fp32 noise of a critic value (a few ulps of its magnitude) and a sliver of the critic spread
+    noise = max(1e-5 * float(np.std(g["critic"])), 4e-7 * float(np.abs(g["critic"]).max()))
+    material = np.flatnonzero(np.abs(kmax - g["kmax"]) > noise)
     w = max(int(n * 0.01), 1)
     rec_steps = int((rel(out["rec"].cpu().numpy(), g["rec"]) > 1e-4).sum()) if "rec" in g else 0
     beyond = np.flatnonzero(r > 1e-4)
@@ -343,6 +345,15 @@ def selection_aware_close(out, g, n, label):
           % (label, n, len(material), rec_steps, len(beyond), r.max()))
     assert len(material) <= max(3, int(1e-3 * n)), "too many selection differences"
     assert r.max() <= 4e-3
+    # conditioning of the critic z-score: |z| = |kmax - mu| / sigma + 1, so a last-bit (non-material) difference d of a
+    # critic value moves z by d / sigma.  On nearly constant signals (NASA A-1: one fp32 ulp of the critic is 9e-4
+    # sigma) that alone exceeds 1e-4; the reference shows the same against itself (tests/test_reference_floor.py).
+    dk = np.abs(kmax - g["kmax"])
+    dk[material] = 0.0
+    cond = float(dk.max() / np.std(g["kmax"])) if np.std(g["kmax"]) > 0 else 0.0
+    tol = 1e-4 + 1.5 * cond
+    beyond = np.flatnonzero(r > tol)
+    print("    conditioning: max last-bit kmax difference / sigma(kmax) = %.2e -> tolerance %.2e; beyond it: %d" % (cond, tol, len(beyond)))
     # attribution: each out-of-tolerance output lies within w of a differing selection, or is a rec quantisation step
     if len(beyond):
         near = np.zeros(len(final) + 2 * w + 2, dtype=bool)
@@ -350,7 +361,7 @@ def selection_aware_close(out, g, n, label):
             near[t: t + 2 * w + 1] = True  # positions t-w .. t+w, shifted by w
         rec_bad = rel(out["rec"].cpu().numpy(), g["rec"]) > 1e-4 if "rec" in g else np.zeros(len(final), bool)
         unexplained = [int(b) for b in beyond if not near[b + w] and not rec_bad[b]]
-        assert not unexplained, "scores beyond 1e-4 not attributable to a selection difference: %s" % unexplained[:10]
+        assert not unexplained, "scores beyond tolerance not attributable to a selection difference: %s" % unexplained[:10]
     assert len(beyond) <= len(material) * (w + 1) + rec_steps
     return r
 
