@@ -177,6 +177,11 @@ int hypad_threshold_windows(hypad_ctx* ctx, const double* errors, int64_t len, i
                             int64_t n_analysis, int ddof, int anomaly_padding, double* stats, double* runs,
                             int32_t* n_runs, int max_runs, void* stream);
 
+/* Diagnostic (not on the product path): D (128,N) = A (128,K) B(N,K)^T on the tcgen05 tensor cores with the fp32
+ * operands split into `pieces` TF32 parts and `terms` partial products accumulated in TMEM: (1,1) plain TF32,
+ * (2,3) 3xTF32, (3,6) six-term split.  Used to measure whether a tensor-core contraction can hold score parity. */
+int hypad_tc_probe_gemm(const float* A, const float* B, float* D, int K, int N, int pieces, int terms, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
