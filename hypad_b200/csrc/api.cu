@@ -39,19 +39,11 @@ int ensure_workspace(hypad_ctx* ctx, size_t bytes) {
 
 int launch_forward(const hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_t row_stride, const float* z_in,
                    int stages, const hypad_forward_out* out, cudaStream_t stream);
+int launch_forward_tc(const hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_t row_stride, const float* z_in,
+                      int stages, const hypad_forward_out* out, cudaStream_t stream);
+int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream);
 int launch_mobius(int device, const float* x, int64_t n, int in_f, int out_f, const float* panel, const float* bias,
                   const float* y2, int has_bias, float* out, cudaStream_t stream);
-
-// One packed output column: where its weight row and its biases come from.
-struct ColSrc {
-    const float* w;   // row-major (rows, K) source matrix or nullptr (zero column)
-    const float* b1;  // bias source or nullptr
-    const float* b2;
-    int32_t row;      // weight row
-    int32_t K;        // source row length
-    int32_t bidx;     // bias index
-    int32_t pad;
-};
 
 __global__ void pack_panel_kernel(const ColSrc* __restrict__ cols, int ncols, int kpad, float* __restrict__ panel,
                                   float* __restrict__ bias) {
@@ -135,6 +127,8 @@ int hypad_ctx_destroy(hypad_ctx* ctx) {
     cudaDeviceSynchronize();
     if (ctx->packed) cudaFree(ctx->packed);
     if (ctx->workspace) cudaFree(ctx->workspace);
+    if (ctx->tc_packed) cudaFree(ctx->tc_packed);
+    if (ctx->tc_error) cudaFree(ctx->tc_error);
     delete ctx;
     return HYPAD_OK;
 }
@@ -275,12 +269,14 @@ int hypad_pack_weights(hypad_ctx* ctx, const hypad_weights* w, void* stream_) {
     // the column table in the workspace must outlive the pack kernels before the workspace is reused
     HYPAD_CUDA_TRY(cudaStreamSynchronize(stream));
     ctx->prog = prog;
+    rc = pack_tc(ctx, w, stream);
+    if (rc != HYPAD_OK) return rc;
     ctx->has_weights = true;
     return HYPAD_OK;
 }
 
-int hypad_forward(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_t row_stride, const float* z_in,
-                  int stages, const hypad_forward_out* out, void* stream) {
+static int check_forward_args(hypad_ctx* ctx, const void* x, int64_t n, int64_t row_stride, const float* z_in, int stages,
+                              const hypad_forward_out* out) {
     HYPAD_REQUIRE(ctx && out, "hypad_forward: NULL argument");
     if (!ctx->has_weights) {
         set_error("hypad_forward: call hypad_pack_weights first");
@@ -297,9 +293,36 @@ int hypad_forward(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_
     HYPAD_REQUIRE(!(stages & HYPAD_STAGE_MOBIUS_X) || ctx->prog.hyperbolic, "hypad_forward: MOBIUS_X needs a hyperbolic decoder");
     HYPAD_REQUIRE(!out->rec || ((stages & HYPAD_STAGE_DECODER) && (stages & HYPAD_STAGE_MOBIUS_X)),
                   "hypad_forward: rec needs DECODER|MOBIUS_X");
-    if (n == 0) return HYPAD_OK;
+    return HYPAD_OK;
+}
+
+int hypad_forward(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_t row_stride, const float* z_in,
+                  int stages, const hypad_forward_out* out, void* stream) {
+    int rc = check_forward_args(ctx, x, n, row_stride, z_in, stages, out);
+    if (rc != HYPAD_OK || n == 0) return rc;
+    HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
+    return launch_forward_tc(ctx, x, x_is_f64, n, row_stride, z_in, stages, out, (cudaStream_t)stream);
+}
+
+int hypad_forward_ffma(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_t row_stride, const float* z_in,
+                       int stages, const hypad_forward_out* out, void* stream) {
+    int rc = check_forward_args(ctx, x, n, row_stride, z_in, stages, out);
+    if (rc != HYPAD_OK || n == 0) return rc;
     HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
     return launch_forward(ctx, x, x_is_f64, n, row_stride, z_in, stages, out, (cudaStream_t)stream);
+}
+
+int hypad_ctx_poll_error(hypad_ctx* ctx) {
+    HYPAD_REQUIRE(ctx != nullptr, "hypad_ctx_poll_error: NULL context");
+    if (!ctx->tc_error) return HYPAD_OK;
+    HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
+    int flag = 0;
+    HYPAD_CUDA_TRY(cudaMemcpy(&flag, ctx->tc_error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+        set_error("forward_tc_kernel: a barrier wait timed out (pipeline protocol error)");
+        return HYPAD_ECUDA;
+    }
+    return HYPAD_OK;
 }
 
 int hypad_mobius_linear(hypad_ctx* ctx, const float* x, int64_t n, int in_features, int out_features,

@@ -91,6 +91,17 @@ struct NetProgram {
     int32_t critic5_off;   // float offset of critic dense5: W[latent_c] then b[1]
 };
 
+// One packed output column: where its weight row and its biases come from (weight packing kernels).
+struct ColSrc {
+    const float* w = nullptr;   // row-major (rows, K) source matrix or nullptr (zero column)
+    const float* b1 = nullptr;  // bias source or nullptr
+    const float* b2 = nullptr;
+    int32_t row = 0;            // weight row
+    int32_t K = 0;              // source row length
+    int32_t bidx = 0;           // bias index
+    int32_t pad = 0;
+};
+
 }  // namespace hypad
 
 struct hypad_ctx {
@@ -102,6 +113,12 @@ struct hypad_ctx {
     void* workspace;      // device scratch, grown on demand
     size_t workspace_bytes;
     int max_smem_optin;
+    // tensor-core path (forward_tc.cu)
+    unsigned char* tc_packed;   // TF32-split weight stages followed by the small-parameter block
+    size_t tc_bytes;
+    size_t tc_small_off;
+    int* tc_error;              // device flag raised when a barrier wait times out
+    unsigned char tc_prog_storage[1024];
 };
 
 namespace hypad {

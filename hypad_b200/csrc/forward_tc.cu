@@ -1,0 +1,715 @@
+// Fused TadGAN forward on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM) -- the
+// product path of hypad_forward.  Same arithmetic contract as the FFMA kernel in forward.cu (which stays as the
+// in-library cross-check, hypad_forward_ffma): Encoder -> Decoder -> MobiusLinear x2 -> Poincare row distance, CriticX.
+//
+// Every layer is a dense contraction  D[128 windows x N] = A[128 x K] * W[N x K]^T  with fp32-class accuracy obtained
+// from three TF32 products ("3xTF32"): A = A_hi + A_lo, W = W_hi + W_lo (each piece rounded to TF32 with cvt.rna),
+// D = A_lo W_hi + A_hi W_lo + A_hi W_hi accumulated in fp32 in TMEM.  Measured on the B200 (tests/test_gpu_tensor_probe.py):
+// rms error 3.4-4.3e-8 of sum|a||w| against 2.6e-8 for the fp32 FFMA order, no bias -- plain TF32 is 1000x worse.
+//
+// One persistent CTA per SM owns tiles of 128 windows (TMEM lane = window).  Warp roles:
+//   warps 0-15 epilogue: warp w reads TMEM lanes 32*(w%4).. (its 32 windows) and every 4th 8-column chunk (w/4);
+//              gate / activation math in registers, then writes the next layer's A operand (hi and lo pieces) into shared
+//              memory in the UMMA K-major core-matrix layout, element (row r, feature k) at ((k/4)*128 + r)*16 B + (k%4)*4 B
+//   warp 16    weight producer: cp.async.bulk (TMA engine) of one <=16 KB weight stage (16 k x <=128 columns, hi+lo)
+//              per mbarrier slot, a ring of 5 slots running ahead across layers and tiles
+//   warp 17    MMA issuer: one thread issues the six tcgen05.mma per stage, tcgen05.commit frees the slot and, per
+//              layer, signals the epilogue
+// Activations never leave the SM: the A operand buffer (128 KB = 128 features x 128 windows x hi/lo) is overwritten in
+// place layer by layer (all MMAs of a layer retire before its epilogue runs).  Weights stream from L2.
+#include <vector>
+
+#include "common.cuh"
+
+namespace hypad {
+
+constexpr int TC_M = 128;                 // windows per tile
+constexpr int TC_NSPLIT = 4;              // epilogue warps per TMEM lane quarter (column chunks dealt round-robin)
+constexpr int TC_EPI_THREADS = 128 * TC_NSPLIT;
+constexpr int TC_THREADS = TC_EPI_THREADS + 64;
+constexpr int TC_PRODUCER_WARP = TC_EPI_THREADS / 32, TC_MMA_WARP = TC_PRODUCER_WARP + 1;
+constexpr int TC_PIECE_BYTES = 65536;     // one piece of the A buffer: 128 features x 128 rows x 4 B
+constexpr int TC_KSTAGE = 2;              // k-steps (of 8) per weight stage
+constexpr int TC_STAGE_BYTES = TC_KSTAGE * 8192;  // 16 k x 128 columns x (hi + lo) x 4 B
+constexpr int TC_NSLOT = 5;
+constexpr int TC_RED_BYTES = TC_NSPLIT * TC_M * 3 * 8;
+
+enum TcEpi : int32_t { TE_LSTM = 0, TE_Z, TE_LINEAR, TE_TANH, TE_MOB_R, TE_MOB_X, TE_CRITIC_HID, TE_CRITIC_OUT };
+enum TcPassIdx : int32_t { T_ENC = 0, T_Z, T_D0, T_L0, T_L1, T_D2, T_MR, T_MX, T_C1, T_C2, T_C3, T_C4, T_COUNT };
+
+struct TcPass {
+    int32_t k8;      // K / 8
+    int32_t nblk;    // column blocks (3 for an LSTM layer: i | g | o)
+    int32_t n;       // columns per block, multiple of 16, <= 128
+    int32_t d_col;   // TMEM column of block 0 (block b at d_col + b*n)
+    int32_t w_off;   // byte offset of the packed weights: [k8][nblk]{hi,lo}[2 chunks][n][4]
+    int32_t b_off;   // float offset of the biases: b1[nblk*n] then b2[nblk*n]
+    int32_t epi;     // TcEpi
+    int32_t needs_x; // the A operand is the window itself
+};
+
+struct TcProgram {
+    TcPass pass[T_COUNT];
+    int32_t S, S8, latent, latent_c, hyperbolic;
+    int32_t mob_bias_off, mob_y2_off, critic5_off;  // float offsets into the small-parameter buffer
+};
+
+struct TcParams {
+    const void* x;
+    const float* z_in;
+    const unsigned char* wpacked;  // TF32-split weight stages
+    const float* small;            // biases and row-phase parameters
+    int64_t n, row_stride;
+    int32_t x_is_f64, stages;
+    uint32_t pass_mask;
+    int32_t want_rowstats;
+    hypad_forward_out out;
+    int* error_flag;
+    TcProgram prog;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ uint32_t idesc_tf32(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | (8u << 24); }
+__device__ __forceinline__ void mma_tf32(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(d),
+        "l"(a), "l"(b), "r"(idesc), "r"(acc), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol error must never hang the GPU.  Returns false on timeout (and raises the error flag).
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* error_flag) {
+    uint32_t done = 0;
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return true;
+    }
+    atomicExch(error_flag, 1);
+    return false;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+                 "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// features k0..k0+7 of row r (fp32) -> hi / lo TF32 pieces of the A operand buffer
+__device__ __forceinline__ void store_act8(unsigned char* act, int r, int k0, const float (&v)[8]) {
+    float hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        hi[i] = tf32_rna(v[i]);
+        lo[i] = tf32_rna(v[i] - hi[i]);
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const int off = (((k0 >> 2) + c) * TC_M + r) * 16;
+        *reinterpret_cast<float4*>(act + off) = make_float4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+        *reinterpret_cast<float4*>(act + TC_PIECE_BYTES + off) = make_float4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+    }
+}
+
+// 1 / (1 + exp(-x)); the reciprocal is MUFU.RCP refined by one Newton step (<= 1 ulp, branch-free)
+__device__ __forceinline__ float sigmoid_tc(float x) {
+    const float d = __fadd_rn(1.0f, expf(-x));
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    return fmaf(r, fmaf(-d, r, 1.0f), r);
+}
+
+// sum of the column-split partials of a row (fp64, fixed order); every split gets the same value
+template <int NV>
+__device__ __forceinline__ void row_allreduce_tc(double (&v)[NV], double* red, int r, int split) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[(i * TC_NSPLIT + split) * TC_M + r] = v[i];
+    epi_bar();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double t = red[(i * TC_NSPLIT) * TC_M + r];
+#pragma unroll
+        for (int q = 1; q < TC_NSPLIT; ++q) t += red[(i * TC_NSPLIT + q) * TC_M + r];
+        v[i] = t;
+    }
+    epi_bar();
+}
+
+// the window tile (or a caller-provided latent) -> A operand buffer; threads: row = t & 127, chunk lane = t >> 7
+template <typename T>
+__device__ __forceinline__ void load_rows_to_act(unsigned char* act, const T* __restrict__ x, int64_t w0, int64_t n, int64_t stride,
+                                                 int width, int width8, int t) {
+    const int r = t & (TC_M - 1);
+    const bool live = w0 + r < n;
+    const T* row = x + (w0 + r) * stride;
+    for (int c = t >> 7; c < width8 / 4; c += TC_NSPLIT) {
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = 4 * c + e;
+            v[e] = (live && k < width) ? (float)row[k] : 0.0f;
+        }
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            hi[e] = tf32_rna(v[e]);
+            lo[e] = tf32_rna(v[e] - hi[e]);
+        }
+        const int off = (c * TC_M + r) * 16;
+        *reinterpret_cast<float4*>(act + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(act + TC_PIECE_BYTES + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// In place on TMEM columns [col0, col0+ncols): y = x W^T -> project(mobius_add(expmap0(y), bias)); see forward.cu row_mobius.
+__device__ void row_mobius_tc(uint32_t trow, int col0, int ncols, const float* __restrict__ bias, float y2, double* red, int r,
+                              int split, float* gout, bool want_out, int S) {
+    const int cbeg = 8 * split, cend = ncols, cstep = 8 * TC_NSPLIT;
+    double s1[1] = {0.0};
+    for (int c = cbeg; c < cend; c += cstep) {
+        float y[8];
+        tmem_ld8(trow + col0 + c, y);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s1[0] += (double)__fmul_rn(y[i], y[i]);
+    }
+    row_allreduce_tc<1>(s1, red, r, split);
+    const float nrm = fmaxf(sqrtf((float)s1[0]), 1e-15f);
+    const float th = (float)tanh((double)fminf(nrm, 15.0f));
+    double s2[2] = {0.0, 0.0};
+    for (int c = cbeg; c < cend; c += cstep) {
+        float y[8];
+        tmem_ld8(trow + col0 + c, y);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float p = __fmul_rn(th, __fdiv_rn(y[i], nrm));
+            s2[0] += (double)__fmul_rn(p, p);
+            s2[1] += (double)__fmul_rn(p, bias[c + i]);
+        }
+    }
+    row_allreduce_tc<2>(s2, red, r, split);
+    const float x2 = (float)s2[0], xy = (float)s2[1];
+    const float one_2xy = __fadd_rn(1.0f, __fmul_rn(2.0f, xy));
+    const float ca = __fadd_rn(one_2xy, y2);
+    const float cb = __fsub_rn(1.0f, x2);
+    const float den = fmaxf(__fadd_rn(one_2xy, __fmul_rn(x2, y2)), 1e-15f);
+    double s3[1] = {0.0};
+    for (int c = cbeg; c < cend; c += cstep) {
+        float y[8], q[8];
+        tmem_ld8(trow + col0 + c, y);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float p = __fmul_rn(th, __fdiv_rn(y[i], nrm));
+            q[i] = __fdiv_rn(__fadd_rn(__fmul_rn(ca, p), __fmul_rn(cb, bias[c + i])), den);
+            s3[0] += (double)__fmul_rn(q[i], q[i]);
+        }
+        tmem_st8(trow + col0 + c, q);
+    }
+    tmem_st_wait();
+    row_allreduce_tc<1>(s3, red, r, split);
+    const float norm = fmaxf(sqrtf((float)s3[0]), 1e-15f);
+    const float maxnorm = 0.996f;
+    const bool proj = norm > maxnorm;
+    // tcgen05.ld / .st are warp-collective: the loop runs for the whole warp or not at all
+    const bool any_proj = __any_sync(0xffffffffu, proj);
+    if (any_proj || want_out) {
+        for (int c = cbeg; c < cend; c += cstep) {
+            float q[8];
+            tmem_ld8(trow + col0 + c, q);
+            tmem_ld_wait();
+            if (any_proj) {
+                if (proj) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) q[i] = __fmul_rn(__fdiv_rn(q[i], norm), maxnorm);
+                }
+                tmem_st8(trow + col0 + c, q);
+            }
+            if (gout) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (c + i < S) gout[c + i] = q[i];
+            }
+        }
+        tmem_st_wait();
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_constant__ TcParams P) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* act = smem;                                   // 2 pieces x 64 KB
+    unsigned char* ring = smem + 2 * TC_PIECE_BYTES;             // TC_NSLOT x 8 KB
+    double* red = reinterpret_cast<double*>(ring + TC_NSLOT * TC_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(red) + TC_RED_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_NSLOT + 2);
+    const uint32_t bar_full = s_u32(bars), bar_empty = s_u32(bars + TC_NSLOT);
+    const uint32_t bar_acc = s_u32(bars + 2 * TC_NSLOT), bar_a = s_u32(bars + 2 * TC_NSLOT + 1);
+
+    const TcProgram& prog = P.prog;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = prog.S, S8 = prog.S8;
+    const int64_t ntiles = (P.n + TC_M - 1) / TC_M;
+    const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == TC_PRODUCER_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < TC_NSLOT; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_acc, 1);
+        mbar_init(bar_a, TC_EPI_THREADS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == TC_PRODUCER_WARP) {
+        // ===== weight producer (one lane) ==================================================================
+        if (lane == 0) {
+            uint32_t it = 0;
+            bool ok = true;
+            for (int64_t t = 0; t < my_tiles && ok; ++t)
+                for (int p = 0; p < T_COUNT && ok; ++p) {
+                    if (!((P.pass_mask >> p) & 1u)) continue;
+                    const TcPass& ps = prog.pass[p];
+                    const unsigned char* src = P.wpacked + ps.w_off;
+                    // stages in (k-step pair, block) order; the last pair of an odd layer holds one k-step
+                    for (int kp = 0; kp < ps.k8; kp += TC_KSTAGE) {
+                        const int kk = ps.k8 - kp < TC_KSTAGE ? ps.k8 - kp : TC_KSTAGE;
+                        const uint32_t bytes = (uint32_t)(kk * ps.n) * 64u;
+                        for (int b = 0; b < ps.nblk && ok; ++b, ++it) {
+                            const uint32_t slot = it % TC_NSLOT, use = it / TC_NSLOT;
+                            if (use > 0) ok = mbar_wait(bar_empty + 8 * slot, (use - 1) & 1, P.error_flag);
+                            if (!ok) break;
+                            mbar_expect_tx(bar_full + 8 * slot, bytes);
+                            bulk_g2s(s_u32(ring + slot * TC_STAGE_BYTES), src, bytes, bar_full + 8 * slot);
+                            src += bytes;
+                        }
+                    }
+                }
+        }
+    } else if (warp == TC_MMA_WARP) {
+        // ===== MMA issuer (one lane) =======================================================================
+        if (lane == 0) {
+            uint32_t it = 0, npass = 0;
+            bool ok = true;
+            const uint32_t act_hi = s_u32(act), act_lo = s_u32(act + TC_PIECE_BYTES);
+            for (int64_t t = 0; t < my_tiles && ok; ++t)
+                for (int p = 0; p < T_COUNT && ok; ++p) {
+                    if (!((P.pass_mask >> p) & 1u)) continue;
+                    const TcPass& ps = prog.pass[p];
+                    ok = mbar_wait(bar_a, npass & 1, P.error_flag);  // A operand written, TMEM of the previous pass drained
+                    if (!ok) break;
+                    tc_fence_after();
+                    const uint32_t idesc = idesc_tf32(ps.n);
+                    const uint32_t nb16 = (uint32_t)ps.n * 16u;
+                    for (int kp = 0; kp < ps.k8 && ok; kp += TC_KSTAGE) {
+                        const int kk = ps.k8 - kp < TC_KSTAGE ? ps.k8 - kp : TC_KSTAGE;
+                        for (int b = 0; b < ps.nblk; ++b, ++it) {
+                            const uint32_t slot = it % TC_NSLOT, use = it / TC_NSLOT;
+                            ok = mbar_wait(bar_full + 8 * slot, use & 1, P.error_flag);
+                            if (!ok) break;
+                            tc_fence_after();
+                            const uint32_t d = tmem + (uint32_t)(ps.d_col + b * ps.n);
+                            for (int j = 0; j < kk; ++j) {
+                                const int ks = kp + j;
+                                const uint64_t a_hi = smem_desc(act_hi + ks * 4096, 2048, 128);
+                                const uint64_t a_lo = smem_desc(act_lo + ks * 4096, 2048, 128);
+                                const uint32_t wbase = s_u32(ring + slot * TC_STAGE_BYTES) + (uint32_t)j * 4u * nb16;
+                                const uint64_t w_hi = smem_desc(wbase, nb16, 128);
+                                const uint64_t w_lo = smem_desc(wbase + 2 * nb16, nb16, 128);
+                                mma_tf32(d, a_lo, w_hi, idesc, ks > 0);  // small terms first
+                                mma_tf32(d, a_hi, w_lo, idesc, 1);
+                                mma_tf32(d, a_hi, w_hi, idesc, 1);
+                            }
+                            mma_commit(bar_empty + 8 * slot);  // slot is free once these MMAs have read it
+                        }
+                    }
+                    mma_commit(bar_acc);  // accumulators of this pass complete
+                    ++npass;
+                }
+        }
+    } else {
+        // ===== epilogue warps ==============================================================================
+        const int quarter = warp & 3, split = warp >> 2;
+        const int r = quarter * 32 + lane;                         // TMEM lane = window within the tile
+        const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+        const float* __restrict__ small = P.small;
+        uint32_t npass = 0;
+        bool ok = true;
+        for (int64_t t = 0; t < my_tiles && ok; ++t) {
+            const int64_t w0 = (blockIdx.x + t * gridDim.x) * TC_M;
+            const bool live = w0 + r < P.n;
+            bool act_has_x = false;
+            for (int p = 0; p < T_COUNT && ok; ++p) {
+                if (!((P.pass_mask >> p) & 1u)) continue;
+                const TcPass& ps = prog.pass[p];
+                // ---- make the A operand of pass p available, then hand over to the MMA warp -----------------
+                if (ps.needs_x && !act_has_x) {
+                    epi_bar();  // both column halves of every row are done writing the previous layer's output
+                    if (P.x_is_f64) load_rows_to_act<double>(act, (const double*)P.x, w0, P.n, P.row_stride, S, S8, tid);
+                    else load_rows_to_act<float>(act, (const float*)P.x, w0, P.n, P.row_stride, S, S8, tid);
+                    act_has_x = true;
+                } else if (p == T_D0 && !(P.stages & HYPAD_STAGE_ENCODER)) {
+                    epi_bar();
+                    load_rows_to_act<float>(act, P.z_in, w0, P.n, prog.latent, prog.latent, 32, tid);
+                }
+                fence_async_smem();
+                tc_fence_before();
+                mbar_arrive(bar_a);
+                // ---- wait for the accumulators --------------------------------------------------------------
+                ok = mbar_wait(bar_acc, npass & 1, P.error_flag);
+                ++npass;
+                if (!ok) break;
+                tc_fence_after();
+                const float* __restrict__ b1 = small + ps.b_off;
+                const float* __restrict__ b2 = b1 + ps.nblk * ps.n;
+                const int cbeg = 8 * split, cend = ps.n, cstep = 8 * TC_NSPLIT;
+                if (ps.epi == TE_LSTM) {
+                    for (int c = cbeg; c < cend; c += cstep) {
+                        float gi[8], gg[8], go[8], h[8];
+                        tmem_ld8(trow + ps.d_col + c, gi);
+                        tmem_ld8(trow + ps.d_col + ps.n + c, gg);
+                        tmem_ld8(trow + ps.d_col + 2 * ps.n + c, go);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int u = c + i;
+                            const float vi = __fadd_rn(__fadd_rn(gi[i], b1[u]), b2[u]);
+                            const float vg = __fadd_rn(__fadd_rn(gg[i], b1[ps.n + u]), b2[ps.n + u]);
+                            const float vo = __fadd_rn(__fadd_rn(go[i], b1[2 * ps.n + u]), b2[2 * ps.n + u]);
+                            const float cc = __fmul_rn(sigmoid_tc(vi), tanhf(vg));
+                            h[i] = __fmul_rn(sigmoid_tc(vo), tanhf(cc));
+                        }
+                        store_act8(act, r, c, h);
+                    }
+                    act_has_x = false;
+                } else if (ps.epi == TE_Z || ps.epi == TE_LINEAR || ps.epi == TE_TANH || ps.epi == TE_CRITIC_HID || ps.epi == TE_CRITIC_OUT) {
+                    float* gout = nullptr;
+                    int gw = 0;
+                    if (ps.epi == TE_Z && P.out.z && live) gout = P.out.z + (w0 + r) * prog.latent, gw = prog.latent;
+                    if (ps.epi == TE_TANH && P.out.eucl && live) gout = P.out.eucl + (w0 + r) * (int64_t)S, gw = S;
+                    if (ps.epi == TE_CRITIC_OUT) {
+                        // dense4 + LeakyReLU, then Linear(latent_c -> 1) as one ascending-k FFMA chain (split 0 only)
+                        if (split == 0) {
+                            const float* w5 = small + prog.critic5_off;
+                            float fdot = 0.0f;
+                            for (int c = 0; c < ((prog.latent_c + 7) & ~7); c += 8) {
+                                float v[8];
+                                tmem_ld8(trow + ps.d_col + c, v);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    float tv = __fadd_rn(v[i], b1[c + i]);
+                                    tv = tv > 0.0f ? tv : __fmul_rn(tv, 0.2f);
+                                    if (c + i < prog.latent_c) fdot = fmaf(tv, w5[c + i], fdot);
+                                }
+                            }
+                            if (live) P.out.critic[w0 + r] = __fadd_rn(fdot, w5[prog.latent_c]);
+                        }
+                    } else {
+                        for (int c = cbeg; c < cend; c += cstep) {
+                            float v[8];
+                            tmem_ld8(trow + ps.d_col + c, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float tv = __fadd_rn(v[i], b1[c + i]);
+                                if (ps.epi == TE_TANH) tv = tanhf(tv);
+                                else if (ps.epi == TE_CRITIC_HID) tv = tv > 0.0f ? tv : __fmul_rn(tv, 0.2f);
+                                v[i] = tv;
+                            }
+                            store_act8(act, r, c, v);
+                            if (gout) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    if (c + i < gw) gout[c + i] = v[i];
+                            }
+                        }
+                    }
+                    act_has_x = false;
+                } else if (ps.epi == TE_MOB_R) {
+                    float* gout = (P.out.hyper && live) ? P.out.hyper + (w0 + r) * (int64_t)S : nullptr;
+                    row_mobius_tc(trow, ps.d_col, ps.n, small + prog.mob_bias_off, small[prog.mob_y2_off], red, r, split, gout, P.out.hyper != nullptr, S);
+                } else if (ps.epi == TE_MOB_X) {
+                    float* gout = (P.out.hyper_x && live) ? P.out.hyper_x + (w0 + r) * (int64_t)S : nullptr;
+                    row_mobius_tc(trow, ps.d_col, ps.n, small + prog.mob_bias_off, small[prog.mob_y2_off], red, r, split, gout, P.out.hyper_x != nullptr, S);
+                }
+                // ---- row statistics once both hyperbolic points are in TMEM ---------------------------------
+                const bool last_hyp = (p == T_MX) || (p == T_MR && !((P.pass_mask >> T_MX) & 1u));
+                if (P.want_rowstats && last_hyp) {
+                    const TcPass& pr = prog.pass[T_MR];
+                    const bool both = P.out.rec != nullptr;
+                    double s[3] = {0.0, 0.0, 0.0};
+                    for (int c = 8 * split; c < pr.n; c += 8 * TC_NSPLIT) {
+                        float h[8], hx[8];
+                        tmem_ld8(trow + pr.d_col + c, h);
+                        if (both) tmem_ld8(trow + prog.pass[T_MX].d_col + c, hx);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            s[2] += (double)__fmul_rn(h[i], h[i]);
+                            if (both) {
+                                const float d = __fsub_rn(hx[i], h[i]);
+                                s[0] += (double)__fmul_rn(d, d);
+                                s[1] += (double)__fmul_rn(hx[i], hx[i]);
+                            }
+                        }
+                    }
+                    row_allreduce_tc<3>(s, red, r, split);
+                    if (split == 0 && live) {
+                        const float sqdist = (float)s[0], squnorm = (float)s[1], sqvnorm = (float)s[2];
+                        if (both) {
+                            const float tt = __fdiv_rn(__fmul_rn(2.0f, sqdist), __fmul_rn(__fsub_rn(1.0f, squnorm), __fsub_rn(1.0f, sqvnorm)));
+                            const float xt = __fadd_rn(__fadd_rn(1.0f, tt), 1e-7f);
+                            P.out.rec[w0 + r] = (float)acosh((double)xt);
+                        }
+                        if (P.out.unorm) P.out.unorm[w0 + r] = sqrtf(sqvnorm);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_PRODUCER_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// weight packing: fp32 parameters -> TF32 hi/lo stages [k8][nblk]{hi,lo}[2 chunks][n][4]
+// ------------------------------------------------------------------------------------------------------------
+__global__ void pack_tc_kernel(const ColSrc* __restrict__ cols, int k8, int nblk, int n, float* __restrict__ dst, float* __restrict__ bias) {
+    const int ncols = nblk * n;
+    const int total = k8 * 8 * ncols;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int k = e / ncols, cc = e - k * ncols;
+        const int blk = cc / n, c = cc - blk * n;
+        const ColSrc s = cols[cc];
+        const float v = (s.w != nullptr && k < s.K) ? s.w[(size_t)s.row * s.K + k] : 0.0f;
+        const float hi = tf32_rna(v), lo = tf32_rna(v - hi);
+        const int ks = k >> 3, ch = (k >> 2) & 1, el = k & 3;
+        const int kp = ks / TC_KSTAGE, j = ks - kp * TC_KSTAGE;
+        const int kk = k8 - kp * TC_KSTAGE < TC_KSTAGE ? k8 - kp * TC_KSTAGE : TC_KSTAGE;  // k-steps in this stage
+        // floats: full pairs before this one, then the blocks of this pair, then the k-step inside the stage
+        const size_t stage = (size_t)kp * TC_KSTAGE * nblk * n * 16 + (size_t)blk * kk * n * 16 + (size_t)j * n * 16;
+        const size_t off = stage + (size_t)ch * n * 4 + (size_t)c * 4 + el;
+        dst[off] = hi;
+        dst[off + (size_t)n * 8] = lo;  // lo piece follows the hi piece: n*32 B = n*8 floats
+        if (k == 0) {
+            bias[cc] = s.b1 ? s.b1[s.bidx] : 0.0f;
+            bias[ncols + cc] = s.b2 ? s.b2[s.bidx] : 0.0f;
+        }
+    }
+}
+
+static inline int round8i(int v) { return (v + 7) / 8 * 8; }
+static inline int round16i(int v) { return (v + 15) / 16 * 16; }
+
+size_t forward_tc_smem_bytes() {
+    return 2 * (size_t)TC_PIECE_BYTES + (size_t)TC_NSLOT * TC_STAGE_BYTES + TC_RED_BYTES + (2 * TC_NSLOT + 2) * 8 + 16;
+}
+
+// Builds the tensor-core program and packs the weights (called from hypad_pack_weights).
+int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
+    const int S = w->signal_shape, L = w->latent_dim, C = w->critic_dim, hyp = w->hyperbolic != 0;
+    const int S8 = round8i(S), NS = round16i(S), NL = round16i(L), NC = round16i(C);
+    TcProgram prog;
+    memset(&prog, 0, sizeof(prog));
+    prog.S = S; prog.S8 = S8; prog.latent = L; prog.latent_c = C; prog.hyperbolic = hyp;
+
+    std::vector<std::vector<ColSrc>> cols(T_COUNT);
+    auto set_pass = [&](int idx, int K, int nblk, int n, int d_col, int epi, int needs_x) {
+        TcPass& p = prog.pass[idx];
+        p.k8 = K / 8; p.nblk = nblk; p.n = n; p.d_col = d_col; p.epi = epi; p.needs_x = needs_x;
+        cols[idx].assign((size_t)nblk * n, ColSrc{});
+    };
+    auto linear_cols = [&](int idx, const float* W, const float* b, int rows, int K) {
+        for (int c = 0; c < rows; ++c) {
+            ColSrc& s = cols[idx][c];
+            s.w = W; s.row = c; s.K = K; s.b1 = b; s.bidx = c;
+        }
+    };
+    auto lstm_cols = [&](int idx, int H, int n_units, const float* const* Wd, const float* const* bih, const float* const* bhh, int K) {
+        const int n = prog.pass[idx].n;
+        const int gate_row[3] = {0, 2 * H, 3 * H};
+        for (int u = 0; u < n_units; ++u) {
+            const int dir = u / H, j = u % H;
+            for (int g = 0; g < 3; ++g) {
+                ColSrc& s = cols[idx][(size_t)g * n + u];
+                s.w = Wd[dir]; s.row = gate_row[g] + j; s.K = K; s.b1 = bih[dir]; s.b2 = bhh[dir]; s.bidx = gate_row[g] + j;
+            }
+        }
+    };
+    set_pass(T_ENC, S8, 3, 112, 0, TE_LSTM, 1);
+    lstm_cols(T_ENC, 50, 100, w->enc_w_ih, w->enc_b_ih, w->enc_b_hh, S);
+    set_pass(T_Z, 104, 1, NL, 0, TE_Z, 0);
+    linear_cols(T_Z, w->enc_dense_w, w->enc_dense_b, L, 100);
+    set_pass(T_D0, round8i(L), 1, 64, 0, TE_LINEAR, 0);
+    linear_cols(T_D0, w->dec_dense1_w, w->dec_dense1_b, 50, L);
+    set_pass(T_L0, 56, 3, 128, 0, TE_LSTM, 0);
+    lstm_cols(T_L0, 64, 128, w->dec_w_ih[0], w->dec_b_ih[0], w->dec_b_hh[0], 50);
+    set_pass(T_L1, 128, 3, 128, 0, TE_LSTM, 0);
+    lstm_cols(T_L1, 64, 128, w->dec_w_ih[1], w->dec_b_ih[1], w->dec_b_hh[1], 128);
+    set_pass(T_D2, 128, 1, NS, 0, TE_TANH, 0);
+    linear_cols(T_D2, w->dec_dense2_w, w->dec_dense2_b, S, 128);
+    set_pass(T_MR, S8, 1, NS, 384, TE_MOB_R, 0);
+    if (hyp) linear_cols(T_MR, w->mobius_w, nullptr, S, S);
+    set_pass(T_MX, S8, 1, NS, 0, TE_MOB_X, 1);
+    if (hyp) linear_cols(T_MX, w->mobius_w, nullptr, S, S);
+    set_pass(T_C1, S8, 1, NC, 0, TE_CRITIC_HID, 1);
+    linear_cols(T_C1, w->critic_w[0], w->critic_b[0], C, S);
+    for (int i = 0; i < 3; ++i) {
+        set_pass(T_C2 + i, round8i(C), 1, NC, 0, i == 2 ? TE_CRITIC_OUT : TE_CRITIC_HID, 0);
+        linear_cols(T_C2 + i, w->critic_w[1 + i], w->critic_b[1 + i], C, C);
+    }
+    if (NL > 32 || NC > 32) {
+        set_error("tensor-core path: latent_dim / critic_dim above 32 not supported (got %d / %d)", L, C);
+        return HYPAD_EINVAL;
+    }
+    size_t wbytes = 0, sfloats = 0, ncols_total = 0;
+    for (int i = 0; i < T_COUNT; ++i) {
+        TcPass& p = prog.pass[i];
+        p.w_off = (int32_t)wbytes;
+        wbytes += (size_t)p.k8 * p.nblk * p.n * 64;
+        p.b_off = (int32_t)sfloats;
+        sfloats += 2 * (size_t)p.nblk * p.n;
+        ncols_total += (size_t)p.nblk * p.n;
+    }
+    prog.mob_bias_off = (int32_t)sfloats; sfloats += 128;
+    prog.mob_y2_off = (int32_t)sfloats; sfloats += 4;
+    prog.critic5_off = (int32_t)sfloats; sfloats += 68;
+    const size_t need = wbytes + sfloats * sizeof(float) + 256;
+    if (ctx->tc_bytes < need) {
+        HYPAD_CUDA_TRY(cudaDeviceSynchronize());
+        if (ctx->tc_packed) cudaFree(ctx->tc_packed);
+        ctx->tc_packed = nullptr;
+        ctx->tc_bytes = 0;
+        HYPAD_CUDA_TRY(cudaMalloc(&ctx->tc_packed, need));
+        ctx->tc_bytes = need;
+    }
+    if (!ctx->tc_error) HYPAD_CUDA_TRY(cudaMalloc(&ctx->tc_error, sizeof(int)));
+    HYPAD_CUDA_TRY(cudaMemsetAsync(ctx->tc_error, 0, sizeof(int), stream));
+    int rc = ensure_workspace(ctx, ncols_total * sizeof(ColSrc));
+    if (rc != HYPAD_OK) return rc;
+    std::vector<ColSrc> flat;
+    std::vector<size_t> start(T_COUNT, 0);
+    for (int i = 0; i < T_COUNT; ++i) {
+        start[i] = flat.size();
+        flat.insert(flat.end(), cols[i].begin(), cols[i].end());
+    }
+    HYPAD_CUDA_TRY(cudaMemcpyAsync(ctx->workspace, flat.data(), flat.size() * sizeof(ColSrc), cudaMemcpyHostToDevice, stream));
+    HYPAD_CUDA_TRY(cudaMemsetAsync(ctx->tc_packed, 0, ctx->tc_bytes, stream));
+    float* small = reinterpret_cast<float*>(ctx->tc_packed + ((wbytes + 255) / 256) * 256);
+    ctx->tc_small_off = ((wbytes + 255) / 256) * 256;
+    for (int i = 0; i < T_COUNT; ++i) {
+        const TcPass& p = prog.pass[i];
+        const int total = p.k8 * 8 * p.nblk * p.n;
+        pack_tc_kernel<<<(total + 255) / 256, 256, 0, stream>>>((const ColSrc*)ctx->workspace + start[i], p.k8, p.nblk, p.n,
+                                                               reinterpret_cast<float*>(ctx->tc_packed + p.w_off), small + p.b_off);
+        HYPAD_LAUNCH_CHECK();
+    }
+    // Mobius bias / y2 / critic dense5 come from the FFMA context's packed buffer (already built by hypad_pack_weights)
+    HYPAD_CUDA_TRY(cudaMemcpyAsync(small + prog.mob_bias_off, ctx->packed + ctx->prog.mob_bias_off, 128 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    HYPAD_CUDA_TRY(cudaMemcpyAsync(small + prog.mob_y2_off, ctx->packed + ctx->prog.mob_y2_off, sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    HYPAD_CUDA_TRY(cudaMemcpyAsync(small + prog.critic5_off, ctx->packed + ctx->prog.critic5_off, (C + 1) * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    HYPAD_CUDA_TRY(cudaStreamSynchronize(stream));
+    static_assert(sizeof(TcProgram) <= sizeof(ctx->tc_prog_storage), "tc_prog_storage too small");
+    memcpy(ctx->tc_prog_storage, &prog, sizeof(prog));
+    return HYPAD_OK;
+}
+
+int launch_forward_tc(const hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_t row_stride, const float* z_in,
+                      int stages, const hypad_forward_out* out, cudaStream_t stream) {
+    TcParams P;
+    memset(&P, 0, sizeof(P));
+    memcpy(&P.prog, ctx->tc_prog_storage, sizeof(TcProgram));
+    P.x = x; P.z_in = z_in;
+    P.wpacked = ctx->tc_packed;
+    P.small = reinterpret_cast<const float*>(ctx->tc_packed + ctx->tc_small_off);
+    P.n = n; P.row_stride = row_stride; P.x_is_f64 = x_is_f64; P.stages = stages;
+    P.out = *out;
+    P.error_flag = ctx->tc_error;
+    const bool hyp = P.prog.hyperbolic != 0;
+    uint32_t mask = 0;
+    if (stages & HYPAD_STAGE_ENCODER) mask |= (1u << T_ENC) | (1u << T_Z);
+    if (stages & HYPAD_STAGE_DECODER) {
+        mask |= (1u << T_D0) | (1u << T_L0) | (1u << T_L1) | (1u << T_D2);
+        if (hyp) mask |= (1u << T_MR);
+    }
+    if (hyp && (stages & HYPAD_STAGE_MOBIUS_X)) mask |= (1u << T_MX);
+    if (stages & HYPAD_STAGE_CRITIC) mask |= (1u << T_C1) | (1u << T_C2) | (1u << T_C3) | (1u << T_C4);
+    P.pass_mask = mask;
+    if (!(hyp && (stages & HYPAD_STAGE_DECODER))) P.out.unorm = nullptr, P.out.hyper = nullptr;
+    if (!(hyp && (stages & HYPAD_STAGE_DECODER) && (stages & HYPAD_STAGE_MOBIUS_X))) P.out.rec = nullptr;
+    if (!(hyp && (stages & HYPAD_STAGE_MOBIUS_X))) P.out.hyper_x = nullptr;
+    P.want_rowstats = (P.out.rec != nullptr) || (P.out.unorm != nullptr);
+    const size_t smem = forward_tc_smem_bytes();
+    static thread_local bool configured = false;
+    if (!configured) {
+        HYPAD_CUDA_TRY(cudaFuncSetAttribute(forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int sms = kNumSMs;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const int64_t ntiles = ceil_div(n, TC_M);
+    const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
+    forward_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(P);
+    HYPAD_LAUNCH_CHECK();
+    return HYPAD_OK;
+}
+
+}  // namespace hypad

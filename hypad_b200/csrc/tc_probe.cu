@@ -170,7 +170,7 @@ extern "C" int hypad_tc_probe_gemm(const float* A, const float* B, float* D, int
     HYPAD_REQUIRE((pieces == 1 && terms == 1) || (pieces == 2 && terms == 3) || (pieces == 3 && terms == 6),
                   "hypad_tc_probe_gemm: (pieces, terms) must be (1,1), (2,3) or (3,6)");
     const size_t smem = (size_t)pieces * (K * 128 + K * N) * sizeof(float);
-    HYPAD_REQUIRE(smem <= 200 * 1024, "hypad_tc_probe_gemm: operands need %zu bytes of shared memory", smem);
+    HYPAD_REQUIRE(smem <= 220 * 1024, "hypad_tc_probe_gemm: operands need %zu bytes of shared memory", smem);
     HYPAD_CUDA_TRY(cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TcProbeArgs a{A, B, D, K, N, pieces, terms};
     tc_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a);

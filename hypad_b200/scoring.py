@@ -328,9 +328,10 @@ class WindowScorer:
             raise HypadError("hypad_b200: windows have %d samples, the model expects %d" % (x.shape[1], self.S))
         return x, x.shape[0], self.S
 
-    def forward(self, x, sliding, keep=(), first=0, count=None):
+    def forward(self, x, sliding, keep=(), first=0, count=None, ffma=False):
         """Runs the fused network over windows [first, first+count).  Returns dict of device tensors:
-        critic (n,) always; rec, unorm (n,) when hyperbolic; plus any of z/eucl/hyper/hyper_x named in `keep`."""
+        critic (n,) always; rec, unorm (n,) when hyperbolic; plus any of z/eucl/hyper/hyper_x named in `keep`.
+        ffma=True runs the FFMA cross-check kernel instead of the tensor-core product path."""
         self.net.ensure(self.encoder, self.decoder, self.critic_x)
         x, n_all, stride = self._input(x, sliding)
         count = n_all - first if count is None else count
@@ -353,11 +354,16 @@ class WindowScorer:
         if self.hyperbolic:
             stages |= _native.STAGE_MOBIUS_X
         base = x.data_ptr() + first * stride * x.element_size()
+        fn = self.net.ctx.lib.hypad_forward_ffma if ffma else self.net.ctx.lib.hypad_forward
         with torch.cuda.device(dev):
-            check(self.net.ctx.lib.hypad_forward(self.net.ctx.handle, base, int(x.dtype == torch.float64), count, stride, None,
-                                                 stages, out, self.net.ctx.stream()))
+            check(fn(self.net.ctx.handle, base, int(x.dtype == torch.float64), count, stride, None, stages, out,
+                     self.net.ctx.stream()))
         res["_x"], res["_n"], res["_stride"] = x, n_all, stride
         return res
+
+    def poll_error(self):
+        """Synchronises and raises if the forward kernel reported a pipeline error (bounded barrier wait timed out)."""
+        check(self.net.ctx.lib.hypad_ctx_poll_error(self.net.ctx.handle))
 
     # -- scoring -------------------------------------------------------------------------------------------
     def critic_scores(self, critic, n_windows):

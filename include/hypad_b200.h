@@ -103,6 +103,13 @@ int hypad_pack_weights(hypad_ctx* ctx, const hypad_weights* w, void* stream);
  */
 int hypad_forward(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_t row_stride,
                   const float* z_in, int stages, const hypad_forward_out* out, void* stream);
+/* Same contract, contractions on the fp32 FFMA pipe instead of the tensor cores (3xTF32): the in-library
+ * cross-check of hypad_forward, not the product path. */
+int hypad_forward_ffma(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_t row_stride,
+                       const float* z_in, int stages, const hypad_forward_out* out, void* stream);
+/* Synchronises with the device and reports a sticky error raised inside hypad_forward's kernel (a bounded
+ * barrier wait that timed out).  0 = healthy. */
+int hypad_ctx_poll_error(hypad_ctx* ctx);
 
 /* hyperspace/hyrnn_nets.py:13-35 mobius_linear with hyperbolic_input=False, k=-1:
  * project(mobius_add(expmap0(x W^T), bias)).  x (n,in) W (out,in) bias (out,) or NULL, out (n,out).

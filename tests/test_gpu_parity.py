@@ -76,6 +76,7 @@ def test_fused_forward_hyperbolic_vs_reference(case, hyp_scorer, cuda_device):
     g = golden(case)
     sig = torch.from_numpy(a1_signal(g) if case.startswith("a1test") else full_signal(g)).to(cuda_device)
     fw = hyp_scorer.forward(sig, True, keep=("z", "eucl", "hyper", "hyper_x"))
+    hyp_scorer.poll_error()
     n = g["critic"].shape[0]
     assert fw["critic"].shape[0] == n
     rows = g["rows"]
@@ -88,6 +89,23 @@ def test_fused_forward_hyperbolic_vs_reference(case, hyp_scorer, cuda_device):
     np.testing.assert_allclose(fw["unorm"].cpu().numpy(), g["unorm"], rtol=3e-6)
     r = quantised_close(fw["rec"].cpu().numpy(), g["rec"])
     print("%s: rec windows off by a quantisation step: %d of %d" % (case, int((r > 1e-4).sum()), n))
+
+
+@pytest.mark.parametrize("case", ["noisy1500_hyp_uncertainty.npz", "edge_n65_hyp.npz", "cfg1_hyp_uncertainty.npz"])
+def test_tensor_core_forward_matches_ffma_cross_check(case, hyp_scorer, cuda_device):
+    """hypad_forward (tcgen05, 3xTF32, TMEM accumulators) against hypad_forward_ffma (fp32 FFMA pipe) on the same input."""
+    g = golden(case)
+    sig = dev_signal(g, cuda_device)
+    keep = ("z", "eucl", "hyper", "hyper_x")
+    tc = hyp_scorer.forward(sig, True, keep=keep)
+    hyp_scorer.poll_error()
+    ff = hyp_scorer.forward(sig, True, keep=keep, ffma=True)
+    for k, atol in (("critic", 1.5e-7), ("z", 4e-7), ("eucl", 2e-7), ("hyper", 3e-9), ("hyper_x", 3e-9)):
+        d = (tc[k] - ff[k]).abs().max().item()
+        print("%s: max |tensor - ffma| of %s = %.2e" % (case, k, d))
+        assert d <= atol, (k, d)
+    np.testing.assert_allclose(tc["unorm"].cpu().numpy(), ff["unorm"].cpu().numpy(), rtol=1e-6)
+    quantised_close(tc["rec"].cpu().numpy(), ff["rec"].cpu().numpy())
 
 
 @pytest.mark.parametrize("case", EUCL_CASES)
@@ -135,7 +153,7 @@ def test_module_forwards_match_fused(hyp_scorer, cuda_device):
         assert hyper.shape == (1, hi - lo, 100) and eucl.shape == (1, hi - lo, 100)
         assert torch.equal(hyper[0], fw["hyper"][lo:hi]) and torch.equal(eucl[0], fw["eucl"][lo:hi])
         hx = dec.hyperbolic_linear(sample.view(-1, 100).float())
-        np.testing.assert_allclose(hx.cpu().numpy(), fw["hyper_x"][lo:hi].cpu().numpy(), rtol=0, atol=1e-9)
+        np.testing.assert_allclose(hx.cpu().numpy(), fw["hyper_x"][lo:hi].cpu().numpy(), rtol=0, atol=4e-9)  # FFMA stand-alone vs tensor-core fused
         c = cx(sample)
         assert c.shape == (1, hi - lo, 1) and torch.equal(c.reshape(-1), fw["critic"][lo:hi])
     enc.train()
@@ -426,7 +444,6 @@ def test_multivariate_shape_s123(cuda_device):
     out = WindowScorer(enc, dec, cx).score(torch.from_numpy(rows).to(cuda_device), False, "mult", index=index, multivariate=True)
     np.testing.assert_allclose(out["critic"].cpu().numpy(), want["critic"], rtol=0, atol=3e-7)
     assert np.array_equal(out["kmax"].cpu().numpy(), ho.kde_argmax_overlap(out["critic"].cpu().numpy(), 123))
-    r = rel(out["final"].cpu().numpy(), want["final"])
-    print("multivariate: final beyond 1e-4: %d of %d, max %.2e" % (int((r > 1e-4).sum()), len(r), r.max()))
-    assert (r <= 1e-4).mean() > 0.99
+    g = {"final": want["final"], "kmax": want["kmax"], "critic": want["critic"]}
+    selection_aware_close(out, g, 3000, "multivariate S=123")
     check_intervals(out["intervals"], want["intervals"])

@@ -44,7 +44,7 @@ def test_tcgen05_layout_exact_on_small_integers(K, N, cuda_device):
 def test_tcgen05_split_product_accuracy(cuda_device, capsys):
     rng = np.random.default_rng(1)
     rows = []
-    for K, N in ((104, 192), (128, 192), (56, 192), (64, 64)):
+    for K, N in ((104, 64), (128, 64), (56, 192), (64, 64)):
         A = rng.uniform(-1, 1, (128, K)).astype(np.float32)
         B = (rng.standard_normal((N, K)) * 0.1).astype(np.float32)
         exact = A.astype(np.float64) @ B.astype(np.float64).T
@@ -60,6 +60,6 @@ def test_tcgen05_split_product_accuracy(cuda_device, capsys):
         for r in rows:
             print("%4d %4d  %-10s  %.3e           %.3e  %+.3e" % r)
     by = {(r[0], r[1], r[2]): r for r in rows}
-    for K, N in ((104, 192), (128, 192), (56, 192)):
+    for K, N in ((104, 64), (128, 64), (56, 192)):
         assert by[(K, N, "tf32x1")][3] < 2e-3          # plain TF32: ~2^-11 per operand
         assert by[(K, N, "tf32x3")][3] < 2e-6          # compensated product: fp32 class
