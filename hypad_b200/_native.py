@@ -58,6 +58,7 @@ _SIGNATURES = {
     "hypad_forward": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _int, ctypes.POINTER(hypad_forward_out), _vp]),
     "hypad_forward_ffma": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _int, ctypes.POINTER(hypad_forward_out), _vp]),
     "hypad_ctx_poll_error": (_int, [_vp]),
+    "hypad_forward_debug_cycles": (_int, [_vp, _int, _vp]),
     "hypad_mobius_linear": (_int, [_vp, _vp, _i64, _int, _int, _vp, _vp, _int, _vp, _vp]),
     "hypad_poincare_rowdist": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
     "hypad_rownorm": (_int, [_vp, _i64, _int, _vp, _vp]),
@@ -75,6 +76,7 @@ _SIGNATURES = {
     "hypad_area_error": (_int, [_vp, _vp, _int, _i64, _int, _vp, _vp]),
     "hypad_threshold_windows": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp, _int, _vp]),
     "hypad_tc_probe_gemm": (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _vp]),
+    "hypad_tc_probe_bench": (_int, [_int, _int, _int, _vp, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

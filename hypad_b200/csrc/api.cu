@@ -129,6 +129,7 @@ int hypad_ctx_destroy(hypad_ctx* ctx) {
     if (ctx->workspace) cudaFree(ctx->workspace);
     if (ctx->tc_packed) cudaFree(ctx->tc_packed);
     if (ctx->tc_error) cudaFree(ctx->tc_error);
+    if (ctx->tc_debug) cudaFree(ctx->tc_debug);
     delete ctx;
     return HYPAD_OK;
 }
@@ -310,6 +311,22 @@ int hypad_forward_ffma(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, i
     if (rc != HYPAD_OK || n == 0) return rc;
     HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
     return launch_forward(ctx, x, x_is_f64, n, row_stride, z_in, stages, out, (cudaStream_t)stream);
+}
+
+int hypad_forward_debug_cycles(hypad_ctx* ctx, int enable, long long* h_out8) {
+    HYPAD_REQUIRE(ctx != nullptr, "hypad_forward_debug_cycles: NULL context");
+    HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (enable && !ctx->tc_debug) {
+        HYPAD_CUDA_TRY(cudaMalloc(&ctx->tc_debug, 8 * sizeof(long long)));
+        HYPAD_CUDA_TRY(cudaMemset(ctx->tc_debug, 0, 8 * sizeof(long long)));
+    }
+    if (h_out8 && ctx->tc_debug) HYPAD_CUDA_TRY(cudaMemcpy(h_out8, ctx->tc_debug, 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (!enable && ctx->tc_debug) {
+        HYPAD_CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(ctx->tc_debug);
+        ctx->tc_debug = nullptr;
+    }
+    return HYPAD_OK;
 }
 
 int hypad_ctx_poll_error(hypad_ctx* ctx) {

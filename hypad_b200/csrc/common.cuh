@@ -118,6 +118,7 @@ struct hypad_ctx {
     size_t tc_bytes;
     size_t tc_small_off;
     int* tc_error;              // device flag raised when a barrier wait times out
+    long long* tc_debug;        // optional device cycle counters (hypad_forward_debug_cycles)
     unsigned char tc_prog_storage[1024];
 };
 

@@ -65,6 +65,7 @@ struct TcParams {
     int32_t want_rowstats;
     hypad_forward_out out;
     int* error_flag;
+    long long* debug;  // optional cycle counters (block 0 only), see hypad_forward_debug_cycles
     TcProgram prog;
 };
 
@@ -120,6 +121,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "r"(bytes), "r"(bar)
                  : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -132,6 +138,10 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
                  : "r"(taddr));
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void ldg8(const float* __restrict__ p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
@@ -322,66 +332,85 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
         if (lane == 0) {
             uint32_t it = 0;
             bool ok = true;
+            long long dbg_prod = 0;
             for (int64_t t = 0; t < my_tiles && ok; ++t)
                 for (int p = 0; p < T_COUNT && ok; ++p) {
                     if (!((P.pass_mask >> p) & 1u)) continue;
                     const TcPass& ps = prog.pass[p];
                     const unsigned char* src = P.wpacked + ps.w_off;
-                    // stages in (k-step pair, block) order; the last pair of an odd layer holds one k-step
-                    for (int kp = 0; kp < ps.k8; kp += TC_KSTAGE) {
-                        const int kk = ps.k8 - kp < TC_KSTAGE ? ps.k8 - kp : TC_KSTAGE;
-                        const uint32_t bytes = (uint32_t)(kk * ps.n) * 64u;
-                        for (int b = 0; b < ps.nblk && ok; ++b, ++it) {
+                    // stages in (block, k-step pair) order -- the accumulator address changes only between blocks (a change
+                    // costs ~120 cycles of tensor-pipe drain, scripts/tc_mma_rate.py); the last pair of an odd layer holds one k-step
+                    for (int b = 0; b < ps.nblk && ok; ++b)
+                        for (int kp = 0; kp < ps.k8; kp += TC_KSTAGE, ++it) {
+                            const int kk = ps.k8 - kp < TC_KSTAGE ? ps.k8 - kp : TC_KSTAGE;
+                            const uint32_t bytes = (uint32_t)(kk * ps.n) * 64u;
                             const uint32_t slot = it % TC_NSLOT, use = it / TC_NSLOT;
+                            const long long c0 = P.debug ? clock64() : 0;
                             if (use > 0) ok = mbar_wait(bar_empty + 8 * slot, (use - 1) & 1, P.error_flag);
+                            if (P.debug) dbg_prod += clock64() - c0;
                             if (!ok) break;
                             mbar_expect_tx(bar_full + 8 * slot, bytes);
                             bulk_g2s(s_u32(ring + slot * TC_STAGE_BYTES), src, bytes, bar_full + 8 * slot);
                             src += bytes;
                         }
-                    }
                 }
+            if (P.debug && blockIdx.x == 0) P.debug[4] = dbg_prod;
         }
     } else if (warp == TC_MMA_WARP) {
-        // ===== MMA issuer (one lane) =======================================================================
-        if (lane == 0) {
+        // ===== MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues ============
+        {
             uint32_t it = 0, npass = 0;
             bool ok = true;
+            long long dbg_a = 0, dbg_full = 0;
+            const bool dbg = P.debug != nullptr;
             const uint32_t act_hi = s_u32(act), act_lo = s_u32(act + TC_PIECE_BYTES);
+            const uint32_t ring_u32 = s_u32(ring);
             for (int64_t t = 0; t < my_tiles && ok; ++t)
                 for (int p = 0; p < T_COUNT && ok; ++p) {
                     if (!((P.pass_mask >> p) & 1u)) continue;
                     const TcPass& ps = prog.pass[p];
+                    long long c0 = dbg ? clock64() : 0;
                     ok = mbar_wait(bar_a, npass & 1, P.error_flag);  // A operand written, TMEM of the previous pass drained
+                    if (dbg) dbg_a += clock64() - c0;
                     if (!ok) break;
                     tc_fence_after();
                     const uint32_t idesc = idesc_tf32(ps.n);
                     const uint32_t nb16 = (uint32_t)ps.n * 16u;
-                    for (int kp = 0; kp < ps.k8 && ok; kp += TC_KSTAGE) {
-                        const int kk = ps.k8 - kp < TC_KSTAGE ? ps.k8 - kp : TC_KSTAGE;
-                        for (int b = 0; b < ps.nblk; ++b, ++it) {
+                    for (int b = 0; b < ps.nblk && ok; ++b) {
+                        const uint32_t d = tmem + (uint32_t)(ps.d_col + b * ps.n);
+                        for (int kp = 0; kp < ps.k8; kp += TC_KSTAGE, ++it) {
+                            const int kk = ps.k8 - kp < TC_KSTAGE ? ps.k8 - kp : TC_KSTAGE;
                             const uint32_t slot = it % TC_NSLOT, use = it / TC_NSLOT;
+                            if (dbg) c0 = clock64();
                             ok = mbar_wait(bar_full + 8 * slot, use & 1, P.error_flag);
+                            if (dbg) dbg_full += clock64() - c0;
                             if (!ok) break;
                             tc_fence_after();
-                            const uint32_t d = tmem + (uint32_t)(ps.d_col + b * ps.n);
-                            for (int j = 0; j < kk; ++j) {
-                                const int ks = kp + j;
-                                const uint64_t a_hi = smem_desc(act_hi + ks * 4096, 2048, 128);
-                                const uint64_t a_lo = smem_desc(act_lo + ks * 4096, 2048, 128);
-                                const uint32_t wbase = s_u32(ring + slot * TC_STAGE_BYTES) + (uint32_t)j * 4u * nb16;
-                                const uint64_t w_hi = smem_desc(wbase, nb16, 128);
-                                const uint64_t w_lo = smem_desc(wbase + 2 * nb16, nb16, 128);
-                                mma_tf32(d, a_lo, w_hi, idesc, ks > 0);  // small terms first
-                                mma_tf32(d, a_hi, w_lo, idesc, 1);
-                                mma_tf32(d, a_hi, w_hi, idesc, 1);
+                            if (elect_one()) {
+                                for (int j = 0; j < kk; ++j) {
+                                    const int ks = kp + j;
+                                    const uint64_t a_hi = smem_desc(act_hi + ks * 4096, 2048, 128);
+                                    const uint64_t a_lo = smem_desc(act_lo + ks * 4096, 2048, 128);
+                                    const uint32_t wbase = ring_u32 + slot * TC_STAGE_BYTES + (uint32_t)j * 4u * nb16;
+                                    const uint64_t w_hi = smem_desc(wbase, nb16, 128);
+                                    const uint64_t w_lo = smem_desc(wbase + 2 * nb16, nb16, 128);
+                                    mma_tf32(d, a_lo, w_hi, idesc, ks > 0);  // small terms first
+                                    mma_tf32(d, a_hi, w_lo, idesc, 1);
+                                    mma_tf32(d, a_hi, w_hi, idesc, 1);
+                                }
+                                mma_commit(bar_empty + 8 * slot);  // slot is free once these MMAs have read it
                             }
-                            mma_commit(bar_empty + 8 * slot);  // slot is free once these MMAs have read it
+                            __syncwarp();
                         }
                     }
-                    mma_commit(bar_acc);  // accumulators of this pass complete
+                    if (elect_one()) mma_commit(bar_acc);  // accumulators of this pass complete
+                    __syncwarp();
                     ++npass;
                 }
+            if (dbg && blockIdx.x == 0 && lane == 0) {
+                P.debug[2] = dbg_a;
+                P.debug[3] = dbg_full;
+            }
         }
     } else {
         // ===== epilogue warps ==============================================================================
@@ -391,6 +420,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
         const float* __restrict__ small = P.small;
         uint32_t npass = 0;
         bool ok = true;
+        long long dbg_wait = 0, dbg_xload = 0;
+        const bool dbg = P.debug != nullptr;
+        const long long dbg_t0 = dbg ? clock64() : 0;
         for (int64_t t = 0; t < my_tiles && ok; ++t) {
             const int64_t w0 = (blockIdx.x + t * gridDim.x) * TC_M;
             const bool live = w0 + r < P.n;
@@ -399,8 +431,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                 if (!((P.pass_mask >> p) & 1u)) continue;
                 const TcPass& ps = prog.pass[p];
                 // ---- make the A operand of pass p available, then hand over to the MMA warp -----------------
+                const long long cx0 = dbg ? clock64() : 0;
                 if (ps.needs_x && !act_has_x) {
-                    epi_bar();  // both column halves of every row are done writing the previous layer's output
+                    epi_bar();  // every column split of every row is done writing the previous layer's output
                     if (P.x_is_f64) load_rows_to_act<double>(act, (const double*)P.x, w0, P.n, P.row_stride, S, S8, tid);
                     else load_rows_to_act<float>(act, (const float*)P.x, w0, P.n, P.row_stride, S, S8, tid);
                     act_has_x = true;
@@ -412,26 +445,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                 tc_fence_before();
                 mbar_arrive(bar_a);
                 // ---- wait for the accumulators --------------------------------------------------------------
+                const long long cw0 = dbg ? clock64() : 0;
+                dbg_xload += cw0 - cx0;
                 ok = mbar_wait(bar_acc, npass & 1, P.error_flag);
+                if (dbg) dbg_wait += clock64() - cw0;
                 ++npass;
                 if (!ok) break;
                 tc_fence_after();
                 const float* __restrict__ b1 = small + ps.b_off;
-                const float* __restrict__ b2 = b1 + ps.nblk * ps.n;
                 const int cbeg = 8 * split, cend = ps.n, cstep = 8 * TC_NSPLIT;
                 if (ps.epi == TE_LSTM) {
                     for (int c = cbeg; c < cend; c += cstep) {
-                        float gi[8], gg[8], go[8], h[8];
+                        float gi[8], gg[8], go[8], h[8], bi[8], bg[8], bo[8];
                         tmem_ld8(trow + ps.d_col + c, gi);
                         tmem_ld8(trow + ps.d_col + ps.n + c, gg);
                         tmem_ld8(trow + ps.d_col + 2 * ps.n + c, go);
+                        ldg8(b1 + c, bi);
+                        ldg8(b1 + ps.n + c, bg);
+                        ldg8(b1 + 2 * ps.n + c, bo);
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const int u = c + i;
-                            const float vi = __fadd_rn(__fadd_rn(gi[i], b1[u]), b2[u]);
-                            const float vg = __fadd_rn(__fadd_rn(gg[i], b1[ps.n + u]), b2[ps.n + u]);
-                            const float vo = __fadd_rn(__fadd_rn(go[i], b1[2 * ps.n + u]), b2[2 * ps.n + u]);
+                            const float vi = __fadd_rn(gi[i], bi[i]);
+                            const float vg = __fadd_rn(gg[i], bg[i]);
+                            const float vo = __fadd_rn(go[i], bo[i]);
                             const float cc = __fmul_rn(sigmoid_tc(vi), tanhf(vg));
                             h[i] = __fmul_rn(sigmoid_tc(vo), tanhf(cc));
                         }
@@ -463,12 +500,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                         }
                     } else {
                         for (int c = cbeg; c < cend; c += cstep) {
-                            float v[8];
+                            float v[8], bv[8];
                             tmem_ld8(trow + ps.d_col + c, v);
+                            ldg8(b1 + c, bv);
                             tmem_ld_wait();
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                float tv = __fadd_rn(v[i], b1[c + i]);
+                                float tv = __fadd_rn(v[i], bv[i]);
                                 if (ps.epi == TE_TANH) tv = tanhf(tv);
                                 else if (ps.epi == TE_CRITIC_HID) tv = tv > 0.0f ? tv : __fmul_rn(tv, 0.2f);
                                 v[i] = tv;
@@ -523,6 +561,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                 }
             }
         }
+        if (dbg && blockIdx.x == 0 && tid == 0) {
+            P.debug[0] = clock64() - dbg_t0;
+            P.debug[1] = dbg_wait;
+            P.debug[5] = dbg_xload;
+        }
+    }
+    if (P.debug && blockIdx.x == 0 && tid == 0) {
+        P.debug[6] = my_tiles;
     }
     tc_fence_before();
     __syncthreads();
@@ -542,16 +588,16 @@ __global__ void pack_tc_kernel(const ColSrc* __restrict__ cols, int k8, int nblk
         const float v = (s.w != nullptr && k < s.K) ? s.w[(size_t)s.row * s.K + k] : 0.0f;
         const float hi = tf32_rna(v), lo = tf32_rna(v - hi);
         const int ks = k >> 3, ch = (k >> 2) & 1, el = k & 3;
-        const int kp = ks / TC_KSTAGE, j = ks - kp * TC_KSTAGE;
-        const int kk = k8 - kp * TC_KSTAGE < TC_KSTAGE ? k8 - kp * TC_KSTAGE : TC_KSTAGE;  // k-steps in this stage
-        // floats: full pairs before this one, then the blocks of this pair, then the k-step inside the stage
-        const size_t stage = (size_t)kp * TC_KSTAGE * nblk * n * 16 + (size_t)blk * kk * n * 16 + (size_t)j * n * 16;
-        const size_t off = stage + (size_t)ch * n * 4 + (size_t)c * 4 + el;
+        // k-steps of one block are contiguous: a stage is TC_KSTAGE consecutive k-steps of a block
+        const size_t off = ((size_t)blk * k8 + ks) * (size_t)n * 16 + (size_t)ch * n * 4 + (size_t)c * 4 + el;
         dst[off] = hi;
         dst[off + (size_t)n * 8] = lo;  // lo piece follows the hi piece: n*32 B = n*8 floats
         if (k == 0) {
-            bias[cc] = s.b1 ? s.b1[s.bidx] : 0.0f;
-            bias[ncols + cc] = s.b2 ? s.b2[s.bidx] : 0.0f;
+            // one bias per column: b_ih + b_hh pre-added in fp32 (the reference adds them one after the other: the
+            // results differ by at most one ulp of the gate pre-activation, below the contraction's own rounding)
+            const float ba = s.b1 ? s.b1[s.bidx] : 0.0f, bb = s.b2 ? s.b2[s.bidx] : 0.0f;
+            bias[cc] = __fadd_rn(ba, bb);
+            bias[ncols + cc] = 0.0f;
         }
     }
 }
@@ -683,6 +729,7 @@ int launch_forward_tc(const hypad_ctx* ctx, const void* x, int x_is_f64, int64_t
     P.n = n; P.row_stride = row_stride; P.x_is_f64 = x_is_f64; P.stages = stages;
     P.out = *out;
     P.error_flag = ctx->tc_error;
+    P.debug = ctx->tc_debug;
     const bool hyp = P.prog.hyperbolic != 0;
     uint32_t mask = 0;
     if (stages & HYPAD_STAGE_ENCODER) mask |= (1u << T_ENC) | (1u << T_Z);

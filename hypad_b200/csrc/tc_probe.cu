@@ -160,9 +160,77 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const TcProbeArgs a) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u));
 }
 
+// Throughput microbenchmark: `reps` tcgen05.mma (M=128, K=8, tf32) issued back to back by one thread, operands in shared
+// memory (contents irrelevant).  mode 0: every MMA accumulates into the same TMEM columns; mode 1: rotate over
+// 512/N accumulators; mode 2: like 0 but A and B descriptors alternate between two buffers.  out[0] = cycles.
+__global__ void __launch_bounds__(128) tc_bench_kernel(int N, int reps, int mode, long long* out) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int e = tid; e < 2 * (128 * 8 + 256 * 8); e += 128) smem[e] = 1.0f;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_slot;
+    if (warp == 1) {
+        const uint32_t idesc = make_idesc_tf32(128, N);
+        const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 2 * 128 * 8);
+        const uint32_t a1 = a0 + 128 * 8 * 4, b1 = b0 + 256 * 8 * 4;
+        const int nacc = 512 / N;
+        long long t0 = 0, t1 = 0;
+        uint32_t pred;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+        if (pred) {
+            t0 = clock64();
+            for (int r = 0; r < reps; ++r) {
+                const bool alt = (mode == 2) && (r & 1);
+                const uint64_t ad = make_smem_desc(alt ? a1 : a0, 128 * 16, 128);
+                const uint64_t bd = make_smem_desc(alt ? b1 : b0, N * 16, 128);
+                const uint32_t d = tmem + (mode == 1 ? (uint32_t)((r % nacc) * N) : 0u);
+                umma_tf32(d, ad, bd, idesc, 1);
+            }
+            t1 = clock64();
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+            out[1] = t1 - t0;  // issue time
+        }
+        __syncwarp();
+        uint32_t done = 0;
+        for (long long spin = 0; !done && spin < (1ll << 26); ++spin)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(done) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+        if (pred) out[0] = clock64() - t0;  // until retired
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+}
+
 }  // namespace hypad
 
 using namespace hypad;
+
+extern "C" int hypad_tc_probe_bench(int N, int reps, int mode, long long* h_out2, void* stream) {
+    HYPAD_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && reps >= 1 && h_out2, "hypad_tc_probe_bench: bad argument");
+    long long* d = nullptr;
+    HYPAD_CUDA_TRY(cudaMalloc(&d, 2 * sizeof(long long)));
+    const size_t smem = 2 * (128 * 8 + 256 * 8) * sizeof(float);
+    tc_bench_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(N, reps, mode, d);
+    HYPAD_LAUNCH_CHECK();
+    HYPAD_CUDA_TRY(cudaMemcpy(h_out2, d, 2 * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return HYPAD_OK;
+}
+
 
 extern "C" int hypad_tc_probe_gemm(const float* A, const float* B, float* D, int K, int N, int pieces, int terms, void* stream) {
     HYPAD_REQUIRE(A && B && D, "hypad_tc_probe_gemm: NULL argument");

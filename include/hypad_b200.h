@@ -110,6 +110,10 @@ int hypad_forward_ffma(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, i
 /* Synchronises with the device and reports a sticky error raised inside hypad_forward's kernel (a bounded
  * barrier wait that timed out).  0 = healthy. */
 int hypad_ctx_poll_error(hypad_ctx* ctx);
+/* Diagnostic: enable/disable per-role cycle counters of hypad_forward's kernel (CTA 0) and read them back into
+ * h_out8 (host): [0] epilogue total, [1] epilogue waiting for accumulators, [2] MMA warp waiting for operands,
+ * [3] MMA warp waiting for weights, [4] producer waiting for free slots, [5] operand (re)load + hand-over, [6] tiles. */
+int hypad_forward_debug_cycles(hypad_ctx* ctx, int enable, long long* h_out8);
 
 /* hyperspace/hyrnn_nets.py:13-35 mobius_linear with hyperbolic_input=False, k=-1:
  * project(mobius_add(expmap0(x W^T), bias)).  x (n,in) W (out,in) bias (out,) or NULL, out (n,out).
@@ -188,6 +192,9 @@ int hypad_threshold_windows(hypad_ctx* ctx, const double* errors, int64_t len, i
  * operands split into `pieces` TF32 parts and `terms` partial products accumulated in TMEM: (1,1) plain TF32,
  * (2,3) 3xTF32, (3,6) six-term split.  Used to measure whether a tensor-core contraction can hold score parity. */
 int hypad_tc_probe_gemm(const float* A, const float* B, float* D, int K, int N, int pieces, int terms, void* stream);
+/* Diagnostic: cycles for `reps` back-to-back tcgen05.mma (M=128, K=8, tf32, width N) on one SM; h_out2[0] = cycles
+ * until retired, h_out2[1] = cycles spent issuing.  mode 0 same accumulator, 1 rotating accumulators, 2 alternating operands. */
+int hypad_tc_probe_bench(int N, int reps, int mode, long long* h_out2, void* stream);
 
 #ifdef __cplusplus
 }

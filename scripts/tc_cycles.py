@@ -1,0 +1,23 @@
+"""Prints the per-role cycle breakdown of forward_tc_kernel (CTA 0) on the bench workload."""
+import ctypes, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from bench import make_signal
+from hypad_b200 import _native, scoring
+from hypad_b200.models.tadgan import Encoder, Decoder, CriticX
+dev = torch.device("cuda", 0)
+torch.manual_seed(0)
+mods = [Encoder(100, 20), Decoder(100, 20, True), CriticX(100, 20)]
+for m in mods: m.to(dev).eval()
+sc = scoring.WindowScorer(*mods)
+sig = torch.from_numpy(make_signal(1000000)).to(dev)
+lib = _native.load_library()
+for _ in range(3): sc.forward(sig, True)
+_native.check(lib.hypad_forward_debug_cycles(sc.net.ctx.handle, 1, None))
+sc.forward(sig, True); torch.cuda.synchronize()
+buf = (ctypes.c_longlong * 8)()
+_native.check(lib.hypad_forward_debug_cycles(sc.net.ctx.handle, 0, buf))
+v = list(buf)
+tot = max(v[0], 1)
+print("tiles %d  epilogue total %.0f cyc/tile | wait acc %.1f%% | xload+handover %.1f%% | work %.1f%%" % (v[6], tot / max(v[6], 1), 100 * v[1] / tot, 100 * v[5] / tot, 100 * (tot - v[1] - v[5]) / tot))
+print("MMA warp: wait operands %.1f%%  wait weights %.1f%% of epilogue total;  producer wait slots %.1f%%" % (100 * v[2] / tot, 100 * v[3] / tot, 100 * v[4] / tot))
