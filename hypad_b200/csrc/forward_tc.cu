@@ -73,10 +73,15 @@ struct TcParams {
 // PTX helpers
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+// fp32 -> TF32 (10-bit mantissa), round to nearest, ties away from zero -- what cvt.rna.tf32.f32 computes for finite
+// inputs, in two integer instructions (ptxas expands the cvt into ~7): add half an ulp of the TF32 grid, clear 13 bits.
+__device__ __forceinline__ float tf32_rna(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+
+// y / d given r ~ 1/d: one residual correction makes the quotient correctly rounded (barring the usual ties),
+// 3 instructions instead of the IEEE division sequence
+__device__ __forceinline__ float div_refined(float y, float d, float r) {
+    const float q = __fmul_rn(y, r);
+    return fmaf(fmaf(-q, d, y), r, q);
 }
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
@@ -232,6 +237,7 @@ __device__ void row_mobius_tc(uint32_t trow, int col0, int ncols, const float* _
     }
     row_allreduce_tc<1>(s1, red, r, split);
     const float nrm = fmaxf(sqrtf((float)s1[0]), 1e-15f);
+    const float rnrm = __frcp_rn(nrm);
     const float th = (float)tanh((double)fminf(nrm, 15.0f));
     double s2[2] = {0.0, 0.0};
     for (int c = cbeg; c < cend; c += cstep) {
@@ -240,7 +246,7 @@ __device__ void row_mobius_tc(uint32_t trow, int col0, int ncols, const float* _
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float p = __fmul_rn(th, __fdiv_rn(y[i], nrm));
+            const float p = __fmul_rn(th, div_refined(y[i], nrm, rnrm));
             s2[0] += (double)__fmul_rn(p, p);
             s2[1] += (double)__fmul_rn(p, bias[c + i]);
         }
@@ -251,6 +257,7 @@ __device__ void row_mobius_tc(uint32_t trow, int col0, int ncols, const float* _
     const float ca = __fadd_rn(one_2xy, y2);
     const float cb = __fsub_rn(1.0f, x2);
     const float den = fmaxf(__fadd_rn(one_2xy, __fmul_rn(x2, y2)), 1e-15f);
+    const float rden = __frcp_rn(den);
     double s3[1] = {0.0};
     for (int c = cbeg; c < cend; c += cstep) {
         float y[8], q[8];
@@ -258,8 +265,8 @@ __device__ void row_mobius_tc(uint32_t trow, int col0, int ncols, const float* _
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float p = __fmul_rn(th, __fdiv_rn(y[i], nrm));
-            q[i] = __fdiv_rn(__fadd_rn(__fmul_rn(ca, p), __fmul_rn(cb, bias[c + i])), den);
+            const float p = __fmul_rn(th, div_refined(y[i], nrm, rnrm));
+            q[i] = div_refined(__fadd_rn(__fmul_rn(ca, p), __fmul_rn(cb, bias[c + i])), den, rden);
             s3[0] += (double)__fmul_rn(q[i], q[i]);
         }
         tmem_st8(trow + col0 + c, q);

@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const TcProbeArgs a) {
 __global__ void __launch_bounds__(128) tc_bench_kernel(int N, int reps, int mode, long long* out) {
     extern __shared__ __align__(128) float smem[];
     __shared__ uint64_t bar;
+    __shared__ uint64_t bar2[2];
     __shared__ uint32_t tmem_base_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int e = tid; e < 2 * (128 * 8 + 256 * 8); e += 128) smem[e] = 1.0f;
@@ -175,6 +176,8 @@ __global__ void __launch_bounds__(128) tc_bench_kernel(int N, int reps, int mode
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2[1])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -198,6 +201,16 @@ __global__ void __launch_bounds__(128) tc_bench_kernel(int N, int reps, int mode
                 const uint64_t bd = make_smem_desc(alt ? b1 : b0, N * 16, 128);
                 const uint32_t d = tmem + (mode == 1 ? (uint32_t)((r % nacc) * N) : 0u);
                 umma_tf32(d, ad, bd, idesc, 1);
+                if (mode >= 3 && (r % 6) == 5) {
+                    // mode 3: a commit (to a spare barrier) after every 6 MMAs; mode 4: plus a try_wait that is already satisfied
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2[0])) : "memory");
+                    if (mode >= 4) {
+                        uint32_t ok;
+                        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                                     : "=r"(ok) : "r"(smem_u32(&bar2[1])), "r"(1u) : "memory");
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                }
             }
             t1 = clock64();
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
