@@ -1,0 +1,51 @@
+"""Run under torchrun (one process per GPU): the window-sharded scoring of a golden case must equal the single-GPU run
+bit for bit (same kernels, same per-window arithmetic; only the gather is added).  Rank 0 prints the verdict."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from conftest import build_modules, full_signal, golden
+from hypad_b200.distributed import ShardedScorer
+from hypad_b200.scoring import WindowScorer
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=dev)
+    ok = True
+    for case in ("cfg1_hyp_uncertainty.npz", "noisy1500_hyp_uncertainty.npz", "edge_n300_hyp.npz"):
+        g = golden(case)
+        enc, dec, cx, _ = build_modules("weights_hyp_s100.npz", 100, True, dev)
+        scorer = WindowScorer(enc, dec, cx)
+        sig = full_signal(g)
+        n = sig.shape[0] - 100
+        sh = ShardedScorer(scorer)
+        first, count, h0, lo, hi = sh.plan(n)
+        local_slice = torch.from_numpy(sig[lo:hi].copy()).to(dev)
+        out = sh.score_hyperbolic(local_slice, n, "uncertainty", index=g["index"])
+        ref = scorer.score(torch.from_numpy(sig).to(dev), True, "uncertainty", index=g["index"])
+        same = all(torch.equal(out[k], ref[k]) for k in ("final", "kmax", "rec", "unorm"))
+        same = same and out["intervals"].shape == ref["intervals"].shape and np.array_equal(out["intervals"], ref["intervals"])
+        t = torch.tensor([int(same)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print("%s: world=%d sharded == single-GPU: %s" % (case, world, bool(t.item())))
+        ok = ok and bool(t.item())
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("SHARDED_CHECK", "OK" if ok else "FAIL")
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
