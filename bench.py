@@ -278,11 +278,16 @@ def run_native(args):
         achieved = flops / (fw_ms / 1e3) / 1e12
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         simt_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12  # fp32 FFMA lanes at the clock seen under load
-        roofline = {"kernel": "forward_kernel (fused TadGAN forward, fp32 FFMA)", "bound": "tensor", "achieved": achieved,
-                    "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None, "peak_source": peak_src,
-                    "note": "the contraction runs on the fp32 FFMA pipe (score parity rules out TF32/bf16 inputs); "
-                            "fraction of the fp32 SIMT peak at the observed clock is in frac_fp32_simt",
-                    "fp32_simt_peak_tflops": simt_peak, "frac_fp32_simt": achieved / simt_peak,
+        # 3xTF32: every algorithmic MAC is executed as three TF32 tensor-core MACs; nominal dense TF32 peak is half of bf16
+        tf32_peak = tf_peak / 2.0
+        roofline = {"kernel": "forward_tc_kernel (fused TadGAN forward: tcgen05.mma kind::tf32, 3xTF32, TMEM accumulators)",
+                    "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                    "traffic": None, "peak_source": peak_src,
+                    "note": "achieved = algorithmic fp32 FLOP (340,312 per window) / event-timed launch; the kernel executes 3x that "
+                            "on the tensor pipe as TF32 (error-compensated split, needed for score parity), whose dense peak is half "
+                            "the bf16 peak: executed_tf32_tflops / tf32_peak_tflops is the tensor-pipe view",
+                    "executed_tf32_tflops": 3.0 * achieved, "tf32_peak_tflops": tf32_peak, "frac_tf32_executed": 3.0 * achieved / tf32_peak,
+                    "fp32_simt_peak_tflops": simt_peak, "speedup_vs_fp32_simt_peak": achieved / simt_peak,
                     "algorithmic_flop_per_window": FLOP_PER_WINDOW_HYP, "windows_per_launch": n_local,
                     "avg_launch_ms": fw_ms}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -292,7 +297,7 @@ def run_native(args):
                         "h2d_bytes_per_step": int(host_slice.numel() * 8), "d2h_bytes_per_step": int(n_windows * 8),
                         "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": int(launches), "roofline": roofline,
-                "kernels_ms": {"forward_kernel": fw_ms, "kde_screened_kernel": kde_ms, "step_total": ms_per_step},
+                "kernels_ms": {"forward_tc_kernel": fw_ms, "kde_screened_kernel": kde_ms, "step_total": ms_per_step},
                 "kde": {"pair_evals_per_timestep": 4950, "timesteps_per_launch": n_local + S - 1,
                         "gpair_evals_per_s": 4950 * (n_local + S - 1) / (kde_ms / 1e3) / 1e9}}
         if world == 1 and not args.no_cpu_baseline:

@@ -185,26 +185,59 @@ __global__ void __launch_bounds__(KDE_WARPS * 32) kde_screened_kernel(const KdeA
             continue;
         }
         const double cho = sqrt(var) * sScott[n];
-        const double dscale = kScale / cho;
+        const double rcho = 1.0 / cho;
+        const double dscale = kScale * rcho;
         float d[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int j = lane + 32 * q;
             d[q] = (float)((v[q] - mean) * dscale);
             if (j < n) {
-                P[j] = v[q] / cho;
+                P[j] = v[q] * rcho;  // scipy divides; a last-bit difference of the scaled points cannot change the arg-max
                 D[j] = d[q];
             }
         }
         __syncwarp();
         // ---- fp32 screening: all n^2 kernel values with ex2.approx -------------------------------------
         float e32[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int k = 0; k < n; ++k) {
-            const float dk = D[k];
+        if (n == 100) {
+            // The interior case of the reference's window length.  Points 0..95 are handled slot-wise (lane owns points
+            // lane, lane+32, lane+64 and loops over all k); the last 4 points would cost a full warp-wide MUFU per k for
+            // 4 live lanes, so the lanes split k instead and the partial sums are reduced with shuffles.
+#pragma unroll 4
+            for (int k = 0; k < 100; ++k) {
+                const float dk = D[k];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float r = dk - d[q];
-                e32[q] += ex2_approx(-(r * r));
+                for (int q = 0; q < 3; ++q) {
+                    const float r = dk - d[q];
+                    e32[q] += ex2_approx(-(r * r));
+                }
+            }
+            float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int k = lane + 32 * kk;
+                const float dk = k < 100 ? D[k] : 1e18f;  // padded k contributes ex2(-huge) = 0
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float r = dk - D[96 + t];
+                    part[t] += ex2_approx(-(r * r));
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part[t] += __shfl_xor_sync(0xffffffffu, part[t], o);
+                if (lane == t) e32[3] = part[t];
+            }
+        } else {
+            for (int k = 0; k < n; ++k) {
+                const float dk = D[k];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float r = dk - d[q];
+                    e32[q] += ex2_approx(-(r * r));
+                }
             }
         }
         float m32 = 0.f;
@@ -214,8 +247,7 @@ __global__ void __launch_bounds__(KDE_WARPS * 32) kde_screened_kernel(const KdeA
         m32 = warp_max(m32);
         const float thr = m32 * (1.0f - 1e-3f);
         // ---- fp64 re-evaluation of the candidates, ascending j -----------------------------------------
-        const double norm = 0.3989422804014327 / cho;
-        const double w = 1.0 / (double)n;
+        // (the positive constants w = 1/n and norm = (2 pi)^(-1/2)/cho multiply every density alike: left out)
         double best = -1.0;
         int bj = 0;
 #pragma unroll
@@ -229,7 +261,7 @@ __global__ void __launch_bounds__(KDE_WARPS * 32) kde_screened_kernel(const KdeA
                 double part = 0.0;
                 for (int k = lane; k < n; k += 32) {
                     const double r = P[k] - pj;
-                    part += w * (exp(-(r * r) / 2.0) * norm);
+                    part += exp(-0.5 * (r * r));
                 }
                 const double tot = warp_sum(part);  // xor tree: bitwise identical in every lane
                 if (tot > best) {
