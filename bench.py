@@ -280,9 +280,15 @@ def run_native(args):
         simt_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12  # fp32 FFMA lanes at the clock seen under load
         # 3xTF32: every algorithmic MAC is executed as three TF32 tensor-core MACs; nominal dense TF32 peak is half of bf16
         tf32_peak = tf_peak / 2.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["forward_tc_kernel"]["bytes"]
+        except Exception:
+            pass
         roofline = {"kernel": "forward_tc_kernel (fused TadGAN forward: tcgen05.mma kind::tf32, 3xTF32, TMEM accumulators)",
                     "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per launch (ncu --set full, profiles/traffic.json)",
+                    "peak_source": peak_src,
                     "note": "achieved = algorithmic fp32 FLOP (340,312 per window) / event-timed launch; the kernel executes 3x that "
                             "on the tensor pipe as TF32 (error-compensated split, needed for score parity), whose dense peak is half "
                             "the bf16 peak: executed_tf32_tflops / tf32_peak_tflops is the tensor-pipe view",

@@ -46,7 +46,10 @@ def launches(src, dst):
         fh.write("Per-launch times are cold-cache and serialised; compare SHARES.\n\n| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n")
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             fh.write("| `%s` | %d | %.1f | %.1f | %.1f%% |\n" % (k.split("(")[0][:70], n, t, t / n, 100 * t / tot))
-    print(open(dst).read())
+    try:
+        print(open(dst).read())
+    except BrokenPipeError:
+        pass
 
 
 def kernel(src, dst):
