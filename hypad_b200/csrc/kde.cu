@@ -12,10 +12,13 @@
 //
 // kde_exhaustive_kernel evaluates all n^2 kernel values in fp64, accumulating over i in scipy's order.
 // kde_screened_kernel (the product path) first evaluates all densities in fp32 with ex2.approx on centred,
-// bandwidth-scaled values; every j whose fp32 density is within 1e-3 (relative) of the fp32 maximum is a
-// candidate -- the fp32 error is bounded well below that -- and only candidates are
+// bandwidth-scaled values; every j whose fp32 density is within 2.5e-4 (relative) of the fp32 maximum is a
+// candidate -- the fp32 error is bounded by ~2.5e-5 (centred operands |D| <= 25, contributing pairs |r| <= 4.5:
+// exponent error 2 r dr <= 1.3e-5, ex2.approx 2^-22, 100 additions <= 6e-6) -- and only candidates are
 // re-evaluated in fp64.  The arg-max is then taken over the fp64 densities of the candidates in ascending j,
 // which equals the arg-max over all j.
+#include <math_constants.h>
+
 #include "common.cuh"
 
 namespace hypad {
@@ -245,11 +248,14 @@ __global__ void __launch_bounds__(KDE_WARPS * 32) kde_screened_kernel(const KdeA
         for (int q = 0; q < 4; ++q)
             if (lane + 32 * q < n) m32 = fmaxf(m32, e32[q]);
         m32 = warp_max(m32);
-        const float thr = m32 * (1.0f - 1e-3f);
+        const float thr = m32 * (1.0f - 2.5e-4f);  // 10x the fp32 error bound (header comment); a flat density top yields ~2 candidates
         // ---- fp64 re-evaluation of the candidates, ascending j -----------------------------------------
         // (the positive constants w = 1/n and norm = (2 pi)^(-1/2)/cho multiply every density alike: left out)
         double best = -1.0;
         int bj = 0;
+        // A candidate whose value repeats an already evaluated one has bitwise the same density and loses the tie to
+        // the earlier index, so it is skipped (periodic and plateau signals produce many exact repeats).
+        double seen0 = CUDART_NAN, seen1 = CUDART_NAN, seen2 = CUDART_NAN, seen3 = CUDART_NAN;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             unsigned cand = __ballot_sync(0xffffffffu, (lane + 32 * q < n) && e32[q] >= thr);
@@ -258,6 +264,11 @@ __global__ void __launch_bounds__(KDE_WARPS * 32) kde_screened_kernel(const KdeA
                 cand &= cand - 1;
                 const int j = src + 32 * q;
                 const double pj = P[j];
+                if (pj == seen0 || pj == seen1 || pj == seen2 || pj == seen3) continue;
+                seen3 = seen2;
+                seen2 = seen1;
+                seen1 = seen0;
+                seen0 = pj;
                 double part = 0.0;
                 for (int k = lane; k < n; k += 32) {
                     const double r = P[k] - pj;
