@@ -313,14 +313,14 @@ int hypad_forward_ffma(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, i
     return launch_forward(ctx, x, x_is_f64, n, row_stride, z_in, stages, out, (cudaStream_t)stream);
 }
 
-int hypad_forward_debug_cycles(hypad_ctx* ctx, int enable, long long* h_out8) {
+int hypad_forward_debug_cycles(hypad_ctx* ctx, int enable, long long* h_out) {
     HYPAD_REQUIRE(ctx != nullptr, "hypad_forward_debug_cycles: NULL context");
     HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
     if (enable && !ctx->tc_debug) {
-        HYPAD_CUDA_TRY(cudaMalloc(&ctx->tc_debug, 8 * sizeof(long long)));
-        HYPAD_CUDA_TRY(cudaMemset(ctx->tc_debug, 0, 8 * sizeof(long long)));
+        HYPAD_CUDA_TRY(cudaMalloc(&ctx->tc_debug, HYPAD_DEBUG_SLOTS * sizeof(long long)));
+        HYPAD_CUDA_TRY(cudaMemset(ctx->tc_debug, 0, HYPAD_DEBUG_SLOTS * sizeof(long long)));
     }
-    if (h_out8 && ctx->tc_debug) HYPAD_CUDA_TRY(cudaMemcpy(h_out8, ctx->tc_debug, 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (h_out && ctx->tc_debug) HYPAD_CUDA_TRY(cudaMemcpy(h_out, ctx->tc_debug, HYPAD_DEBUG_SLOTS * sizeof(long long), cudaMemcpyDeviceToHost));
     if (!enable && ctx->tc_debug) {
         HYPAD_CUDA_TRY(cudaDeviceSynchronize());
         cudaFree(ctx->tc_debug);
@@ -335,6 +335,12 @@ int hypad_ctx_poll_error(hypad_ctx* ctx) {
     HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
     int flag = 0;
     HYPAD_CUDA_TRY(cudaMemcpy(&flag, ctx->tc_error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag == 2) {
+        set_error("forward_tc_kernel: an activation left the range of the scaled fp16 operand split (|x| < 63, linear / critic "
+                  "activations < 255); results of that call are invalid -- use hypad_forward_ffma for such data");
+        HYPAD_CUDA_TRY(cudaMemset(ctx->tc_error, 0, sizeof(int)));
+        return HYPAD_EINVAL;
+    }
     if (flag) {
         set_error("forward_tc_kernel: a barrier wait timed out (pipeline protocol error)");
         return HYPAD_ECUDA;

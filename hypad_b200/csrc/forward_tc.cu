@@ -1,22 +1,31 @@
-// Fused TadGAN forward on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM) -- the
+// Fused TadGAN forward on the 5th-generation tensor cores (tcgen05.mma kind::f16, accumulators in TMEM) -- the
 // product path of hypad_forward.  Same arithmetic contract as the FFMA kernel in forward.cu (which stays as the
 // in-library cross-check, hypad_forward_ffma): Encoder -> Decoder -> MobiusLinear x2 -> Poincare row distance, CriticX.
 //
 // Every layer is a dense contraction  D[128 windows x N] = A[128 x K] * W[N x K]^T  with fp32-class accuracy obtained
-// from three TF32 products ("3xTF32"): A = A_hi + A_lo, W = W_hi + W_lo (each piece rounded to TF32 with cvt.rna),
-// D = A_lo W_hi + A_hi W_lo + A_hi W_hi accumulated in fp32 in TMEM.  Measured on the B200 (tests/test_gpu_tensor_probe.py):
-// rms error 3.4-4.3e-8 of sum|a||w| against 2.6e-8 for the fp32 FFMA order, no bias -- plain TF32 is 1000x worse.
+// from three half-precision products of an error-compensated split: with power-of-two scales 2^sa, 2^sw chosen so that
+// both pieces stay in fp16's normal range, A 2^sa = A_hi + A_lo and W 2^sw = W_hi + W_lo (A_hi = fp16(A 2^sa),
+// A_lo = fp16(A 2^sa - A_hi): 11 + 11 significant bits plus the sign of the residual), and
+// D 2^(sa+sw) = A_lo W_hi + A_hi W_lo + A_hi W_hi accumulated in fp32 in TMEM by tcgen05.mma kind::f16 (fp16 products are
+// exact in fp32); the epilogue undoes the scale for free inside the bias FMA.  Same accuracy as the 3xTF32 split measured
+// in tests/test_gpu_tensor_probe.py (rms 3.4-4.3e-8 of sum|a||w| against 2.6e-8 for the fp32 FFMA order; plain TF32 or
+// fp16 is 1000x worse) at HALF the tensor instructions, shared-memory operand traffic and weight bytes: one kind::f16
+// MMA covers K = 16.  Range: |activation| 2^sa and |weight| 2^sw must stay below 65504; sw is chosen per layer from the
+// weights at pack time, sa is 11 for activations bounded by 1 (LSTM outputs, tanh), 10 for the window itself (|x| < 63),
+// 8 for unbounded linear / LeakyReLU outputs (|a| < 255); leaving the range raises the context's sticky error flag.
 //
 // One persistent CTA per SM owns tiles of 128 windows (TMEM lane = window).  Warp roles:
 //   warps 0-15 epilogue: warp w reads TMEM lanes 32*(w%4).. (its 32 windows) and every 4th 8-column chunk (w/4);
 //              gate / activation math in registers, then writes the next layer's A operand (hi and lo pieces) into shared
-//              memory in the UMMA K-major core-matrix layout, element (row r, feature k) at ((k/4)*128 + r)*16 B + (k%4)*4 B
-//   warp 16    weight producer: cp.async.bulk (TMA engine) of one <=16 KB weight stage (16 k x <=128 columns, hi+lo)
+//              memory in the UMMA K-major core-matrix layout, element (row r, feature k) at ((k/8)*128 + r)*16 B + (k%8)*2 B
+//   warp 16    weight producer: cp.async.bulk (TMA engine) of one <=16 KB weight stage (32 k x <=128 columns, hi+lo)
 //              per mbarrier slot, a ring of 5 slots running ahead across layers and tiles
 //   warp 17    MMA issuer: one thread issues the six tcgen05.mma per stage, tcgen05.commit frees the slot and, per
 //              layer, signals the epilogue
-// Activations never leave the SM: the A operand buffer (128 KB = 128 features x 128 windows x hi/lo) is overwritten in
+// Activations never leave the SM: the A operand buffer (64 KB = 128 features x 128 windows x hi/lo) is overwritten in
 // place layer by layer (all MMAs of a layer retire before its epilogue runs).  Weights stream from L2.
+#include <cuda_fp16.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -28,9 +37,9 @@ constexpr int TC_NSPLIT = 4;              // epilogue warps per TMEM lane quarte
 constexpr int TC_EPI_THREADS = 128 * TC_NSPLIT;
 constexpr int TC_THREADS = TC_EPI_THREADS + 64;
 constexpr int TC_PRODUCER_WARP = TC_EPI_THREADS / 32, TC_MMA_WARP = TC_PRODUCER_WARP + 1;
-constexpr int TC_PIECE_BYTES = 65536;     // one piece of the A buffer: 128 features x 128 rows x 4 B
-constexpr int TC_KSTAGE = 2;              // k-steps (of 8) per weight stage
-constexpr int TC_STAGE_BYTES = TC_KSTAGE * 8192;  // 16 k x 128 columns x (hi + lo) x 4 B
+constexpr int TC_PIECE_BYTES = 32768;     // one piece of the A buffer: 128 features x 128 rows x 2 B
+constexpr int TC_KSTAGE = 2;              // k-steps (of 16) per weight stage
+constexpr int TC_STAGE_BYTES = TC_KSTAGE * 8192;  // 32 k x 128 columns x (hi + lo) x 2 B
 constexpr int TC_NSLOT = 5;
 constexpr int TC_RED_BYTES = TC_NSPLIT * TC_M * 3 * 8;
 
@@ -38,20 +47,23 @@ enum TcEpi : int32_t { TE_LSTM = 0, TE_Z, TE_LINEAR, TE_TANH, TE_MOB_R, TE_MOB_X
 enum TcPassIdx : int32_t { T_ENC = 0, T_Z, T_D0, T_L0, T_L1, T_D2, T_MR, T_MX, T_C1, T_C2, T_C3, T_C4, T_COUNT };
 
 struct TcPass {
-    int32_t k8;      // K / 8
+    int32_t k16;     // K / 16
     int32_t nblk;    // column blocks (3 for an LSTM layer: i | g | o)
     int32_t n;       // columns per block, multiple of 16, <= 128
     int32_t d_col;   // TMEM column of block 0 (block b at d_col + b*n)
-    int32_t w_off;   // byte offset of the packed weights: [k8][nblk]{hi,lo}[2 chunks][n][4]
+    int32_t w_off;   // byte offset of the packed weights: [nblk][k16]{hi,lo}[2 chunks][n][8] fp16
     int32_t b_off;   // float offset of the biases: b1[nblk*n] then b2[nblk*n]
     int32_t epi;     // TcEpi
     int32_t needs_x; // the A operand is the window itself
+    int32_t in_shift;   // sa of this pass's A operand
+    float out_scale;    // 2^sa of the pass that consumes this pass's output
 };
 
 struct TcProgram {
     TcPass pass[T_COUNT];
-    int32_t S, S8, latent, latent_c, hyperbolic;
+    int32_t S, S16, latent, latent_c, hyperbolic;
     int32_t mob_bias_off, mob_y2_off, critic5_off;  // float offsets into the small-parameter buffer
+    int32_t post_off;   // per pass: {2^sw, 2^-(sa+sw)} written by tc_wscale_kernel
 };
 
 struct TcParams {
@@ -73,9 +85,19 @@ struct TcParams {
 // PTX helpers
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-// fp32 -> TF32 (10-bit mantissa), round to nearest, ties away from zero -- what cvt.rna.tf32.f32 computes for finite
-// inputs, in two integer instructions (ptxas expands the cvt into ~7): add half an ulp of the TF32 grid, clear 13 bits.
-__device__ __forceinline__ float tf32_rna(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+// two fp32 -> packed fp16x2 (round to nearest even, saturating to +-65504 instead of inf so that a range violation
+// can never put a NaN into a contraction); e0 goes to the low half
+__device__ __forceinline__ uint32_t pack_h2(float e0, float e1) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
+    return r;
+}
+// the error-compensated split of two (already scaled) values: hi = fp16(t), lo = fp16(t - hi)
+__device__ __forceinline__ void split_h2(float t0, float t1, uint32_t& hi, uint32_t& lo) {
+    hi = pack_h2(t0, t1);
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    lo = pack_h2(t0 - hf.x, t1 - hf.y);
+}
 
 // y / d given r ~ 1/d: one residual correction makes the quotient correctly rounded (barring the usual ties),
 // 3 instructions instead of the IEEE division sequence
@@ -87,11 +109,12 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
            ((uint64_t)1 << 46);
 }
-__device__ __forceinline__ uint32_t idesc_tf32(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | (8u << 24); }
-__device__ __forceinline__ void mma_tf32(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+// instruction descriptor, kind::f16: fp32 accumulate (bit 4), A and B fp16 (formats 0), K-major both, N >> 3, M = 128
+__device__ __forceinline__ uint32_t idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | (8u << 24); }
+__device__ __forceinline__ void mma_f16(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(d),
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(d),
         "l"(a), "l"(b), "r"(idesc), "r"(acc), "r"(0u)
         : "memory");
 }
@@ -157,20 +180,22 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// features k0..k0+7 of row r (fp32) -> hi / lo TF32 pieces of the A operand buffer
-__device__ __forceinline__ void store_act8(unsigned char* act, int r, int k0, const float (&v)[8]) {
-    float hi[8], lo[8];
+// features k0..k0+7 (k0 a multiple of 8) of row r, times the consumer's scale -> hi / lo fp16 pieces of the A operand
+// buffer: one 16-byte core-matrix row each
+__device__ __forceinline__ void store_act8(unsigned char* act, int r, int k0, const float (&v)[8], float sc) {
+    uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        hi[i] = tf32_rna(v[i]);
-        lo[i] = tf32_rna(v[i] - hi[i]);
-    }
+    for (int i = 0; i < 4; ++i) split_h2(__fmul_rn(v[2 * i], sc), __fmul_rn(v[2 * i + 1], sc), hi[i], lo[i]);
+    const int off = ((k0 >> 3) * TC_M + r) * 16;
+    *reinterpret_cast<uint4*>(act + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(act + TC_PIECE_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+// unbounded activations: flag a value the scaled fp16 split cannot hold (the store itself saturates)
+__device__ __forceinline__ void check_range8(const float (&v)[8], float sc, int* error_flag) {
+    float m = fabsf(v[0]);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        const int off = (((k0 >> 2) + c) * TC_M + r) * 16;
-        *reinterpret_cast<float4*>(act + off) = make_float4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-        *reinterpret_cast<float4*>(act + TC_PIECE_BYTES + off) = make_float4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
-    }
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, fabsf(v[i]));
+    if (!(m * sc < 65000.0f)) atomicExch(error_flag, 2);
 }
 
 // 1 / (1 + exp(-x)); the reciprocal is MUFU.RCP refined by one Newton step (<= 1 ulp, branch-free)
@@ -200,32 +225,26 @@ __device__ __forceinline__ void row_allreduce_tc(double (&v)[NV], double* red, i
 // the window tile (or a caller-provided latent) -> A operand buffer; threads: row = t & 127, chunk lane = t >> 7
 template <typename T>
 __device__ __forceinline__ void load_rows_to_act(unsigned char* act, const T* __restrict__ x, int64_t w0, int64_t n, int64_t stride,
-                                                 int width, int width8, int t) {
+                                                 int width, int width16, int t, float sc, int* error_flag) {
     const int r = t & (TC_M - 1);
     const bool live = w0 + r < n;
     const T* row = x + (w0 + r) * stride;
-    for (int c = t >> 7; c < width8 / 4; c += TC_NSPLIT) {
-        float v[4];
+    for (int c = t >> 7; c < width16 / 8; c += TC_NSPLIT) {
+        float v[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int k = 4 * c + e;
+        for (int e = 0; e < 8; ++e) {
+            const int k = 8 * c + e;
             v[e] = (live && k < width) ? (float)row[k] : 0.0f;
         }
-        float hi[4], lo[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            hi[e] = tf32_rna(v[e]);
-            lo[e] = tf32_rna(v[e] - hi[e]);
-        }
-        const int off = (c * TC_M + r) * 16;
-        *reinterpret_cast<float4*>(act + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(act + TC_PIECE_BYTES + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        check_range8(v, sc, error_flag);
+        store_act8(act, r, 8 * c, v, sc);
     }
 }
 
 // In place on TMEM columns [col0, col0+ncols): y = x W^T -> project(mobius_add(expmap0(y), bias)); see forward.cu row_mobius.
+// post = 2^-(sa+sw) undoes the operand scales (exact).
 __device__ void row_mobius_tc(uint32_t trow, int col0, int ncols, const float* __restrict__ bias, float y2, double* red, int r,
-                              int split, float* gout, bool want_out, int S) {
+                              int split, float* gout, bool want_out, int S, float post) {
     const int cbeg = 8 * split, cend = ncols, cstep = 8 * TC_NSPLIT;
     double s1[1] = {0.0};
     for (int c = cbeg; c < cend; c += cstep) {
@@ -233,7 +252,10 @@ __device__ void row_mobius_tc(uint32_t trow, int col0, int ncols, const float* _
         tmem_ld8(trow + col0 + c, y);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s1[0] += (double)__fmul_rn(y[i], y[i]);
+        for (int i = 0; i < 8; ++i) {
+            y[i] *= post;
+            s1[0] += (double)__fmul_rn(y[i], y[i]);
+        }
     }
     row_allreduce_tc<1>(s1, red, r, split);
     const float nrm = fmaxf(sqrtf((float)s1[0]), 1e-15f);
@@ -246,7 +268,7 @@ __device__ void row_mobius_tc(uint32_t trow, int col0, int ncols, const float* _
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float p = __fmul_rn(th, div_refined(y[i], nrm, rnrm));
+            const float p = __fmul_rn(th, div_refined(y[i] * post, nrm, rnrm));
             s2[0] += (double)__fmul_rn(p, p);
             s2[1] += (double)__fmul_rn(p, bias[c + i]);
         }
@@ -265,7 +287,7 @@ __device__ void row_mobius_tc(uint32_t trow, int col0, int ncols, const float* _
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float p = __fmul_rn(th, div_refined(y[i], nrm, rnrm));
+            const float p = __fmul_rn(th, div_refined(y[i] * post, nrm, rnrm));
             q[i] = div_refined(__fadd_rn(__fmul_rn(ca, p), __fmul_rn(cb, bias[c + i])), den, rden);
             s3[0] += (double)__fmul_rn(q[i], q[i]);
         }
@@ -312,7 +334,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
 
     const TcProgram& prog = P.prog;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int S = prog.S, S8 = prog.S8;
+    const int S = prog.S, S16 = prog.S16;
     const int64_t ntiles = (P.n + TC_M - 1) / TC_M;
     const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
@@ -348,8 +370,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                     // stages in (block, k-step pair) order -- the accumulator address changes only between blocks (a change
                     // costs ~120 cycles of tensor-pipe drain, scripts/tc_mma_rate.py); the last pair of an odd layer holds one k-step
                     for (int b = 0; b < ps.nblk && ok; ++b)
-                        for (int kp = 0; kp < ps.k8; kp += TC_KSTAGE, ++it) {
-                            const int kk = ps.k8 - kp < TC_KSTAGE ? ps.k8 - kp : TC_KSTAGE;
+                        for (int kp = 0; kp < ps.k16; kp += TC_KSTAGE, ++it) {
+                            const int kk = ps.k16 - kp < TC_KSTAGE ? ps.k16 - kp : TC_KSTAGE;
                             const uint32_t bytes = (uint32_t)(kk * ps.n) * 64u;
                             const uint32_t slot = it % TC_NSLOT, use = it / TC_NSLOT;
                             const long long c0 = P.debug ? clock64() : 0;
@@ -365,13 +387,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
         }
     } else if (warp == TC_MMA_WARP) {
         // ===== MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues ============
+        // The issuing thread is a scalar instruction stream next to the tensor pipe: whatever it executes between two
+        // tcgen05.mma is hidden only while earlier MMAs are still queued.  So descriptors are additive (one IADD per
+        // operand), and the full barrier of the NEXT stage is peeked right after the first k-step of the current one.
         {
-            uint32_t it = 0, npass = 0;
-            bool ok = true;
+            uint32_t slot = 0, par = 0, npass = 0;
+            bool ok = true, have = false;
+            const bool lead = elect_one();  // the one thread that issues every tcgen05.mma / commit of this CTA
             long long dbg_a = 0, dbg_full = 0;
             const bool dbg = P.debug != nullptr;
-            const uint32_t act_hi = s_u32(act), act_lo = s_u32(act + TC_PIECE_BYTES);
-            const uint32_t ring_u32 = s_u32(ring);
+            const uint32_t a_hi0 = ((s_u32(act) & 0x3FFFFu) >> 4) | (128u << 16);                    // LBO 2048 B
+            const uint32_t a_lo0 = ((s_u32(act + TC_PIECE_BYTES) & 0x3FFFFu) >> 4) | (128u << 16);
+            const uint32_t ring0 = (s_u32(ring) & 0x3FFFFu) >> 4;
+            auto desc64 = [](uint32_t lo32) { return ((uint64_t)0x4008u << 32) | lo32; };  // SBO 128 B, descriptor version 1
+            int64_t stages_left = 0;
+            for (int p = 0; p < T_COUNT; ++p)
+                if ((P.pass_mask >> p) & 1u) stages_left += (int64_t)prog.pass[p].nblk * ((prog.pass[p].k16 + TC_KSTAGE - 1) / TC_KSTAGE);
+            stages_left *= my_tiles;
             for (int64_t t = 0; t < my_tiles && ok; ++t)
                 for (int p = 0; p < T_COUNT && ok; ++p) {
                     if (!((P.pass_mask >> p) & 1u)) continue;
@@ -379,39 +411,57 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                     long long c0 = dbg ? clock64() : 0;
                     ok = mbar_wait(bar_a, npass & 1, P.error_flag);  // A operand written, TMEM of the previous pass drained
                     if (dbg) dbg_a += clock64() - c0;
+                    if (dbg && blockIdx.x == 0 && lead) P.debug[40 + 5 * p + 2] = clock64();
                     if (!ok) break;
                     tc_fence_after();
-                    const uint32_t idesc = idesc_tf32(ps.n);
-                    const uint32_t nb16 = (uint32_t)ps.n * 16u;
+                    const uint32_t idesc = idesc_f16(ps.n);
+                    const uint32_t n = (uint32_t)ps.n;
+                    const uint32_t w_lbo = n << 16;  // LBO = 16 n bytes: the two 4-k chunks of a k-step
                     for (int b = 0; b < ps.nblk && ok; ++b) {
                         const uint32_t d = tmem + (uint32_t)(ps.d_col + b * ps.n);
-                        for (int kp = 0; kp < ps.k8; kp += TC_KSTAGE, ++it) {
-                            const int kk = ps.k8 - kp < TC_KSTAGE ? ps.k8 - kp : TC_KSTAGE;
-                            const uint32_t slot = it % TC_NSLOT, use = it / TC_NSLOT;
-                            if (dbg) c0 = clock64();
-                            ok = mbar_wait(bar_full + 8 * slot, use & 1, P.error_flag);
-                            if (dbg) dbg_full += clock64() - c0;
-                            if (!ok) break;
-                            tc_fence_after();
-                            if (elect_one()) {
-                                for (int j = 0; j < kk; ++j) {
-                                    const int ks = kp + j;
-                                    const uint64_t a_hi = smem_desc(act_hi + ks * 4096, 2048, 128);
-                                    const uint64_t a_lo = smem_desc(act_lo + ks * 4096, 2048, 128);
-                                    const uint32_t wbase = ring_u32 + slot * TC_STAGE_BYTES + (uint32_t)j * 4u * nb16;
-                                    const uint64_t w_hi = smem_desc(wbase, nb16, 128);
-                                    const uint64_t w_lo = smem_desc(wbase + 2 * nb16, nb16, 128);
-                                    mma_tf32(d, a_lo, w_hi, idesc, ks > 0);  // small terms first
-                                    mma_tf32(d, a_hi, w_lo, idesc, 1);
-                                    mma_tf32(d, a_hi, w_hi, idesc, 1);
+                        for (int kp = 0; kp < ps.k16; kp += TC_KSTAGE) {
+                            const int kk = ps.k16 - kp < TC_KSTAGE ? ps.k16 - kp : TC_KSTAGE;
+                            if (!have) {
+                                if (dbg) c0 = clock64();
+                                ok = mbar_wait(bar_full + 8 * slot, par, P.error_flag);
+                                if (dbg) dbg_full += clock64() - c0;
+                                if (!ok) break;
+                            }
+                            have = false;
+                            --stages_left;
+                            const uint32_t w0 = (ring0 + slot * (TC_STAGE_BYTES >> 4)) | w_lbo;
+                            const uint32_t nslot = slot + 1 == TC_NSLOT ? 0 : slot + 1, npar = slot + 1 == TC_NSLOT ? par ^ 1u : par;
+                            if (lead) {
+                                const uint32_t ka = (uint32_t)kp * 256u;  // 4096 B per k-step (16 features) of A
+                                mma_f16(d, desc64(a_lo0 + ka), desc64(w0), idesc, kp > 0);  // small terms first
+                                mma_f16(d, desc64(a_hi0 + ka), desc64(w0 + 2 * n), idesc, 1);
+                                mma_f16(d, desc64(a_hi0 + ka), desc64(w0), idesc, 1);
+                            }
+                            if (stages_left > 0) {
+                                // non-blocking peek, in the shadow of the MMAs just queued
+                                uint32_t done;
+                                asm volatile(
+                                    "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                                    : "=r"(done)
+                                    : "r"(bar_full + 8 * nslot), "r"(npar)
+                                    : "memory");
+                                have = done != 0;
+                            }
+                            if (lead) {
+                                for (int j = 1; j < kk; ++j) {
+                                    const uint32_t ka = (uint32_t)(kp + j) * 256u, wj = w0 + (uint32_t)j * 4u * n;
+                                    mma_f16(d, desc64(a_lo0 + ka), desc64(wj), idesc, 1);
+                                    mma_f16(d, desc64(a_hi0 + ka), desc64(wj + 2 * n), idesc, 1);
+                                    mma_f16(d, desc64(a_hi0 + ka), desc64(wj), idesc, 1);
                                 }
                                 mma_commit(bar_empty + 8 * slot);  // slot is free once these MMAs have read it
                             }
-                            __syncwarp();
+                            slot = nslot;
+                            par = npar;
                         }
                     }
-                    if (elect_one()) mma_commit(bar_acc);  // accumulators of this pass complete
-                    __syncwarp();
+                    if (lead) mma_commit(bar_acc);  // accumulators of this pass complete
+                    if (dbg && blockIdx.x == 0 && lead) P.debug[40 + 5 * p + 3] = clock64();
                     ++npass;
                 }
             if (dbg && blockIdx.x == 0 && lane == 0) {
@@ -441,25 +491,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                 const long long cx0 = dbg ? clock64() : 0;
                 if (ps.needs_x && !act_has_x) {
                     epi_bar();  // every column split of every row is done writing the previous layer's output
-                    if (P.x_is_f64) load_rows_to_act<double>(act, (const double*)P.x, w0, P.n, P.row_stride, S, S8, tid);
-                    else load_rows_to_act<float>(act, (const float*)P.x, w0, P.n, P.row_stride, S, S8, tid);
+                    const float xs = __int_as_float((127 + ps.in_shift) << 23);
+                    if (P.x_is_f64) load_rows_to_act<double>(act, (const double*)P.x, w0, P.n, P.row_stride, S, S16, tid, xs, P.error_flag);
+                    else load_rows_to_act<float>(act, (const float*)P.x, w0, P.n, P.row_stride, S, S16, tid, xs, P.error_flag);
                     act_has_x = true;
                 } else if (p == T_D0 && !(P.stages & HYPAD_STAGE_ENCODER)) {
                     epi_bar();
-                    load_rows_to_act<float>(act, P.z_in, w0, P.n, prog.latent, prog.latent, 32, tid);
+                    load_rows_to_act<float>(act, P.z_in, w0, P.n, prog.latent, prog.latent, 16 * ps.k16, tid,
+                                            __int_as_float((127 + ps.in_shift) << 23), P.error_flag);
                 }
                 fence_async_smem();
                 tc_fence_before();
                 mbar_arrive(bar_a);
                 // ---- wait for the accumulators --------------------------------------------------------------
                 const long long cw0 = dbg ? clock64() : 0;
+                if (dbg && blockIdx.x == 0 && lane == 0) P.debug[104 + 16 * p + warp] = cw0;  // per-warp arrival time
                 dbg_xload += cw0 - cx0;
                 ok = mbar_wait(bar_acc, npass & 1, P.error_flag);
-                if (dbg) dbg_wait += clock64() - cw0;
+                const long long ce0 = dbg ? clock64() : 0;
+                if (dbg) dbg_wait += ce0 - cw0;
+                if (dbg && blockIdx.x == 0 && tid == 0) P.debug[8 + p] += ce0 - cw0, P.debug[40 + 5 * p + 4] = ce0;
                 ++npass;
                 if (!ok) break;
                 tc_fence_after();
                 const float* __restrict__ b1 = small + ps.b_off;
+                const float post = small[prog.post_off + 2 * p + 1];  // 2^-(sa+sw): exact, folded into the bias FMA
                 const int cbeg = 8 * split, cend = ps.n, cstep = 8 * TC_NSPLIT;
                 if (ps.epi == TE_LSTM) {
                     for (int c = cbeg; c < cend; c += cstep) {
@@ -473,13 +529,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const float vi = __fadd_rn(gi[i], bi[i]);
-                            const float vg = __fadd_rn(gg[i], bg[i]);
-                            const float vo = __fadd_rn(go[i], bo[i]);
+                            const float vi = fmaf(gi[i], post, bi[i]);
+                            const float vg = fmaf(gg[i], post, bg[i]);
+                            const float vo = fmaf(go[i], post, bo[i]);
                             const float cc = __fmul_rn(sigmoid_tc(vi), tanhf(vg));
                             h[i] = __fmul_rn(sigmoid_tc(vo), tanhf(cc));
                         }
-                        store_act8(act, r, c, h);
+                        store_act8(act, r, c, h, ps.out_scale);
                     }
                     act_has_x = false;
                 } else if (ps.epi == TE_Z || ps.epi == TE_LINEAR || ps.epi == TE_TANH || ps.epi == TE_CRITIC_HID || ps.epi == TE_CRITIC_OUT) {
@@ -498,7 +554,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                                 tmem_ld_wait();
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
-                                    float tv = __fadd_rn(v[i], b1[c + i]);
+                                    float tv = fmaf(v[i], post, b1[c + i]);
                                     tv = tv > 0.0f ? tv : __fmul_rn(tv, 0.2f);
                                     if (c + i < prog.latent_c) fdot = fmaf(tv, w5[c + i], fdot);
                                 }
@@ -513,12 +569,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                             tmem_ld_wait();
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                float tv = __fadd_rn(v[i], bv[i]);
+                                float tv = fmaf(v[i], post, bv[i]);
                                 if (ps.epi == TE_TANH) tv = tanhf(tv);
                                 else if (ps.epi == TE_CRITIC_HID) tv = tv > 0.0f ? tv : __fmul_rn(tv, 0.2f);
                                 v[i] = tv;
                             }
-                            store_act8(act, r, c, v);
+                            if (ps.epi != TE_TANH) check_range8(v, ps.out_scale, P.error_flag);
+                            store_act8(act, r, c, v, ps.out_scale);
                             if (gout) {
 #pragma unroll
                                 for (int i = 0; i < 8; ++i)
@@ -529,10 +586,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                     act_has_x = false;
                 } else if (ps.epi == TE_MOB_R) {
                     float* gout = (P.out.hyper && live) ? P.out.hyper + (w0 + r) * (int64_t)S : nullptr;
-                    row_mobius_tc(trow, ps.d_col, ps.n, small + prog.mob_bias_off, small[prog.mob_y2_off], red, r, split, gout, P.out.hyper != nullptr, S);
+                    row_mobius_tc(trow, ps.d_col, ps.n, small + prog.mob_bias_off, small[prog.mob_y2_off], red, r, split, gout, P.out.hyper != nullptr, S, post);
                 } else if (ps.epi == TE_MOB_X) {
                     float* gout = (P.out.hyper_x && live) ? P.out.hyper_x + (w0 + r) * (int64_t)S : nullptr;
-                    row_mobius_tc(trow, ps.d_col, ps.n, small + prog.mob_bias_off, small[prog.mob_y2_off], red, r, split, gout, P.out.hyper_x != nullptr, S);
+                    row_mobius_tc(trow, ps.d_col, ps.n, small + prog.mob_bias_off, small[prog.mob_y2_off], red, r, split, gout, P.out.hyper_x != nullptr, S, post);
                 }
                 // ---- row statistics once both hyperbolic points are in TMEM ---------------------------------
                 const bool last_hyp = (p == T_MX) || (p == T_MR && !((P.pass_mask >> T_MX) & 1u));
@@ -566,6 +623,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                         if (P.out.unorm) P.out.unorm[w0 + r] = sqrtf(sqvnorm);
                     }
                 }
+                if (dbg && blockIdx.x == 0 && tid == 0) P.debug[24 + p] += clock64() - ce0;
             }
         }
         if (dbg && blockIdx.x == 0 && tid == 0) {
@@ -583,22 +641,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// weight packing: fp32 parameters -> TF32 hi/lo stages [k8][nblk]{hi,lo}[2 chunks][n][4]
+// weight packing: fp32 parameters -> scaled fp16 hi/lo stages [nblk][k16]{hi,lo}[2 chunks][n][8]
 // ------------------------------------------------------------------------------------------------------------
-__global__ void pack_tc_kernel(const ColSrc* __restrict__ cols, int k8, int nblk, int n, float* __restrict__ dst, float* __restrict__ bias) {
+// One CTA per pass: sw = the largest power of two that keeps max|w| 2^sw below 2^15; scale[0] = 2^sw,
+// scale[1] = 2^-(sa+sw) (what the epilogue multiplies the accumulators by).
+__global__ void tc_wscale_kernel(const ColSrc* __restrict__ cols, int ncols, int in_shift, float* __restrict__ scale) {
+    __shared__ float smax[256];
+    float m = 0.0f;
+    for (int cc = 0; cc < ncols; ++cc) {
+        const ColSrc s = cols[cc];
+        if (s.w == nullptr) continue;
+        for (int k = threadIdx.x; k < s.K; k += blockDim.x) m = fmaxf(m, fabsf(s.w[(size_t)s.row * s.K + k]));
+    }
+    smax[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) smax[threadIdx.x] = fmaxf(smax[threadIdx.x], smax[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        int e = 0;
+        int sw = 11;
+        if (smax[0] > 0.0f && smax[0] < 3.0e38f) {
+            frexpf(smax[0], &e);  // max|w| < 2^e
+            sw = 15 - e;
+        }
+        sw = sw > 24 ? 24 : (sw < -60 ? -60 : sw);
+        scale[0] = ldexpf(1.0f, sw);
+        scale[1] = ldexpf(1.0f, -(sw + in_shift));
+    }
+}
+
+__global__ void pack_tc_kernel(const ColSrc* __restrict__ cols, int k16, int nblk, int n, __half* __restrict__ dst, float* __restrict__ bias,
+                               const float* __restrict__ scale) {
     const int ncols = nblk * n;
-    const int total = k8 * 8 * ncols;
+    const int total = k16 * 16 * ncols;
+    const float wscale = scale[0];
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const int k = e / ncols, cc = e - k * ncols;
         const int blk = cc / n, c = cc - blk * n;
         const ColSrc s = cols[cc];
         const float v = (s.w != nullptr && k < s.K) ? s.w[(size_t)s.row * s.K + k] : 0.0f;
-        const float hi = tf32_rna(v), lo = tf32_rna(v - hi);
-        const int ks = k >> 3, ch = (k >> 2) & 1, el = k & 3;
+        const float t = __fmul_rn(v, wscale);
+        const __half hi = __float2half_rn(t), lo = __float2half_rn(t - __half2float(hi));
+        const int ks = k >> 4, ch = (k >> 3) & 1, el = k & 7;
         // k-steps of one block are contiguous: a stage is TC_KSTAGE consecutive k-steps of a block
-        const size_t off = ((size_t)blk * k8 + ks) * (size_t)n * 16 + (size_t)ch * n * 4 + (size_t)c * 4 + el;
+        const size_t off = ((size_t)blk * k16 + ks) * (size_t)n * 32 + (size_t)ch * n * 8 + (size_t)c * 8 + el;
         dst[off] = hi;
-        dst[off + (size_t)n * 8] = lo;  // lo piece follows the hi piece: n*32 B = n*8 floats
+        dst[off + (size_t)n * 16] = lo;  // lo piece follows the hi piece: n*32 B = n*16 halves
         if (k == 0) {
             // one bias per column: b_ih + b_hh pre-added in fp32 (the reference adds them one after the other: the
             // results differ by at most one ulp of the gate pre-activation, below the contraction's own rounding)
@@ -619,15 +709,18 @@ size_t forward_tc_smem_bytes() {
 // Builds the tensor-core program and packs the weights (called from hypad_pack_weights).
 int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
     const int S = w->signal_shape, L = w->latent_dim, C = w->critic_dim, hyp = w->hyperbolic != 0;
-    const int S8 = round8i(S), NS = round16i(S), NL = round16i(L), NC = round16i(C);
+    const int S16 = round16i(S), NS = round16i(S), NL = round16i(L), NC = round16i(C);
     TcProgram prog;
     memset(&prog, 0, sizeof(prog));
-    prog.S = S; prog.S8 = S8; prog.latent = L; prog.latent_c = C; prog.hyperbolic = hyp;
+    prog.S = S; prog.S16 = S16; prog.latent = L; prog.latent_c = C; prog.hyperbolic = hyp;
 
     std::vector<std::vector<ColSrc>> cols(T_COUNT);
-    auto set_pass = [&](int idx, int K, int nblk, int n, int d_col, int epi, int needs_x) {
+    // in_shift = sa of the pass's A operand: 10 for the window, 11 for activations bounded by 1, 8 for unbounded ones
+    const int SH_X = 10, SH_UNIT = 11, SH_FREE = 8;
+    auto set_pass = [&](int idx, int K, int nblk, int n, int d_col, int epi, int needs_x, int in_shift, int consumer_shift) {
         TcPass& p = prog.pass[idx];
-        p.k8 = K / 8; p.nblk = nblk; p.n = n; p.d_col = d_col; p.epi = epi; p.needs_x = needs_x;
+        p.k16 = round16i(K) / 16; p.nblk = nblk; p.n = n; p.d_col = d_col; p.epi = epi; p.needs_x = needs_x;
+        p.in_shift = in_shift; p.out_scale = ldexpf(1.0f, consumer_shift);
         cols[idx].assign((size_t)nblk * n, ColSrc{});
     };
     auto linear_cols = [&](int idx, const float* W, const float* b, int rows, int K) {
@@ -647,26 +740,26 @@ int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
             }
         }
     };
-    set_pass(T_ENC, S8, 3, 112, 0, TE_LSTM, 1);
+    set_pass(T_ENC, S, 3, 112, 0, TE_LSTM, 1, SH_X, SH_UNIT);
     lstm_cols(T_ENC, 50, 100, w->enc_w_ih, w->enc_b_ih, w->enc_b_hh, S);
-    set_pass(T_Z, 104, 1, NL, 0, TE_Z, 0);
+    set_pass(T_Z, 100, 1, NL, 0, TE_Z, 0, SH_UNIT, SH_FREE);
     linear_cols(T_Z, w->enc_dense_w, w->enc_dense_b, L, 100);
-    set_pass(T_D0, round8i(L), 1, 64, 0, TE_LINEAR, 0);
+    set_pass(T_D0, L, 1, 64, 0, TE_LINEAR, 0, SH_FREE, SH_FREE);
     linear_cols(T_D0, w->dec_dense1_w, w->dec_dense1_b, 50, L);
-    set_pass(T_L0, 56, 3, 128, 0, TE_LSTM, 0);
+    set_pass(T_L0, 50, 3, 128, 0, TE_LSTM, 0, SH_FREE, SH_UNIT);
     lstm_cols(T_L0, 64, 128, w->dec_w_ih[0], w->dec_b_ih[0], w->dec_b_hh[0], 50);
-    set_pass(T_L1, 128, 3, 128, 0, TE_LSTM, 0);
+    set_pass(T_L1, 128, 3, 128, 0, TE_LSTM, 0, SH_UNIT, SH_UNIT);
     lstm_cols(T_L1, 64, 128, w->dec_w_ih[1], w->dec_b_ih[1], w->dec_b_hh[1], 128);
-    set_pass(T_D2, 128, 1, NS, 0, TE_TANH, 0);
+    set_pass(T_D2, 128, 1, NS, 0, TE_TANH, 0, SH_UNIT, SH_UNIT);
     linear_cols(T_D2, w->dec_dense2_w, w->dec_dense2_b, S, 128);
-    set_pass(T_MR, S8, 1, NS, 384, TE_MOB_R, 0);
+    set_pass(T_MR, S, 1, NS, 384, TE_MOB_R, 0, SH_UNIT, 0);
     if (hyp) linear_cols(T_MR, w->mobius_w, nullptr, S, S);
-    set_pass(T_MX, S8, 1, NS, 0, TE_MOB_X, 1);
+    set_pass(T_MX, S, 1, NS, 0, TE_MOB_X, 1, SH_X, 0);
     if (hyp) linear_cols(T_MX, w->mobius_w, nullptr, S, S);
-    set_pass(T_C1, S8, 1, NC, 0, TE_CRITIC_HID, 1);
+    set_pass(T_C1, S, 1, NC, 0, TE_CRITIC_HID, 1, SH_X, SH_FREE);
     linear_cols(T_C1, w->critic_w[0], w->critic_b[0], C, S);
     for (int i = 0; i < 3; ++i) {
-        set_pass(T_C2 + i, round8i(C), 1, NC, 0, i == 2 ? TE_CRITIC_OUT : TE_CRITIC_HID, 0);
+        set_pass(T_C2 + i, C, 1, NC, 0, i == 2 ? TE_CRITIC_OUT : TE_CRITIC_HID, 0, SH_FREE, SH_FREE);
         linear_cols(T_C2 + i, w->critic_w[1 + i], w->critic_b[1 + i], C, C);
     }
     if (NL > 32 || NC > 32) {
@@ -677,7 +770,7 @@ int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
     for (int i = 0; i < T_COUNT; ++i) {
         TcPass& p = prog.pass[i];
         p.w_off = (int32_t)wbytes;
-        wbytes += (size_t)p.k8 * p.nblk * p.n * 64;
+        wbytes += (size_t)p.k16 * p.nblk * p.n * 64;
         p.b_off = (int32_t)sfloats;
         sfloats += 2 * (size_t)p.nblk * p.n;
         ncols_total += (size_t)p.nblk * p.n;
@@ -685,6 +778,7 @@ int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
     prog.mob_bias_off = (int32_t)sfloats; sfloats += 128;
     prog.mob_y2_off = (int32_t)sfloats; sfloats += 4;
     prog.critic5_off = (int32_t)sfloats; sfloats += 68;
+    prog.post_off = (int32_t)sfloats; sfloats += 2 * T_COUNT;
     const size_t need = wbytes + sfloats * sizeof(float) + 256;
     if (ctx->tc_bytes < need) {
         HYPAD_CUDA_TRY(cudaDeviceSynchronize());
@@ -710,9 +804,12 @@ int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
     ctx->tc_small_off = ((wbytes + 255) / 256) * 256;
     for (int i = 0; i < T_COUNT; ++i) {
         const TcPass& p = prog.pass[i];
-        const int total = p.k8 * 8 * p.nblk * p.n;
-        pack_tc_kernel<<<(total + 255) / 256, 256, 0, stream>>>((const ColSrc*)ctx->workspace + start[i], p.k8, p.nblk, p.n,
-                                                               reinterpret_cast<float*>(ctx->tc_packed + p.w_off), small + p.b_off);
+        const int total = p.k16 * 16 * p.nblk * p.n;
+        float* scale = small + prog.post_off + 2 * i;
+        tc_wscale_kernel<<<1, 256, 0, stream>>>((const ColSrc*)ctx->workspace + start[i], p.nblk * p.n, p.in_shift, scale);
+        HYPAD_LAUNCH_CHECK();
+        pack_tc_kernel<<<(total + 255) / 256, 256, 0, stream>>>((const ColSrc*)ctx->workspace + start[i], p.k16, p.nblk, p.n,
+                                                               reinterpret_cast<__half*>(ctx->tc_packed + p.w_off), small + p.b_off, scale);
         HYPAD_LAUNCH_CHECK();
     }
     // Mobius bias / y2 / critic dense5 come from the FFMA context's packed buffer (already built by hypad_pack_weights)
