@@ -38,24 +38,32 @@ constexpr int TC_EPI_THREADS = 128 * TC_NSPLIT;
 constexpr int TC_THREADS = TC_EPI_THREADS + 64;
 constexpr int TC_PRODUCER_WARP = TC_EPI_THREADS / 32, TC_MMA_WARP = TC_PRODUCER_WARP + 1;
 constexpr int TC_PIECE_BYTES = 32768;     // one piece of the A buffer: 128 features x 128 rows x 2 B
-constexpr int TC_KSTAGE = 2;              // k-steps (of 16) per weight stage
-constexpr int TC_STAGE_BYTES = TC_KSTAGE * 8192;  // 32 k x 128 columns x (hi + lo) x 2 B
+constexpr int TC_ACT_BYTES = 2 * TC_PIECE_BYTES;  // hi + lo piece of one tile
+constexpr int TC_TILES = 2;               // tiles in flight per CTA (one in the tensor pipe, one in the epilogue warps)
+constexpr int TC_TILE_COLS = 256;         // TMEM columns per tile slot
+constexpr int TC_STAGE_BYTES = 16384;     // one weight stage: kstage k-steps of 16 k x n columns x (hi + lo) x 2 B
 constexpr int TC_NSLOT = 5;
 constexpr int TC_RED_BYTES = TC_NSPLIT * TC_M * 3 * 8;
 
-enum TcEpi : int32_t { TE_LSTM = 0, TE_Z, TE_LINEAR, TE_TANH, TE_MOB_R, TE_MOB_X, TE_CRITIC_HID, TE_CRITIC_OUT };
-enum TcPassIdx : int32_t { T_ENC = 0, T_Z, T_D0, T_L0, T_L1, T_D2, T_MR, T_MX, T_C1, T_C2, T_C3, T_C4, T_COUNT };
+enum TcEpi : int32_t { TE_LSTM_GI = 0, TE_LSTM_O, TE_Z, TE_LINEAR, TE_TANH, TE_MOB_R, TE_MOB_X, TE_CRITIC_HID, TE_CRITIC_OUT };
+// An LSTM layer is two passes over the same A operand: GI accumulates the cell-candidate and input gates of all units
+// as ONE N = 2 nu contraction (columns [0,nu) = g, [nu,2nu) = i), its epilogue leaves tanh(sigmoid(i) tanh(g)) in the i
+// columns; O accumulates the output gate over the g columns and its epilogue writes h.  That keeps a tile within 256
+// TMEM columns, so two tiles are in flight per CTA.
+enum TcPassIdx : int32_t {
+    T_ENC_GI = 0, T_ENC_O, T_Z, T_D0, T_L0_GI, T_L0_O, T_L1_GI, T_L1_O, T_D2, T_MR, T_MX, T_C1, T_C2, T_C3, T_C4, T_COUNT
+};
 
 struct TcPass {
     int32_t k16;     // K / 16
-    int32_t nblk;    // column blocks (3 for an LSTM layer: i | g | o)
-    int32_t n;       // columns per block, multiple of 16, <= 128
-    int32_t d_col;   // TMEM column of block 0 (block b at d_col + b*n)
-    int32_t w_off;   // byte offset of the packed weights: [nblk][k16]{hi,lo}[2 chunks][n][8] fp16
-    int32_t b_off;   // float offset of the biases: b1[nblk*n] then b2[nblk*n]
+    int32_t n;       // accumulator columns, multiple of 16, <= 256
+    int32_t d_col;   // TMEM column within the tile slot's 256
+    int32_t w_off;   // byte offset of the packed weights: [k16]{hi,lo}[2 chunks][n][8] fp16
+    int32_t b_off;   // float offset of the biases b[n]
     int32_t epi;     // TcEpi
     int32_t needs_x; // the A operand is the window itself
     int32_t in_shift;   // sa of this pass's A operand
+    int32_t kstage;     // k-steps per weight stage (<= 16 KB)
     float out_scale;    // 2^sa of the pass that consumes this pass's output
 };
 
@@ -324,19 +332,22 @@ __device__ void row_mobius_tc(uint32_t trow, int col0, int ncols, const float* _
 
 __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_constant__ TcParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* act = smem;                                   // 2 pieces x 64 KB
-    unsigned char* ring = smem + 2 * TC_PIECE_BYTES;             // TC_NSLOT x 8 KB
+    unsigned char* act_base = smem;                                    // TC_TILES x (hi + lo piece)
+    unsigned char* ring = smem + TC_TILES * TC_ACT_BYTES;              // TC_NSLOT weight stages
     double* red = reinterpret_cast<double*>(ring + TC_NSLOT * TC_STAGE_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(red) + TC_RED_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_NSLOT + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_NSLOT + 2 * TC_TILES);
     const uint32_t bar_full = s_u32(bars), bar_empty = s_u32(bars + TC_NSLOT);
-    const uint32_t bar_acc = s_u32(bars + 2 * TC_NSLOT), bar_a = s_u32(bars + 2 * TC_NSLOT + 1);
+    const uint32_t bar_acc = s_u32(bars + 2 * TC_NSLOT), bar_a = s_u32(bars + 2 * TC_NSLOT + TC_TILES);  // one per tile slot
 
     const TcProgram& prog = P.prog;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = prog.S, S16 = prog.S16;
     const int64_t ntiles = (P.n + TC_M - 1) / TC_M;
     const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t npairs = (my_tiles + TC_TILES - 1) / TC_TILES;
+    // Work order of every role: for each pair of tiles, for each pass, tile slot 0 then tile slot 1.  The MMA of one slot
+    // runs while the epilogue warps work on the other slot's accumulators.
 
     if (warp == TC_PRODUCER_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(512u));
@@ -347,8 +358,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
         }
-        mbar_init(bar_acc, 1);
-        mbar_init(bar_a, TC_EPI_THREADS);
+        for (int s = 0; s < TC_TILES; ++s) {
+            mbar_init(bar_acc + 8 * s, 1);
+            mbar_init(bar_a + 8 * s, TC_EPI_THREADS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::);
     }
     tc_fence_before();
@@ -359,29 +372,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
     if (warp == TC_PRODUCER_WARP) {
         // ===== weight producer (one lane) ==================================================================
         if (lane == 0) {
-            uint32_t it = 0;
+            uint32_t slot = 0, par = 1;  // waiting on parity 1 of a fresh barrier returns at once: the first lap is free
             bool ok = true;
             long long dbg_prod = 0;
-            for (int64_t t = 0; t < my_tiles && ok; ++t)
+            for (int64_t pr = 0; pr < npairs && ok; ++pr)
                 for (int p = 0; p < T_COUNT && ok; ++p) {
                     if (!((P.pass_mask >> p) & 1u)) continue;
                     const TcPass& ps = prog.pass[p];
-                    const unsigned char* src = P.wpacked + ps.w_off;
-                    // stages in (block, k-step pair) order -- the accumulator address changes only between blocks (a change
-                    // costs ~120 cycles of tensor-pipe drain, scripts/tc_mma_rate.py); the last pair of an odd layer holds one k-step
-                    for (int b = 0; b < ps.nblk && ok; ++b)
-                        for (int kp = 0; kp < ps.k16; kp += TC_KSTAGE, ++it) {
-                            const int kk = ps.k16 - kp < TC_KSTAGE ? ps.k16 - kp : TC_KSTAGE;
+                    for (int sl = 0; sl < TC_TILES && ok; ++sl) {
+                        if (pr * TC_TILES + sl >= my_tiles) continue;
+                        const unsigned char* src = P.wpacked + ps.w_off;
+                        for (int kp = 0; kp < ps.k16; kp += ps.kstage) {
+                            const int kk = ps.k16 - kp < ps.kstage ? ps.k16 - kp : ps.kstage;
                             const uint32_t bytes = (uint32_t)(kk * ps.n) * 64u;
-                            const uint32_t slot = it % TC_NSLOT, use = it / TC_NSLOT;
                             const long long c0 = P.debug ? clock64() : 0;
-                            if (use > 0) ok = mbar_wait(bar_empty + 8 * slot, (use - 1) & 1, P.error_flag);
+                            ok = mbar_wait(bar_empty + 8 * slot, par, P.error_flag);
                             if (P.debug) dbg_prod += clock64() - c0;
                             if (!ok) break;
                             mbar_expect_tx(bar_full + 8 * slot, bytes);
                             bulk_g2s(s_u32(ring + slot * TC_STAGE_BYTES), src, bytes, bar_full + 8 * slot);
                             src += bytes;
+                            if (++slot == TC_NSLOT) slot = 0, par ^= 1u;
                         }
+                    }
                 }
             if (P.debug && blockIdx.x == 0) P.debug[4] = dbg_prod;
         }
@@ -390,242 +403,269 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
         // The issuing thread is a scalar instruction stream next to the tensor pipe: whatever it executes between two
         // tcgen05.mma is hidden only while earlier MMAs are still queued.  So descriptors are additive (one IADD per
         // operand), and the full barrier of the NEXT stage is peeked right after the first k-step of the current one.
-        {
-            uint32_t slot = 0, par = 0, npass = 0;
-            bool ok = true, have = false;
-            const bool lead = elect_one();  // the one thread that issues every tcgen05.mma / commit of this CTA
-            long long dbg_a = 0, dbg_full = 0;
-            const bool dbg = P.debug != nullptr;
-            const uint32_t a_hi0 = ((s_u32(act) & 0x3FFFFu) >> 4) | (128u << 16);                    // LBO 2048 B
-            const uint32_t a_lo0 = ((s_u32(act + TC_PIECE_BYTES) & 0x3FFFFu) >> 4) | (128u << 16);
-            const uint32_t ring0 = (s_u32(ring) & 0x3FFFFu) >> 4;
-            auto desc64 = [](uint32_t lo32) { return ((uint64_t)0x4008u << 32) | lo32; };  // SBO 128 B, descriptor version 1
-            int64_t stages_left = 0;
-            for (int p = 0; p < T_COUNT; ++p)
-                if ((P.pass_mask >> p) & 1u) stages_left += (int64_t)prog.pass[p].nblk * ((prog.pass[p].k16 + TC_KSTAGE - 1) / TC_KSTAGE);
-            stages_left *= my_tiles;
-            for (int64_t t = 0; t < my_tiles && ok; ++t)
-                for (int p = 0; p < T_COUNT && ok; ++p) {
-                    if (!((P.pass_mask >> p) & 1u)) continue;
-                    const TcPass& ps = prog.pass[p];
+        uint32_t slot = 0, par = 0;
+        uint32_t a_par = 0;  // bit sl = parity of slot sl's next operand hand-over
+        bool ok = true, have = false;
+        const bool lead = elect_one();  // the one thread that issues every tcgen05.mma / commit of this CTA
+        long long dbg_a = 0, dbg_full = 0;
+        const bool dbg = P.debug != nullptr;
+        const uint32_t ring0 = (s_u32(ring) & 0x3FFFFu) >> 4;
+        auto desc64 = [](uint32_t lo32) { return ((uint64_t)0x4008u << 32) | lo32; };  // SBO 128 B, descriptor version 1
+        int64_t stages_left = 0;
+        for (int p = 0; p < T_COUNT; ++p)
+            if ((P.pass_mask >> p) & 1u) stages_left += (prog.pass[p].k16 + prog.pass[p].kstage - 1) / prog.pass[p].kstage;
+        stages_left *= my_tiles;
+        for (int64_t pr = 0; pr < npairs && ok; ++pr)
+            for (int p = 0; p < T_COUNT && ok; ++p) {
+                if (!((P.pass_mask >> p) & 1u)) continue;
+                const TcPass& ps = prog.pass[p];
+                const uint32_t idesc = idesc_f16(ps.n);
+                const uint32_t n = (uint32_t)ps.n;
+                const uint32_t w_lbo = n << 16;  // LBO = 16 n bytes: the two 8-k chunks of a k-step
+#pragma unroll
+                for (int sl = 0; sl < TC_TILES; ++sl) {
+                    if (pr * TC_TILES + sl >= my_tiles || !ok) continue;
+                    const uint32_t a_hi0 = ((s_u32(act_base + sl * TC_ACT_BYTES) & 0x3FFFFu) >> 4) | (128u << 16);  // LBO 2048 B
+                    const uint32_t a_lo0 = a_hi0 + (TC_PIECE_BYTES >> 4);
                     long long c0 = dbg ? clock64() : 0;
-                    ok = mbar_wait(bar_a, npass & 1, P.error_flag);  // A operand written, TMEM of the previous pass drained
+                    ok = mbar_wait(bar_a + 8 * sl, (a_par >> sl) & 1u, P.error_flag);  // A operand written, TMEM of this slot drained
+                    a_par ^= 1u << sl;
                     if (dbg) dbg_a += clock64() - c0;
-                    if (dbg && blockIdx.x == 0 && lead) P.debug[40 + 5 * p + 2] = clock64();
                     if (!ok) break;
                     tc_fence_after();
-                    const uint32_t idesc = idesc_f16(ps.n);
-                    const uint32_t n = (uint32_t)ps.n;
-                    const uint32_t w_lbo = n << 16;  // LBO = 16 n bytes: the two 4-k chunks of a k-step
-                    for (int b = 0; b < ps.nblk && ok; ++b) {
-                        const uint32_t d = tmem + (uint32_t)(ps.d_col + b * ps.n);
-                        for (int kp = 0; kp < ps.k16; kp += TC_KSTAGE) {
-                            const int kk = ps.k16 - kp < TC_KSTAGE ? ps.k16 - kp : TC_KSTAGE;
-                            if (!have) {
-                                if (dbg) c0 = clock64();
-                                ok = mbar_wait(bar_full + 8 * slot, par, P.error_flag);
-                                if (dbg) dbg_full += clock64() - c0;
-                                if (!ok) break;
-                            }
-                            have = false;
-                            --stages_left;
-                            const uint32_t w0 = (ring0 + slot * (TC_STAGE_BYTES >> 4)) | w_lbo;
-                            const uint32_t nslot = slot + 1 == TC_NSLOT ? 0 : slot + 1, npar = slot + 1 == TC_NSLOT ? par ^ 1u : par;
-                            if (lead) {
-                                const uint32_t ka = (uint32_t)kp * 256u;  // 4096 B per k-step (16 features) of A
-                                mma_f16(d, desc64(a_lo0 + ka), desc64(w0), idesc, kp > 0);  // small terms first
-                                mma_f16(d, desc64(a_hi0 + ka), desc64(w0 + 2 * n), idesc, 1);
-                                mma_f16(d, desc64(a_hi0 + ka), desc64(w0), idesc, 1);
-                            }
-                            if (stages_left > 0) {
-                                // non-blocking peek, in the shadow of the MMAs just queued
-                                uint32_t done;
-                                asm volatile(
-                                    "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                                    : "=r"(done)
-                                    : "r"(bar_full + 8 * nslot), "r"(npar)
-                                    : "memory");
-                                have = done != 0;
-                            }
-                            if (lead) {
-                                for (int j = 1; j < kk; ++j) {
-                                    const uint32_t ka = (uint32_t)(kp + j) * 256u, wj = w0 + (uint32_t)j * 4u * n;
-                                    mma_f16(d, desc64(a_lo0 + ka), desc64(wj), idesc, 1);
-                                    mma_f16(d, desc64(a_hi0 + ka), desc64(wj + 2 * n), idesc, 1);
-                                    mma_f16(d, desc64(a_hi0 + ka), desc64(wj), idesc, 1);
-                                }
-                                mma_commit(bar_empty + 8 * slot);  // slot is free once these MMAs have read it
-                            }
-                            slot = nslot;
-                            par = npar;
+                    const uint32_t d = tmem + (uint32_t)(sl * TC_TILE_COLS + ps.d_col);
+                    for (int kp = 0; kp < ps.k16; kp += ps.kstage) {
+                        const int kk = ps.k16 - kp < ps.kstage ? ps.k16 - kp : ps.kstage;
+                        if (!have) {
+                            if (dbg) c0 = clock64();
+                            ok = mbar_wait(bar_full + 8 * slot, par, P.error_flag);
+                            if (dbg) dbg_full += clock64() - c0;
+                            if (!ok) break;
                         }
+                        have = false;
+                        --stages_left;
+                        const uint32_t w0 = (ring0 + slot * (TC_STAGE_BYTES >> 4)) | w_lbo;
+                        const uint32_t nslot = slot + 1 == TC_NSLOT ? 0 : slot + 1, npar = slot + 1 == TC_NSLOT ? par ^ 1u : par;
+                        if (lead) {
+                            const uint32_t ka = (uint32_t)kp * 256u;  // 4096 B per k-step (16 features) of A
+                            mma_f16(d, desc64(a_lo0 + ka), desc64(w0), idesc, kp > 0);  // small terms first
+                            mma_f16(d, desc64(a_hi0 + ka), desc64(w0 + 2 * n), idesc, 1);
+                            mma_f16(d, desc64(a_hi0 + ka), desc64(w0), idesc, 1);
+                        }
+                        if (stages_left > 0) {
+                            // non-blocking peek, in the shadow of the MMAs just queued
+                            uint32_t done;
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                                : "=r"(done)
+                                : "r"(bar_full + 8 * nslot), "r"(npar)
+                                : "memory");
+                            have = done != 0;
+                        }
+                        if (lead) {
+                            for (int j = 1; j < kk; ++j) {
+                                const uint32_t ka = (uint32_t)(kp + j) * 256u, wj = w0 + (uint32_t)j * 4u * n;
+                                mma_f16(d, desc64(a_lo0 + ka), desc64(wj), idesc, 1);
+                                mma_f16(d, desc64(a_hi0 + ka), desc64(wj + 2 * n), idesc, 1);
+                                mma_f16(d, desc64(a_hi0 + ka), desc64(wj), idesc, 1);
+                            }
+                            mma_commit(bar_empty + 8 * slot);  // slot is free once these MMAs have read it
+                        }
+                        slot = nslot;
+                        par = npar;
                     }
-                    if (lead) mma_commit(bar_acc);  // accumulators of this pass complete
-                    if (dbg && blockIdx.x == 0 && lead) P.debug[40 + 5 * p + 3] = clock64();
-                    ++npass;
+                    if (lead) mma_commit(bar_acc + 8 * sl);  // accumulators of this pass and slot complete
                 }
-            if (dbg && blockIdx.x == 0 && lane == 0) {
-                P.debug[2] = dbg_a;
-                P.debug[3] = dbg_full;
             }
+        if (dbg && blockIdx.x == 0 && lane == 0) {
+            P.debug[2] = dbg_a;
+            P.debug[3] = dbg_full;
         }
     } else {
         // ===== epilogue warps ==============================================================================
         const int quarter = warp & 3, split = warp >> 2;
         const int r = quarter * 32 + lane;                         // TMEM lane = window within the tile
-        const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
         const float* __restrict__ small = P.small;
-        uint32_t npass = 0;
+        uint32_t acc_par = 0;   // bit sl = parity of slot sl's next accumulator hand-over
+        uint32_t has_x = 0;     // bit sl = slot sl's A operand buffer currently holds the window tile
         bool ok = true;
         long long dbg_wait = 0, dbg_xload = 0;
         const bool dbg = P.debug != nullptr;
         const long long dbg_t0 = dbg ? clock64() : 0;
-        for (int64_t t = 0; t < my_tiles && ok; ++t) {
+        int p_first = 0;
+        while (p_first < T_COUNT && !((P.pass_mask >> p_first) & 1u)) ++p_first;
+
+        // makes the A operand of (local tile t, pass p) available in slot sl, then hands the slot to the MMA warp
+        auto hand_over = [&](int sl, int64_t t, int p) {
+            const TcPass& ps = prog.pass[p];
+            unsigned char* act = act_base + sl * TC_ACT_BYTES;
             const int64_t w0 = (blockIdx.x + t * gridDim.x) * TC_M;
-            const bool live = w0 + r < P.n;
-            bool act_has_x = false;
+            const long long cx0 = dbg ? clock64() : 0;
+            const float sc = __int_as_float((127 + ps.in_shift) << 23);
+            if (ps.needs_x && !((has_x >> sl) & 1u)) {
+                epi_bar();  // every column split of every row is done writing the previous layer's output
+                if (P.x_is_f64) load_rows_to_act<double>(act, (const double*)P.x, w0, P.n, P.row_stride, S, S16, tid, sc, P.error_flag);
+                else load_rows_to_act<float>(act, (const float*)P.x, w0, P.n, P.row_stride, S, S16, tid, sc, P.error_flag);
+                has_x |= 1u << sl;
+            } else if (p == T_D0 && !(P.stages & HYPAD_STAGE_ENCODER)) {
+                epi_bar();
+                load_rows_to_act<float>(act, P.z_in, w0, P.n, prog.latent, prog.latent, 16 * ps.k16, tid, sc, P.error_flag);
+            }
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar_a + 8 * sl);
+            if (dbg) dbg_xload += clock64() - cx0;
+        };
+        for (int sl = 0; sl < TC_TILES; ++sl)
+            if (sl < my_tiles && p_first < T_COUNT) hand_over(sl, sl, p_first);
+
+        for (int64_t pr = 0; pr < npairs && ok; ++pr)
             for (int p = 0; p < T_COUNT && ok; ++p) {
                 if (!((P.pass_mask >> p) & 1u)) continue;
                 const TcPass& ps = prog.pass[p];
-                // ---- make the A operand of pass p available, then hand over to the MMA warp -----------------
-                const long long cx0 = dbg ? clock64() : 0;
-                if (ps.needs_x && !act_has_x) {
-                    epi_bar();  // every column split of every row is done writing the previous layer's output
-                    const float xs = __int_as_float((127 + ps.in_shift) << 23);
-                    if (P.x_is_f64) load_rows_to_act<double>(act, (const double*)P.x, w0, P.n, P.row_stride, S, S16, tid, xs, P.error_flag);
-                    else load_rows_to_act<float>(act, (const float*)P.x, w0, P.n, P.row_stride, S, S16, tid, xs, P.error_flag);
-                    act_has_x = true;
-                } else if (p == T_D0 && !(P.stages & HYPAD_STAGE_ENCODER)) {
-                    epi_bar();
-                    load_rows_to_act<float>(act, P.z_in, w0, P.n, prog.latent, prog.latent, 16 * ps.k16, tid,
-                                            __int_as_float((127 + ps.in_shift) << 23), P.error_flag);
-                }
-                fence_async_smem();
-                tc_fence_before();
-                mbar_arrive(bar_a);
-                // ---- wait for the accumulators --------------------------------------------------------------
-                const long long cw0 = dbg ? clock64() : 0;
-                if (dbg && blockIdx.x == 0 && lane == 0) P.debug[104 + 16 * p + warp] = cw0;  // per-warp arrival time
-                dbg_xload += cw0 - cx0;
-                ok = mbar_wait(bar_acc, npass & 1, P.error_flag);
-                const long long ce0 = dbg ? clock64() : 0;
-                if (dbg) dbg_wait += ce0 - cw0;
-                if (dbg && blockIdx.x == 0 && tid == 0) P.debug[8 + p] += ce0 - cw0, P.debug[40 + 5 * p + 4] = ce0;
-                ++npass;
-                if (!ok) break;
-                tc_fence_after();
                 const float* __restrict__ b1 = small + ps.b_off;
                 const float post = small[prog.post_off + 2 * p + 1];  // 2^-(sa+sw): exact, folded into the bias FMA
-                const int cbeg = 8 * split, cend = ps.n, cstep = 8 * TC_NSPLIT;
-                if (ps.epi == TE_LSTM) {
-                    for (int c = cbeg; c < cend; c += cstep) {
-                        float gi[8], gg[8], go[8], h[8], bi[8], bg[8], bo[8];
-                        tmem_ld8(trow + ps.d_col + c, gi);
-                        tmem_ld8(trow + ps.d_col + ps.n + c, gg);
-                        tmem_ld8(trow + ps.d_col + 2 * ps.n + c, go);
-                        ldg8(b1 + c, bi);
-                        ldg8(b1 + ps.n + c, bg);
-                        ldg8(b1 + 2 * ps.n + c, bo);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float vi = fmaf(gi[i], post, bi[i]);
-                            const float vg = fmaf(gg[i], post, bg[i]);
-                            const float vo = fmaf(go[i], post, bo[i]);
-                            const float cc = __fmul_rn(sigmoid_tc(vi), tanhf(vg));
-                            h[i] = __fmul_rn(sigmoid_tc(vo), tanhf(cc));
-                        }
-                        store_act8(act, r, c, h, ps.out_scale);
-                    }
-                    act_has_x = false;
-                } else if (ps.epi == TE_Z || ps.epi == TE_LINEAR || ps.epi == TE_TANH || ps.epi == TE_CRITIC_HID || ps.epi == TE_CRITIC_OUT) {
-                    float* gout = nullptr;
-                    int gw = 0;
-                    if (ps.epi == TE_Z && P.out.z && live) gout = P.out.z + (w0 + r) * prog.latent, gw = prog.latent;
-                    if (ps.epi == TE_TANH && P.out.eucl && live) gout = P.out.eucl + (w0 + r) * (int64_t)S, gw = S;
-                    if (ps.epi == TE_CRITIC_OUT) {
-                        // dense4 + LeakyReLU, then Linear(latent_c -> 1) as one ascending-k FFMA chain (split 0 only)
-                        if (split == 0) {
-                            const float* w5 = small + prog.critic5_off;
-                            float fdot = 0.0f;
-                            for (int c = 0; c < ((prog.latent_c + 7) & ~7); c += 8) {
-                                float v[8];
-                                tmem_ld8(trow + ps.d_col + c, v);
-                                tmem_ld_wait();
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    float tv = fmaf(v[i], post, b1[c + i]);
-                                    tv = tv > 0.0f ? tv : __fmul_rn(tv, 0.2f);
-                                    if (c + i < prog.latent_c) fdot = fmaf(tv, w5[c + i], fdot);
-                                }
-                            }
-                            if (live) P.out.critic[w0 + r] = __fadd_rn(fdot, w5[prog.latent_c]);
-                        }
-                    } else {
-                        for (int c = cbeg; c < cend; c += cstep) {
-                            float v[8], bv[8];
-                            tmem_ld8(trow + ps.d_col + c, v);
-                            ldg8(b1 + c, bv);
+                const int cbeg = 8 * split, cstep = 8 * TC_NSPLIT;
+#pragma unroll 1
+                for (int sl = 0; sl < TC_TILES; ++sl) {
+                    const int64_t t = pr * TC_TILES + sl;
+                    if (t >= my_tiles) continue;
+                    unsigned char* act = act_base + sl * TC_ACT_BYTES;
+                    const int64_t w0 = (blockIdx.x + t * gridDim.x) * TC_M;
+                    const bool live = w0 + r < P.n;
+                    const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(sl * TC_TILE_COLS);
+                    // ---- wait for the accumulators --------------------------------------------------------------
+                    const long long cw0 = dbg ? clock64() : 0;
+                    ok = mbar_wait(bar_acc + 8 * sl, (acc_par >> sl) & 1u, P.error_flag);
+                    acc_par ^= 1u << sl;
+                    const long long ce0 = dbg ? clock64() : 0;
+                    if (dbg) dbg_wait += ce0 - cw0;
+                    if (dbg && blockIdx.x == 0 && tid == 0) P.debug[8 + p] += ce0 - cw0;
+                    if (!ok) break;
+                    tc_fence_after();
+                    if (ps.epi == TE_LSTM_GI) {
+                        const int nu = ps.n >> 1;
+                        for (int c = cbeg; c < nu; c += cstep) {
+                            float gg[8], gi[8], bg[8], bi[8], tc[8];
+                            tmem_ld8(trow + ps.d_col + c, gg);
+                            tmem_ld8(trow + ps.d_col + nu + c, gi);
+                            ldg8(b1 + c, bg);
+                            ldg8(b1 + nu + c, bi);
                             tmem_ld_wait();
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                float tv = fmaf(v[i], post, bv[i]);
-                                if (ps.epi == TE_TANH) tv = tanhf(tv);
-                                else if (ps.epi == TE_CRITIC_HID) tv = tv > 0.0f ? tv : __fmul_rn(tv, 0.2f);
-                                v[i] = tv;
+                                const float vg = fmaf(gg[i], post, bg[i]);
+                                const float vi = fmaf(gi[i], post, bi[i]);
+                                tc[i] = tanhf(__fmul_rn(sigmoid_tc(vi), tanhf(vg)));
                             }
-                            if (ps.epi != TE_TANH) check_range8(v, ps.out_scale, P.error_flag);
-                            store_act8(act, r, c, v, ps.out_scale);
-                            if (gout) {
+                            tmem_st8(trow + ps.d_col + nu + c, tc);
+                        }
+                        tmem_st_wait();
+                    } else if (ps.epi == TE_LSTM_O) {
+                        for (int c = cbeg; c < ps.n; c += cstep) {
+                            float go[8], tc[8], bo[8], h[8];
+                            tmem_ld8(trow + ps.d_col + c, go);
+                            tmem_ld8(trow + ps.d_col + ps.n + c, tc);
+                            ldg8(b1 + c, bo);
+                            tmem_ld_wait();
 #pragma unroll
-                                for (int i = 0; i < 8; ++i)
-                                    if (c + i < gw) gout[c + i] = v[i];
+                            for (int i = 0; i < 8; ++i) h[i] = __fmul_rn(sigmoid_tc(fmaf(go[i], post, bo[i])), tc[i]);
+                            store_act8(act, r, c, h, ps.out_scale);
+                        }
+                        has_x &= ~(1u << sl);
+                    } else if (ps.epi == TE_Z || ps.epi == TE_LINEAR || ps.epi == TE_TANH || ps.epi == TE_CRITIC_HID || ps.epi == TE_CRITIC_OUT) {
+                        float* gout = nullptr;
+                        int gw = 0;
+                        if (ps.epi == TE_Z && P.out.z && live) gout = P.out.z + (w0 + r) * prog.latent, gw = prog.latent;
+                        if (ps.epi == TE_TANH && P.out.eucl && live) gout = P.out.eucl + (w0 + r) * (int64_t)S, gw = S;
+                        if (ps.epi == TE_CRITIC_OUT) {
+                            // dense4 + LeakyReLU, then Linear(latent_c -> 1) as one ascending-k FFMA chain (split 0 only)
+                            if (split == 0) {
+                                const float* w5 = small + prog.critic5_off;
+                                float fdot = 0.0f;
+                                for (int c = 0; c < ((prog.latent_c + 7) & ~7); c += 8) {
+                                    float v[8];
+                                    tmem_ld8(trow + ps.d_col + c, v);
+                                    tmem_ld_wait();
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        float tv = fmaf(v[i], post, b1[c + i]);
+                                        tv = tv > 0.0f ? tv : __fmul_rn(tv, 0.2f);
+                                        if (c + i < prog.latent_c) fdot = fmaf(tv, w5[c + i], fdot);
+                                    }
+                                }
+                                if (live) P.out.critic[w0 + r] = __fadd_rn(fdot, w5[prog.latent_c]);
+                            }
+                        } else {
+                            for (int c = cbeg; c < ps.n; c += cstep) {
+                                float v[8], bv[8];
+                                tmem_ld8(trow + ps.d_col + c, v);
+                                ldg8(b1 + c, bv);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    float tv = fmaf(v[i], post, bv[i]);
+                                    if (ps.epi == TE_TANH) tv = tanhf(tv);
+                                    else if (ps.epi == TE_CRITIC_HID) tv = tv > 0.0f ? tv : __fmul_rn(tv, 0.2f);
+                                    v[i] = tv;
+                                }
+                                if (ps.epi != TE_TANH) check_range8(v, ps.out_scale, P.error_flag);
+                                store_act8(act, r, c, v, ps.out_scale);
+                                if (gout) {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i)
+                                        if (c + i < gw) gout[c + i] = v[i];
+                                }
                             }
                         }
+                        has_x &= ~(1u << sl);
+                    } else if (ps.epi == TE_MOB_R) {
+                        float* gout = (P.out.hyper && live) ? P.out.hyper + (w0 + r) * (int64_t)S : nullptr;
+                        row_mobius_tc(trow, ps.d_col, ps.n, small + prog.mob_bias_off, small[prog.mob_y2_off], red, r, split, gout, P.out.hyper != nullptr, S, post);
+                    } else if (ps.epi == TE_MOB_X) {
+                        float* gout = (P.out.hyper_x && live) ? P.out.hyper_x + (w0 + r) * (int64_t)S : nullptr;
+                        row_mobius_tc(trow, ps.d_col, ps.n, small + prog.mob_bias_off, small[prog.mob_y2_off], red, r, split, gout, P.out.hyper_x != nullptr, S, post);
                     }
-                    act_has_x = false;
-                } else if (ps.epi == TE_MOB_R) {
-                    float* gout = (P.out.hyper && live) ? P.out.hyper + (w0 + r) * (int64_t)S : nullptr;
-                    row_mobius_tc(trow, ps.d_col, ps.n, small + prog.mob_bias_off, small[prog.mob_y2_off], red, r, split, gout, P.out.hyper != nullptr, S, post);
-                } else if (ps.epi == TE_MOB_X) {
-                    float* gout = (P.out.hyper_x && live) ? P.out.hyper_x + (w0 + r) * (int64_t)S : nullptr;
-                    row_mobius_tc(trow, ps.d_col, ps.n, small + prog.mob_bias_off, small[prog.mob_y2_off], red, r, split, gout, P.out.hyper_x != nullptr, S, post);
-                }
-                // ---- row statistics once both hyperbolic points are in TMEM ---------------------------------
-                const bool last_hyp = (p == T_MX) || (p == T_MR && !((P.pass_mask >> T_MX) & 1u));
-                if (P.want_rowstats && last_hyp) {
-                    const TcPass& pr = prog.pass[T_MR];
-                    const bool both = P.out.rec != nullptr;
-                    double s[3] = {0.0, 0.0, 0.0};
-                    for (int c = 8 * split; c < pr.n; c += 8 * TC_NSPLIT) {
-                        float h[8], hx[8];
-                        tmem_ld8(trow + pr.d_col + c, h);
-                        if (both) tmem_ld8(trow + prog.pass[T_MX].d_col + c, hx);
-                        tmem_ld_wait();
+                    // ---- row statistics once both hyperbolic points are in TMEM ---------------------------------
+                    const bool last_hyp = (p == T_MX) || (p == T_MR && !((P.pass_mask >> T_MX) & 1u));
+                    if (P.want_rowstats && last_hyp) {
+                        const TcPass& pm = prog.pass[T_MR];
+                        const bool both = P.out.rec != nullptr;
+                        double s[3] = {0.0, 0.0, 0.0};
+                        for (int c = 8 * split; c < pm.n; c += 8 * TC_NSPLIT) {
+                            float h[8], hx[8];
+                            tmem_ld8(trow + pm.d_col + c, h);
+                            if (both) tmem_ld8(trow + prog.pass[T_MX].d_col + c, hx);
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            s[2] += (double)__fmul_rn(h[i], h[i]);
+                            for (int i = 0; i < 8; ++i) {
+                                s[2] += (double)__fmul_rn(h[i], h[i]);
+                                if (both) {
+                                    const float d = __fsub_rn(hx[i], h[i]);
+                                    s[0] += (double)__fmul_rn(d, d);
+                                    s[1] += (double)__fmul_rn(hx[i], hx[i]);
+                                }
+                            }
+                        }
+                        row_allreduce_tc<3>(s, red, r, split);
+                        if (split == 0 && live) {
+                            const float sqdist = (float)s[0], squnorm = (float)s[1], sqvnorm = (float)s[2];
                             if (both) {
-                                const float d = __fsub_rn(hx[i], h[i]);
-                                s[0] += (double)__fmul_rn(d, d);
-                                s[1] += (double)__fmul_rn(hx[i], hx[i]);
+                                const float tt = __fdiv_rn(__fmul_rn(2.0f, sqdist), __fmul_rn(__fsub_rn(1.0f, squnorm), __fsub_rn(1.0f, sqvnorm)));
+                                const float xt = __fadd_rn(__fadd_rn(1.0f, tt), 1e-7f);
+                                P.out.rec[w0 + r] = (float)acosh((double)xt);
                             }
+                            if (P.out.unorm) P.out.unorm[w0 + r] = sqrtf(sqvnorm);
                         }
                     }
-                    row_allreduce_tc<3>(s, red, r, split);
-                    if (split == 0 && live) {
-                        const float sqdist = (float)s[0], squnorm = (float)s[1], sqvnorm = (float)s[2];
-                        if (both) {
-                            const float tt = __fdiv_rn(__fmul_rn(2.0f, sqdist), __fmul_rn(__fsub_rn(1.0f, squnorm), __fsub_rn(1.0f, sqvnorm)));
-                            const float xt = __fadd_rn(__fadd_rn(1.0f, tt), 1e-7f);
-                            P.out.rec[w0 + r] = (float)acosh((double)xt);
-                        }
-                        if (P.out.unorm) P.out.unorm[w0 + r] = sqrtf(sqvnorm);
-                    }
+                    if (dbg && blockIdx.x == 0 && tid == 0) P.debug[24 + p] += clock64() - ce0;
+                    // ---- next step of this slot: the following pass of the tile, or the first pass of the slot's next tile
+                    int pn = p + 1;
+                    while (pn < T_COUNT && !((P.pass_mask >> pn) & 1u)) ++pn;
+                    if (pn < T_COUNT) hand_over(sl, t, pn);
+                    else if (t + TC_TILES < my_tiles) hand_over(sl, t + TC_TILES, p_first);
                 }
-                if (dbg && blockIdx.x == 0 && tid == 0) P.debug[24 + p] += clock64() - ce0;
             }
-        }
         if (dbg && blockIdx.x == 0 && tid == 0) {
             P.debug[0] = clock64() - dbg_t0;
             P.debug[1] = dbg_wait;
@@ -703,7 +743,7 @@ static inline int round8i(int v) { return (v + 7) / 8 * 8; }
 static inline int round16i(int v) { return (v + 15) / 16 * 16; }
 
 size_t forward_tc_smem_bytes() {
-    return 2 * (size_t)TC_PIECE_BYTES + (size_t)TC_NSLOT * TC_STAGE_BYTES + TC_RED_BYTES + (2 * TC_NSLOT + 2) * 8 + 16;
+    return (size_t)TC_TILES * TC_ACT_BYTES + (size_t)TC_NSLOT * TC_STAGE_BYTES + TC_RED_BYTES + (2 * TC_NSLOT + 2 * TC_TILES) * 8 + 16;
 }
 
 // Builds the tensor-core program and packs the weights (called from hypad_pack_weights).
@@ -717,11 +757,13 @@ int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
     std::vector<std::vector<ColSrc>> cols(T_COUNT);
     // in_shift = sa of the pass's A operand: 10 for the window, 11 for activations bounded by 1, 8 for unbounded ones
     const int SH_X = 10, SH_UNIT = 11, SH_FREE = 8;
-    auto set_pass = [&](int idx, int K, int nblk, int n, int d_col, int epi, int needs_x, int in_shift, int consumer_shift) {
+    auto set_pass = [&](int idx, int K, int n, int d_col, int epi, int needs_x, int in_shift, int consumer_shift) {
         TcPass& p = prog.pass[idx];
-        p.k16 = round16i(K) / 16; p.nblk = nblk; p.n = n; p.d_col = d_col; p.epi = epi; p.needs_x = needs_x;
+        p.k16 = round16i(K) / 16; p.n = n; p.d_col = d_col; p.epi = epi; p.needs_x = needs_x;
         p.in_shift = in_shift; p.out_scale = ldexpf(1.0f, consumer_shift);
-        cols[idx].assign((size_t)nblk * n, ColSrc{});
+        p.kstage = TC_STAGE_BYTES / (n * 64);
+        if (p.kstage > p.k16) p.kstage = p.k16;
+        cols[idx].assign((size_t)n, ColSrc{});
     };
     auto linear_cols = [&](int idx, const float* W, const float* b, int rows, int K) {
         for (int c = 0; c < rows; ++c) {
@@ -729,40 +771,45 @@ int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
             s.w = W; s.row = c; s.K = K; s.b1 = b; s.bidx = c;
         }
     };
-    auto lstm_cols = [&](int idx, int H, int n_units, const float* const* Wd, const float* const* bih, const float* const* bhh, int K) {
-        const int n = prog.pass[idx].n;
-        const int gate_row[3] = {0, 2 * H, 3 * H};
+    // torch gate order in weight_ih: i | f | g | o (f is dead: c0 = 0).  GI pass: columns [0,nu) = g, [nu,2nu) = i.
+    auto lstm_cols = [&](int idx_gi, int idx_o, int H, int n_units, const float* const* Wd, const float* const* bih, const float* const* bhh, int K) {
+        const int nu = prog.pass[idx_o].n;
         for (int u = 0; u < n_units; ++u) {
             const int dir = u / H, j = u % H;
+            const int rows[3] = {2 * H + j, j, 3 * H + j};  // g, i, o
+            ColSrc* dst[3] = {&cols[idx_gi][u], &cols[idx_gi][(size_t)nu + u], &cols[idx_o][u]};
             for (int g = 0; g < 3; ++g) {
-                ColSrc& s = cols[idx][(size_t)g * n + u];
-                s.w = Wd[dir]; s.row = gate_row[g] + j; s.K = K; s.b1 = bih[dir]; s.b2 = bhh[dir]; s.bidx = gate_row[g] + j;
+                ColSrc& s = *dst[g];
+                s.w = Wd[dir]; s.row = rows[g]; s.K = K; s.b1 = bih[dir]; s.b2 = bhh[dir]; s.bidx = rows[g];
             }
         }
     };
-    set_pass(T_ENC, S, 3, 112, 0, TE_LSTM, 1, SH_X, SH_UNIT);
-    lstm_cols(T_ENC, 50, 100, w->enc_w_ih, w->enc_b_ih, w->enc_b_hh, S);
-    set_pass(T_Z, 100, 1, NL, 0, TE_Z, 0, SH_UNIT, SH_FREE);
+    set_pass(T_ENC_GI, S, 224, 0, TE_LSTM_GI, 1, SH_X, 0);
+    set_pass(T_ENC_O, S, 112, 0, TE_LSTM_O, 1, SH_X, SH_UNIT);
+    lstm_cols(T_ENC_GI, T_ENC_O, 50, 100, w->enc_w_ih, w->enc_b_ih, w->enc_b_hh, S);
+    set_pass(T_Z, 100, NL, 0, TE_Z, 0, SH_UNIT, SH_FREE);
     linear_cols(T_Z, w->enc_dense_w, w->enc_dense_b, L, 100);
-    set_pass(T_D0, L, 1, 64, 0, TE_LINEAR, 0, SH_FREE, SH_FREE);
+    set_pass(T_D0, L, 64, 0, TE_LINEAR, 0, SH_FREE, SH_FREE);
     linear_cols(T_D0, w->dec_dense1_w, w->dec_dense1_b, 50, L);
-    set_pass(T_L0, 50, 3, 128, 0, TE_LSTM, 0, SH_FREE, SH_UNIT);
-    lstm_cols(T_L0, 64, 128, w->dec_w_ih[0], w->dec_b_ih[0], w->dec_b_hh[0], 50);
-    set_pass(T_L1, 128, 3, 128, 0, TE_LSTM, 0, SH_UNIT, SH_UNIT);
-    lstm_cols(T_L1, 64, 128, w->dec_w_ih[1], w->dec_b_ih[1], w->dec_b_hh[1], 128);
-    set_pass(T_D2, 128, 1, NS, 0, TE_TANH, 0, SH_UNIT, SH_UNIT);
+    set_pass(T_L0_GI, 50, 256, 0, TE_LSTM_GI, 0, SH_FREE, 0);
+    set_pass(T_L0_O, 50, 128, 0, TE_LSTM_O, 0, SH_FREE, SH_UNIT);
+    lstm_cols(T_L0_GI, T_L0_O, 64, 128, w->dec_w_ih[0], w->dec_b_ih[0], w->dec_b_hh[0], 50);
+    set_pass(T_L1_GI, 128, 256, 0, TE_LSTM_GI, 0, SH_UNIT, 0);
+    set_pass(T_L1_O, 128, 128, 0, TE_LSTM_O, 0, SH_UNIT, SH_UNIT);
+    lstm_cols(T_L1_GI, T_L1_O, 64, 128, w->dec_w_ih[1], w->dec_b_ih[1], w->dec_b_hh[1], 128);
+    set_pass(T_D2, 128, NS, 0, TE_TANH, 0, SH_UNIT, SH_UNIT);
     linear_cols(T_D2, w->dec_dense2_w, w->dec_dense2_b, S, 128);
-    set_pass(T_MR, S, 1, NS, 384, TE_MOB_R, 0, SH_UNIT, 0);
+    set_pass(T_MR, S, NS, 0, TE_MOB_R, 0, SH_UNIT, 0);  // stays in columns [0, NS) until the row statistics after T_MX
     if (hyp) linear_cols(T_MR, w->mobius_w, nullptr, S, S);
-    set_pass(T_MX, S, 1, NS, 0, TE_MOB_X, 1, SH_X, 0);
+    set_pass(T_MX, S, NS, 128, TE_MOB_X, 1, SH_X, 0);
     if (hyp) linear_cols(T_MX, w->mobius_w, nullptr, S, S);
-    set_pass(T_C1, S, 1, NC, 0, TE_CRITIC_HID, 1, SH_X, SH_FREE);
+    set_pass(T_C1, S, NC, 0, TE_CRITIC_HID, 1, SH_X, SH_FREE);
     linear_cols(T_C1, w->critic_w[0], w->critic_b[0], C, S);
     for (int i = 0; i < 3; ++i) {
-        set_pass(T_C2 + i, C, 1, NC, 0, i == 2 ? TE_CRITIC_OUT : TE_CRITIC_HID, 0, SH_FREE, SH_FREE);
+        set_pass(T_C2 + i, C, NC, 0, i == 2 ? TE_CRITIC_OUT : TE_CRITIC_HID, 0, SH_FREE, SH_FREE);
         linear_cols(T_C2 + i, w->critic_w[1 + i], w->critic_b[1 + i], C, C);
     }
-    if (NL > 32 || NC > 32) {
+    if (NL > 32 || NC > 32 || NS > 128) {
         set_error("tensor-core path: latent_dim / critic_dim above 32 not supported (got %d / %d)", L, C);
         return HYPAD_EINVAL;
     }
@@ -770,10 +817,10 @@ int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
     for (int i = 0; i < T_COUNT; ++i) {
         TcPass& p = prog.pass[i];
         p.w_off = (int32_t)wbytes;
-        wbytes += (size_t)p.k16 * p.nblk * p.n * 64;
+        wbytes += (size_t)p.k16 * p.n * 64;
         p.b_off = (int32_t)sfloats;
-        sfloats += 2 * (size_t)p.nblk * p.n;
-        ncols_total += (size_t)p.nblk * p.n;
+        sfloats += 2 * (size_t)p.n;
+        ncols_total += (size_t)p.n;
     }
     prog.mob_bias_off = (int32_t)sfloats; sfloats += 128;
     prog.mob_y2_off = (int32_t)sfloats; sfloats += 4;
@@ -804,11 +851,11 @@ int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
     ctx->tc_small_off = ((wbytes + 255) / 256) * 256;
     for (int i = 0; i < T_COUNT; ++i) {
         const TcPass& p = prog.pass[i];
-        const int total = p.k16 * 16 * p.nblk * p.n;
+        const int total = p.k16 * 16 * p.n;
         float* scale = small + prog.post_off + 2 * i;
-        tc_wscale_kernel<<<1, 256, 0, stream>>>((const ColSrc*)ctx->workspace + start[i], p.nblk * p.n, p.in_shift, scale);
+        tc_wscale_kernel<<<1, 256, 0, stream>>>((const ColSrc*)ctx->workspace + start[i], p.n, p.in_shift, scale);
         HYPAD_LAUNCH_CHECK();
-        pack_tc_kernel<<<(total + 255) / 256, 256, 0, stream>>>((const ColSrc*)ctx->workspace + start[i], p.k16, p.nblk, p.n,
+        pack_tc_kernel<<<(total + 255) / 256, 256, 0, stream>>>((const ColSrc*)ctx->workspace + start[i], p.k16, 1, p.n,
                                                                reinterpret_cast<__half*>(ctx->tc_packed + p.w_off), small + p.b_off, scale);
         HYPAD_LAUNCH_CHECK();
     }
@@ -836,9 +883,9 @@ int launch_forward_tc(const hypad_ctx* ctx, const void* x, int x_is_f64, int64_t
     P.debug = ctx->tc_debug;
     const bool hyp = P.prog.hyperbolic != 0;
     uint32_t mask = 0;
-    if (stages & HYPAD_STAGE_ENCODER) mask |= (1u << T_ENC) | (1u << T_Z);
+    if (stages & HYPAD_STAGE_ENCODER) mask |= (1u << T_ENC_GI) | (1u << T_ENC_O) | (1u << T_Z);
     if (stages & HYPAD_STAGE_DECODER) {
-        mask |= (1u << T_D0) | (1u << T_L0) | (1u << T_L1) | (1u << T_D2);
+        mask |= (1u << T_D0) | (1u << T_L0_GI) | (1u << T_L0_O) | (1u << T_L1_GI) | (1u << T_L1_O) | (1u << T_D2);
         if (hyp) mask |= (1u << T_MR);
     }
     if (hyp && (stages & HYPAD_STAGE_MOBIUS_X)) mask |= (1u << T_MX);

@@ -113,10 +113,8 @@ int hypad_ctx_poll_error(hypad_ctx* ctx);
 /* Diagnostic: enable/disable per-role cycle counters of hypad_forward's kernel (CTA 0) and read them back into
  * h_out (host, HYPAD_DEBUG_SLOTS values): [0] epilogue total, [1] epilogue waiting for accumulators, [2] MMA warp waiting
  * for operands, [3] MMA warp waiting for weights, [4] producer waiting for free slots, [5] operand (re)load + hand-over,
- * [6] tiles, [8+p] accumulator wait of pass p, [24+p] epilogue work of pass p (thread 0); last tile only, clock64 stamps:
- * [40+5p+2] MMA warp sees the operands, [40+5p+3] last commit issued, [40+5p+4] epilogue thread 0 sees the accumulators,
- * [104+16p+w] epilogue warp w handed over its operands. */
-#define HYPAD_DEBUG_SLOTS 320
+ * [6] tiles, [8+p] accumulator wait of pass p, [24+p] epilogue work of pass p (thread 0). */
+#define HYPAD_DEBUG_SLOTS 40
 int hypad_forward_debug_cycles(hypad_ctx* ctx, int enable, long long* h_out);
 
 /* hyperspace/hyrnn_nets.py:13-35 mobius_linear with hyperbolic_input=False, k=-1:

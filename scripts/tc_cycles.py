@@ -15,17 +15,13 @@ lib = _native.load_library()
 for _ in range(3): sc.forward(sig, True)
 _native.check(lib.hypad_forward_debug_cycles(sc.net.ctx.handle, 1, None))
 sc.forward(sig, True); torch.cuda.synchronize()
-buf = (ctypes.c_longlong * 320)()
+buf = (ctypes.c_longlong * 40)()
 _native.check(lib.hypad_forward_debug_cycles(sc.net.ctx.handle, 0, buf))
 v = list(buf)
 tot = max(v[0], 1)
 print("tiles %d  epilogue total %.0f cyc/tile | wait acc %.1f%% | xload+handover %.1f%% | work %.1f%%" % (v[6], tot / max(v[6], 1), 100 * v[1] / tot, 100 * v[5] / tot, 100 * (tot - v[1] - v[5]) / tot))
 print("MMA warp: wait operands %.1f%%  wait weights %.1f%% of epilogue total;  producer wait slots %.1f%%" % (100 * v[2] / tot, 100 * v[3] / tot, 100 * v[4] / tot))
-names = "ENC Z D0 L0 L1 D2 MR MX C1 C2 C3 C4".split()
+names = "ENC_GI ENC_O Z D0 L0_GI L0_O L1_GI L1_O D2 MR MX C1 C2 C3 C4".split()
 nt = max(v[6], 1)
 for p, nm in enumerate(names):
-    print("%-4s wait acc %7.0f  work %7.0f cyc/tile" % (nm, v[8 + p] / nt, v[24 + p] / nt))
-print("last tile, per pass: arrival skew of the 16 epilogue warps | last arrival -> MMA warp awake | MMA issue span | last commit -> epilogue awake")
-for p, nm in enumerate(names):
-    arr = v[104 + 16 * p: 104 + 16 * p + 16]
-    print("%-4s skew %6d | wake %6d | issue %6d | drain+wake %6d" % (nm, max(arr) - min(arr), v[40 + 5 * p + 2] - max(arr), v[40 + 5 * p + 3] - v[40 + 5 * p + 2], v[40 + 5 * p + 4] - v[40 + 5 * p + 3]))
+    print("%-6s wait acc %7.0f  work %7.0f cyc/tile" % (nm, v[8 + p] / nt, v[24 + p] / nt))
