@@ -57,6 +57,8 @@ enum TcPassIdx : int32_t {
 struct TcPass {
     int32_t k16;     // K / 16
     int32_t n;       // accumulator columns, multiple of 16, <= 256
+    int32_t n_live;  // columns (units for an LSTM pass) the epilogue processes: real outputs rounded up to 8; the rest are
+                     // zero-weight padding whose operand features keep whatever finite value they had
     int32_t d_col;   // TMEM column within the tile slot's 256
     int32_t w_off;   // byte offset of the packed weights: [k16]{hi,lo}[2 chunks][n][8] fp16
     int32_t b_off;   // float offset of the biases b[n]
@@ -214,12 +216,25 @@ __device__ __forceinline__ float sigmoid_tc(float x) {
     return fmaf(r, fmaf(-d, r, 1.0f), r);
 }
 
+// the 4 column splits of a row live in the 4 warps of one TMEM lane quarter: a 128-thread named barrier per quarter
+__device__ __forceinline__ void quarter_bar(int quarter) { asm volatile("bar.sync %0, 128;" ::"r"(2 + quarter) : "memory"); }
+// the same barrier, returning the OR of `pred` over the quarter
+__device__ __forceinline__ bool quarter_bar_or(int quarter, bool pred) {
+    uint32_t out;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %2, 0;\n\tbar.red.or.pred p, %1, 128, q;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(out)
+        : "r"(2 + quarter), "r"((uint32_t)pred)
+        : "memory");
+    return out != 0;
+}
+
 // sum of the column-split partials of a row (fp64, fixed order); every split gets the same value
 template <int NV>
 __device__ __forceinline__ void row_allreduce_tc(double (&v)[NV], double* red, int r, int split) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) red[(i * TC_NSPLIT + split) * TC_M + r] = v[i];
-    epi_bar();
+    quarter_bar(r >> 5);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         double t = red[(i * TC_NSPLIT) * TC_M + r];
@@ -227,7 +242,7 @@ __device__ __forceinline__ void row_allreduce_tc(double (&v)[NV], double* red, i
         for (int q = 1; q < TC_NSPLIT; ++q) t += red[(i * TC_NSPLIT + q) * TC_M + r];
         v[i] = t;
     }
-    epi_bar();
+    quarter_bar(r >> 5);
 }
 
 // the window tile (or a caller-provided latent) -> A operand buffer; threads: row = t & 127, chunk lane = t >> 7
@@ -249,38 +264,47 @@ __device__ __forceinline__ void load_rows_to_act(unsigned char* act, const T* __
     }
 }
 
-// In place on TMEM columns [col0, col0+ncols): y = x W^T -> project(mobius_add(expmap0(y), bias)); see forward.cu row_mobius.
-// post = 2^-(sa+sw) undoes the operand scales (exact).
-__device__ void row_mobius_tc(uint32_t trow, int col0, int ncols, const float* __restrict__ bias, float y2, double* red, int r,
-                              int split, float* gout, bool want_out, int S, float post) {
-    const int cbeg = 8 * split, cend = ncols, cstep = 8 * TC_NSPLIT;
-    double s1[1] = {0.0};
-    for (int c = cbeg; c < cend; c += cstep) {
-        float y[8];
-        tmem_ld8(trow + col0 + c, y);
-        tmem_ld_wait();
+constexpr int TC_ROWCH = 4;  // 8-column chunks a thread owns of a <= 128 column row phase (chunk j = columns 8 (split + 4 j))
+
+// y = x W^T (accumulators of this thread's chunks, TMEM columns col0 + ..) -> q = project(mobius_add(expmap0(y), bias)),
+// the reference's MobiusLinear row phase (see forward.cu row_mobius): returned in registers, optionally written back to
+// TMEM (to_tmem) and to global memory (gout).  post = 2^-(sa+sw) undoes the operand scales (exact).  Returns the row's
+// squared norm (fp32-rounded squares summed in fp64, rounded once) that the Poincare distance needs, identical in every split.
+__device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncols, const float* __restrict__ bias, float y2, double* red,
+                                               int r, int split, float* gout, bool to_tmem, int S, float post, float (&q)[TC_ROWCH][8]) {
+    const int cbeg = 8 * split, cstep = 8 * TC_NSPLIT;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            y[i] *= post;
-            s1[0] += (double)__fmul_rn(y[i], y[i]);
+    for (int j = 0; j < TC_ROWCH; ++j)
+        if (cbeg + j * cstep < ncols) tmem_ld8(trow + col0 + cbeg + j * cstep, q[j]);
+    tmem_ld_wait();
+    double s1[1] = {0.0};
+#pragma unroll
+    for (int j = 0; j < TC_ROWCH; ++j)
+        if (cbeg + j * cstep < ncols) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                q[j][i] *= post;
+                s1[0] += (double)__fmul_rn(q[j][i], q[j][i]);
+            }
         }
-    }
     row_allreduce_tc<1>(s1, red, r, split);
     const float nrm = fmaxf(sqrtf((float)s1[0]), 1e-15f);
     const float rnrm = __frcp_rn(nrm);
     const float th = (float)tanh((double)fminf(nrm, 15.0f));
     double s2[2] = {0.0, 0.0};
-    for (int c = cbeg; c < cend; c += cstep) {
-        float y[8];
-        tmem_ld8(trow + col0 + c, y);
-        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float p = __fmul_rn(th, div_refined(y[i] * post, nrm, rnrm));
-            s2[0] += (double)__fmul_rn(p, p);
-            s2[1] += (double)__fmul_rn(p, bias[c + i]);
+    for (int j = 0; j < TC_ROWCH; ++j)
+        if (cbeg + j * cstep < ncols) {
+            float bv[8];
+            ldg8(bias + cbeg + j * cstep, bv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float p = __fmul_rn(th, div_refined(q[j][i], nrm, rnrm));
+                q[j][i] = p;
+                s2[0] += (double)__fmul_rn(p, p);
+                s2[1] += (double)__fmul_rn(p, bv[i]);
+            }
         }
-    }
     row_allreduce_tc<2>(s2, red, r, split);
     const float x2 = (float)s2[0], xy = (float)s2[1];
     const float one_2xy = __fadd_rn(1.0f, __fmul_rn(2.0f, xy));
@@ -289,47 +313,64 @@ __device__ void row_mobius_tc(uint32_t trow, int col0, int ncols, const float* _
     const float den = fmaxf(__fadd_rn(one_2xy, __fmul_rn(x2, y2)), 1e-15f);
     const float rden = __frcp_rn(den);
     double s3[1] = {0.0};
-    for (int c = cbeg; c < cend; c += cstep) {
-        float y[8], q[8];
-        tmem_ld8(trow + col0 + c, y);
-        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float p = __fmul_rn(th, div_refined(y[i] * post, nrm, rnrm));
-            q[i] = div_refined(__fadd_rn(__fmul_rn(ca, p), __fmul_rn(cb, bias[c + i])), den, rden);
-            s3[0] += (double)__fmul_rn(q[i], q[i]);
+    for (int j = 0; j < TC_ROWCH; ++j)
+        if (cbeg + j * cstep < ncols) {
+            float bv[8];
+            ldg8(bias + cbeg + j * cstep, bv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                q[j][i] = div_refined(__fadd_rn(__fmul_rn(ca, q[j][i]), __fmul_rn(cb, bv[i])), den, rden);
+                s3[0] += (double)__fmul_rn(q[j][i], q[j][i]);
+            }
         }
-        tmem_st8(trow + col0 + c, q);
-    }
-    tmem_st_wait();
-    row_allreduce_tc<1>(s3, red, r, split);
-    const float norm = fmaxf(sqrtf((float)s3[0]), 1e-15f);
+    // last reduction by hand: its trailing barrier also ORs the (rare) "this row must be projected back into the ball"
+    // predicate over the quarter, so the projection's extra reduction is collective without costing the common case a barrier
+    red[split * TC_M + r] = s3[0];
+    quarter_bar(r >> 5);
+    double t3 = red[r];
+#pragma unroll
+    for (int k = 1; k < TC_NSPLIT; ++k) t3 += red[k * TC_M + r];
+    float sq = (float)t3;
+    const float norm = fmaxf(sqrtf(sq), 1e-15f);
     const float maxnorm = 0.996f;
     const bool proj = norm > maxnorm;
-    // tcgen05.ld / .st are warp-collective: the loop runs for the whole warp or not at all
-    const bool any_proj = __any_sync(0xffffffffu, proj);
-    if (any_proj || want_out) {
-        for (int c = cbeg; c < cend; c += cstep) {
-            float q[8];
-            tmem_ld8(trow + col0 + c, q);
-            tmem_ld_wait();
-            if (any_proj) {
-                if (proj) {
+    if (quarter_bar_or(r >> 5, proj)) {
+        double s4[1] = {0.0};
+        if (proj) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) q[i] = __fmul_rn(__fdiv_rn(q[i], norm), maxnorm);
+            for (int j = 0; j < TC_ROWCH; ++j)
+                if (cbeg + j * cstep < ncols) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        q[j][i] = __fmul_rn(__fdiv_rn(q[j][i], norm), maxnorm);
+                        s4[0] += (double)__fmul_rn(q[j][i], q[j][i]);
+                    }
                 }
-                tmem_st8(trow + col0 + c, q);
-            }
-            if (gout) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (c + i < S) gout[c + i] = q[i];
-            }
         }
+        row_allreduce_tc<1>(s4, red, r, split);
+        if (proj) sq = (float)s4[0];
+    }
+    if (to_tmem) {
+#pragma unroll
+        for (int j = 0; j < TC_ROWCH; ++j)
+            if (cbeg + j * cstep < ncols) tmem_st8(trow + col0 + cbeg + j * cstep, q[j]);
         tmem_st_wait();
     }
+    if (gout) {
+#pragma unroll
+        for (int j = 0; j < TC_ROWCH; ++j)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = cbeg + j * cstep + i;
+                if (c < S) gout[c] = q[j][i];
+            }
+    }
+    return sq;
 }
 
+// DBG: cycle counters for scripts/tc_cycles.py (hypad_forward_debug_cycles); the product instantiation carries none.
+template <bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_constant__ TcParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* act_base = smem;                                    // TC_TILES x (hi + lo piece)
@@ -364,6 +405,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::);
     }
+    // operand buffers start as zeros: padding features are never written, and must never be NaN bit patterns
+    for (int i = tid; i < TC_TILES * TC_ACT_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(act_base)[i] = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -385,9 +429,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                         for (int kp = 0; kp < ps.k16; kp += ps.kstage) {
                             const int kk = ps.k16 - kp < ps.kstage ? ps.k16 - kp : ps.kstage;
                             const uint32_t bytes = (uint32_t)(kk * ps.n) * 64u;
-                            const long long c0 = P.debug ? clock64() : 0;
+                            const long long c0 = DBG ? clock64() : 0;
                             ok = mbar_wait(bar_empty + 8 * slot, par, P.error_flag);
-                            if (P.debug) dbg_prod += clock64() - c0;
+                            if (DBG) dbg_prod += clock64() - c0;
                             if (!ok) break;
                             mbar_expect_tx(bar_full + 8 * slot, bytes);
                             bulk_g2s(s_u32(ring + slot * TC_STAGE_BYTES), src, bytes, bar_full + 8 * slot);
@@ -396,7 +440,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                         }
                     }
                 }
-            if (P.debug && blockIdx.x == 0) P.debug[4] = dbg_prod;
+            if (DBG && blockIdx.x == 0) P.debug[4] = dbg_prod;
         }
     } else if (warp == TC_MMA_WARP) {
         // ===== MMA issuer: the whole warp runs the (uniform) control flow, one elected lane issues ============
@@ -408,7 +452,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
         bool ok = true, have = false;
         const bool lead = elect_one();  // the one thread that issues every tcgen05.mma / commit of this CTA
         long long dbg_a = 0, dbg_full = 0;
-        const bool dbg = P.debug != nullptr;
+        constexpr bool dbg = DBG;
         const uint32_t ring0 = (s_u32(ring) & 0x3FFFFu) >> 4;
         auto desc64 = [](uint32_t lo32) { return ((uint64_t)0x4008u << 32) | lo32; };  // SBO 128 B, descriptor version 1
         int64_t stages_left = 0;
@@ -488,9 +532,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
         const float* __restrict__ small = P.small;
         uint32_t acc_par = 0;   // bit sl = parity of slot sl's next accumulator hand-over
         uint32_t has_x = 0;     // bit sl = slot sl's A operand buffer currently holds the window tile
+        float sq_mr0 = 0.0f, sq_mr1 = 0.0f;  // squared norm of the reconstruction's hyperbolic point, per slot
         bool ok = true;
         long long dbg_wait = 0, dbg_xload = 0;
-        const bool dbg = P.debug != nullptr;
+        constexpr bool dbg = DBG;
         const long long dbg_t0 = dbg ? clock64() : 0;
         int p_first = 0;
         while (p_first < T_COUNT && !((P.pass_mask >> p_first) & 1u)) ++p_first;
@@ -545,7 +590,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                     tc_fence_after();
                     if (ps.epi == TE_LSTM_GI) {
                         const int nu = ps.n >> 1;
-                        for (int c = cbeg; c < nu; c += cstep) {
+                        for (int c = cbeg; c < ps.n_live; c += cstep) {
                             float gg[8], gi[8], bg[8], bi[8], tc[8];
                             tmem_ld8(trow + ps.d_col + c, gg);
                             tmem_ld8(trow + ps.d_col + nu + c, gi);
@@ -562,7 +607,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                         }
                         tmem_st_wait();
                     } else if (ps.epi == TE_LSTM_O) {
-                        for (int c = cbeg; c < ps.n; c += cstep) {
+                        for (int c = cbeg; c < ps.n_live; c += cstep) {
                             float go[8], tc[8], bo[8], h[8];
                             tmem_ld8(trow + ps.d_col + c, go);
                             tmem_ld8(trow + ps.d_col + ps.n + c, tc);
@@ -597,7 +642,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                                 if (live) P.out.critic[w0 + r] = __fadd_rn(fdot, w5[prog.latent_c]);
                             }
                         } else {
-                            for (int c = cbeg; c < ps.n; c += cstep) {
+                            for (int c = cbeg; c < ps.n_live; c += cstep) {
                                 float v[8], bv[8];
                                 tmem_ld8(trow + ps.d_col + c, v);
                                 ldg8(b1 + c, bv);
@@ -619,43 +664,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                             }
                         }
                         has_x &= ~(1u << sl);
-                    } else if (ps.epi == TE_MOB_R) {
-                        float* gout = (P.out.hyper && live) ? P.out.hyper + (w0 + r) * (int64_t)S : nullptr;
-                        row_mobius_tc(trow, ps.d_col, ps.n, small + prog.mob_bias_off, small[prog.mob_y2_off], red, r, split, gout, P.out.hyper != nullptr, S, post);
-                    } else if (ps.epi == TE_MOB_X) {
-                        float* gout = (P.out.hyper_x && live) ? P.out.hyper_x + (w0 + r) * (int64_t)S : nullptr;
-                        row_mobius_tc(trow, ps.d_col, ps.n, small + prog.mob_bias_off, small[prog.mob_y2_off], red, r, split, gout, P.out.hyper_x != nullptr, S, post);
-                    }
-                    // ---- row statistics once both hyperbolic points are in TMEM ---------------------------------
-                    const bool last_hyp = (p == T_MX) || (p == T_MR && !((P.pass_mask >> T_MX) & 1u));
-                    if (P.want_rowstats && last_hyp) {
-                        const TcPass& pm = prog.pass[T_MR];
-                        const bool both = P.out.rec != nullptr;
-                        double s[3] = {0.0, 0.0, 0.0};
-                        for (int c = 8 * split; c < pm.n; c += 8 * TC_NSPLIT) {
-                            float h[8], hx[8];
-                            tmem_ld8(trow + pm.d_col + c, h);
-                            if (both) tmem_ld8(trow + prog.pass[T_MX].d_col + c, hx);
-                            tmem_ld_wait();
+                    } else if (ps.epi == TE_MOB_R || ps.epi == TE_MOB_X) {
+                        const bool is_x = ps.epi == TE_MOB_X;
+                        float* gbase = is_x ? P.out.hyper_x : P.out.hyper;
+                        float* gout = (gbase && live) ? gbase + (w0 + r) * (int64_t)S : nullptr;
+                        float q[TC_ROWCH][8];
+                        // the reconstruction's point stays in TMEM until the window's point has been computed
+                        const float sq = row_mobius_tc(trow, ps.d_col, ps.n_live, small + prog.mob_bias_off, small[prog.mob_y2_off], red, r, split,
+                                                       gout, !is_x, S, post, q);
+                        if (!is_x) {
+                            if (sl == 0) sq_mr0 = sq;
+                            else sq_mr1 = sq;
+                        }
+                        // ---- row statistics once both hyperbolic points exist ---------------------------------------
+                        const bool with_x = (P.pass_mask >> T_MX) & 1u;
+                        if (P.want_rowstats && (is_x || !with_x)) {
+                            const float sqvnorm = is_x ? (sl == 0 ? sq_mr0 : sq_mr1) : sq;
+                            if (is_x && P.out.rec != nullptr) {
+                                const TcPass& pm = prog.pass[T_MR];
+                                double sd[1] = {0.0};
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                s[2] += (double)__fmul_rn(h[i], h[i]);
-                                if (both) {
-                                    const float d = __fsub_rn(hx[i], h[i]);
-                                    s[0] += (double)__fmul_rn(d, d);
-                                    s[1] += (double)__fmul_rn(hx[i], hx[i]);
+                                for (int j = 0; j < TC_ROWCH; ++j)
+                                    if (cbeg + j * cstep < pm.n_live) {
+                                        float h[8];
+                                        tmem_ld8(trow + pm.d_col + cbeg + j * cstep, h);
+                                        tmem_ld_wait();
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) {
+                                            const float d = __fsub_rn(q[j][i], h[i]);
+                                            sd[0] += (double)__fmul_rn(d, d);
+                                        }
+                                    }
+                                row_allreduce_tc<1>(sd, red, r, split);
+                                if (split == 0 && live) {
+                                    const float sqdist = (float)sd[0], squnorm = sq;
+                                    const float tt = __fdiv_rn(__fmul_rn(2.0f, sqdist), __fmul_rn(__fsub_rn(1.0f, squnorm), __fsub_rn(1.0f, sqvnorm)));
+                                    const float xt = __fadd_rn(__fadd_rn(1.0f, tt), 1e-7f);
+                                    P.out.rec[w0 + r] = (float)acosh((double)xt);
                                 }
                             }
-                        }
-                        row_allreduce_tc<3>(s, red, r, split);
-                        if (split == 0 && live) {
-                            const float sqdist = (float)s[0], squnorm = (float)s[1], sqvnorm = (float)s[2];
-                            if (both) {
-                                const float tt = __fdiv_rn(__fmul_rn(2.0f, sqdist), __fmul_rn(__fsub_rn(1.0f, squnorm), __fsub_rn(1.0f, sqvnorm)));
-                                const float xt = __fadd_rn(__fadd_rn(1.0f, tt), 1e-7f);
-                                P.out.rec[w0 + r] = (float)acosh((double)xt);
-                            }
-                            if (P.out.unorm) P.out.unorm[w0 + r] = sqrtf(sqvnorm);
+                            if (split == 0 && live && P.out.unorm) P.out.unorm[w0 + r] = sqrtf(sqvnorm);
                         }
                     }
                     if (dbg && blockIdx.x == 0 && tid == 0) P.debug[24 + p] += clock64() - ce0;
@@ -672,9 +720,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
             P.debug[5] = dbg_xload;
         }
     }
-    if (P.debug && blockIdx.x == 0 && tid == 0) {
-        P.debug[6] = my_tiles;
-    }
+    if (DBG && blockIdx.x == 0 && tid == 0) P.debug[6] = my_tiles;
     tc_fence_before();
     __syncthreads();
     if (warp == TC_PRODUCER_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
@@ -757,9 +803,9 @@ int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
     std::vector<std::vector<ColSrc>> cols(T_COUNT);
     // in_shift = sa of the pass's A operand: 10 for the window, 11 for activations bounded by 1, 8 for unbounded ones
     const int SH_X = 10, SH_UNIT = 11, SH_FREE = 8;
-    auto set_pass = [&](int idx, int K, int n, int d_col, int epi, int needs_x, int in_shift, int consumer_shift) {
+    auto set_pass = [&](int idx, int K, int n, int live, int d_col, int epi, int needs_x, int in_shift, int consumer_shift) {
         TcPass& p = prog.pass[idx];
-        p.k16 = round16i(K) / 16; p.n = n; p.d_col = d_col; p.epi = epi; p.needs_x = needs_x;
+        p.k16 = round16i(K) / 16; p.n = n; p.n_live = round8i(live); p.d_col = d_col; p.epi = epi; p.needs_x = needs_x;
         p.in_shift = in_shift; p.out_scale = ldexpf(1.0f, consumer_shift);
         p.kstage = TC_STAGE_BYTES / (n * 64);
         if (p.kstage > p.k16) p.kstage = p.k16;
@@ -784,29 +830,29 @@ int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
             }
         }
     };
-    set_pass(T_ENC_GI, S, 224, 0, TE_LSTM_GI, 1, SH_X, 0);
-    set_pass(T_ENC_O, S, 112, 0, TE_LSTM_O, 1, SH_X, SH_UNIT);
+    set_pass(T_ENC_GI, S, 224, 100, 0, TE_LSTM_GI, 1, SH_X, 0);
+    set_pass(T_ENC_O, S, 112, 100, 0, TE_LSTM_O, 1, SH_X, SH_UNIT);
     lstm_cols(T_ENC_GI, T_ENC_O, 50, 100, w->enc_w_ih, w->enc_b_ih, w->enc_b_hh, S);
-    set_pass(T_Z, 100, NL, 0, TE_Z, 0, SH_UNIT, SH_FREE);
+    set_pass(T_Z, 100, NL, L, 0, TE_Z, 0, SH_UNIT, SH_FREE);
     linear_cols(T_Z, w->enc_dense_w, w->enc_dense_b, L, 100);
-    set_pass(T_D0, L, 64, 0, TE_LINEAR, 0, SH_FREE, SH_FREE);
+    set_pass(T_D0, L, 64, 50, 0, TE_LINEAR, 0, SH_FREE, SH_FREE);
     linear_cols(T_D0, w->dec_dense1_w, w->dec_dense1_b, 50, L);
-    set_pass(T_L0_GI, 50, 256, 0, TE_LSTM_GI, 0, SH_FREE, 0);
-    set_pass(T_L0_O, 50, 128, 0, TE_LSTM_O, 0, SH_FREE, SH_UNIT);
+    set_pass(T_L0_GI, 50, 256, 128, 0, TE_LSTM_GI, 0, SH_FREE, 0);
+    set_pass(T_L0_O, 50, 128, 128, 0, TE_LSTM_O, 0, SH_FREE, SH_UNIT);
     lstm_cols(T_L0_GI, T_L0_O, 64, 128, w->dec_w_ih[0], w->dec_b_ih[0], w->dec_b_hh[0], 50);
-    set_pass(T_L1_GI, 128, 256, 0, TE_LSTM_GI, 0, SH_UNIT, 0);
-    set_pass(T_L1_O, 128, 128, 0, TE_LSTM_O, 0, SH_UNIT, SH_UNIT);
+    set_pass(T_L1_GI, 128, 256, 128, 0, TE_LSTM_GI, 0, SH_UNIT, 0);
+    set_pass(T_L1_O, 128, 128, 128, 0, TE_LSTM_O, 0, SH_UNIT, SH_UNIT);
     lstm_cols(T_L1_GI, T_L1_O, 64, 128, w->dec_w_ih[1], w->dec_b_ih[1], w->dec_b_hh[1], 128);
-    set_pass(T_D2, 128, NS, 0, TE_TANH, 0, SH_UNIT, SH_UNIT);
+    set_pass(T_D2, 128, NS, S, 0, TE_TANH, 0, SH_UNIT, SH_UNIT);
     linear_cols(T_D2, w->dec_dense2_w, w->dec_dense2_b, S, 128);
-    set_pass(T_MR, S, NS, 0, TE_MOB_R, 0, SH_UNIT, 0);  // stays in columns [0, NS) until the row statistics after T_MX
+    set_pass(T_MR, S, NS, S, 0, TE_MOB_R, 0, SH_UNIT, 0);  // stays in columns [0, NS) until the row statistics after T_MX
     if (hyp) linear_cols(T_MR, w->mobius_w, nullptr, S, S);
-    set_pass(T_MX, S, NS, 128, TE_MOB_X, 1, SH_X, 0);
+    set_pass(T_MX, S, NS, S, 128, TE_MOB_X, 1, SH_X, 0);
     if (hyp) linear_cols(T_MX, w->mobius_w, nullptr, S, S);
-    set_pass(T_C1, S, NC, 0, TE_CRITIC_HID, 1, SH_X, SH_FREE);
+    set_pass(T_C1, S, NC, C, 0, TE_CRITIC_HID, 1, SH_X, SH_FREE);
     linear_cols(T_C1, w->critic_w[0], w->critic_b[0], C, S);
     for (int i = 0; i < 3; ++i) {
-        set_pass(T_C2 + i, C, NC, 0, i == 2 ? TE_CRITIC_OUT : TE_CRITIC_HID, 0, SH_FREE, SH_FREE);
+        set_pass(T_C2 + i, C, NC, C, 0, i == 2 ? TE_CRITIC_OUT : TE_CRITIC_HID, 0, SH_FREE, SH_FREE);
         linear_cols(T_C2 + i, w->critic_w[1 + i], w->critic_b[1 + i], C, C);
     }
     if (NL > 32 || NC > 32 || NS > 128) {
@@ -898,14 +944,16 @@ int launch_forward_tc(const hypad_ctx* ctx, const void* x, int x_is_f64, int64_t
     const size_t smem = forward_tc_smem_bytes();
     static thread_local bool configured = false;
     if (!configured) {
-        HYPAD_CUDA_TRY(cudaFuncSetAttribute(forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HYPAD_CUDA_TRY(cudaFuncSetAttribute(forward_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HYPAD_CUDA_TRY(cudaFuncSetAttribute(forward_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     int sms = kNumSMs;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     const int64_t ntiles = ceil_div(n, TC_M);
     const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
-    forward_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(P);
+    if (P.debug) forward_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(P);
+    else forward_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(P);
     HYPAD_LAUNCH_CHECK();
     return HYPAD_OK;
 }

@@ -362,7 +362,8 @@ class WindowScorer:
         return res
 
     def poll_error(self):
-        """Synchronises and raises if the forward kernel reported a pipeline error (bounded barrier wait timed out)."""
+        """Synchronises and raises if the forward kernel reported an error: a bounded barrier wait timed out, or an
+        operand left the range of the scaled fp16 split (|x| < 63; see include/hypad_b200.h, hypad_forward)."""
         check(self.net.ctx.lib.hypad_ctx_poll_error(self.net.ctx.handle))
 
     # -- scoring -------------------------------------------------------------------------------------------
@@ -424,6 +425,7 @@ class WindowScorer:
             out.update(kmax=kmax, critic_scores=cs, rec=rec, pred=pred, true=true, errors=errors)
             ddof = 0
         out["final"] = final
+        self.poll_error()  # loud failure: pipeline protocol error, or an operand outside the tensor-core path's range
         if index is not None:
             if multivariate:
                 out["intervals"] = find_anomaly_intervals(final, index, 0.2, 0.1, anomaly_padding=200, ddof=ddof)

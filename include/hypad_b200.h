@@ -100,10 +100,14 @@ int hypad_pack_weights(hypad_ctx* ctx, const hypad_weights* w, void* stream);
  *                 (utils/dataloader.py:139-222 never materialised), S = materialised rows (N,S).
  *   z_in        : when HYPAD_STAGE_ENCODER is not requested and HYPAD_STAGE_DECODER is, the latent
  *                 input (N, latent) fp32 of Decoder.forward; else NULL.
+ * Contractions run on the tensor cores on a scaled hi/lo fp16 split of both operands (fp32-class accuracy,
+ * csrc/forward_tc.cu).  Operand range: |x| < 63, linear-layer / LeakyReLU activations < 255, weights of any
+ * magnitude (scaled per layer at pack time); a value outside raises the context's sticky error, reported by
+ * hypad_ctx_poll_error -- hypad_forward_ffma has no such limit.
  */
 int hypad_forward(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_t row_stride,
                   const float* z_in, int stages, const hypad_forward_out* out, void* stream);
-/* Same contract, contractions on the fp32 FFMA pipe instead of the tensor cores (3xTF32): the in-library
+/* Same contract, contractions on the fp32 FFMA pipe instead of the tensor cores: the in-library
  * cross-check of hypad_forward, not the product path. */
 int hypad_forward_ffma(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_t row_stride,
                        const float* z_in, int stages, const hypad_forward_out* out, void* stream);

@@ -93,7 +93,8 @@ def test_fused_forward_hyperbolic_vs_reference(case, hyp_scorer, cuda_device):
 
 @pytest.mark.parametrize("case", ["noisy1500_hyp_uncertainty.npz", "edge_n65_hyp.npz", "cfg1_hyp_uncertainty.npz"])
 def test_tensor_core_forward_matches_ffma_cross_check(case, hyp_scorer, cuda_device):
-    """hypad_forward (tcgen05, 3xTF32, TMEM accumulators) against hypad_forward_ffma (fp32 FFMA pipe) on the same input."""
+    """hypad_forward (tcgen05 kind::f16 on the scaled hi/lo split, TMEM accumulators) against hypad_forward_ffma (fp32 FFMA
+    pipe) on the same input."""
     g = golden(case)
     sig = dev_signal(g, cuda_device)
     keep = ("z", "eucl", "hyper", "hyper_x")
@@ -106,6 +107,26 @@ def test_tensor_core_forward_matches_ffma_cross_check(case, hyp_scorer, cuda_dev
         assert d <= atol, (k, d)
     np.testing.assert_allclose(tc["unorm"].cpu().numpy(), ff["unorm"].cpu().numpy(), rtol=1e-6)
     quantised_close(tc["rec"].cpu().numpy(), ff["rec"].cpu().numpy())
+
+
+def test_tensor_core_forward_flags_operands_outside_its_range(hyp_scorer, cuda_device):
+    """The scaled fp16 split holds |x| < 63: beyond that the kernel saturates and raises the context's sticky error
+    (include/hypad_b200.h, hypad_forward); the FFMA kernel has no such limit, and the flag clears once reported."""
+    from hypad_b200._native import HypadError
+
+    g = golden("edge_n300_hyp.npz")
+    sig = dev_signal(g, cuda_device).clone()
+    sig[150] = 100.0
+    hyp_scorer.forward(sig, True)
+    with pytest.raises(HypadError, match="range"):
+        hyp_scorer.poll_error()
+    hyp_scorer.poll_error()
+    ff = hyp_scorer.forward(sig, True, ffma=True)
+    assert torch.isfinite(ff["critic"]).all()
+    hyp_scorer.poll_error()
+    ok = hyp_scorer.forward(dev_signal(g, cuda_device), True)
+    hyp_scorer.poll_error()
+    assert torch.isfinite(ok["critic"]).all()
 
 
 @pytest.mark.parametrize("case", EUCL_CASES)
