@@ -161,9 +161,9 @@ __global__ void __launch_bounds__(KDE_WARPS * 32) kde_exhaustive_kernel(const Kd
     }
 }
 
-__global__ void __launch_bounds__(KDE_WARPS * 32) kde_screened_kernel(const KdeArgs a) {
+__global__ void __launch_bounds__(KDE_WARPS * 32, 8) kde_screened_kernel(const KdeArgs a) {
     __shared__ double sP[KDE_WARPS][KDE_MAXPTS];
-    __shared__ float sD[KDE_WARPS][KDE_MAXPTS];
+    __shared__ float sD[KDE_WARPS][2 * KDE_MAXPTS];
     __shared__ double sScott[KDE_MAXPTS + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* P = sP[warp];
@@ -195,45 +195,94 @@ __global__ void __launch_bounds__(KDE_WARPS * 32) kde_screened_kernel(const KdeA
         for (int q = 0; q < 4; ++q) {
             const int j = lane + 32 * q;
             d[q] = (float)((v[q] - mean) * dscale);
-            if (j < n) {
-                P[j] = v[q] * rcho;  // scipy divides; a last-bit difference of the scaled points cannot change the arg-max
-                D[j] = d[q];
-            }
+            if (j < n) P[j] = v[q] * rcho;  // scipy divides; a last-bit difference of the scaled points cannot change the arg-max
         }
-        __syncwarp();
         // ---- fp32 screening: all n^2 kernel values with ex2.approx -------------------------------------
         float e32[4] = {0.f, 0.f, 0.f, 0.f};
         if (n == 100) {
-            // The interior case of the reference's window length.  Points 0..95 are handled slot-wise (lane owns points
-            // lane, lane+32, lane+64 and loops over all k); the last 4 points would cost a full warp-wide MUFU per k for
-            // 4 live lanes, so the lanes split k instead and the partial sums are reduced with shuffles.
-#pragma unroll 4
-            for (int k = 0; k < 100; ++k) {
-                const float dk = D[k];
+            // The interior case of the reference's window length.  K(a,b) = K(b,a): every unordered pair is evaluated ONCE and
+            // credited to both points.  Points 0..95 form three groups of 32 (lane l owns point l of each group).  For a pair of
+            // groups (X, Y), step s pairs x_l with y_(l+s): the value goes to lane l's own sum for x_l, and into a running sum R
+            // that is handed from lane l+1 to lane l before every step, so that after 32 steps it has collected all 32
+            // contributions of one y and one more rotation delivers it to its owner -- one shuffle instead of one MUFU.EX2.
+            // Inside a group, steps 1..15 cover every unordered pair once and step 16 pairs l with l+16 from both sides.
+            // The groups are stored twice back to back so that the rotated read is a constant offset from a per-lane base.
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const float r = dk - d[q];
-                    e32[q] += ex2_approx(-(r * r));
+            for (int q = 0; q < 3; ++q) {
+                D[64 * q + lane] = d[q];
+                D[64 * q + 32 + lane] = d[q];
+            }
+            if (lane < 4) D[192 + lane] = d[3];
+            __syncwarp();
+            const unsigned full = 0xffffffffu;
+            const int nxt = (lane + 1) & 31;
+            float e[3] = {1.f, 1.f, 1.f};  // the point's own kernel value
+#pragma unroll
+            for (int X = 0; X < 3; ++X) {
+                {   // inside group X
+                    const float* px = D + 64 * X + lane;
+                    float R = 0.f;
+#pragma unroll
+                    for (int s = 1; s < 16; ++s) {
+                        if (s > 1) R = __shfl_sync(full, R, nxt);
+                        const float r = px[s] - d[X];
+                        const float val = ex2_approx(-(r * r));
+                        e[X] += val;
+                        R += val;
+                    }
+                    e[X] += __shfl_sync(full, R, (lane + 17) & 31);  // R of lane l belongs to point l+15
+                    const float r = px[16] - d[X];
+                    e[X] += ex2_approx(-(r * r));
+                }
+#pragma unroll
+                for (int Y = X + 1; Y < 3; ++Y) {
+                    const float* py = D + 64 * Y + lane;
+                    float R = 0.f;
+#pragma unroll
+                    for (int s = 0; s < 32; ++s) {
+                        if (s > 0) R = __shfl_sync(full, R, nxt);
+                        const float r = py[s] - d[X];
+                        const float val = ex2_approx(-(r * r));
+                        e[X] += val;
+                        R += val;
+                    }
+                    e[Y] += __shfl_sync(full, R, nxt);  // R of lane l belongs to point l+31
                 }
             }
-            float part[4] = {0.f, 0.f, 0.f, 0.f};
+            // the last 4 points against the 96 (credited to both sides) and against each other
+            float L[4];
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const int k = lane + 32 * kk;
-                const float dk = k < 100 ? D[k] : 1e18f;  // padded k contributes ex2(-huge) = 0
+            for (int t = 0; t < 4; ++t) {
+                const float dt = D[192 + t];
+                L[t] = 0.f;
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const float r = dk - D[96 + t];
-                    part[t] += ex2_approx(-(r * r));
+                for (int q = 0; q < 3; ++q) {
+                    const float r = dt - d[q];
+                    const float val = ex2_approx(-(r * r));
+                    e[q] += val;
+                    L[t] += val;
                 }
+            }
+            {
+                const float r = D[192 + ((lane >> 2) & 3)] - D[192 + (lane & 3)];
+                const float val = lane < 16 ? ex2_approx(-(r * r)) : 0.f;  // includes the own value (1) on the diagonal
+#pragma unroll
+                for (int t = 0; t < 4; ++t) L[t] += (lane >> 2) == t ? val : 0.f;
             }
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) part[t] += __shfl_xor_sync(0xffffffffu, part[t], o);
-                if (lane == t) e32[3] = part[t];
+                for (int o = 16; o > 0; o >>= 1) L[t] += __shfl_xor_sync(full, L[t], o);
+                if (lane == t) e32[3] = L[t];
             }
+            e32[0] = e[0];
+            e32[1] = e[1];
+            e32[2] = e[2];
         } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (lane + 32 * q < n) D[lane + 32 * q] = d[q];
+            __syncwarp();
             for (int k = 0; k < n; ++k) {
                 const float dk = D[k];
 #pragma unroll
