@@ -219,18 +219,17 @@ __global__ void __launch_bounds__(KDE_WARPS * 32, 8) kde_screened_kernel(const K
             float e[3] = {1.f, 1.f, 1.f};  // the point's own kernel value
 #pragma unroll
             for (int X = 0; X < 3; ++X) {
-                {   // inside group X
+                {   // inside group X: the running sum is handed on after every step
                     const float* px = D + 64 * X + lane;
                     float R = 0.f;
 #pragma unroll
                     for (int s = 1; s < 16; ++s) {
-                        if (s > 1) R = __shfl_sync(full, R, nxt);
                         const float r = px[s] - d[X];
                         const float val = ex2_approx(-(r * r));
                         e[X] += val;
-                        R += val;
+                        R = __shfl_sync(full, R + val, nxt);
                     }
-                    e[X] += __shfl_sync(full, R, (lane + 17) & 31);  // R of lane l belongs to point l+15
+                    e[X] += __shfl_sync(full, R, (lane + 16) & 31);  // after 15 hand-overs lane l holds the sum of point l+16
                     const float r = px[16] - d[X];
                     e[X] += ex2_approx(-(r * r));
                 }
@@ -239,14 +238,19 @@ __global__ void __launch_bounds__(KDE_WARPS * 32, 8) kde_screened_kernel(const K
                     const float* py = D + 64 * Y + lane;
                     float R = 0.f;
 #pragma unroll
-                    for (int s = 0; s < 32; ++s) {
-                        if (s > 0) R = __shfl_sync(full, R, nxt);
-                        const float r = py[s] - d[X];
-                        const float val = ex2_approx(-(r * r));
-                        e[X] += val;
-                        R += val;
+                    for (int s0 = 0; s0 < 32; s0 += 8) {
+                        float y[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) y[u] = py[s0 + u];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const float r = y[u] - d[X];
+                            const float val = ex2_approx(-(r * r));
+                            e[X] += val;
+                            R = __shfl_sync(full, R + val, nxt);
+                        }
                     }
-                    e[Y] += __shfl_sync(full, R, nxt);  // R of lane l belongs to point l+31
+                    e[Y] += R;  // 32 hand-overs: back at the owner
                 }
             }
             // the last 4 points against the 96 (credited to both sides) and against each other
@@ -305,9 +309,12 @@ __global__ void __launch_bounds__(KDE_WARPS * 32, 8) kde_screened_kernel(const K
         // A candidate whose value repeats an already evaluated one has bitwise the same density and loses the tie to
         // the earlier index, so it is skipped (periodic and plateau signals produce many exact repeats).
         double seen0 = CUDART_NAN, seen1 = CUDART_NAN, seen2 = CUDART_NAN, seen3 = CUDART_NAN;
+        unsigned cands[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            unsigned cand = __ballot_sync(0xffffffffu, (lane + 32 * q < n) && e32[q] >= thr);
+        for (int q = 0; q < 4; ++q) cands[q] = __ballot_sync(0xffffffffu, (lane + 32 * q < n) && e32[q] >= thr);
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {  // one copy of the fp64 evaluation in the instruction stream
+            unsigned cand = q == 0 ? cands[0] : q == 1 ? cands[1] : q == 2 ? cands[2] : cands[3];
             while (cand) {
                 const int src = __ffs(cand) - 1;
                 cand &= cand - 1;
