@@ -302,38 +302,100 @@ __global__ void __launch_bounds__(KDE_WARPS * 32, 8) kde_screened_kernel(const K
             if (lane + 32 * q < n) m32 = fmaxf(m32, e32[q]);
         m32 = warp_max(m32);
         const float thr = m32 * (1.0f - 2.5e-4f);  // 10x the fp32 error bound (header comment); a flat density top yields ~2 candidates
-        // ---- fp64 re-evaluation of the candidates, ascending j -----------------------------------------
-        // (the positive constants w = 1/n and norm = (2 pi)^(-1/2)/cho multiply every density alike: left out)
-        double best = -1.0;
-        int bj = 0;
-        // A candidate whose value repeats an already evaluated one has bitwise the same density and loses the tie to
-        // the earlier index, so it is skipped (periodic and plateau signals produce many exact repeats).
-        double seen0 = CUDART_NAN, seen1 = CUDART_NAN, seen2 = CUDART_NAN, seen3 = CUDART_NAN;
         unsigned cands[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) cands[q] = __ballot_sync(0xffffffffu, (lane + 32 * q < n) && e32[q] >= thr);
+        // ---- stage 2: the candidates again, in fp32 but from the fp64 differences and with expf -----------------
+        // Relative error of such a density: expf 2 ulp (2.4e-7), the rounded difference and its square perturb a term's
+        // exponent b = r^2/2 by <= 1.8e-7 b, i.e. the term by <= 0.37 x 1.8e-7 whatever b is, (n/32 + 5) fp32 additions of
+        // positive terms <= 6e-7: < 1e-6 in all.  Every candidate within 1e-5 of the stage-2 maximum survives (5x the
+        // margin two such errors need) -- usually exactly one distinct value, which then IS the arg-max and needs no fp64.
+        // A candidate whose value repeats a recently evaluated one has bitwise the same density and loses the tie to the
+        // earlier index, so it is skipped (periodic and plateau signals produce many exact repeats).
+        // Lane c keeps the c-th distinct candidate; more than 32 of them (a flat-topped density) fall back to fp64 for all.
+        int ncand = 0, myj = 0;
+        float myest = -1.0f;
+        {
+            double seen0 = CUDART_NAN, seen1 = CUDART_NAN, seen2 = CUDART_NAN, seen3 = CUDART_NAN;
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q) {  // one copy of the fp64 evaluation in the instruction stream
-            unsigned cand = q == 0 ? cands[0] : q == 1 ? cands[1] : q == 2 ? cands[2] : cands[3];
-            while (cand) {
-                const int src = __ffs(cand) - 1;
-                cand &= cand - 1;
-                const int j = src + 32 * q;
-                const double pj = P[j];
-                if (pj == seen0 || pj == seen1 || pj == seen2 || pj == seen3) continue;
-                seen3 = seen2;
-                seen2 = seen1;
-                seen1 = seen0;
-                seen0 = pj;
-                double part = 0.0;
-                for (int k = lane; k < n; k += 32) {
-                    const double r = P[k] - pj;
-                    part += exp(-0.5 * (r * r));
+            for (int q = 0; q < 4; ++q) {
+                unsigned cand = q == 0 ? cands[0] : q == 1 ? cands[1] : q == 2 ? cands[2] : cands[3];
+                while (cand) {
+                    const int src = __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    const int j = src + 32 * q;
+                    const double pj = P[j];
+                    if (pj == seen0 || pj == seen1 || pj == seen2 || pj == seen3) continue;
+                    seen3 = seen2;
+                    seen2 = seen1;
+                    seen1 = seen0;
+                    seen0 = pj;
+                    float part = 0.0f;
+                    for (int k = lane; k < n; k += 32) {
+                        const float r = (float)(P[k] - pj);
+                        part += expf(-0.5f * (r * r));
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                    if (lane == ncand) {
+                        myj = j;
+                        myest = part;
+                    }
+                    ++ncand;
                 }
-                const double tot = warp_sum(part);  // xor tree: bitwise identical in every lane
-                if (tot > best) {
-                    best = tot;
-                    bj = j;
+            }
+        }
+        int bj = 0;
+        unsigned keep[4] = {cands[0], cands[1], cands[2], cands[3]};
+        bool decided = false;
+        if (ncand <= 32) {
+            const float m2 = warp_max(myest);
+            unsigned surv = __ballot_sync(0xffffffffu, lane < ncand && myest >= m2 * (1.0f - 1e-5f));
+            if (__popc(surv) == 1) {
+                bj = __shfl_sync(0xffffffffu, myj, __ffs(surv) - 1);
+                decided = true;
+            } else {
+                keep[0] = keep[1] = keep[2] = keep[3] = 0u;
+                while (surv) {
+                    const int c = __ffs(surv) - 1;
+                    surv &= surv - 1;
+                    const int j = __shfl_sync(0xffffffffu, myj, c);
+                    const unsigned bit = 1u << (j & 31);
+                    if ((j >> 5) == 0) keep[0] |= bit;
+                    else if ((j >> 5) == 1) keep[1] |= bit;
+                    else if ((j >> 5) == 2) keep[2] |= bit;
+                    else keep[3] |= bit;
+                }
+            }
+        }
+        // ---- fp64 decision among the survivors, ascending j (first maximum wins) ----------------------------------
+        // (the positive constants w = 1/n and norm = (2 pi)^(-1/2)/cho multiply every density alike: left out)
+        if (!decided) {
+            double best = -1.0;
+            double seen0 = CUDART_NAN, seen1 = CUDART_NAN, seen2 = CUDART_NAN, seen3 = CUDART_NAN;
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                unsigned cand = q == 0 ? keep[0] : q == 1 ? keep[1] : q == 2 ? keep[2] : keep[3];
+                while (cand) {
+                    const int src = __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    const int j = src + 32 * q;
+                    const double pj = P[j];
+                    if (pj == seen0 || pj == seen1 || pj == seen2 || pj == seen3) continue;
+                    seen3 = seen2;
+                    seen2 = seen1;
+                    seen1 = seen0;
+                    seen0 = pj;
+                    double part = 0.0;
+                    for (int k = lane; k < n; k += 32) {
+                        const double r = P[k] - pj;
+                        part += exp(-0.5 * (r * r));
+                    }
+                    const double tot = warp_sum(part);  // xor tree: bitwise identical in every lane
+                    if (tot > best) {
+                        best = tot;
+                        bj = j;
+                    }
                 }
             }
         }
