@@ -425,10 +425,12 @@ class WindowScorer:
             out.update(kmax=kmax, critic_scores=cs, rec=rec, pred=pred, true=true, errors=errors)
             ddof = 0
         out["final"] = final
-        self.poll_error()  # loud failure: pipeline protocol error, or an operand outside the tensor-core path's range
         if index is not None:
             if multivariate:
                 out["intervals"] = find_anomaly_intervals(final, index, 0.2, 0.1, anomaly_padding=200, ddof=ddof)
             else:
                 out["intervals"] = find_anomaly_intervals(final, index, 0.33, 0.1, anomaly_padding=50, ddof=ddof)
+        # loud failure: pipeline protocol error, or an operand outside the tensor-core path's range.  Last, so that the
+        # synchronisation it implies does not stall the launches above.
+        self.poll_error()
         return out
