@@ -123,6 +123,24 @@ __global__ void poincare_rowdist_kernel(const float* __restrict__ recons, const 
     }
 }
 
+// ---- np.linalg.norm(true - recons, axis=1), utils/anomaly_detection_utils.py:157 (Euclidean multivariate) -----------
+// true rows are float64 (the dataloader's samples) or float32, the reconstruction float32: the difference and the norm are
+// float64 like numpy's (whose pairwise summation order differs in the last bits only).
+template <typename T>
+__global__ void rowdiff_norm_kernel(const T* __restrict__ truth, const float* __restrict__ recons, int64_t n, int S, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+        double s = 0.0;
+        for (int c = lane; c < S; c += 32) {
+            const double d = (double)truth[row * S + c] - (double)recons[row * S + c];
+            s += d * d;
+        }
+        s = warp_sum_d(s);
+        if (lane == 0) out[row] = sqrt(s);
+    }
+}
+
 static unsigned grid_for(int64_t items, int per_block, int dev_mult = 16) {
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
@@ -183,6 +201,16 @@ int hypad_rownorm(const float* x, int64_t n, int S, float* out, void* stream) {
     HYPAD_REQUIRE(n >= 0 && S >= 1, "hypad_rownorm: bad shape");
     if (n == 0) return HYPAD_OK;
     poincare_rowdist_kernel<<<grid_for(n, 8), 256, 0, (cudaStream_t)stream>>>(x, nullptr, n, S, nullptr, out);
+    HYPAD_LAUNCH_CHECK();
+    return HYPAD_OK;
+}
+
+int hypad_rowdiff_norm(const void* truth, int truth_is_f64, const float* recons, int64_t n, int S, double* out, void* stream) {
+    HYPAD_REQUIRE(truth && recons && out, "hypad_rowdiff_norm: NULL argument");
+    HYPAD_REQUIRE(n >= 0 && S >= 1, "hypad_rowdiff_norm: bad shape");
+    if (n == 0) return HYPAD_OK;
+    if (truth_is_f64) rowdiff_norm_kernel<double><<<grid_for(n, 8), 256, 0, (cudaStream_t)stream>>>((const double*)truth, recons, n, S, out);
+    else rowdiff_norm_kernel<float><<<grid_for(n, 8), 256, 0, (cudaStream_t)stream>>>((const float*)truth, recons, n, S, out);
     HYPAD_LAUNCH_CHECK();
     return HYPAD_OK;
 }

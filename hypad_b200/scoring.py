@@ -79,6 +79,23 @@ def rownorm(x):
     return out
 
 
+def rowdiff_norm(truth, recons):
+    """np.linalg.norm(truth - recons, axis=1) in float64 (utils/anomaly_detection_utils.py:157)."""
+    truth = _native.require_cuda(truth, "truth")
+    if truth.dtype not in (torch.float32, torch.float64):
+        truth = truth.double()
+    truth = truth.reshape(truth.shape[0], -1).contiguous()
+    recons = _native.require_cuda(recons, "recons").float().contiguous()
+    n, S = recons.shape
+    if tuple(truth.shape) != (n, S):
+        raise HypadError("hypad_b200: rowdiff_norm shapes differ: %s vs %s" % (tuple(truth.shape), (n, S)))
+    out = torch.empty(n, dtype=torch.float64, device=recons.device)
+    c = _ctx(recons)
+    with torch.cuda.device(recons.device):
+        check(c.lib.hypad_rowdiff_norm(ptr(truth), int(truth.dtype == torch.float64), ptr(recons), n, S, ptr(out), c.stream()))
+    return out
+
+
 def kde_argmax_overlap(critic, S, n_windows=None, critic_offset=0, t0=0, t_count=None, exhaustive=False):
     """critic (fp32, one value per window) -> kmax (float64, one value per timestep in [t0, t0+t_count))."""
     critic = _native.require_cuda(critic, "critic").reshape(-1)
@@ -400,10 +417,22 @@ class WindowScorer:
             out["critic_scores"] = cs
             final = combine(combination, cs, rec, fw["unorm"], n=n)
             ddof = 0 if multivariate else 1  # torch tensor (unbiased) vs ndarray
+        elif multivariate:
+            # utils/anomaly_detection_utils.py:153-213, Euclidean branch: one score per row
+            if sliding:
+                raise ValueError("multivariate scoring takes (N, C) rows (sliding=False)")
+            rec = zscore_clip(rowdiff_norm(fw["_x"], fw["eucl"]))  # :157-161
+            out["rec"] = rec
+            cs = None
+            if combination in _NEEDS_CRITIC:
+                cs_full, kmax = self.critic_scores(fw["critic"], n)
+                out["kmax"], out["critic_scores_full"] = kmax, cs_full
+                cs = cs_full[:n]
+            out["critic_scores"] = cs
+            unorm = rownorm(fw["eucl"]) if "uncertainty" in combination else None
+            final = combine(combination, cs, rec, unorm, n=n)
+            ddof = 0
         else:
-            if multivariate:
-                raise NotImplementedError("hypad_b200: Euclidean multivariate scoring (utils/anomaly_detection_utils.py:157-161) "
-                                          "is not built yet")
             mode = {"mult": "mult", "sum": "euclidean_sum", "rec": "rec", "critic": "critic"}.get(combination)
             if mode is None:
                 raise ValueError('Unknown combination specified {}, use "mult", "sum", or "rec" instead.'.format(combination))

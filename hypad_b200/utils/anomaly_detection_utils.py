@@ -278,8 +278,11 @@ def multivariate_anomaly_detection(recons_signal, true_signal, params, combinati
         x_index = datetime.timestamp(datetime(2012, 11, 24)) + np.arange(n, dtype=np.float64)
     torch.save(x_index, path + "x_index.pt")
     if not params.hyperbolic:
-        raise NotImplementedError("hypad_b200: Euclidean multivariate scoring (:157-161) is not built yet")
-    rec = _np(_sc.zscore_clip(_hyperbolic_rec_scores(recons, true_signal, params.signal_shape, dev)))
+        # :157-161: np.linalg.norm(true_signal - recons_signal, axis=1) -> zscore -> clip(0) + 1
+        truth = _sc._as_dev(np.asarray(true_signal).reshape(n, -1), torch.float64, dev)
+        rec = _np(_sc.zscore_clip(_sc.rowdiff_norm(truth, _sc._as_dev(recons.reshape(n, -1), torch.float32, dev))))
+    else:
+        rec = _np(_sc.zscore_clip(_hyperbolic_rec_scores(recons, true_signal, params.signal_shape, dev)))
     critic_scores = []
     if combination in _sc._NEEDS_CRITIC:
         critic_scores = compute_critic_scores(rec, critic_score, np.asarray(true_signal), params, path)

@@ -131,6 +131,9 @@ int hypad_mobius_linear(hypad_ctx* ctx, const float* x, int64_t n, int in_featur
 int hypad_poincare_rowdist(const float* recons, const float* truth, int64_t n, int S, float* out, void* stream);
 /* np.linalg.norm(x, axis=1) on fp32 rows, utils/anomaly_detection_utils.py:342. */
 int hypad_rownorm(const float* x, int64_t n, int S, float* out, void* stream);
+/* np.linalg.norm(true_signal - recons_signal, axis=1), utils/anomaly_detection_utils.py:157 (Euclidean multivariate
+ * reconstruction error): truth (n,S) float64 or float32, recons (n,S) float32, out (n,) float64. */
+int hypad_rowdiff_norm(const void* truth, int truth_is_f64, const float* recons, int64_t n, int S, double* out, void* stream);
 
 /* utils/dataloader.py:139-222 rolling_window_sequences(window_size=S, target_size=1, step_size=1):
  * out[w, j] = X[w + j], w in [0, n_windows).  Output fp32 or fp64. */

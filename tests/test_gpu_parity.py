@@ -467,3 +467,35 @@ def test_multivariate_shape_s123(cuda_device):
     g = {"final": want["final"], "kmax": want["kmax"], "critic": want["critic"]}
     selection_aware_close(out, g, 3000, "multivariate S=123")
     check_intervals(out["intervals"], want["intervals"])
+
+
+@pytest.mark.gpu
+def test_multivariate_euclidean_s123(cuda_device):
+    """utils/anomaly_detection_utils.py:153-213, Euclidean branch (:157-161): rec = zscore(|row - recon|_2) clipped + 1,
+    KDE critic scores over <= 123 points, mult, find_anomalies(0.2, 0.1, padding 200); GPU vs oracle on seeded rows."""
+    from conftest import weights
+    from hypad_b200.models.tadgan import CriticX, Decoder, Encoder
+    from hypad_b200 import scoring
+    from hypad_b200.scoring import WindowScorer
+
+    w = {k: v for k, v in weights("weights_hyp_s123.npz").items() if "hyperbolic_linear" not in k}
+    enc, dec, cx = Encoder(123, 20), Decoder(123, 20, False), CriticX(123, 20)
+    for pre, m in (("encoder.", enc), ("decoder.", dec), ("critic_x.", cx)):
+        m.load_state_dict({k[len(pre):]: v for k, v in w.items() if k.startswith(pre)})
+        m.eval().to(cuda_device)
+    rng = np.random.default_rng(22)
+    rows = rng.uniform(-1, 1, (3000, 123))
+    rows[700:712] *= 3
+    index = 1353715200.0 + np.arange(3000)
+    want = ho.multivariate_scores(rows, w, False, "mult", index)
+    dev_rows = torch.from_numpy(rows).to(cuda_device)
+    out = WindowScorer(enc, dec, cx).score(dev_rows, False, "mult", index=index, multivariate=True)
+    np.testing.assert_allclose(out["critic"].cpu().numpy(), want["critic"], rtol=0, atol=3e-7)
+    # the row norm itself, float64 from float64 rows and the float32 reconstruction
+    nrm = scoring.rowdiff_norm(dev_rows, out["eucl"]).cpu().numpy()
+    np.testing.assert_allclose(nrm, np.linalg.norm(rows - out["eucl"].cpu().numpy(), axis=1), rtol=1e-14)
+    np.testing.assert_allclose(out["rec"].cpu().numpy(), want["rec"], rtol=2e-5, atol=2e-5)
+    assert np.array_equal(out["kmax"].cpu().numpy(), ho.kde_argmax_overlap(out["critic"].cpu().numpy(), 123))
+    g = {"final": want["final"], "kmax": want["kmax"], "critic": want["critic"]}
+    selection_aware_close(out, g, 3000, "multivariate Euclidean S=123")
+    check_intervals(out["intervals"], want["intervals"])
