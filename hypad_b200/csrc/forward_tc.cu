@@ -141,14 +141,25 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(bar), "r"(bytes) : "memory");
 }
 // Bounded wait: a protocol error must never hang the GPU.  Returns false on timeout (and raises the error flag).
+// HINT_NS > 0 lets the hardware park the thread for up to that long per probe: the producer and MMA warps share their
+// scheduler with epilogue warps, and a tight probe loop costs those ~10 % of their issue slots.
+template <int HINT_NS = 0>
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* error_flag) {
     uint32_t done = 0;
     for (int spin = 0; spin < (1 << 22); ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
+        if (HINT_NS > 0) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                : "=r"(done)
+                : "r"(bar), "r"(parity), "r"((uint32_t)HINT_NS)
+                : "memory");
+        } else {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                : "=r"(done)
+                : "r"(bar), "r"(parity)
+                : "memory");
+        }
         if (done) return true;
     }
     atomicExch(error_flag, 1);
@@ -208,12 +219,30 @@ __device__ __forceinline__ void check_range8(const float (&v)[8], float sc, int*
     if (!(m * sc < 65000.0f)) atomicExch(error_flag, 2);
 }
 
-// 1 / (1 + exp(-x)); the reciprocal is MUFU.RCP refined by one Newton step (<= 1 ulp, branch-free)
+// 1 / (1 + exp(-x)).  exp(-x) = 2^(-x log2 e) straight through MUFU.EX2 (relative error 2^-22, like expf's own core):
+// without expf's two-step argument reduction the exponent carries a rounding error of |x| 2^-24, which moves the result by
+// sigma (1 - sigma) |x| 6e-8 <= 1.3e-8 in absolute terms whatever x is -- below half an ulp of the gate values that matter.
+// The reciprocal is MUFU.RCP refined by one Newton step (<= 1 ulp, branch-free).  6 instructions instead of 12.
 __device__ __forceinline__ float sigmoid_tc(float x) {
-    const float d = __fadd_rn(1.0f, expf(-x));
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(x, -1.4426950408889634f)));
+    const float d = __fadd_rn(1.0f, e);
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
     return fmaf(r, fmaf(-d, r, 1.0f), r);
+}
+
+// tanh(x) for |x| <= 1 (the LSTM cell value c = sigmoid(i) tanh(g)): x + x s C(s) / B(s), s = x^2, a (1,2) rational fit of
+// (tanh(x)/x - 1)/s with relative error 1.6e-9 on [0,1].  The correction is at most 0.24 |x|, so the rounding of its 8
+// operations (one MUFU.RCP, unrefined) weighs a quarter: measured against fp64 over 2.5M points max 1.5 ulp, mean 0.26 ulp --
+// tighter than tanhf (2 ulp) at half its instructions and one MUFU instead of two.
+__device__ __forceinline__ float tanh_unit(float x) {
+    const float s = __fmul_rn(x, x);
+    const float c = fmaf(-0.014719938859343529f, s, -0.3333333432674408f);
+    const float b = fmaf(fmaf(0.01575944945216179f, s, 0.44415977597236633f), s, 1.0f);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+    return fmaf(x, __fmul_rn(__fmul_rn(s, c), r), x);
 }
 
 // the 4 column splits of a row live in the 4 warps of one TMEM lane quarter: a 128-thread named barrier per quarter
@@ -430,7 +459,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                             const int kk = ps.k16 - kp < ps.kstage ? ps.k16 - kp : ps.kstage;
                             const uint32_t bytes = (uint32_t)(kk * ps.n) * 64u;
                             const long long c0 = DBG ? clock64() : 0;
-                            ok = mbar_wait(bar_empty + 8 * slot, par, P.error_flag);
+                            ok = mbar_wait<2000>(bar_empty + 8 * slot, par, P.error_flag);
                             if (DBG) dbg_prod += clock64() - c0;
                             if (!ok) break;
                             mbar_expect_tx(bar_full + 8 * slot, bytes);
@@ -472,7 +501,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                     const uint32_t a_hi0 = ((s_u32(act_base + sl * TC_ACT_BYTES) & 0x3FFFFu) >> 4) | (128u << 16);  // LBO 2048 B
                     const uint32_t a_lo0 = a_hi0 + (TC_PIECE_BYTES >> 4);
                     long long c0 = dbg ? clock64() : 0;
-                    ok = mbar_wait(bar_a + 8 * sl, (a_par >> sl) & 1u, P.error_flag);  // A operand written, TMEM of this slot drained
+                    ok = mbar_wait<500>(bar_a + 8 * sl, (a_par >> sl) & 1u, P.error_flag);  // A operand written, TMEM of this slot drained
                     a_par ^= 1u << sl;
                     if (dbg) dbg_a += clock64() - c0;
                     if (!ok) break;
@@ -601,7 +630,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                             for (int i = 0; i < 8; ++i) {
                                 const float vg = fmaf(gg[i], post, bg[i]);
                                 const float vi = fmaf(gi[i], post, bi[i]);
-                                tc[i] = tanhf(__fmul_rn(sigmoid_tc(vi), tanhf(vg)));
+                                tc[i] = tanh_unit(__fmul_rn(sigmoid_tc(vi), tanhf(vg)));
                             }
                             tmem_st8(trow + ps.d_col + nu + c, tc);
                         }
