@@ -73,6 +73,7 @@ struct TcProgram {
     TcPass pass[T_COUNT];
     int32_t S, S16, latent, latent_c, hyperbolic;
     int32_t mob_bias_off, mob_y2_off, critic5_off;  // float offsets into the small-parameter buffer
+    int32_t mob_bias_d_off;  // the Mobius bias again as 128 doubles (16-byte aligned)
     int32_t post_off;   // per pass: {2^sw, 2^-(sa+sw)} written by tc_wscale_kernel
 };
 
@@ -299,8 +300,11 @@ constexpr int TC_ROWCH = 4;  // 8-column chunks a thread owns of a <= 128 column
 // the reference's MobiusLinear row phase (see forward.cu row_mobius): returned in registers, optionally written back to
 // TMEM (to_tmem) and to global memory (gout).  post = 2^-(sa+sw) undoes the operand scales (exact).  Returns the row's
 // squared norm (fp32-rounded squares summed in fp64, rounded once) that the Poincare distance needs, identical in every split.
-__device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncols, const float* __restrict__ bias, float y2, double* red,
-                                               int r, int split, float* gout, bool to_tmem, int S, float post, float (&q)[TC_ROWCH][8]) {
+// Row sums: every term is widened once (F2F) and squared / multiplied inside a DFMA -- exact products accumulated in fp64,
+// rounded to fp32 once per sum -- two instructions per term.
+__device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncols, const float* __restrict__ bias,
+                                               const double* __restrict__ bias_d, float y2, double* red, int r, int split, float* gout,
+                                               bool to_tmem, int S, float post, float (&q)[TC_ROWCH][8]) {
     const int cbeg = 8 * split, cstep = 8 * TC_NSPLIT;
 #pragma unroll
     for (int j = 0; j < TC_ROWCH; ++j)
@@ -313,7 +317,8 @@ __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncol
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 q[j][i] *= post;
-                s1[0] += (double)__fmul_rn(q[j][i], q[j][i]);
+                const double yd = (double)q[j][i];
+                s1[0] = fma(yd, yd, s1[0]);
             }
         }
     row_allreduce_tc<1>(s1, red, r, split);
@@ -324,14 +329,19 @@ __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncol
 #pragma unroll
     for (int j = 0; j < TC_ROWCH; ++j)
         if (cbeg + j * cstep < ncols) {
-            float bv[8];
-            ldg8(bias + cbeg + j * cstep, bv);
+            const double2* bd = reinterpret_cast<const double2*>(bias_d + cbeg + j * cstep);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float p = __fmul_rn(th, div_refined(q[j][i], nrm, rnrm));
-                q[j][i] = p;
-                s2[0] += (double)__fmul_rn(p, p);
-                s2[1] += (double)__fmul_rn(p, bv[i]);
+            for (int i = 0; i < 8; i += 2) {
+                const double2 b2 = __ldg(bd + (i >> 1));
+                const float p0 = __fmul_rn(th, div_refined(q[j][i], nrm, rnrm));
+                const float p1 = __fmul_rn(th, div_refined(q[j][i + 1], nrm, rnrm));
+                q[j][i] = p0;
+                q[j][i + 1] = p1;
+                const double d0 = (double)p0, d1 = (double)p1;
+                s2[0] = fma(d0, d0, s2[0]);
+                s2[1] = fma(d0, b2.x, s2[1]);
+                s2[0] = fma(d1, d1, s2[0]);
+                s2[1] = fma(d1, b2.y, s2[1]);
             }
         }
     row_allreduce_tc<2>(s2, red, r, split);
@@ -350,7 +360,8 @@ __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncol
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 q[j][i] = div_refined(__fadd_rn(__fmul_rn(ca, q[j][i]), __fmul_rn(cb, bv[i])), den, rden);
-                s3[0] += (double)__fmul_rn(q[j][i], q[j][i]);
+                const double qd = (double)q[j][i];
+                s3[0] = fma(qd, qd, s3[0]);
             }
         }
     // last reduction by hand: its trailing barrier also ORs the (rare) "this row must be projected back into the ball"
@@ -373,7 +384,8 @@ __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncol
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         q[j][i] = __fmul_rn(__fdiv_rn(q[j][i], norm), maxnorm);
-                        s4[0] += (double)__fmul_rn(q[j][i], q[j][i]);
+                        const double qd = (double)q[j][i];
+                        s4[0] = fma(qd, qd, s4[0]);
                     }
                 }
         }
@@ -699,7 +711,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                         float* gout = (gbase && live) ? gbase + (w0 + r) * (int64_t)S : nullptr;
                         float q[TC_ROWCH][8];
                         // the reconstruction's point stays in TMEM until the window's point has been computed
-                        const float sq = row_mobius_tc(trow, ps.d_col, ps.n_live, small + prog.mob_bias_off, small[prog.mob_y2_off], red, r, split,
+                        const float sq = row_mobius_tc(trow, ps.d_col, ps.n_live, small + prog.mob_bias_off,
+                                                       reinterpret_cast<const double*>(small + prog.mob_bias_d_off), small[prog.mob_y2_off], red, r, split,
                                                        gout, !is_x, S, post, q);
                         if (!is_x) {
                             if (sl == 0) sq_mr0 = sq;
@@ -720,8 +733,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                                         tmem_ld_wait();
 #pragma unroll
                                         for (int i = 0; i < 8; ++i) {
-                                            const float d = __fsub_rn(q[j][i], h[i]);
-                                            sd[0] += (double)__fmul_rn(d, d);
+                                            const double d = (double)__fsub_rn(q[j][i], h[i]);
+                                            sd[0] = fma(d, d, sd[0]);
                                         }
                                     }
                                 row_allreduce_tc<1>(sd, red, r, split);
@@ -785,6 +798,10 @@ __global__ void tc_wscale_kernel(const ColSrc* __restrict__ cols, int ncols, int
         scale[0] = ldexpf(1.0f, sw);
         scale[1] = ldexpf(1.0f, -(sw + in_shift));
     }
+}
+
+__global__ void widen_kernel(const float* __restrict__ src, double* __restrict__ dst, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = (double)src[i];
 }
 
 __global__ void pack_tc_kernel(const ColSrc* __restrict__ cols, int k16, int nblk, int n, __half* __restrict__ dst, float* __restrict__ bias,
@@ -898,6 +915,8 @@ int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
         ncols_total += (size_t)p.n;
     }
     prog.mob_bias_off = (int32_t)sfloats; sfloats += 128;
+    sfloats = (sfloats + 3) / 4 * 4;
+    prog.mob_bias_d_off = (int32_t)sfloats; sfloats += 256;
     prog.mob_y2_off = (int32_t)sfloats; sfloats += 4;
     prog.critic5_off = (int32_t)sfloats; sfloats += 68;
     prog.post_off = (int32_t)sfloats; sfloats += 2 * T_COUNT;
@@ -936,6 +955,8 @@ int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
     }
     // Mobius bias / y2 / critic dense5 come from the FFMA context's packed buffer (already built by hypad_pack_weights)
     HYPAD_CUDA_TRY(cudaMemcpyAsync(small + prog.mob_bias_off, ctx->packed + ctx->prog.mob_bias_off, 128 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    widen_kernel<<<1, 128, 0, stream>>>(small + prog.mob_bias_off, reinterpret_cast<double*>(small + prog.mob_bias_d_off), 128);
+    HYPAD_LAUNCH_CHECK();
     HYPAD_CUDA_TRY(cudaMemcpyAsync(small + prog.mob_y2_off, ctx->packed + ctx->prog.mob_y2_off, sizeof(float), cudaMemcpyDeviceToDevice, stream));
     HYPAD_CUDA_TRY(cudaMemcpyAsync(small + prog.critic5_off, ctx->packed + ctx->prog.critic5_off, (C + 1) * sizeof(float), cudaMemcpyDeviceToDevice, stream));
     HYPAD_CUDA_TRY(cudaStreamSynchronize(stream));
