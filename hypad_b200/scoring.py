@@ -245,53 +245,89 @@ def analysis_windows(n, window_size=None, window_size_portion=None, window_step_
     return int(window_size), int(step), count
 
 
-def threshold_windows(errors, window_size, step, count, ddof, anomaly_padding, max_runs=256):
-    """Per analysis window: (mean, std, threshold, max_below) and the padded above-threshold runs."""
+def threshold_windows(errors, window_size, step, count, ddof, anomaly_padding, max_runs=64):
+    """Per analysis window: (mean, std, threshold, max_below) and the padded above-threshold runs.
+    One device buffer holds the three outputs so that a single device-to-host copy (one synchronisation) brings them back."""
     errors = _native.require_cuda(errors, "errors").reshape(-1).double().contiguous()
     dev = errors.device
     c = _ctx(errors)
     while True:
-        stats = torch.empty((count, 4), dtype=torch.float64, device=dev)
-        runs = torch.empty((count, max_runs, 3), dtype=torch.float64, device=dev)
-        n_runs = torch.empty(count, dtype=torch.int32, device=dev)
+        n_stats, n_runs_f = count * 4, count * max_runs * 3
+        buf = torch.empty(n_stats + n_runs_f + (count + 1) // 2, dtype=torch.float64, device=dev)
+        base = buf.data_ptr()
         with torch.cuda.device(dev):
             check(c.lib.hypad_threshold_windows(c.handle, ptr(errors), errors.shape[0], window_size, step, count, int(ddof),
-                                                int(anomaly_padding), ptr(stats), ptr(runs), ptr(n_runs), max_runs, c.stream()))
-        nr = n_runs.cpu().numpy()
+                                                int(anomaly_padding), base, base + 8 * n_stats, base + 8 * (n_stats + n_runs_f),
+                                                max_runs, c.stream()))
+        host = buf.cpu().numpy()
+        nr = host[n_stats + n_runs_f:].view(np.int32)[:count]
         if nr.max(initial=0) <= max_runs:
-            return stats.cpu().numpy(), runs.cpu().numpy(), nr
+            return host[:n_stats].reshape(count, 4), host[n_stats:n_stats + n_runs_f].reshape(count, max_runs, 3), nr
         max_runs = int(nr.max()) + 16
 
 
+def _ieee_div(a, b):
+    """a / b with numpy's float64 semantics for a zero divisor (the reference divides ndarrays, :1226)."""
+    try:
+        return a / b
+    except ZeroDivisionError:
+        if a != a or a == 0.0:
+            return float("nan")
+        return math.copysign(float("inf"), a) * math.copysign(1.0, b)
+
+
+def _np_average(values, weights):
+    """np.average(values, weights=weights) (:1297): (v*w).sum() / w.sum() in numpy's summation order, which is a plain
+    left-to-right loop below 8 elements."""
+    if len(values) < 8:
+        num = den = 0.0
+        for v, w in zip(values, weights):
+            num += v * w
+            den += w
+        return _ieee_div(num, den)
+    v, w = np.asarray(values, dtype=np.float64), np.asarray(weights, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return float(np.add.reduce(v * w) / np.add.reduce(w))
+
+
 def intervals_from_runs(stats, runs, n_runs, step, min_percent):
-    """Host tail of find_anomalies on the few runs per window: prune (:1203-1237), score (:1240-1269), merge (:1272-1313)."""
+    """Host tail of find_anomalies on the few runs per window: prune (:1203-1237), score (:1240-1269), merge (:1272-1313).
+    Plain Python floats: the arrays hold a handful of values per window and numpy's per-call overhead would dominate."""
+    stats, n_runs = np.asarray(stats).tolist(), np.asarray(n_runs).tolist()
     sequences = []
-    for k in range(stats.shape[0]):
+    for k in range(len(stats)):
         mean, std, thr, max_below = stats[k]
-        rows = [(max_below, -1.0, -1.0)] + [(runs[k, r, 2], runs[k, r, 0], runs[k, r, 1]) for r in range(int(n_runs[k]))]
+        rk = runs[k][: int(n_runs[k])].tolist()
+        rows = [(max_below, -1.0, -1.0)] + [(r[2], r[0], r[1]) for r in rk]
         rows.sort(key=lambda t: -t[0])  # descending by max error, stable
-        me = np.array([r[0] for r in rows], dtype=np.float64)
-        with np.errstate(divide="ignore", invalid="ignore"):
-            increase = (me[:-1] - me[1:]) / me[:-1]
-        too_small = increase < min_percent
-        last = -1 if too_small.all() else int(np.flatnonzero(~too_small)[-1])
+        last = -1  # the last position whose drop to the next maximum is not "too small" (increase < min_percent is False)
+        for i in range(len(rows) - 1):
+            if not (_ieee_div(rows[i][0] - rows[i + 1][0], rows[i][0]) < min_percent):
+                last = i
         denom = mean + std
+        shift = k * step
         for m, s, e in rows[: last + 1]:
-            sequences.append([s + k * step, e + k * step, (m - thr) / denom])
+            sequences.append([s + shift, e + shift, _ieee_div(m - thr, denom)])
     if not sequences:
         return []
     sequences.sort(key=lambda s: s[0])
     merged = [sequences[0]]
     score, weights = [sequences[0][2]], [sequences[0][1] - sequences[0][0]]
+    grouped = False
     for seq in sequences[1:]:
         prev = merged[-1]
         if seq[0] <= prev[1] + 1:
             score.append(seq[2])
             weights.append(seq[1] - seq[0])
-            merged[-1] = [prev[0], max(prev[1], seq[1]), float(np.average(score, weights=weights))]
+            merged[-1] = [prev[0], max(prev[1], seq[1]), None]  # the weighted mean is taken once, when the group closes
+            grouped = True
         else:
-            score, weights = [seq[2]], [seq[1] - seq[0]]
+            if grouped:
+                merged[-1][2] = _np_average(score, weights)
+            score, weights, grouped = [seq[2]], [seq[1] - seq[0]], False
             merged.append(seq)
+    if grouped:
+        merged[-1][2] = _np_average(score, weights)
     return merged
 
 
