@@ -7,11 +7,14 @@ timestep i needs the critic value of windows i-S+1 .. i.  Rank r 
   * recomputes the S-1 windows to the left of its range (the "halo": 0.01 % extra work at 1M windows/GPU),
   * runs the fused network + KDE arg-max on its range with no communication,
 and the per-timestep / per-window arrays (kmax f64, rec f32, unorm f32) are gathered once over NCCL
-(NVLink 5 / NVSwitch; <= 16 B per timestep).  The O(T) finish (quantile band, z-score, smoothing, combine,
-thresholding) is then run redundantly on every rank.  There is no collective inside a kernel.
+(NVLink 5 / NVSwitch; <= 16 B per timestep).  The elementwise O(T) finish (quantile band, z-score, smoothing, combine)
+is then run redundantly on every rank; the analysis windows of find_anomalies -- each a third of the signal, twenty-odd
+of them, the one part of the finish whose cost grows with the total length -- are dealt out to the ranks and their few
+runs gathered (a few KB).  There is no collective inside a kernel.
 """
 import math
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -92,5 +95,46 @@ class ShardedScorer:
         final = scoring.combine(combination, cs[:n_windows], rec, unorm, n=n_windows)
         out = {"final": final, "kmax": kmax, "rec": rec, "unorm": unorm, "critic_scores": cs[:n_windows]}
         if index is not None:
-            out["intervals"] = scoring.find_anomaly_intervals(final, index, 0.33, 0.1, anomaly_padding=50, ddof=1)
+            out["intervals"] = self.find_anomaly_intervals(final, index, 0.33, 0.1, anomaly_padding=50, ddof=1)
         return out
+
+    MAX_RUNS = 64  # per analysis window in the gathered buffer; more (never seen) -> every rank redoes all windows
+
+    def find_anomaly_intervals(self, final, index, window_size_portion, window_step_size_portion, min_percent=0.1,
+                               anomaly_padding=50, ddof=0):
+        """scoring.find_anomaly_intervals with the analysis windows dealt out to the ranks: rank r thresholds windows
+        [r*per, (r+1)*per) of the (identical, gathered) score array, the packed per-window results are all-gathered and the
+        host tail (prune, score, merge) runs on every rank.  Window k of a sub-array that starts at k0*step is window k0+k of
+        the full array, so the kernels need no notion of a window subset and the result is bitwise the single-GPU one."""
+        n = final.numel()
+        wsize, step, count = scoring.analysis_windows(n, None, window_size_portion, None, window_step_size_portion)
+        per = -(-count // self.world)
+        k0 = min(self.rank * per, count)
+        kc = max(0, min(per, count - k0))
+        R = self.MAX_RUNS
+        blen = scoring.threshold_buffer_len(per, R)
+        local = torch.zeros(blen, dtype=torch.float64, device=final.device)
+        if kc > 0:
+            sub = scoring.threshold_windows_launch(final[k0 * step:], wsize, step, kc, ddof, anomaly_padding, R)
+            # re-pack the kc-window buffer into the fixed per-window layout of `per` windows
+            s_loc, r_loc, n_loc = scoring.threshold_buffer_len(kc, R), kc * 4, kc * R * 3
+            local[: kc * 4] = sub[:r_loc]
+            local[per * 4: per * 4 + n_loc] = sub[r_loc:r_loc + n_loc]
+            local[per * 4 + per * R * 3: per * 4 + per * R * 3 + (kc + 1) // 2] = sub[r_loc + n_loc:s_loc]
+        parts = [torch.empty_like(local) for _ in range(self.world)]
+        dist.all_gather(parts, local, group=self.group)
+        host = torch.stack(parts).cpu().numpy()
+        stats, runs, n_runs = [], [], []
+        for r in range(self.world):
+            rk0 = min(r * per, count)
+            rkc = max(0, min(per, count - rk0))
+            st, ru, nr = scoring.threshold_windows_parse(host[r], per, R)
+            stats.append(st[:rkc])
+            runs.append(ru[:rkc])
+            n_runs.append(nr[:rkc])
+        stats, runs, n_runs = np.concatenate(stats), np.concatenate(runs), np.concatenate(n_runs)
+        if n_runs.max(initial=0) > R:  # same decision on every rank: the gathered counts are identical
+            return scoring.find_anomaly_intervals(final, index, window_size_portion, window_step_size_portion,
+                                                  min_percent=min_percent, anomaly_padding=anomaly_padding, ddof=ddof)
+        merged = scoring.intervals_from_runs(stats, runs, n_runs, step, min_percent)
+        return scoring.intervals_to_index(merged, index)

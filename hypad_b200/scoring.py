@@ -245,24 +245,41 @@ def analysis_windows(n, window_size=None, window_size_portion=None, window_step_
     return int(window_size), int(step), count
 
 
-def threshold_windows(errors, window_size, step, count, ddof, anomaly_padding, max_runs=64):
-    """Per analysis window: (mean, std, threshold, max_below) and the padded above-threshold runs.
-    One device buffer holds the three outputs so that a single device-to-host copy (one synchronisation) brings them back."""
+def threshold_buffer_len(count, max_runs):
+    """float64 slots of the packed threshold result: stats (count,4) | runs (count,max_runs,3) | n_runs int32 (count,)."""
+    return count * 4 + count * max_runs * 3 + (count + 1) // 2
+
+
+def threshold_windows_launch(errors, window_size, step, count, ddof, anomaly_padding, max_runs, out=None):
+    """Enqueues the per-window statistics / run kernels; returns the packed device buffer (no synchronisation)."""
     errors = _native.require_cuda(errors, "errors").reshape(-1).double().contiguous()
     dev = errors.device
     c = _ctx(errors)
+    n_stats, n_runs_f = count * 4, count * max_runs * 3
+    buf = torch.empty(threshold_buffer_len(count, max_runs), dtype=torch.float64, device=dev) if out is None else out
+    base = buf.data_ptr()
+    with torch.cuda.device(dev):
+        check(c.lib.hypad_threshold_windows(c.handle, ptr(errors), errors.shape[0], window_size, step, count, int(ddof),
+                                            int(anomaly_padding), base, base + 8 * n_stats, base + 8 * (n_stats + n_runs_f),
+                                            max_runs, c.stream()))
+    return buf
+
+
+def threshold_windows_parse(host, count, max_runs):
+    """(stats (count,4), runs (count,max_runs,3), n_runs (count,)) views of a packed buffer brought to the host."""
+    n_stats, n_runs_f = count * 4, count * max_runs * 3
+    nr = host[n_stats + n_runs_f: n_stats + n_runs_f + (count + 1) // 2].view(np.int32)[:count]
+    return host[:n_stats].reshape(count, 4), host[n_stats:n_stats + n_runs_f].reshape(count, max_runs, 3), nr
+
+
+def threshold_windows(errors, window_size, step, count, ddof, anomaly_padding, max_runs=64):
+    """Per analysis window: (mean, std, threshold, max_below) and the padded above-threshold runs.
+    One device buffer holds the three outputs so that a single device-to-host copy (one synchronisation) brings them back."""
     while True:
-        n_stats, n_runs_f = count * 4, count * max_runs * 3
-        buf = torch.empty(n_stats + n_runs_f + (count + 1) // 2, dtype=torch.float64, device=dev)
-        base = buf.data_ptr()
-        with torch.cuda.device(dev):
-            check(c.lib.hypad_threshold_windows(c.handle, ptr(errors), errors.shape[0], window_size, step, count, int(ddof),
-                                                int(anomaly_padding), base, base + 8 * n_stats, base + 8 * (n_stats + n_runs_f),
-                                                max_runs, c.stream()))
-        host = buf.cpu().numpy()
-        nr = host[n_stats + n_runs_f:].view(np.int32)[:count]
+        host = threshold_windows_launch(errors, window_size, step, count, ddof, anomaly_padding, max_runs).cpu().numpy()
+        stats, runs, nr = threshold_windows_parse(host, count, max_runs)
         if nr.max(initial=0) <= max_runs:
-            return host[:n_stats].reshape(count, 4), host[n_stats:n_stats + n_runs_f].reshape(count, max_runs, 3), nr
+            return stats, runs, nr
         max_runs = int(nr.max()) + 16
 
 
@@ -331,6 +348,12 @@ def intervals_from_runs(stats, runs, n_runs, step, min_percent):
     return merged
 
 
+def intervals_to_index(merged, index):
+    idx = index.detach().cpu().numpy() if isinstance(index, torch.Tensor) else np.asarray(index)
+    out = [[float(idx[int(s)]), float(idx[int(e)]), float(sc)] for s, e, sc in merged]
+    return np.asarray(out, dtype=np.float64).reshape(-1, 3)
+
+
 def find_anomaly_intervals(errors, index, window_size_portion=None, window_step_size_portion=None, window_size=None,
                            window_step_size=None, min_percent=0.1, anomaly_padding=50, ddof=0):
     """find_anomalies(..., fixed_threshold=True) on a device array; returns (K,3) float64 [index[start], index[end], score]."""
@@ -338,9 +361,7 @@ def find_anomaly_intervals(errors, index, window_size_portion=None, window_step_
     wsize, step, count = analysis_windows(n, window_size, window_size_portion, window_step_size, window_step_size_portion)
     stats, runs, n_runs = threshold_windows(errors, wsize, step, count, ddof, anomaly_padding)
     merged = intervals_from_runs(stats, runs, n_runs, step, min_percent)
-    idx = index.detach().cpu().numpy() if isinstance(index, torch.Tensor) else np.asarray(index)
-    out = [[float(idx[int(s)]), float(idx[int(e)]), float(sc)] for s, e, sc in merged]
-    return np.asarray(out, dtype=np.float64).reshape(-1, 3)
+    return intervals_to_index(merged, index)
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -56,3 +56,31 @@ def test_analysis_window_count_matches_reference_loop():
             start += step
         assert count == k, n
         assert (count - 1) * step < n
+
+
+def test_window_subset_of_a_suffix_equals_the_same_windows_of_the_full_array():
+    """What ShardedScorer.find_anomaly_intervals relies on: analysis window k of errors[k0*step:] is window k0+k of errors
+    (same elements, same clamp at the end), so dealing window ranges out to ranks and concatenating reproduces the
+    single-rank result."""
+    from hypad_b200 import scoring
+
+    p = golden("pieces.npz")
+    e = p["fa_errors"]
+    wsize, step, count = scoring.analysis_windows(len(e), None, 0.33, None, 0.1)
+    full = numpy_threshold_windows(e, wsize, step, count, 1, 50)
+    for world in (2, 3, 8):
+        per = -(-count // world)
+        stats, nruns, runs = [], [], []
+        for r in range(world):
+            k0 = min(r * per, count)
+            kc = max(0, min(per, count - k0))
+            if kc == 0:
+                continue
+            st, ru, nr = numpy_threshold_windows(e[k0 * step:], wsize, step, kc, 1, 50)
+            stats.append(st)
+            nruns.append(nr)
+            runs.extend(ru[k, :nr[k]] for k in range(kc))
+        assert np.array_equal(np.concatenate(stats), full[0])
+        assert np.array_equal(np.concatenate(nruns), full[2])
+        for k, rk in enumerate(runs):
+            assert np.array_equal(rk, full[1][k, :full[2][k]])
