@@ -349,6 +349,12 @@ struct TwArgs {
     long long* starts;      // [n_analysis][max_runs]
     long long* ends;        // [n_analysis][max_runs]
     unsigned long long* rmax;   // [n_analysis][max_runs]
+    // block summaries and work list of the product path
+    double* bsum1;              // [blocks] sum(x - c)
+    double* bsum2;              // [blocks] sum((x - c)^2)
+    unsigned long long* bmax;   // [blocks] order-preserving key of the block maximum
+    int* work_cnt;
+    longlong2* work;            // (window, block) pairs that need the element-wise pass
 };
 
 __device__ __forceinline__ void tw_window(const TwArgs& a, int k, const double*& e, int64_t& n) {
@@ -413,50 +419,55 @@ __device__ __forceinline__ bool any_bits(const unsigned* w, int lo, int hi) {
     return acc != 0u;
 }
 
-__global__ void __launch_bounds__(TW_TILE) tw_events_kernel(const TwArgs a) {
-    constexpr int REGION = TW_TILE + 2 * TW_MAXPAD + 2;
-    __shared__ unsigned s_bits[(REGION + 31) / 32 + 1];
-    __shared__ unsigned char s_dil[TW_TILE + 2];
-    __shared__ unsigned long long s_below;
-    const int k = blockIdx.y, tid = threadIdx.x;
+// One tile [t0, t0+len) (window-relative, len <= TW_TILE) of window k: flags, dilation, run starts / ends, max outside runs.
+__device__ __forceinline__ void tw_events_tile(const TwArgs& a, int k, int64_t t0, int len, unsigned* s_bits, unsigned char* s_dil,
+                                               unsigned long long* s_below) {
+    const int tid = threadIdx.x;
     const double* e;
     int64_t n;
     tw_window(a, k, e, n);
-    const int64_t t0 = (int64_t)blockIdx.x * TW_TILE;
-    if (t0 >= n) return;
     const double thr = a.stats[k * 4 + 2];
     const int pad = a.pad;
     const int region = TW_TILE + 2 * pad + 2;       // positions t0-pad-1 .. t0+TILE+pad
     const int64_t r0 = t0 - pad - 1;
-    if (tid == 0) s_below = 0ull;
+    if (tid == 0) *s_below = 0ull;
+    bool any_flag = false;
     for (int f = tid; f < ((region + 31) & ~31); f += TW_TILE) {
         const int64_t q = r0 + f;
         const bool flag = f < region && q >= 0 && q < n && e[q] > thr;
         const unsigned word = __ballot_sync(0xffffffffu, flag);
+        any_flag |= word != 0u;
         if ((tid & 31) == 0) s_bits[f >> 5] = word;
     }
-    __syncthreads();
-    // dilation of positions t0-1 .. t0+TILE: bit range [j, j+2pad] of the packed window
-    for (int j = tid; j < TW_TILE + 2; j += TW_TILE) {
-        const int64_t p = t0 - 1 + j;
-        s_dil[j] = (p >= 0 && p < n && any_bits(s_bits, j, j + 2 * pad)) ? 1 : 0;
-    }
-    __syncthreads();
+    // Almost every tile of almost every window has nothing above the threshold in reach: then no position is in a run
+    // and the tile only contributes its maximum to max_below.  (The barrier also publishes s_bits and s_below.)
+    const bool quiet = !__syncthreads_or(any_flag);
     const int64_t i = t0 + tid;
+    const bool mine = tid < len && i < n;
     unsigned long long below_key = 0ull;
-    if (i < n) {
-        const bool dil = s_dil[tid + 1] != 0;
-        if (dil) {
-            if (!s_dil[tid]) {  // run start (shift(1).fillna(False), :1151-1160)
-                const int slot = atomicAdd(&a.cnt[k * 2], 1);
-                if (slot < a.max_runs) a.starts[(size_t)k * a.max_runs + slot] = i;
+    if (quiet) {
+        below_key = mine ? dkey(e[i]) : 0ull;
+    } else {
+        // dilation of positions t0-1 .. t0+TILE: bit range [j, j+2pad] of the packed window
+        for (int j = tid; j < TW_TILE + 2; j += TW_TILE) {
+            const int64_t p = t0 - 1 + j;
+            s_dil[j] = (p >= 0 && p < n && any_bits(s_bits, j, j + 2 * pad)) ? 1 : 0;
+        }
+        __syncthreads();
+        if (mine) {
+            const bool dil = s_dil[tid + 1] != 0;
+            if (dil) {
+                if (!s_dil[tid]) {  // run start (shift(1).fillna(False), :1151-1160)
+                    const int slot = atomicAdd(&a.cnt[k * 2], 1);
+                    if (slot < a.max_runs) a.starts[(size_t)k * a.max_runs + slot] = i;
+                }
+                if (!s_dil[tid + 2]) {  // run end (the last element closes an open run, :1163-1164)
+                    const int slot = atomicAdd(&a.cnt[k * 2 + 1], 1);
+                    if (slot < a.max_runs) a.ends[(size_t)k * a.max_runs + slot] = i;
+                }
+            } else {
+                below_key = dkey(e[i]);
             }
-            if (!s_dil[tid + 2]) {  // run end (the last element closes an open run, :1163-1164)
-                const int slot = atomicAdd(&a.cnt[k * 2 + 1], 1);
-                if (slot < a.max_runs) a.ends[(size_t)k * a.max_runs + slot] = i;
-            }
-        } else {
-            below_key = dkey(e[i]);
         }
     }
     // block max of the not-in-any-run values -> one atomic per CTA
@@ -465,19 +476,29 @@ __global__ void __launch_bounds__(TW_TILE) tw_events_kernel(const TwArgs a) {
         const unsigned long long v = __shfl_xor_sync(0xffffffffu, below_key, o);
         below_key = v > below_key ? v : below_key;
     }
-    if ((tid & 31) == 0 && below_key) atomicMax(&s_below, below_key);
+    if ((tid & 31) == 0 && below_key) atomicMax(s_below, below_key);
     __syncthreads();
-    if (tid == 0 && s_below) atomicMax(&a.below[k], s_below);
+    if (tid == 0 && *s_below) atomicMax(&a.below[k], *s_below);
+    __syncthreads();  // the shared state is reused by the caller's next tile
 }
 
-// every above-threshold value goes to the run whose start is the largest start <= its position
-__global__ void __launch_bounds__(TW_TILE) tw_runmax_kernel(const TwArgs a) {
+// exhaustive version: every tile of every window
+__global__ void __launch_bounds__(TW_TILE) tw_events_kernel(const TwArgs a) {
+    constexpr int REGION = TW_TILE + 2 * TW_MAXPAD + 2;
+    __shared__ unsigned s_bits[(REGION + 31) / 32 + 1];
+    __shared__ unsigned char s_dil[TW_TILE + 2];
+    __shared__ unsigned long long s_below;
     const int k = blockIdx.y;
     const double* e;
     int64_t n;
     tw_window(a, k, e, n);
-    const int64_t i = (int64_t)blockIdx.x * TW_TILE + threadIdx.x;
-    if (i >= n) return;
+    const int64_t t0 = (int64_t)blockIdx.x * TW_TILE;
+    if (t0 >= n) return;
+    tw_events_tile(a, k, t0, TW_TILE, s_bits, s_dil, &s_below);
+}
+
+// the run a position belongs to: the one with the largest start <= the position
+__device__ __forceinline__ void tw_runmax_elem(const TwArgs& a, int k, const double* e, int64_t i) {
     const double v = e[i];
     if (!(v > a.stats[k * 4 + 2])) return;
     const int R = a.cnt[k * 2] < a.max_runs ? a.cnt[k * 2] : a.max_runs;
@@ -492,6 +513,156 @@ __global__ void __launch_bounds__(TW_TILE) tw_runmax_kernel(const TwArgs a) {
         }
     }
     if (arg >= 0) atomicMax(&a.rmax[(size_t)k * a.max_runs + arg], dkey(v));
+}
+
+// every above-threshold value goes to the run whose start is the largest start <= its position
+__global__ void __launch_bounds__(TW_TILE) tw_runmax_kernel(const TwArgs a) {
+    const int k = blockIdx.y;
+    const double* e;
+    int64_t n;
+    tw_window(a, k, e, n);
+    const int64_t i = (int64_t)blockIdx.x * TW_TILE + threadIdx.x;
+    if (i >= n) return;
+    tw_runmax_elem(a, k, e, i);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The product path reads the array ONCE.  The analysis windows overlap ten-fold and nearly all of their elements are far
+// from any anomaly, so per aligned block of TW_TILE elements the kernel below keeps sum(x-c), sum((x-c)^2) and the maximum
+// (c = a sample of the data, against cancellation); a window's statistics are the sums of its inner blocks plus its two
+// ragged edges, and a block whose own and neighbouring maxima are all below the window's threshold cannot touch a run:
+// it contributes its maximum to max_below and nothing else.  Only the remaining (window, block) pairs -- the blocks near
+// anomalies and the window edges -- go through the element-wise tile code above, from a work list.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RB) tw_blocks_kernel(const TwArgs a) {
+    __shared__ double sh[32];
+    const int64_t b = blockIdx.x, i0 = b * TW_TILE, i1 = i0 + TW_TILE < a.len ? i0 + TW_TILE : a.len;
+    const double c = a.errors[a.len / 2];
+    double s1 = 0.0, s2 = 0.0;
+    unsigned long long m = 0ull;
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += RB) {
+        const double x = a.errors[i], d = x - c;
+        s1 += d;
+        s2 += d * d;
+        const unsigned long long key = dkey(x);
+        m = key > m ? key : m;
+    }
+    s1 = block_sum(s1, sh);
+    s2 = block_sum(s2, sh);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long v = __shfl_xor_sync(0xffffffffu, m, o);
+        m = v > m ? v : m;
+    }
+    __shared__ unsigned long long shm[RB / 32];
+    if ((threadIdx.x & 31) == 0) shm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < RB / 32; ++w) m = shm[w] > m ? shm[w] : m;
+        a.bsum1[b] = s1;
+        a.bsum2[b] = s2;
+        a.bmax[b] = m;
+    }
+}
+
+// one CTA per window: statistics, reset of the event state, classification of the window's blocks
+__global__ void __launch_bounds__(RB) tw_window_kernel(const TwArgs a) {
+    __shared__ double sh[32];
+    __shared__ unsigned long long s_quiet;
+    const int k = blockIdx.x, tid = threadIdx.x;
+    const int64_t w0 = (int64_t)k * a.step, w1 = w0 + a.window_size < a.len ? w0 + a.window_size : a.len, n = w1 - w0;
+    const double c = a.errors[a.len / 2];
+    const int64_t bf0 = (w0 + TW_TILE - 1) / TW_TILE, bf1 = w1 / TW_TILE;  // blocks [bf0, bf1) lie fully inside
+    double s1 = 0.0, s2 = 0.0;
+    if (bf0 < bf1) {
+        for (int64_t b = bf0 + tid; b < bf1; b += RB) {
+            s1 += a.bsum1[b];
+            s2 += a.bsum2[b];
+        }
+        for (int64_t i = w0 + tid; i < bf0 * TW_TILE; i += RB) {
+            const double d = a.errors[i] - c;
+            s1 += d;
+            s2 += d * d;
+        }
+        for (int64_t i = bf1 * TW_TILE + tid; i < w1; i += RB) {
+            const double d = a.errors[i] - c;
+            s1 += d;
+            s2 += d * d;
+        }
+    } else {
+        for (int64_t i = w0 + tid; i < w1; i += RB) {
+            const double d = a.errors[i] - c;
+            s1 += d;
+            s2 += d * d;
+        }
+    }
+    s1 = block_sum(s1, sh);
+    s2 = block_sum(s2, sh);
+    const double dm = s1 / (double)n;                   // mean - c
+    double var = (s2 - s1 * dm) / (double)(n - a.ddof);  // sum((x-mean)^2) = sum((x-c)^2) - n (mean-c)^2
+    var = var > 0.0 ? var : 0.0;
+    const double mean = c + dm, sd = sqrt(var), thr = mean + 4.0 * sd;  // _fixed_threshold, k = 4 (:1098-1114)
+    if (tid == 0) {
+        a.stats[k * 4 + 0] = mean;
+        a.stats[k * 4 + 1] = sd;
+        a.stats[k * 4 + 2] = thr;
+        a.cnt[k * 2] = 0;
+        a.cnt[k * 2 + 1] = 0;
+        s_quiet = 0ull;
+    }
+    for (int r = tid; r < a.max_runs; r += RB) a.rmax[(size_t)k * a.max_runs + r] = 0ull;
+    __syncthreads();
+    // blocks overlapping the window: quiet ones give their maximum, the others go to the work list
+    const int64_t nb = (a.len + TW_TILE - 1) / TW_TILE;
+    const int64_t b_lo = w0 / TW_TILE, b_hi = (w1 - 1) / TW_TILE;
+    unsigned long long quiet = 0ull;
+    for (int64_t b = b_lo + tid; b <= b_hi; b += RB) {
+        const bool inner = b >= bf0 && b < bf1;
+        bool hot = !inner || a.bmax[b] > dkey(thr);
+        if (b > 0) hot |= a.bmax[b - 1] > dkey(thr);
+        if (b + 1 < nb) hot |= a.bmax[b + 1] > dkey(thr);
+        if (hot) {
+            const int slot = atomicAdd(a.work_cnt, 1);
+            a.work[slot] = make_longlong2((long long)k, (long long)b);
+        } else {
+            quiet = a.bmax[b] > quiet ? a.bmax[b] : quiet;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long v = __shfl_xor_sync(0xffffffffu, quiet, o);
+        quiet = v > quiet ? v : quiet;
+    }
+    if ((tid & 31) == 0 && quiet) atomicMax(&s_quiet, quiet);
+    __syncthreads();
+    if (tid == 0) a.below[k] = s_quiet;
+}
+
+// the work list's (window, block) pairs through the element-wise tile code
+__global__ void __launch_bounds__(TW_TILE) tw_events_work_kernel(const TwArgs a) {
+    constexpr int REGION = TW_TILE + 2 * TW_MAXPAD + 2;
+    __shared__ unsigned s_bits[(REGION + 31) / 32 + 1];
+    __shared__ unsigned char s_dil[TW_TILE + 2];
+    __shared__ unsigned long long s_below;
+    const int total = *a.work_cnt;
+    for (int j = blockIdx.x; j < total; j += gridDim.x) {
+        const longlong2 kb = a.work[j];
+        const int k = (int)kb.x;
+        const int64_t w0 = (int64_t)k * a.step, w1 = w0 + a.window_size < a.len ? w0 + a.window_size : a.len;
+        const int64_t g0 = kb.y * TW_TILE > w0 ? kb.y * TW_TILE : w0, g1 = (kb.y + 1) * TW_TILE < w1 ? (kb.y + 1) * TW_TILE : w1;
+        tw_events_tile(a, k, g0 - w0, (int)(g1 - g0), s_bits, s_dil, &s_below);
+    }
+}
+
+__global__ void __launch_bounds__(TW_TILE) tw_runmax_work_kernel(const TwArgs a) {
+    const int total = *a.work_cnt;
+    for (int j = blockIdx.x; j < total; j += gridDim.x) {
+        const longlong2 kb = a.work[j];
+        const int k = (int)kb.x;
+        const int64_t w0 = (int64_t)k * a.step, w1 = w0 + a.window_size < a.len ? w0 + a.window_size : a.len;
+        const int64_t g = kb.y * TW_TILE + threadIdx.x;
+        if (g >= w0 && g < w1) tw_runmax_elem(a, k, a.errors + w0, g - w0);
+    }
 }
 
 // per window: order the runs by start, pair the r-th start with the r-th end, emit (start, end, max)
@@ -663,9 +834,9 @@ int hypad_combine_scores(int mode, const double* critic_scores, const void* rec,
     return HYPAD_OK;
 }
 
-int hypad_threshold_windows(hypad_ctx* ctx, const double* errors, int64_t len, int64_t window_size, int64_t step,
-                            int64_t n_analysis, int ddof, int anomaly_padding, double* stats, double* runs,
-                            int32_t* n_runs, int max_runs, void* stream_) {
+static int threshold_windows_impl(hypad_ctx* ctx, const double* errors, int64_t len, int64_t window_size, int64_t step,
+                                  int64_t n_analysis, int ddof, int anomaly_padding, double* stats, double* runs,
+                                  int32_t* n_runs, int max_runs, cudaStream_t stream, bool exhaustive) {
     HYPAD_REQUIRE(ctx && errors && stats && runs && n_runs, "hypad_threshold_windows: NULL argument");
     HYPAD_REQUIRE(len >= 1 && window_size >= 1 && step >= 1 && n_analysis >= 1 && max_runs >= 1, "hypad_threshold_windows: bad shape");
     HYPAD_REQUIRE(n_analysis <= 65535, "hypad_threshold_windows: more than 65535 analysis windows");
@@ -673,7 +844,6 @@ int hypad_threshold_windows(hypad_ctx* ctx, const double* errors, int64_t len, i
     HYPAD_REQUIRE(anomaly_padding >= 0 && anomaly_padding <= TW_MAXPAD, "hypad_threshold_windows: padding %d outside 0..%d",
                   anomaly_padding, TW_MAXPAD);
     HYPAD_REQUIRE(ddof == 0 || ddof == 1, "hypad_threshold_windows: ddof must be 0 or 1");
-    cudaStream_t stream = (cudaStream_t)stream_;
     HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
     const int64_t wlen = window_size < len ? window_size : len;
     TwArgs a;
@@ -682,31 +852,64 @@ int hypad_threshold_windows(hypad_ctx* ctx, const double* errors, int64_t len, i
     a.n_slices = (int)ceil_div(wlen, TW_CHUNK);
     a.stats = stats; a.runs = runs; a.n_runs = n_runs;
     const size_t na = (size_t)n_analysis, mr = (size_t)max_runs;
+    const size_t nb = (size_t)ceil_div(len, TW_TILE), wb = (size_t)ceil_div(wlen, TW_TILE) + 2;  // blocks a window can overlap
     const size_t o_partial = 0, o_mean = o_partial + align256(na * a.n_slices * 8), o_cnt = o_mean + align256(na * 8);
     const size_t o_below = o_cnt + align256(na * 2 * 4), o_starts = o_below + align256(na * 8);
     const size_t o_ends = o_starts + align256(na * mr * 8), o_rmax = o_ends + align256(na * mr * 8);
-    int rc = ensure_workspace(ctx, o_rmax + align256(na * mr * 8));
+    const size_t o_b1 = o_rmax + align256(na * mr * 8), o_b2 = o_b1 + align256(nb * 8), o_bm = o_b2 + align256(nb * 8);
+    const size_t o_wc = o_bm + align256(nb * 8), o_work = o_wc + 256, o_end = o_work + align256(na * wb * 16);
+    int rc = ensure_workspace(ctx, o_end);
     if (rc != HYPAD_OK) return rc;
     char* ws = (char*)ctx->workspace;
     a.partial = (double*)(ws + o_partial); a.mean = (double*)(ws + o_mean); a.cnt = (int*)(ws + o_cnt);
     a.below = (unsigned long long*)(ws + o_below); a.starts = (long long*)(ws + o_starts);
     a.ends = (long long*)(ws + o_ends); a.rmax = (unsigned long long*)(ws + o_rmax);
-    const dim3 gsum((unsigned)a.n_slices, (unsigned)n_analysis), gtile((unsigned)ceil_div(wlen, TW_TILE), (unsigned)n_analysis);
-    tw_partial_kernel<<<gsum, 256, 0, stream>>>(a, 0);
-    HYPAD_LAUNCH_CHECK();
-    tw_final_kernel<<<(unsigned)n_analysis, 32, 0, stream>>>(a, 0);
-    HYPAD_LAUNCH_CHECK();
-    tw_partial_kernel<<<gsum, 256, 0, stream>>>(a, 1);
-    HYPAD_LAUNCH_CHECK();
-    tw_final_kernel<<<(unsigned)n_analysis, 32, 0, stream>>>(a, 1);
-    HYPAD_LAUNCH_CHECK();
-    tw_events_kernel<<<gtile, TW_TILE, 0, stream>>>(a);
-    HYPAD_LAUNCH_CHECK();
-    tw_runmax_kernel<<<gtile, TW_TILE, 0, stream>>>(a);
-    HYPAD_LAUNCH_CHECK();
+    a.bsum1 = (double*)(ws + o_b1); a.bsum2 = (double*)(ws + o_b2); a.bmax = (unsigned long long*)(ws + o_bm);
+    a.work_cnt = (int*)(ws + o_wc); a.work = (longlong2*)(ws + o_work);
+    if (exhaustive) {
+        const dim3 gsum((unsigned)a.n_slices, (unsigned)n_analysis), gtile((unsigned)ceil_div(wlen, TW_TILE), (unsigned)n_analysis);
+        tw_partial_kernel<<<gsum, 256, 0, stream>>>(a, 0);
+        HYPAD_LAUNCH_CHECK();
+        tw_final_kernel<<<(unsigned)n_analysis, 32, 0, stream>>>(a, 0);
+        HYPAD_LAUNCH_CHECK();
+        tw_partial_kernel<<<gsum, 256, 0, stream>>>(a, 1);
+        HYPAD_LAUNCH_CHECK();
+        tw_final_kernel<<<(unsigned)n_analysis, 32, 0, stream>>>(a, 1);
+        HYPAD_LAUNCH_CHECK();
+        tw_events_kernel<<<gtile, TW_TILE, 0, stream>>>(a);
+        HYPAD_LAUNCH_CHECK();
+        tw_runmax_kernel<<<gtile, TW_TILE, 0, stream>>>(a);
+        HYPAD_LAUNCH_CHECK();
+    } else {
+        int sms = kNumSMs;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        HYPAD_CUDA_TRY(cudaMemsetAsync(a.work_cnt, 0, sizeof(int), stream));
+        tw_blocks_kernel<<<(unsigned)nb, RB, 0, stream>>>(a);
+        HYPAD_LAUNCH_CHECK();
+        tw_window_kernel<<<(unsigned)n_analysis, RB, 0, stream>>>(a);
+        HYPAD_LAUNCH_CHECK();
+        tw_events_work_kernel<<<(unsigned)(2 * sms), TW_TILE, 0, stream>>>(a);
+        HYPAD_LAUNCH_CHECK();
+        tw_runmax_work_kernel<<<(unsigned)(2 * sms), TW_TILE, 0, stream>>>(a);
+        HYPAD_LAUNCH_CHECK();
+    }
     tw_emit_kernel<<<(unsigned)n_analysis, 256, 0, stream>>>(a);
     HYPAD_LAUNCH_CHECK();
     return HYPAD_OK;
+}
+
+int hypad_threshold_windows(hypad_ctx* ctx, const double* errors, int64_t len, int64_t window_size, int64_t step,
+                            int64_t n_analysis, int ddof, int anomaly_padding, double* stats, double* runs,
+                            int32_t* n_runs, int max_runs, void* stream_) {
+    return threshold_windows_impl(ctx, errors, len, window_size, step, n_analysis, ddof, anomaly_padding, stats, runs, n_runs,
+                                  max_runs, (cudaStream_t)stream_, false);
+}
+
+int hypad_threshold_windows_exhaustive(hypad_ctx* ctx, const double* errors, int64_t len, int64_t window_size, int64_t step,
+                                       int64_t n_analysis, int ddof, int anomaly_padding, double* stats, double* runs,
+                                       int32_t* n_runs, int max_runs, void* stream_) {
+    return threshold_windows_impl(ctx, errors, len, window_size, step, n_analysis, ddof, anomaly_padding, stats, runs, n_runs,
+                                  max_runs, (cudaStream_t)stream_, true);
 }
 
 }  // extern "C"

@@ -250,7 +250,7 @@ def threshold_buffer_len(count, max_runs):
     return count * 4 + count * max_runs * 3 + (count + 1) // 2
 
 
-def threshold_windows_launch(errors, window_size, step, count, ddof, anomaly_padding, max_runs, out=None):
+def threshold_windows_launch(errors, window_size, step, count, ddof, anomaly_padding, max_runs, out=None, exhaustive=False):
     """Enqueues the per-window statistics / run kernels; returns the packed device buffer (no synchronisation)."""
     errors = _native.require_cuda(errors, "errors").reshape(-1).double().contiguous()
     dev = errors.device
@@ -259,9 +259,9 @@ def threshold_windows_launch(errors, window_size, step, count, ddof, anomaly_pad
     buf = torch.empty(threshold_buffer_len(count, max_runs), dtype=torch.float64, device=dev) if out is None else out
     base = buf.data_ptr()
     with torch.cuda.device(dev):
-        check(c.lib.hypad_threshold_windows(c.handle, ptr(errors), errors.shape[0], window_size, step, count, int(ddof),
-                                            int(anomaly_padding), base, base + 8 * n_stats, base + 8 * (n_stats + n_runs_f),
-                                            max_runs, c.stream()))
+        fn = c.lib.hypad_threshold_windows_exhaustive if exhaustive else c.lib.hypad_threshold_windows
+        check(fn(c.handle, ptr(errors), errors.shape[0], window_size, step, count, int(ddof), int(anomaly_padding), base,
+                 base + 8 * n_stats, base + 8 * (n_stats + n_runs_f), max_runs, c.stream()))
     return buf
 
 
@@ -272,11 +272,12 @@ def threshold_windows_parse(host, count, max_runs):
     return host[:n_stats].reshape(count, 4), host[n_stats:n_stats + n_runs_f].reshape(count, max_runs, 3), nr
 
 
-def threshold_windows(errors, window_size, step, count, ddof, anomaly_padding, max_runs=64):
+def threshold_windows(errors, window_size, step, count, ddof, anomaly_padding, max_runs=64, exhaustive=False):
     """Per analysis window: (mean, std, threshold, max_below) and the padded above-threshold runs.
     One device buffer holds the three outputs so that a single device-to-host copy (one synchronisation) brings them back."""
     while True:
-        host = threshold_windows_launch(errors, window_size, step, count, ddof, anomaly_padding, max_runs).cpu().numpy()
+        host = threshold_windows_launch(errors, window_size, step, count, ddof, anomaly_padding, max_runs,
+                                        exhaustive=exhaustive).cpu().numpy()
         stats, runs, nr = threshold_windows_parse(host, count, max_runs)
         if nr.max(initial=0) <= max_runs:
             return stats, runs, nr
@@ -293,18 +294,33 @@ def _ieee_div(a, b):
         return math.copysign(float("inf"), a) * math.copysign(1.0, b)
 
 
+def _np_sum(vals):
+    """np.add.reduce of a 1-D float64 array, in numpy's order: a plain loop below 8 elements, else eight interleaved
+    accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) and the tail added one by one (numpy's pairwise_sum for
+    n <= 128, its unrolled block size)."""
+    n = len(vals)
+    if n < 8:
+        res = 0.0
+        for v in vals:
+            res += v
+        return res
+    if n > 128:
+        return float(np.add.reduce(np.asarray(vals, dtype=np.float64)))
+    r = list(vals[:8])
+    i = 8
+    while i < n - (n % 8):
+        for j in range(8):
+            r[j] += vals[i + j]
+        i += 8
+    res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]))
+    for v in vals[i:]:
+        res += v
+    return res
+
+
 def _np_average(values, weights):
-    """np.average(values, weights=weights) (:1297): (v*w).sum() / w.sum() in numpy's summation order, which is a plain
-    left-to-right loop below 8 elements."""
-    if len(values) < 8:
-        num = den = 0.0
-        for v, w in zip(values, weights):
-            num += v * w
-            den += w
-        return _ieee_div(num, den)
-    v, w = np.asarray(values, dtype=np.float64), np.asarray(weights, dtype=np.float64)
-    with np.errstate(divide="ignore", invalid="ignore"):
-        return float(np.add.reduce(v * w) / np.add.reduce(w))
+    """np.average(values, weights=weights) (:1297): (v*w).sum() / w.sum(), bit for bit, without numpy's per-call cost."""
+    return _ieee_div(_np_sum([v * w for v, w in zip(values, weights)]), _np_sum(weights))
 
 
 def intervals_from_runs(stats, runs, n_runs, step, min_percent):

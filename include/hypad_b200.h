@@ -196,6 +196,12 @@ int hypad_area_error(const double* y, const void* y_hat, int y_hat_is_f32, int64
 int hypad_threshold_windows(hypad_ctx* ctx, const double* errors, int64_t len, int64_t window_size, int64_t step,
                             int64_t n_analysis, int ddof, int anomaly_padding, double* stats, double* runs,
                             int32_t* n_runs, int max_runs, void* stream);
+/* Same contract and results (statistics to the last few bits, runs exactly); every tile of every window is visited
+ * element-wise with two-pass statistics: the in-library cross-check of hypad_threshold_windows, which reads the array
+ * once (per-block sums and maxima) and visits only the blocks near anomalies and window edges. */
+int hypad_threshold_windows_exhaustive(hypad_ctx* ctx, const double* errors, int64_t len, int64_t window_size, int64_t step,
+                            int64_t n_analysis, int ddof, int anomaly_padding, double* stats, double* runs,
+                            int32_t* n_runs, int max_runs, void* stream);
 
 /* Diagnostic (not on the product path): D (128,N) = A (128,K) B(N,K)^T on the tcgen05 tensor cores with the fp32
  * operands split into `pieces` TF32 parts and `terms` partial products accumulated in TMEM: (1,1) plain TF32,

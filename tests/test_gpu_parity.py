@@ -499,3 +499,33 @@ def test_multivariate_euclidean_s123(cuda_device):
     g = {"final": want["final"], "kmax": want["kmax"], "critic": want["critic"]}
     selection_aware_close(out, g, 3000, "multivariate Euclidean S=123")
     check_intervals(out["intervals"], want["intervals"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,portion,pad,ddof", [(999900, 0.33, 50, 1), (8639, 0.33, 50, 0), (3000, 0.2, 200, 0), (20000, 0.33, 512, 1),
+                                                 (5000, 0.33, 0, 0), (1025, 0.33, 50, 1), (700, 1.0, 50, 0)])
+def test_threshold_windows_block_path_equals_exhaustive(n, portion, pad, ddof, cuda_device):
+    """hypad_threshold_windows (block sums / maxima + work list) against hypad_threshold_windows_exhaustive (every tile,
+    two-pass statistics): identical runs, run maxima and max_below; statistics to 1e-12; and against numpy."""
+    from hypad_b200 import scoring
+
+    rng = np.random.default_rng(n + pad)
+    e = 1.0 + 0.3 * np.abs(rng.standard_normal(n))
+    for c in rng.integers(0, n, size=max(3, n // 40000)):           # anomaly bursts, some at block / window edges
+        e[c:c + rng.integers(1, 8)] += rng.uniform(3, 9)
+    e[0] += 6.0
+    e[-1] += 6.0
+    if n > 2048:
+        e[1023:1026] += 5.0
+    dev_e = torch.from_numpy(e).to(cuda_device)
+    wsize, step, count = scoring.analysis_windows(n, None, portion, None, 0.1)
+    got = scoring.threshold_windows(dev_e, wsize, step, count, ddof, pad)
+    want = scoring.threshold_windows(dev_e, wsize, step, count, ddof, pad, exhaustive=True)
+    assert np.array_equal(got[2], want[2]) and got[2].max() > 0
+    for k in range(count):
+        r = int(got[2][k])
+        assert np.array_equal(got[1][k, :r], want[1][k, :r]), k
+        w = e[k * step:k * step + wsize]
+        np.testing.assert_allclose(got[0][k, :2], (w.mean(), w.std(ddof=ddof)), rtol=1e-12)
+    np.testing.assert_allclose(got[0][:, :3], want[0][:, :3], rtol=1e-12)
+    assert np.array_equal(got[0][:, 3], want[0][:, 3])

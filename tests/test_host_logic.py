@@ -84,3 +84,16 @@ def test_window_subset_of_a_suffix_equals_the_same_windows_of_the_full_array():
         assert np.array_equal(np.concatenate(nruns), full[2])
         for k, rk in enumerate(runs):
             assert np.array_equal(rk, full[1][k, :full[2][k]])
+
+
+def test_numpy_order_sum_and_average_are_bitwise_numpy():
+    """The host tail averages interval scores with np.average in the reference (:1297); the product's pure-Python version
+    reproduces numpy's summation order (8 interleaved accumulators) exactly."""
+    from hypad_b200.scoring import _np_average, _np_sum
+
+    rng = np.random.default_rng(5)
+    for n in list(range(1, 140)) + [200, 257]:
+        v = rng.standard_normal(n) * 10 ** rng.uniform(-3, 3, n)
+        w = rng.uniform(1, 500, n)
+        assert _np_sum(list(v)) == float(np.add.reduce(v)), n
+        assert _np_average(list(v), list(w)) == float(np.average(v, weights=w)), n
