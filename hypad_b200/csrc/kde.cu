@@ -12,10 +12,10 @@
 //
 // kde_exhaustive_kernel evaluates all n^2 kernel values in fp64, accumulating over i in scipy's order.
 // kde_screened_kernel (the product path) first evaluates all densities in fp32 with ex2.approx on centred,
-// bandwidth-scaled values; every j whose fp32 density is within 2.5e-4 (relative) of the fp32 maximum is a
-// candidate -- the fp32 error is bounded by ~2.5e-5 (centred operands |D| <= 25, contributing pairs |r| <= 4.5:
-// exponent error 2 r dr <= 1.3e-5, ex2.approx 2^-22, 100 additions <= 6e-6) -- and only candidates are
-// re-evaluated in fp64.  The arg-max is then taken over the fp64 densities of the candidates in ascending j,
+// bandwidth-scaled values, every unordered pair once; every j whose fp32 density is within 2.5e-5 + 1e-6 max|D|
+// (relative) of the fp32 maximum is a candidate -- four times the worst-case fp32 error derived at the threshold below.
+// Candidates are re-evaluated in fp32 from fp64 differences with expf (error < 1e-6); those within 1e-5 of that maximum
+// survive, and only if several distinct values survive are they decided in fp64, in ascending j (first maximum wins),
 // which equals the arg-max over all j.
 #include <math_constants.h>
 
@@ -301,7 +301,17 @@ __global__ void __launch_bounds__(KDE_WARPS * 32, 8) kde_screened_kernel(const K
         for (int q = 0; q < 4; ++q)
             if (lane + 32 * q < n) m32 = fmaxf(m32, e32[q]);
         m32 = warp_max(m32);
-        const float thr = m32 * (1.0f - 2.5e-4f);  // 10x the fp32 error bound (header comment); a flat density top yields ~2 candidates
+        // Stage-1 margin.  Worst-case relative error of an fp32 density: ~90 sequential fp32 additions of positive terms
+        // (5.4e-6), ex2.approx (2.4e-7), and the rounding of the centred operands, their difference r and r^2, which moves
+        // a term's exponent by 2^-24 (2 r (|D_k| + |D_j| + r) + r^2) -- weighted by the term itself (r 2^(-r^2) <= 0.52,
+        // r^2 2^(-r^2) <= 0.53) at most 4.1e-8 (2.1 Dmax + 1.6): 6.3e-6 + 8.6e-8 Dmax in all, Dmax = max |D|.  Two such
+        // errors separate a true maximum from its fp32 rank; the margin is twice that again.
+        float dmax = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (lane + 32 * q < n) dmax = fmaxf(dmax, fabsf(d[q]));
+        dmax = warp_max(dmax);
+        const float thr = m32 * (1.0f - (2.5e-5f + 1e-6f * dmax));
         unsigned cands[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) cands[q] = __ballot_sync(0xffffffffu, (lane + 32 * q < n) && e32[q] >= thr);
