@@ -99,7 +99,8 @@ struct ColSrc {
     int32_t row = 0;            // weight row
     int32_t K = 0;              // source row length
     int32_t bidx = 0;           // bias index
-    int32_t pad = 0;
+    int32_t k0 = 0;             // operand feature of the source row's element 0 (tensor-core packing: the critic chain reads
+                                // its hidden state from features 104.. of the shared operand buffer)
 };
 
 }  // namespace hypad
@@ -119,7 +120,7 @@ struct hypad_ctx {
     size_t tc_small_off;
     int* tc_error;              // device flag raised when a barrier wait times out
     long long* tc_debug;        // optional device cycle counters (hypad_forward_debug_cycles)
-    unsigned char tc_prog_storage[1024];
+    unsigned char tc_prog_storage[2048];
 };
 
 namespace hypad {

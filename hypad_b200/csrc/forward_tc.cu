@@ -44,6 +44,8 @@ constexpr int TC_TILE_COLS = 256;         // TMEM columns per tile slot
 constexpr int TC_STAGE_BYTES = 16384;     // one weight stage: kstage k-steps of 16 k x n columns x (hi + lo) x 2 B
 constexpr int TC_NSLOT = 5;
 constexpr int TC_RED_BYTES = TC_NSPLIT * TC_M * 3 * 8;
+constexpr int TC_CRITIC_SHIFT = 8;        // sa of the critic's hidden activations (unbounded LeakyReLU outputs)
+constexpr int TC_CRITIC_K0 = 104;         // operand feature where the critic chain keeps its hidden state when it rides along
 
 enum TcEpi : int32_t { TE_LSTM_GI = 0, TE_LSTM_O, TE_Z, TE_LINEAR, TE_TANH, TE_MOB_R, TE_MOB_X, TE_CRITIC_HID, TE_CRITIC_OUT };
 // An LSTM layer is two passes over the same A operand: GI accumulates the cell-candidate and input gates of all units
@@ -55,7 +57,9 @@ enum TcPassIdx : int32_t {
 };
 
 struct TcPass {
-    int32_t k16;     // K / 16
+    int32_t k16;     // K / 16 (k-steps of the pass)
+    int32_t k_lo;    // first k-step of the operand buffer the pass reads (0 except for stand-alone critic layers)
+    int32_t out_k0;  // operand feature where the epilogue stores its output row (0 except for critic layers)
     int32_t n;       // accumulator columns, multiple of 16, <= 256
     int32_t n_live;  // columns (units for an LSTM pass) the epilogue processes: real outputs rounded up to 8; the rest are
                      // zero-weight padding whose operand features keep whatever finite value they had
@@ -67,6 +71,14 @@ struct TcPass {
     int32_t in_shift;   // sa of this pass's A operand
     int32_t kstage;     // k-steps per weight stage (<= 16 KB)
     float out_scale;    // 2^sa of the pass that consumes this pass's output
+    // Rider: one CriticX layer contracted in the same pass from the same operand buffer (its hidden state lives in features
+    // TC_CRITIC_K0.. of the buffer, beyond everything the main chain uses before the decoder LSTMs).  n2 == 0: none.
+    int32_t n2, n2_live;  // accumulator columns / live columns
+    int32_t d_col2;       // TMEM column within the tile slot
+    int32_t k2_lo, k2_n;  // first k-step and number of k-steps of the rider's weights
+    int32_t w_off2, b_off2, kstage2;
+    int32_t epi2;         // TE_CRITIC_HID or TE_CRITIC_OUT
+    int32_t in_shift2;    // sa of the features the rider reads
 };
 
 struct TcProgram {
@@ -74,7 +86,8 @@ struct TcProgram {
     int32_t S, S16, latent, latent_c, hyperbolic;
     int32_t mob_bias_off, mob_y2_off, critic5_off;  // float offsets into the small-parameter buffer
     int32_t mob_bias_d_off;  // the Mobius bias again as 128 doubles (16-byte aligned)
-    int32_t post_off;   // per pass: {2^sw, 2^-(sa+sw)} written by tc_wscale_kernel
+    int32_t post_off;   // per pass: {2^sw, 2^-(sa+sw)} of the pass and of its rider, written by tc_wscale_kernel
+    int32_t can_ride;   // the program holds riders (S and the encoder's hidden state stay below TC_CRITIC_K0)
 };
 
 struct TcParams {
@@ -86,6 +99,7 @@ struct TcParams {
     int32_t x_is_f64, stages;
     uint32_t pass_mask;
     int32_t want_rowstats;
+    int32_t ride;    // the CriticX layers ride along with the encoder passes (riders enabled, T_C1..T_C4 masked out)
     hypad_forward_out out;
     int* error_flag;
     long long* debug;  // optional cycle counters (block 0 only), see hypad_forward_debug_cycles
@@ -410,6 +424,24 @@ __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncol
     return sq;
 }
 
+// CriticX dense4 + LeakyReLU, then Linear(latent_c -> 1) as one ascending-k FFMA chain over the row's accumulators
+__device__ __forceinline__ void critic_out_tc(uint32_t tcol, float post, const float* __restrict__ bias, const float* __restrict__ w5,
+                                              int latent_c, float* out) {
+    float fdot = 0.0f;
+    for (int c = 0; c < ((latent_c + 7) & ~7); c += 8) {
+        float v[8];
+        tmem_ld8(tcol + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float tv = fmaf(v[i], post, bias[c + i]);
+            tv = tv > 0.0f ? tv : __fmul_rn(tv, 0.2f);
+            if (c + i < latent_c) fdot = fmaf(tv, w5[c + i], fdot);
+        }
+    }
+    if (out) *out = __fadd_rn(fdot, w5[latent_c]);
+}
+
 // DBG: cycle counters for scripts/tc_cycles.py (hypad_forward_debug_cycles); the product instantiation carries none.
 template <bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_constant__ TcParams P) {
@@ -466,18 +498,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                     const TcPass& ps = prog.pass[p];
                     for (int sl = 0; sl < TC_TILES && ok; ++sl) {
                         if (pr * TC_TILES + sl >= my_tiles) continue;
-                        const unsigned char* src = P.wpacked + ps.w_off;
-                        for (int kp = 0; kp < ps.k16; kp += ps.kstage) {
-                            const int kk = ps.k16 - kp < ps.kstage ? ps.k16 - kp : ps.kstage;
-                            const uint32_t bytes = (uint32_t)(kk * ps.n) * 64u;
-                            const long long c0 = DBG ? clock64() : 0;
-                            ok = mbar_wait<2000>(bar_empty + 8 * slot, par, P.error_flag);
-                            if (DBG) dbg_prod += clock64() - c0;
-                            if (!ok) break;
-                            mbar_expect_tx(bar_full + 8 * slot, bytes);
-                            bulk_g2s(s_u32(ring + slot * TC_STAGE_BYTES), src, bytes, bar_full + 8 * slot);
-                            src += bytes;
-                            if (++slot == TC_NSLOT) slot = 0, par ^= 1u;
+                        const int nblk = (P.ride && ps.n2) ? 2 : 1;
+                        for (int blk = 0; blk < nblk && ok; ++blk) {
+                            const unsigned char* src = P.wpacked + (blk ? ps.w_off2 : ps.w_off);
+                            const int k16 = blk ? ps.k2_n : ps.k16, kstage = blk ? ps.kstage2 : ps.kstage, n = blk ? ps.n2 : ps.n;
+                            for (int kp = 0; kp < k16; kp += kstage) {
+                                const int kk = k16 - kp < kstage ? k16 - kp : kstage;
+                                const uint32_t bytes = (uint32_t)(kk * n) * 64u;
+                                const long long c0 = DBG ? clock64() : 0;
+                                ok = mbar_wait<2000>(bar_empty + 8 * slot, par, P.error_flag);
+                                if (DBG) dbg_prod += clock64() - c0;
+                                if (!ok) break;
+                                mbar_expect_tx(bar_full + 8 * slot, bytes);
+                                bulk_g2s(s_u32(ring + slot * TC_STAGE_BYTES), src, bytes, bar_full + 8 * slot);
+                                src += bytes;
+                                if (++slot == TC_NSLOT) slot = 0, par ^= 1u;
+                            }
                         }
                     }
                 }
@@ -498,15 +534,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
         auto desc64 = [](uint32_t lo32) { return ((uint64_t)0x4008u << 32) | lo32; };  // SBO 128 B, descriptor version 1
         int64_t stages_left = 0;
         for (int p = 0; p < T_COUNT; ++p)
-            if ((P.pass_mask >> p) & 1u) stages_left += (prog.pass[p].k16 + prog.pass[p].kstage - 1) / prog.pass[p].kstage;
+            if ((P.pass_mask >> p) & 1u) {
+                stages_left += (prog.pass[p].k16 + prog.pass[p].kstage - 1) / prog.pass[p].kstage;
+                if (P.ride && prog.pass[p].n2) stages_left += (prog.pass[p].k2_n + prog.pass[p].kstage2 - 1) / prog.pass[p].kstage2;
+            }
         stages_left *= my_tiles;
         for (int64_t pr = 0; pr < npairs && ok; ++pr)
             for (int p = 0; p < T_COUNT && ok; ++p) {
                 if (!((P.pass_mask >> p) & 1u)) continue;
                 const TcPass& ps = prog.pass[p];
-                const uint32_t idesc = idesc_f16(ps.n);
-                const uint32_t n = (uint32_t)ps.n;
-                const uint32_t w_lbo = n << 16;  // LBO = 16 n bytes: the two 8-k chunks of a k-step
+                const int nblk = (P.ride && ps.n2) ? 2 : 1;
 #pragma unroll
                 for (int sl = 0; sl < TC_TILES; ++sl) {
                     if (pr * TC_TILES + sl >= my_tiles || !ok) continue;
@@ -518,9 +555,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                     if (dbg) dbg_a += clock64() - c0;
                     if (!ok) break;
                     tc_fence_after();
-                    const uint32_t d = tmem + (uint32_t)(sl * TC_TILE_COLS + ps.d_col);
-                    for (int kp = 0; kp < ps.k16; kp += ps.kstage) {
-                        const int kk = ps.k16 - kp < ps.kstage ? ps.k16 - kp : ps.kstage;
+                    for (int blk = 0; blk < nblk && ok; ++blk) {
+                    // block 0: the pass itself; block 1: its rider (own columns, own k range of the same operand buffer)
+                    const uint32_t n = (uint32_t)(blk ? ps.n2 : ps.n);
+                    const uint32_t idesc = idesc_f16((int)n);
+                    const uint32_t w_lbo = n << 16;  // LBO = 16 n bytes: the two 8-k chunks of a k-step
+                    const int k16 = blk ? ps.k2_n : ps.k16, kstage = blk ? ps.kstage2 : ps.kstage, k_lo = blk ? ps.k2_lo : ps.k_lo;
+                    const uint32_t d = tmem + (uint32_t)(sl * TC_TILE_COLS + (blk ? ps.d_col2 : ps.d_col));
+                    for (int kp = 0; kp < k16; kp += kstage) {
+                        const int kk = k16 - kp < kstage ? k16 - kp : kstage;
                         if (!have) {
                             if (dbg) c0 = clock64();
                             ok = mbar_wait(bar_full + 8 * slot, par, P.error_flag);
@@ -532,7 +575,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                         const uint32_t w0 = (ring0 + slot * (TC_STAGE_BYTES >> 4)) | w_lbo;
                         const uint32_t nslot = slot + 1 == TC_NSLOT ? 0 : slot + 1, npar = slot + 1 == TC_NSLOT ? par ^ 1u : par;
                         if (lead) {
-                            const uint32_t ka = (uint32_t)kp * 256u;  // 4096 B per k-step (16 features) of A
+                            const uint32_t ka = (uint32_t)(k_lo + kp) * 256u;  // 4096 B per k-step (16 features) of A
                             mma_f16(d, desc64(a_lo0 + ka), desc64(w0), idesc, kp > 0);  // small terms first
                             mma_f16(d, desc64(a_hi0 + ka), desc64(w0 + 2 * n), idesc, 1);
                             mma_f16(d, desc64(a_hi0 + ka), desc64(w0), idesc, 1);
@@ -549,7 +592,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                         }
                         if (lead) {
                             for (int j = 1; j < kk; ++j) {
-                                const uint32_t ka = (uint32_t)(kp + j) * 256u, wj = w0 + (uint32_t)j * 4u * n;
+                                const uint32_t ka = (uint32_t)(k_lo + kp + j) * 256u, wj = w0 + (uint32_t)j * 4u * n;
                                 mma_f16(d, desc64(a_lo0 + ka), desc64(wj), idesc, 1);
                                 mma_f16(d, desc64(a_hi0 + ka), desc64(wj + 2 * n), idesc, 1);
                                 mma_f16(d, desc64(a_hi0 + ka), desc64(wj), idesc, 1);
@@ -558,6 +601,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                         }
                         slot = nslot;
                         par = npar;
+                    }
                     }
                     if (lead) mma_commit(bar_acc + 8 * sl);  // accumulators of this pass and slot complete
                 }
@@ -610,7 +654,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                 if (!((P.pass_mask >> p) & 1u)) continue;
                 const TcPass& ps = prog.pass[p];
                 const float* __restrict__ b1 = small + ps.b_off;
-                const float post = small[prog.post_off + 2 * p + 1];  // 2^-(sa+sw): exact, folded into the bias FMA
+                const float post = small[prog.post_off + 4 * p + 1];  // 2^-(sa+sw): exact, folded into the bias FMA
                 const int cbeg = 8 * split, cstep = 8 * TC_NSPLIT;
 #pragma unroll 1
                 for (int sl = 0; sl < TC_TILES; ++sl) {
@@ -665,23 +709,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                         if (ps.epi == TE_Z && P.out.z && live) gout = P.out.z + (w0 + r) * prog.latent, gw = prog.latent;
                         if (ps.epi == TE_TANH && P.out.eucl && live) gout = P.out.eucl + (w0 + r) * (int64_t)S, gw = S;
                         if (ps.epi == TE_CRITIC_OUT) {
-                            // dense4 + LeakyReLU, then Linear(latent_c -> 1) as one ascending-k FFMA chain (split 0 only)
-                            if (split == 0) {
-                                const float* w5 = small + prog.critic5_off;
-                                float fdot = 0.0f;
-                                for (int c = 0; c < ((prog.latent_c + 7) & ~7); c += 8) {
-                                    float v[8];
-                                    tmem_ld8(trow + ps.d_col + c, v);
-                                    tmem_ld_wait();
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) {
-                                        float tv = fmaf(v[i], post, b1[c + i]);
-                                        tv = tv > 0.0f ? tv : __fmul_rn(tv, 0.2f);
-                                        if (c + i < prog.latent_c) fdot = fmaf(tv, w5[c + i], fdot);
-                                    }
-                                }
-                                if (live) P.out.critic[w0 + r] = __fadd_rn(fdot, w5[prog.latent_c]);
-                            }
+                            if (split == 0) critic_out_tc(trow + ps.d_col, post, b1, small + prog.critic5_off, prog.latent_c, live ? P.out.critic + w0 + r : nullptr);
                         } else {
                             for (int c = cbeg; c < ps.n_live; c += cstep) {
                                 float v[8], bv[8];
@@ -696,7 +724,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                                     v[i] = tv;
                                 }
                                 if (ps.epi != TE_TANH) check_range8(v, ps.out_scale, P.error_flag);
-                                store_act8(act, r, c, v, ps.out_scale);
+                                store_act8(act, r, ps.out_k0 + c, v, ps.out_scale);
                                 if (gout) {
 #pragma unroll
                                     for (int i = 0; i < 8; ++i)
@@ -746,6 +774,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                                 }
                             }
                             if (split == 0 && live && P.out.unorm) P.out.unorm[w0 + r] = sqrtf(sqvnorm);
+                        }
+                    }
+                    // ---- the CriticX layer riding along with this pass -------------------------------------------
+                    if (P.ride && ps.n2) {
+                        const float post2 = small[prog.post_off + 4 * p + 3];
+                        const float* __restrict__ b2 = small + ps.b_off2;
+                        if (ps.epi2 == TE_CRITIC_OUT) {
+                            if (split == 0) critic_out_tc(trow + ps.d_col2, post2, b2, small + prog.critic5_off, prog.latent_c, live ? P.out.critic + w0 + r : nullptr);
+                        } else {
+                            const float sc2 = __int_as_float((127 + TC_CRITIC_SHIFT) << 23);
+                            for (int c = cbeg; c < ps.n2_live; c += cstep) {
+                                float v[8], bv[8];
+                                tmem_ld8(trow + ps.d_col2 + c, v);
+                                ldg8(b2 + c, bv);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float tv = fmaf(v[i], post2, bv[i]);
+                                    v[i] = tv > 0.0f ? tv : __fmul_rn(tv, 0.2f);
+                                }
+                                check_range8(v, sc2, P.error_flag);
+                                store_act8(act, r, TC_CRITIC_K0 + c, v, sc2);
+                            }
                         }
                     }
                     if (dbg && blockIdx.x == 0 && tid == 0) P.debug[24 + p] += clock64() - ce0;
@@ -804,8 +855,9 @@ __global__ void widen_kernel(const float* __restrict__ src, double* __restrict__
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = (double)src[i];
 }
 
+// f_base: operand feature of the panel's k = 0 (riders start at a later k-step of the shared operand buffer)
 __global__ void pack_tc_kernel(const ColSrc* __restrict__ cols, int k16, int nblk, int n, __half* __restrict__ dst, float* __restrict__ bias,
-                               const float* __restrict__ scale) {
+                               const float* __restrict__ scale, int f_base) {
     const int ncols = nblk * n;
     const int total = k16 * 16 * ncols;
     const float wscale = scale[0];
@@ -813,7 +865,8 @@ __global__ void pack_tc_kernel(const ColSrc* __restrict__ cols, int k16, int nbl
         const int k = e / ncols, cc = e - k * ncols;
         const int blk = cc / n, c = cc - blk * n;
         const ColSrc s = cols[cc];
-        const float v = (s.w != nullptr && k < s.K) ? s.w[(size_t)s.row * s.K + k] : 0.0f;
+        const int ksrc = f_base + k - s.k0;  // index into the source row
+        const float v = (s.w != nullptr && ksrc >= 0 && ksrc < s.K) ? s.w[(size_t)s.row * s.K + ksrc] : 0.0f;
         const float t = __fmul_rn(v, wscale);
         const __half hi = __float2half_rn(t), lo = __float2half_rn(t - __half2float(hi));
         const int ks = k >> 4, ch = (k >> 3) & 1, el = k & 7;
@@ -895,11 +948,49 @@ int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
     if (hyp) linear_cols(T_MR, w->mobius_w, nullptr, S, S);
     set_pass(T_MX, S, NS, S, 128, TE_MOB_X, 1, SH_X, 0);
     if (hyp) linear_cols(T_MX, w->mobius_w, nullptr, S, S);
+    // Stand-alone critic layers (CriticX.forward on its own, or S too wide for riders).  When the program has riders they
+    // use the riders' geometry -- hidden state at features TC_CRITIC_K0.., k-steps from k_lo -- so that both routes issue the
+    // same tensor instructions on the same operands and CriticX.forward equals the fused critic bit for bit.
+    const bool ride_geo = S <= TC_CRITIC_K0 && TC_CRITIC_K0 + round8i(C) <= 128;
+    const int ck0 = ride_geo ? TC_CRITIC_K0 : 0;
     set_pass(T_C1, S, NC, C, 0, TE_CRITIC_HID, 1, SH_X, SH_FREE);
+    prog.pass[T_C1].out_k0 = ck0;
     linear_cols(T_C1, w->critic_w[0], w->critic_b[0], C, S);
     for (int i = 0; i < 3; ++i) {
-        set_pass(T_C2 + i, C, NC, C, 0, i == 2 ? TE_CRITIC_OUT : TE_CRITIC_HID, 0, SH_FREE, SH_FREE);
-        linear_cols(T_C2 + i, w->critic_w[1 + i], w->critic_b[1 + i], C, C);
+        const int idx = T_C2 + i;
+        set_pass(idx, C, NC, C, 0, i == 2 ? TE_CRITIC_OUT : TE_CRITIC_HID, 0, SH_FREE, SH_FREE);
+        linear_cols(idx, w->critic_w[1 + i], w->critic_b[1 + i], C, C);
+        if (ck0) {
+            TcPass& p = prog.pass[idx];
+            p.k_lo = ck0 / 16;
+            p.k16 = (round16i(ck0 + C) - ck0 / 16 * 16) / 16;
+            if (p.kstage > p.k16) p.kstage = p.k16;
+            p.out_k0 = ck0;
+            for (int c = 0; c < C; ++c) cols[idx][c].k0 = ck0;
+        }
+    }
+    // the CriticX layers as riders of the first four passes (see TcPass): possible when the window and the encoder's hidden
+    // state leave features TC_CRITIC_K0.. of the operand buffer alone
+    std::vector<std::vector<ColSrc>> cols2(T_COUNT);
+    prog.can_ride = ride_geo;
+    auto set_rider = [&](int idx, int K_src, int k0, const float* W, const float* b, int epi2, int in_shift2) {
+        TcPass& p = prog.pass[idx];
+        p.n2 = NC; p.n2_live = round8i(C); p.d_col2 = 224; p.epi2 = epi2; p.in_shift2 = in_shift2;
+        const int f_lo = k0 / 16 * 16, f_hi = round16i(k0 + K_src);
+        p.k2_lo = f_lo / 16; p.k2_n = (f_hi - f_lo) / 16;
+        p.kstage2 = TC_STAGE_BYTES / (NC * 64);
+        if (p.kstage2 > p.k2_n) p.kstage2 = p.k2_n;
+        cols2[idx].assign((size_t)NC, ColSrc{});
+        for (int c = 0; c < C; ++c) {
+            ColSrc& s = cols2[idx][c];
+            s.w = W; s.row = c; s.K = K_src; s.b1 = b; s.bidx = c; s.k0 = k0;
+        }
+    };
+    if (prog.can_ride) {
+        set_rider(T_ENC_GI, S, 0, w->critic_w[0], w->critic_b[0], TE_CRITIC_HID, SH_X);
+        set_rider(T_ENC_O, C, TC_CRITIC_K0, w->critic_w[1], w->critic_b[1], TE_CRITIC_HID, SH_FREE);
+        set_rider(T_Z, C, TC_CRITIC_K0, w->critic_w[2], w->critic_b[2], TE_CRITIC_HID, SH_FREE);
+        set_rider(T_D0, C, TC_CRITIC_K0, w->critic_w[3], w->critic_b[3], TE_CRITIC_OUT, SH_FREE);
     }
     if (NL > 32 || NC > 32 || NS > 128) {
         set_error("tensor-core path: latent_dim / critic_dim above 32 not supported (got %d / %d)", L, C);
@@ -913,13 +1004,20 @@ int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
         p.b_off = (int32_t)sfloats;
         sfloats += 2 * (size_t)p.n;
         ncols_total += (size_t)p.n;
+        if (p.n2) {
+            p.w_off2 = (int32_t)wbytes;
+            wbytes += (size_t)p.k2_n * p.n2 * 64;
+            p.b_off2 = (int32_t)sfloats;
+            sfloats += 2 * (size_t)p.n2;
+            ncols_total += (size_t)p.n2;
+        }
     }
     prog.mob_bias_off = (int32_t)sfloats; sfloats += 128;
     sfloats = (sfloats + 3) / 4 * 4;
     prog.mob_bias_d_off = (int32_t)sfloats; sfloats += 256;
     prog.mob_y2_off = (int32_t)sfloats; sfloats += 4;
     prog.critic5_off = (int32_t)sfloats; sfloats += 68;
-    prog.post_off = (int32_t)sfloats; sfloats += 2 * T_COUNT;
+    prog.post_off = (int32_t)sfloats; sfloats += 4 * T_COUNT;
     const size_t need = wbytes + sfloats * sizeof(float) + 256;
     if (ctx->tc_bytes < need) {
         HYPAD_CUDA_TRY(cudaDeviceSynchronize());
@@ -934,10 +1032,12 @@ int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
     int rc = ensure_workspace(ctx, ncols_total * sizeof(ColSrc));
     if (rc != HYPAD_OK) return rc;
     std::vector<ColSrc> flat;
-    std::vector<size_t> start(T_COUNT, 0);
+    std::vector<size_t> start(T_COUNT, 0), start2(T_COUNT, 0);
     for (int i = 0; i < T_COUNT; ++i) {
         start[i] = flat.size();
         flat.insert(flat.end(), cols[i].begin(), cols[i].end());
+        start2[i] = flat.size();
+        flat.insert(flat.end(), cols2[i].begin(), cols2[i].end());
     }
     HYPAD_CUDA_TRY(cudaMemcpyAsync(ctx->workspace, flat.data(), flat.size() * sizeof(ColSrc), cudaMemcpyHostToDevice, stream));
     HYPAD_CUDA_TRY(cudaMemsetAsync(ctx->tc_packed, 0, ctx->tc_bytes, stream));
@@ -946,12 +1046,22 @@ int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
     for (int i = 0; i < T_COUNT; ++i) {
         const TcPass& p = prog.pass[i];
         const int total = p.k16 * 16 * p.n;
-        float* scale = small + prog.post_off + 2 * i;
+        float* scale = small + prog.post_off + 4 * i;
         tc_wscale_kernel<<<1, 256, 0, stream>>>((const ColSrc*)ctx->workspace + start[i], p.n, p.in_shift, scale);
         HYPAD_LAUNCH_CHECK();
         pack_tc_kernel<<<(total + 255) / 256, 256, 0, stream>>>((const ColSrc*)ctx->workspace + start[i], p.k16, 1, p.n,
-                                                               reinterpret_cast<__half*>(ctx->tc_packed + p.w_off), small + p.b_off, scale);
+                                                               reinterpret_cast<__half*>(ctx->tc_packed + p.w_off), small + p.b_off, scale,
+                                                               p.k_lo * 16);
         HYPAD_LAUNCH_CHECK();
+        if (p.n2) {
+            const int total2 = p.k2_n * 16 * p.n2;
+            tc_wscale_kernel<<<1, 256, 0, stream>>>((const ColSrc*)ctx->workspace + start2[i], p.n2, p.in_shift2, scale + 2);
+            HYPAD_LAUNCH_CHECK();
+            pack_tc_kernel<<<(total2 + 255) / 256, 256, 0, stream>>>((const ColSrc*)ctx->workspace + start2[i], p.k2_n, 1, p.n2,
+                                                                    reinterpret_cast<__half*>(ctx->tc_packed + p.w_off2), small + p.b_off2,
+                                                                    scale + 2, p.k2_lo * 16);
+            HYPAD_LAUNCH_CHECK();
+        }
     }
     // Mobius bias / y2 / critic dense5 come from the FFMA context's packed buffer (already built by hypad_pack_weights)
     HYPAD_CUDA_TRY(cudaMemcpyAsync(small + prog.mob_bias_off, ctx->packed + ctx->prog.mob_bias_off, 128 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
@@ -985,7 +1095,9 @@ int launch_forward_tc(const hypad_ctx* ctx, const void* x, int x_is_f64, int64_t
         if (hyp) mask |= (1u << T_MR);
     }
     if (hyp && (stages & HYPAD_STAGE_MOBIUS_X)) mask |= (1u << T_MX);
-    if (stages & HYPAD_STAGE_CRITIC) mask |= (1u << T_C1) | (1u << T_C2) | (1u << T_C3) | (1u << T_C4);
+    // the critic rides along when the encoder and decoder passes it rides on run anyway
+    P.ride = P.prog.can_ride && (stages & HYPAD_STAGE_CRITIC) && (stages & HYPAD_STAGE_ENCODER) && (stages & HYPAD_STAGE_DECODER);
+    if ((stages & HYPAD_STAGE_CRITIC) && !P.ride) mask |= (1u << T_C1) | (1u << T_C2) | (1u << T_C3) | (1u << T_C4);
     P.pass_mask = mask;
     if (!(hyp && (stages & HYPAD_STAGE_DECODER))) P.out.unorm = nullptr, P.out.hyper = nullptr;
     if (!(hyp && (stages & HYPAD_STAGE_DECODER) && (stages & HYPAD_STAGE_MOBIUS_X))) P.out.rec = nullptr;
