@@ -424,11 +424,15 @@ __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncol
     return sq;
 }
 
-// CriticX dense4 + LeakyReLU, then Linear(latent_c -> 1) as one ascending-k FFMA chain over the row's accumulators
+// CriticX dense4 + LeakyReLU, then Linear(latent_c -> 1): column split s forms the FFMA chain over columns 8s..8s+7
+// (ascending), the partial sums are joined through shared memory in ascending order (quarter-scoped barriers) and split 0
+// adds the bias and writes the critic value.  Every epilogue thread of the quarter must call this.
 __device__ __forceinline__ void critic_out_tc(uint32_t tcol, float post, const float* __restrict__ bias, const float* __restrict__ w5,
-                                              int latent_c, float* out) {
+                                              int latent_c, float* out, double* red, int r, int split) {
+    float* part = reinterpret_cast<float*>(red);
+    const int c = 8 * split;
     float fdot = 0.0f;
-    for (int c = 0; c < ((latent_c + 7) & ~7); c += 8) {
+    if (c < latent_c) {  // warp-uniform
         float v[8];
         tmem_ld8(tcol + c, v);
         tmem_ld_wait();
@@ -439,7 +443,15 @@ __device__ __forceinline__ void critic_out_tc(uint32_t tcol, float post, const f
             if (c + i < latent_c) fdot = fmaf(tv, w5[c + i], fdot);
         }
     }
-    if (out) *out = __fadd_rn(fdot, w5[latent_c]);
+    part[split * TC_M + r] = fdot;
+    quarter_bar(r >> 5);
+    if (split == 0 && out) {
+        float tot = part[r];
+#pragma unroll
+        for (int q = 1; q < TC_NSPLIT; ++q) tot = __fadd_rn(tot, part[q * TC_M + r]);
+        *out = __fadd_rn(tot, w5[latent_c]);
+    }
+    quarter_bar(r >> 5);
 }
 
 // DBG: cycle counters for scripts/tc_cycles.py (hypad_forward_debug_cycles); the product instantiation carries none.
@@ -709,7 +721,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                         if (ps.epi == TE_Z && P.out.z && live) gout = P.out.z + (w0 + r) * prog.latent, gw = prog.latent;
                         if (ps.epi == TE_TANH && P.out.eucl && live) gout = P.out.eucl + (w0 + r) * (int64_t)S, gw = S;
                         if (ps.epi == TE_CRITIC_OUT) {
-                            if (split == 0) critic_out_tc(trow + ps.d_col, post, b1, small + prog.critic5_off, prog.latent_c, live ? P.out.critic + w0 + r : nullptr);
+                            critic_out_tc(trow + ps.d_col, post, b1, small + prog.critic5_off, prog.latent_c, live ? P.out.critic + w0 + r : nullptr, red, r, split);
                         } else {
                             for (int c = cbeg; c < ps.n_live; c += cstep) {
                                 float v[8], bv[8];
@@ -781,7 +793,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                         const float post2 = small[prog.post_off + 4 * p + 3];
                         const float* __restrict__ b2 = small + ps.b_off2;
                         if (ps.epi2 == TE_CRITIC_OUT) {
-                            if (split == 0) critic_out_tc(trow + ps.d_col2, post2, b2, small + prog.critic5_off, prog.latent_c, live ? P.out.critic + w0 + r : nullptr);
+                            critic_out_tc(trow + ps.d_col2, post2, b2, small + prog.critic5_off, prog.latent_c, live ? P.out.critic + w0 + r : nullptr, red, r, split);
                         } else {
                             const float sc2 = __int_as_float((127 + TC_CRITIC_SHIFT) << 23);
                             for (int c = cbeg; c < ps.n2_live; c += cstep) {
