@@ -324,22 +324,11 @@ __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncol
     for (int j = 0; j < TC_ROWCH; ++j)
         if (cbeg + j * cstep < ncols) tmem_ld8(trow + col0 + cbeg + j * cstep, q[j]);
     tmem_ld_wait();
-    double s1[1] = {0.0};
-#pragma unroll
-    for (int j = 0; j < TC_ROWCH; ++j)
-        if (cbeg + j * cstep < ncols) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                q[j][i] *= post;
-                const double yd = (double)q[j][i];
-                s1[0] = fma(yd, yd, s1[0]);
-            }
-        }
-    row_allreduce_tc<1>(s1, red, r, split);
-    const float nrm = fmaxf(sqrtf((float)s1[0]), 1e-15f);
-    const float rnrm = __frcp_rn(nrm);
-    const float th = (float)tanh((double)fminf(nrm, 15.0f));
-    double s2[2] = {0.0, 0.0};
+    // One pass over y = x W^T gives both row sums the expmap0 / mobius_add scalars need: with p = tanh(|y|) y / |y|,
+    // |p|^2 = (tanh|y| / |y|)^2 sum y^2 and <p, b> = (tanh|y| / |y|) sum y b.  (The reference sums the rounded p_i; the two
+    // differ by the rounding noise of the p_i, ~1e-8 relative on quantities that enter 1 - |p|^2 and 1 + 2<p,b> with
+    // magnitudes of a few 1e-2 -- far below the fp32 rounding of those expressions.)
+    double s1[2] = {0.0, 0.0};
 #pragma unroll
     for (int j = 0; j < TC_ROWCH; ++j)
         if (cbeg + j * cstep < ncols) {
@@ -347,19 +336,22 @@ __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncol
 #pragma unroll
             for (int i = 0; i < 8; i += 2) {
                 const double2 b2 = __ldg(bd + (i >> 1));
-                const float p0 = __fmul_rn(th, div_refined(q[j][i], nrm, rnrm));
-                const float p1 = __fmul_rn(th, div_refined(q[j][i + 1], nrm, rnrm));
-                q[j][i] = p0;
-                q[j][i + 1] = p1;
-                const double d0 = (double)p0, d1 = (double)p1;
-                s2[0] = fma(d0, d0, s2[0]);
-                s2[1] = fma(d0, b2.x, s2[1]);
-                s2[0] = fma(d1, d1, s2[0]);
-                s2[1] = fma(d1, b2.y, s2[1]);
+                q[j][i] *= post;
+                q[j][i + 1] *= post;
+                const double d0 = (double)q[j][i], d1 = (double)q[j][i + 1];
+                s1[0] = fma(d0, d0, s1[0]);
+                s1[1] = fma(d0, b2.x, s1[1]);
+                s1[0] = fma(d1, d1, s1[0]);
+                s1[1] = fma(d1, b2.y, s1[1]);
             }
         }
-    row_allreduce_tc<2>(s2, red, r, split);
-    const float x2 = (float)s2[0], xy = (float)s2[1];
+    row_allreduce_tc<2>(s1, red, r, split);
+    const float nrm = fmaxf(sqrtf((float)s1[0]), 1e-15f);
+    const float rnrm = __frcp_rn(nrm);
+    const double thd = tanh((double)fminf(nrm, 15.0f));
+    const float th = (float)thd;
+    const double g = (double)th / (double)nrm;
+    const float x2 = (float)(g * g * s1[0]), xy = (float)(g * s1[1]);
     const float one_2xy = __fadd_rn(1.0f, __fmul_rn(2.0f, xy));
     const float ca = __fadd_rn(one_2xy, y2);
     const float cb = __fsub_rn(1.0f, x2);
@@ -373,7 +365,8 @@ __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncol
             ldg8(bias + cbeg + j * cstep, bv);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                q[j][i] = div_refined(__fadd_rn(__fmul_rn(ca, q[j][i]), __fmul_rn(cb, bv[i])), den, rden);
+                const float pi = __fmul_rn(th, div_refined(q[j][i], nrm, rnrm));
+                q[j][i] = div_refined(__fadd_rn(__fmul_rn(ca, pi), __fmul_rn(cb, bv[i])), den, rden);
                 const double qd = (double)q[j][i];
                 s3[0] = fma(qd, qd, s3[0]);
             }

@@ -117,8 +117,9 @@ int hypad_ctx_poll_error(hypad_ctx* ctx);
 /* Diagnostic: enable/disable per-role cycle counters of hypad_forward's kernel (CTA 0) and read them back into
  * h_out (host, HYPAD_DEBUG_SLOTS values): [0] epilogue total, [1] epilogue waiting for accumulators, [2] MMA warp waiting
  * for operands, [3] MMA warp waiting for weights, [4] producer waiting for free slots, [5] operand (re)load + hand-over,
- * [6] tiles, [8+p] accumulator wait of pass p, [24+p] epilogue work of pass p (thread 0). */
-#define HYPAD_DEBUG_SLOTS 40
+ * [6] tiles, [8+p] accumulator wait of pass p, [24+p] epilogue work of pass p (thread 0), [40..47] phases of the Mobius
+ * row phase (load+norm, reduce, scalars, expmap sums, reduce, mobius_add, reduce+projection, store). */
+#define HYPAD_DEBUG_SLOTS 48
 int hypad_forward_debug_cycles(hypad_ctx* ctx, int enable, long long* h_out);
 
 /* hyperspace/hyrnn_nets.py:13-35 mobius_linear with hyperbolic_input=False, k=-1:

@@ -15,7 +15,7 @@ lib = _native.load_library()
 for _ in range(3): sc.forward(sig, True)
 _native.check(lib.hypad_forward_debug_cycles(sc.net.ctx.handle, 1, None))
 sc.forward(sig, True); torch.cuda.synchronize()
-buf = (ctypes.c_longlong * 40)()
+buf = (ctypes.c_longlong * 48)()
 _native.check(lib.hypad_forward_debug_cycles(sc.net.ctx.handle, 0, buf))
 v = list(buf)
 tot = max(v[0], 1)
@@ -25,3 +25,4 @@ names = "ENC_GI ENC_O Z D0 L0_GI L0_O L1_GI L1_O D2 MR MX C1 C2 C3 C4".split()
 nt = max(v[6], 1)
 for p, nm in enumerate(names):
     print("%-6s wait acc %7.0f  work %7.0f cyc/tile" % (nm, v[8 + p] / nt, v[24 + p] / nt))
+print("Mobius row phase (both calls, cyc/tile): " + "  ".join("%s %d" % (n, v[40 + i] / nt) for i, n in enumerate(["load+sum1", "reduce1", "scalars(tanh)", "expmap+sums", "reduce2", "mobius_add", "reduce3+proj", "store"])))
