@@ -43,7 +43,8 @@ constexpr int TC_TILES = 2;               // tiles in flight per CTA (one in the
 constexpr int TC_TILE_COLS = 256;         // TMEM columns per tile slot
 constexpr int TC_STAGE_BYTES = 16384;     // one weight stage: kstage k-steps of 16 k x n columns x (hi + lo) x 2 B
 constexpr int TC_NSLOT = 5;
-constexpr int TC_RED_BYTES = TC_NSPLIT * TC_M * 3 * 8;
+constexpr int TC_RED_BYTES = TC_NSPLIT * TC_M * 2 * 8;  // row reductions of at most two fp64 values per row
+constexpr int TC_BIAS_BYTES = 9216;       // shared copy of every pass's biases and the Mobius bias (fp32 and fp64)
 constexpr int TC_CRITIC_SHIFT = 8;        // sa of the critic's hidden activations (unbounded LeakyReLU outputs)
 constexpr int TC_CRITIC_K0 = 104;         // operand feature where the critic chain keeps its hidden state when it rides along
 
@@ -86,6 +87,7 @@ struct TcProgram {
     int32_t S, S16, latent, latent_c, hyperbolic;
     int32_t mob_bias_off, mob_y2_off, critic5_off;  // float offsets into the small-parameter buffer
     int32_t mob_bias_d_off;  // the Mobius bias again as 128 doubles (16-byte aligned)
+    int32_t bias_floats;  // floats at the start of the small-parameter buffer that the kernel copies to shared memory
     int32_t post_off;   // per pass: {2^sw, 2^-(sa+sw)} of the pass and of its rider, written by tc_wscale_kernel
     int32_t can_ride;   // the program holds riders (S and the encoder's hidden state stay below TC_CRITIC_K0)
 };
@@ -203,8 +205,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 8 consecutive biases (from the shared-memory copy: every lane reads the same address, one broadcast wavefront each)
 __device__ __forceinline__ void ldg8(const float* __restrict__ p, float (&v)[8]) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *(reinterpret_cast<const float4*>(p) + 1);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -316,14 +319,24 @@ constexpr int TC_ROWCH = 4;  // 8-column chunks a thread owns of a <= 128 column
 // squared norm (fp32-rounded squares summed in fp64, rounded once) that the Poincare distance needs, identical in every split.
 // Row sums: every term is widened once (F2F) and squared / multiplied inside a DFMA -- exact products accumulated in fp64,
 // rounded to fp32 once per sum -- two instructions per term.
+template <bool DBG>
 __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncols, const float* __restrict__ bias,
                                                const double* __restrict__ bias_d, float y2, double* red, int r, int split, float* gout,
-                                               bool to_tmem, int S, float post, float (&q)[TC_ROWCH][8]) {
+                                               bool to_tmem, int S, float post, float (&q)[TC_ROWCH][8], long long* dbgp) {
     const int cbeg = 8 * split, cstep = 8 * TC_NSPLIT;
+    long long tprev = DBG ? clock64() : 0;
+    auto mark = [&](int slot) {  // debug instantiation: cycles per phase of thread 0
+        if (DBG && dbgp) {
+            const long long now = clock64();
+            dbgp[slot] += now - tprev;
+            tprev = now;
+        }
+    };
 #pragma unroll
     for (int j = 0; j < TC_ROWCH; ++j)
         if (cbeg + j * cstep < ncols) tmem_ld8(trow + col0 + cbeg + j * cstep, q[j]);
     tmem_ld_wait();
+    mark(0);
     // One pass over y = x W^T gives both row sums the expmap0 / mobius_add scalars need: with p = tanh(|y|) y / |y|,
     // |p|^2 = (tanh|y| / |y|)^2 sum y^2 and <p, b> = (tanh|y| / |y|) sum y b.  (The reference sums the rounded p_i; the two
     // differ by the rounding noise of the p_i, ~1e-8 relative on quantities that enter 1 - |p|^2 and 1 + 2<p,b> with
@@ -335,7 +348,7 @@ __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncol
             const double2* bd = reinterpret_cast<const double2*>(bias_d + cbeg + j * cstep);
 #pragma unroll
             for (int i = 0; i < 8; i += 2) {
-                const double2 b2 = __ldg(bd + (i >> 1));
+                const double2 b2 = bd[i >> 1];
                 q[j][i] *= post;
                 q[j][i + 1] *= post;
                 const double d0 = (double)q[j][i], d1 = (double)q[j][i + 1];
@@ -345,7 +358,9 @@ __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncol
                 s1[1] = fma(d1, b2.y, s1[1]);
             }
         }
+    mark(1);
     row_allreduce_tc<2>(s1, red, r, split);
+    mark(2);
     const float nrm = fmaxf(sqrtf((float)s1[0]), 1e-15f);
     const float rnrm = __frcp_rn(nrm);
     const double thd = tanh((double)fminf(nrm, 15.0f));
@@ -357,6 +372,7 @@ __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncol
     const float cb = __fsub_rn(1.0f, x2);
     const float den = fmaxf(__fadd_rn(one_2xy, __fmul_rn(x2, y2)), 1e-15f);
     const float rden = __frcp_rn(den);
+    mark(3);
     double s3[1] = {0.0};
 #pragma unroll
     for (int j = 0; j < TC_ROWCH; ++j)
@@ -371,6 +387,7 @@ __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncol
                 s3[0] = fma(qd, qd, s3[0]);
             }
         }
+    mark(4);
     // last reduction by hand: its trailing barrier also ORs the (rare) "this row must be projected back into the ball"
     // predicate over the quarter, so the projection's extra reduction is collective without costing the common case a barrier
     red[split * TC_M + r] = s3[0];
@@ -399,6 +416,7 @@ __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncol
         row_allreduce_tc<1>(s4, red, r, split);
         if (proj) sq = (float)s4[0];
     }
+    mark(5);
     if (to_tmem) {
 #pragma unroll
         for (int j = 0; j < TC_ROWCH; ++j)
@@ -414,6 +432,7 @@ __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncol
                 if (c < S) gout[c] = q[j][i];
             }
     }
+    mark(6);
     return sq;
 }
 
@@ -454,7 +473,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
     unsigned char* act_base = smem;                                    // TC_TILES x (hi + lo piece)
     unsigned char* ring = smem + TC_TILES * TC_ACT_BYTES;              // TC_NSLOT weight stages
     double* red = reinterpret_cast<double*>(ring + TC_NSLOT * TC_STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(red) + TC_RED_BYTES);
+    float* sbias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(red) + TC_RED_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(sbias) + TC_BIAS_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_NSLOT + 2 * TC_TILES);
     const uint32_t bar_full = s_u32(bars), bar_empty = s_u32(bars + TC_NSLOT);
     const uint32_t bar_acc = s_u32(bars + 2 * TC_NSLOT), bar_a = s_u32(bars + 2 * TC_NSLOT + TC_TILES);  // one per tile slot
@@ -483,6 +503,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::);
     }
+    // biases: a load from global memory in front of every chunk's math would expose the L2 latency 4 times per row phase
+    for (int i = tid; i < prog.bias_floats; i += TC_THREADS) sbias[i] = P.small[i];
     // operand buffers start as zeros: padding features are never written, and must never be NaN bit patterns
     for (int i = tid; i < TC_TILES * TC_ACT_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(act_base)[i] = make_uint4(0, 0, 0, 0);
     fence_async_smem();
@@ -658,7 +680,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
             for (int p = 0; p < T_COUNT && ok; ++p) {
                 if (!((P.pass_mask >> p) & 1u)) continue;
                 const TcPass& ps = prog.pass[p];
-                const float* __restrict__ b1 = small + ps.b_off;
+                const float* __restrict__ b1 = sbias + ps.b_off;
                 const float post = small[prog.post_off + 4 * p + 1];  // 2^-(sa+sw): exact, folded into the bias FMA
                 const int cbeg = 8 * split, cstep = 8 * TC_NSPLIT;
 #pragma unroll 1
@@ -744,9 +766,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                         float* gout = (gbase && live) ? gbase + (w0 + r) * (int64_t)S : nullptr;
                         float q[TC_ROWCH][8];
                         // the reconstruction's point stays in TMEM until the window's point has been computed
-                        const float sq = row_mobius_tc(trow, ps.d_col, ps.n_live, small + prog.mob_bias_off,
-                                                       reinterpret_cast<const double*>(small + prog.mob_bias_d_off), small[prog.mob_y2_off], red, r, split,
-                                                       gout, !is_x, S, post, q);
+                        const float sq = row_mobius_tc<DBG>(trow, ps.d_col, ps.n_live, sbias + prog.mob_bias_off,
+                                                            reinterpret_cast<const double*>(sbias + prog.mob_bias_d_off), small[prog.mob_y2_off], red, r,
+                                                            split, gout, !is_x, S, post, q, (DBG && blockIdx.x == 0 && tid == 0) ? P.debug + 40 : nullptr);
                         if (!is_x) {
                             if (sl == 0) sq_mr0 = sq;
                             else sq_mr1 = sq;
@@ -784,7 +806,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                     // ---- the CriticX layer riding along with this pass -------------------------------------------
                     if (P.ride && ps.n2) {
                         const float post2 = small[prog.post_off + 4 * p + 3];
-                        const float* __restrict__ b2 = small + ps.b_off2;
+                        const float* __restrict__ b2 = sbias + ps.b_off2;
                         if (ps.epi2 == TE_CRITIC_OUT) {
                             critic_out_tc(trow + ps.d_col2, post2, b2, small + prog.critic5_off, prog.latent_c, live ? P.out.critic + w0 + r : nullptr, red, r, split);
                         } else {
@@ -884,7 +906,6 @@ __global__ void pack_tc_kernel(const ColSrc* __restrict__ cols, int k16, int nbl
             // results differ by at most one ulp of the gate pre-activation, below the contraction's own rounding)
             const float ba = s.b1 ? s.b1[s.bidx] : 0.0f, bb = s.b2 ? s.b2[s.bidx] : 0.0f;
             bias[cc] = __fadd_rn(ba, bb);
-            bias[ncols + cc] = 0.0f;
         }
     }
 }
@@ -893,7 +914,7 @@ static inline int round8i(int v) { return (v + 7) / 8 * 8; }
 static inline int round16i(int v) { return (v + 15) / 16 * 16; }
 
 size_t forward_tc_smem_bytes() {
-    return (size_t)TC_TILES * TC_ACT_BYTES + (size_t)TC_NSLOT * TC_STAGE_BYTES + TC_RED_BYTES + (2 * TC_NSLOT + 2 * TC_TILES) * 8 + 16;
+    return (size_t)TC_TILES * TC_ACT_BYTES + (size_t)TC_NSLOT * TC_STAGE_BYTES + TC_RED_BYTES + TC_BIAS_BYTES + (2 * TC_NSLOT + 2 * TC_TILES) * 8 + 16;
 }
 
 // Builds the tensor-core program and packs the weights (called from hypad_pack_weights).
@@ -1007,19 +1028,24 @@ int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
         p.w_off = (int32_t)wbytes;
         wbytes += (size_t)p.k16 * p.n * 64;
         p.b_off = (int32_t)sfloats;
-        sfloats += 2 * (size_t)p.n;
+        sfloats += (size_t)p.n;
         ncols_total += (size_t)p.n;
         if (p.n2) {
             p.w_off2 = (int32_t)wbytes;
             wbytes += (size_t)p.k2_n * p.n2 * 64;
             p.b_off2 = (int32_t)sfloats;
-            sfloats += 2 * (size_t)p.n2;
+            sfloats += (size_t)p.n2;
             ncols_total += (size_t)p.n2;
         }
     }
     prog.mob_bias_off = (int32_t)sfloats; sfloats += 128;
     sfloats = (sfloats + 3) / 4 * 4;
     prog.mob_bias_d_off = (int32_t)sfloats; sfloats += 256;
+    prog.bias_floats = (int32_t)sfloats;
+    if (sfloats * sizeof(float) > TC_BIAS_BYTES) {
+        set_error("tensor-core path: %zu bytes of biases exceed the shared-memory copy (%d)", sfloats * sizeof(float), TC_BIAS_BYTES);
+        return HYPAD_EINVAL;
+    }
     prog.mob_y2_off = (int32_t)sfloats; sfloats += 4;
     prog.critic5_off = (int32_t)sfloats; sfloats += 68;
     prog.post_off = (int32_t)sfloats; sfloats += 4 * T_COUNT;

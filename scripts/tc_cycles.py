@@ -26,3 +26,4 @@ nt = max(v[6], 1)
 for p, nm in enumerate(names):
     print("%-6s wait acc %7.0f  work %7.0f cyc/tile" % (nm, v[8 + p] / nt, v[24 + p] / nt))
 print("Mobius row phase (both calls, cyc/tile): " + "  ".join("%s %d" % (n, v[40 + i] / nt) for i, n in enumerate(["load+sum1", "reduce1", "scalars(tanh)", "expmap+sums", "reduce2", "mobius_add", "reduce3+proj", "store"])))
+print("Mobius row phase (both calls, cyc/tile): " + "  ".join("%s %d" % (n, v[40 + i] / nt) for i, n in enumerate(["tmem load", "row sums", "reduce", "scalars(tanh)", "mobius_add+sum", "reduce+proj", "store"])))
