@@ -86,7 +86,6 @@ struct TcProgram {
     TcPass pass[T_COUNT];
     int32_t S, S16, latent, latent_c, hyperbolic;
     int32_t mob_bias_off, mob_y2_off, critic5_off;  // float offsets into the small-parameter buffer
-    int32_t mob_bias_d_off;  // the Mobius bias again as 128 doubles (16-byte aligned)
     int32_t bias_floats;  // floats at the start of the small-parameter buffer that the kernel copies to shared memory
     int32_t post_off;   // per pass: {2^sw, 2^-(sa+sw)} of the pass and of its rider, written by tc_wscale_kernel
     int32_t can_ride;   // the program holds riders (S and the encoder's hidden state stay below TC_CRITIC_K0)
@@ -263,6 +262,11 @@ __device__ __forceinline__ float tanh_unit(float x) {
     return fmaf(x, __fmul_rn(__fmul_rn(s, c), r), x);
 }
 
+__device__ __forceinline__ float sumsq4(float a, float b, float c, float d) { return fmaf(d, d, fmaf(c, c, fmaf(b, b, __fmul_rn(a, a)))); }
+__device__ __forceinline__ float dot4(float a, float b, float c, float d, float w, float x, float y, float z) {
+    return fmaf(d, z, fmaf(c, y, fmaf(b, x, __fmul_rn(a, w))));
+}
+
 // the 4 column splits of a row live in the 4 warps of one TMEM lane quarter: a 128-thread named barrier per quarter
 __device__ __forceinline__ void quarter_bar(int quarter) { asm volatile("bar.sync %0, 128;" ::"r"(2 + quarter) : "memory"); }
 // the same barrier, returning the OR of `pred` over the quarter
@@ -316,13 +320,12 @@ constexpr int TC_ROWCH = 4;  // 8-column chunks a thread owns of a <= 128 column
 // y = x W^T (accumulators of this thread's chunks, TMEM columns col0 + ..) -> q = project(mobius_add(expmap0(y), bias)),
 // the reference's MobiusLinear row phase (see forward.cu row_mobius): returned in registers, optionally written back to
 // TMEM (to_tmem) and to global memory (gout).  post = 2^-(sa+sw) undoes the operand scales (exact).  Returns the row's
-// squared norm (fp32-rounded squares summed in fp64, rounded once) that the Poincare distance needs, identical in every split.
-// Row sums: every term is widened once (F2F) and squared / multiplied inside a DFMA -- exact products accumulated in fp64,
-// rounded to fp32 once per sum -- two instructions per term.
+// squared norm that the Poincare distance needs, identical in every split.  Row sums: groups of four terms in fp32 FFMA
+// chains, the groups accumulated in fp64 and rounded to fp32 once per sum.
 template <bool DBG>
 __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncols, const float* __restrict__ bias,
-                                               const double* __restrict__ bias_d, float y2, double* red, int r, int split, float* gout,
-                                               bool to_tmem, int S, float post, float (&q)[TC_ROWCH][8], long long* dbgp) {
+                                               float y2, double* red, int r, int split, float* gout, bool to_tmem, int S, float post,
+                                               float (&q)[TC_ROWCH][8], long long* dbgp) {
     const int cbeg = 8 * split, cstep = 8 * TC_NSPLIT;
     long long tprev = DBG ? clock64() : 0;
     auto mark = [&](int slot) {  // debug instantiation: cycles per phase of thread 0
@@ -341,21 +344,21 @@ __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncol
     // |p|^2 = (tanh|y| / |y|)^2 sum y^2 and <p, b> = (tanh|y| / |y|) sum y b.  (The reference sums the rounded p_i; the two
     // differ by the rounding noise of the p_i, ~1e-8 relative on quantities that enter 1 - |p|^2 and 1 + 2<p,b> with
     // magnitudes of a few 1e-2 -- far below the fp32 rounding of those expressions.)
+    // Row sums: products and groups of four in fp32 (FFMA chains), the groups in fp64 -- the plain fp64 pipe of this GPU
+    // is slow enough that widening every term costs a third of the row phase, and a group's three fp32 roundings average
+    // out over the 25 groups to ~3e-8 relative, half an ulp of the fp32 value the sum is rounded to.
     double s1[2] = {0.0, 0.0};
 #pragma unroll
     for (int j = 0; j < TC_ROWCH; ++j)
         if (cbeg + j * cstep < ncols) {
-            const double2* bd = reinterpret_cast<const double2*>(bias_d + cbeg + j * cstep);
+            float bv[8];
+            ldg8(bias + cbeg + j * cstep, bv);
 #pragma unroll
-            for (int i = 0; i < 8; i += 2) {
-                const double2 b2 = bd[i >> 1];
-                q[j][i] *= post;
-                q[j][i + 1] *= post;
-                const double d0 = (double)q[j][i], d1 = (double)q[j][i + 1];
-                s1[0] = fma(d0, d0, s1[0]);
-                s1[1] = fma(d0, b2.x, s1[1]);
-                s1[0] = fma(d1, d1, s1[0]);
-                s1[1] = fma(d1, b2.y, s1[1]);
+            for (int i = 0; i < 8; ++i) q[j][i] *= post;
+#pragma unroll
+            for (int h = 0; h < 8; h += 4) {
+                s1[0] += (double)sumsq4(q[j][h], q[j][h + 1], q[j][h + 2], q[j][h + 3]);
+                s1[1] += (double)dot4(q[j][h], q[j][h + 1], q[j][h + 2], q[j][h + 3], bv[h], bv[h + 1], bv[h + 2], bv[h + 3]);
             }
         }
     mark(1);
@@ -383,9 +386,9 @@ __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncol
             for (int i = 0; i < 8; ++i) {
                 const float pi = __fmul_rn(th, div_refined(q[j][i], nrm, rnrm));
                 q[j][i] = div_refined(__fadd_rn(__fmul_rn(ca, pi), __fmul_rn(cb, bv[i])), den, rden);
-                const double qd = (double)q[j][i];
-                s3[0] = fma(qd, qd, s3[0]);
             }
+#pragma unroll
+            for (int h = 0; h < 8; h += 4) s3[0] += (double)sumsq4(q[j][h], q[j][h + 1], q[j][h + 2], q[j][h + 3]);
         }
     mark(4);
     // last reduction by hand: its trailing barrier also ORs the (rare) "this row must be projected back into the ball"
@@ -408,9 +411,9 @@ __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncol
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         q[j][i] = __fmul_rn(__fdiv_rn(q[j][i], norm), maxnorm);
-                        const double qd = (double)q[j][i];
-                        s4[0] = fma(qd, qd, s4[0]);
                     }
+#pragma unroll
+                    for (int h = 0; h < 8; h += 4) s4[0] += (double)sumsq4(q[j][h], q[j][h + 1], q[j][h + 2], q[j][h + 3]);
                 }
         }
         row_allreduce_tc<1>(s4, red, r, split);
@@ -503,7 +506,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::);
     }
-    // biases: a load from global memory in front of every chunk's math would expose the L2 latency 4 times per row phase
+    // biases, scales and row-phase parameters: a load from global memory in front of a chunk's math exposes the L2 latency
     for (int i = tid; i < prog.bias_floats; i += TC_THREADS) sbias[i] = P.small[i];
     // operand buffers start as zeros: padding features are never written, and must never be NaN bit patterns
     for (int i = tid; i < TC_TILES * TC_ACT_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(act_base)[i] = make_uint4(0, 0, 0, 0);
@@ -681,7 +684,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                 if (!((P.pass_mask >> p) & 1u)) continue;
                 const TcPass& ps = prog.pass[p];
                 const float* __restrict__ b1 = sbias + ps.b_off;
-                const float post = small[prog.post_off + 4 * p + 1];  // 2^-(sa+sw): exact, folded into the bias FMA
+                const float post = sbias[prog.post_off + 4 * p + 1];  // 2^-(sa+sw): exact, folded into the bias FMA
                 const int cbeg = 8 * split, cstep = 8 * TC_NSPLIT;
 #pragma unroll 1
                 for (int sl = 0; sl < TC_TILES; ++sl) {
@@ -736,7 +739,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                         if (ps.epi == TE_Z && P.out.z && live) gout = P.out.z + (w0 + r) * prog.latent, gw = prog.latent;
                         if (ps.epi == TE_TANH && P.out.eucl && live) gout = P.out.eucl + (w0 + r) * (int64_t)S, gw = S;
                         if (ps.epi == TE_CRITIC_OUT) {
-                            critic_out_tc(trow + ps.d_col, post, b1, small + prog.critic5_off, prog.latent_c, live ? P.out.critic + w0 + r : nullptr, red, r, split);
+                            critic_out_tc(trow + ps.d_col, post, b1, sbias + prog.critic5_off, prog.latent_c, live ? P.out.critic + w0 + r : nullptr, red, r, split);
                         } else {
                             for (int c = cbeg; c < ps.n_live; c += cstep) {
                                 float v[8], bv[8];
@@ -766,8 +769,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                         float* gout = (gbase && live) ? gbase + (w0 + r) * (int64_t)S : nullptr;
                         float q[TC_ROWCH][8];
                         // the reconstruction's point stays in TMEM until the window's point has been computed
-                        const float sq = row_mobius_tc<DBG>(trow, ps.d_col, ps.n_live, sbias + prog.mob_bias_off,
-                                                            reinterpret_cast<const double*>(sbias + prog.mob_bias_d_off), small[prog.mob_y2_off], red, r,
+                        const float sq = row_mobius_tc<DBG>(trow, ps.d_col, ps.n_live, sbias + prog.mob_bias_off, sbias[prog.mob_y2_off], red, r,
                                                             split, gout, !is_x, S, post, q, (DBG && blockIdx.x == 0 && tid == 0) ? P.debug + 40 : nullptr);
                         if (!is_x) {
                             if (sl == 0) sq_mr0 = sq;
@@ -787,10 +789,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                                         tmem_ld8(trow + pm.d_col + cbeg + j * cstep, h);
                                         tmem_ld_wait();
 #pragma unroll
-                                        for (int i = 0; i < 8; ++i) {
-                                            const double d = (double)__fsub_rn(q[j][i], h[i]);
-                                            sd[0] = fma(d, d, sd[0]);
-                                        }
+                                        for (int i = 0; i < 8; ++i) h[i] = __fsub_rn(q[j][i], h[i]);
+                                        sd[0] += (double)sumsq4(h[0], h[1], h[2], h[3]);
+                                        sd[0] += (double)sumsq4(h[4], h[5], h[6], h[7]);
                                     }
                                 row_allreduce_tc<1>(sd, red, r, split);
                                 if (split == 0 && live) {
@@ -805,10 +806,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                     }
                     // ---- the CriticX layer riding along with this pass -------------------------------------------
                     if (P.ride && ps.n2) {
-                        const float post2 = small[prog.post_off + 4 * p + 3];
+                        const float post2 = sbias[prog.post_off + 4 * p + 3];
                         const float* __restrict__ b2 = sbias + ps.b_off2;
                         if (ps.epi2 == TE_CRITIC_OUT) {
-                            critic_out_tc(trow + ps.d_col2, post2, b2, small + prog.critic5_off, prog.latent_c, live ? P.out.critic + w0 + r : nullptr, red, r, split);
+                            critic_out_tc(trow + ps.d_col2, post2, b2, sbias + prog.critic5_off, prog.latent_c, live ? P.out.critic + w0 + r : nullptr, red, r, split);
                         } else {
                             const float sc2 = __int_as_float((127 + TC_CRITIC_SHIFT) << 23);
                             for (int c = cbeg; c < ps.n2_live; c += cstep) {
@@ -876,10 +877,6 @@ __global__ void tc_wscale_kernel(const ColSrc* __restrict__ cols, int ncols, int
         scale[0] = ldexpf(1.0f, sw);
         scale[1] = ldexpf(1.0f, -(sw + in_shift));
     }
-}
-
-__global__ void widen_kernel(const float* __restrict__ src, double* __restrict__ dst, int n) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = (double)src[i];
 }
 
 // f_base: operand feature of the panel's k = 0 (riders start at a later k-step of the shared operand buffer)
@@ -1039,16 +1036,14 @@ int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
         }
     }
     prog.mob_bias_off = (int32_t)sfloats; sfloats += 128;
-    sfloats = (sfloats + 3) / 4 * 4;
-    prog.mob_bias_d_off = (int32_t)sfloats; sfloats += 256;
-    prog.bias_floats = (int32_t)sfloats;
-    if (sfloats * sizeof(float) > TC_BIAS_BYTES) {
-        set_error("tensor-core path: %zu bytes of biases exceed the shared-memory copy (%d)", sfloats * sizeof(float), TC_BIAS_BYTES);
-        return HYPAD_EINVAL;
-    }
     prog.mob_y2_off = (int32_t)sfloats; sfloats += 4;
     prog.critic5_off = (int32_t)sfloats; sfloats += 68;
     prog.post_off = (int32_t)sfloats; sfloats += 4 * T_COUNT;
+    prog.bias_floats = (int32_t)sfloats;  // the whole small-parameter buffer lives in shared memory while the kernel runs
+    if (sfloats * sizeof(float) > TC_BIAS_BYTES) {
+        set_error("tensor-core path: %zu bytes of small parameters exceed the shared-memory copy (%d)", sfloats * sizeof(float), TC_BIAS_BYTES);
+        return HYPAD_EINVAL;
+    }
     const size_t need = wbytes + sfloats * sizeof(float) + 256;
     if (ctx->tc_bytes < need) {
         HYPAD_CUDA_TRY(cudaDeviceSynchronize());
@@ -1096,8 +1091,6 @@ int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
     }
     // Mobius bias / y2 / critic dense5 come from the FFMA context's packed buffer (already built by hypad_pack_weights)
     HYPAD_CUDA_TRY(cudaMemcpyAsync(small + prog.mob_bias_off, ctx->packed + ctx->prog.mob_bias_off, 128 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-    widen_kernel<<<1, 128, 0, stream>>>(small + prog.mob_bias_off, reinterpret_cast<double*>(small + prog.mob_bias_d_off), 128);
-    HYPAD_LAUNCH_CHECK();
     HYPAD_CUDA_TRY(cudaMemcpyAsync(small + prog.mob_y2_off, ctx->packed + ctx->prog.mob_y2_off, sizeof(float), cudaMemcpyDeviceToDevice, stream));
     HYPAD_CUDA_TRY(cudaMemcpyAsync(small + prog.critic5_off, ctx->packed + ctx->prog.critic5_off, (C + 1) * sizeof(float), cudaMemcpyDeviceToDevice, stream));
     HYPAD_CUDA_TRY(cudaStreamSynchronize(stream));
