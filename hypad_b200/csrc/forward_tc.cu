@@ -335,10 +335,9 @@ __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncol
             tprev = now;
         }
     };
-#pragma unroll
-    for (int j = 0; j < TC_ROWCH; ++j)
-        if (cbeg + j * cstep < ncols) tmem_ld8(trow + col0 + cbeg + j * cstep, q[j]);
-    tmem_ld_wait();
+    // TMEM reads run at 64 B/clk per SM and all 16 warps want their row at once: the loads are software-pipelined against
+    // the sums below (tcgen05.wait::ld waits for every outstanding load, so at most one is in flight behind the math)
+    tmem_ld8(trow + col0 + cbeg, q[0]);  // cbeg < 32 <= ncols
     mark(0);
     // One pass over y = x W^T gives both row sums the expmap0 / mobius_add scalars need: with p = tanh(|y|) y / |y|,
     // |p|^2 = (tanh|y| / |y|)^2 sum y^2 and <p, b> = (tanh|y| / |y|) sum y b.  (The reference sums the rounded p_i; the two
@@ -353,6 +352,8 @@ __device__ __forceinline__ float row_mobius_tc(uint32_t trow, int col0, int ncol
         if (cbeg + j * cstep < ncols) {
             float bv[8];
             ldg8(bias + cbeg + j * cstep, bv);
+            tmem_ld_wait();
+            if (j + 1 < TC_ROWCH && cbeg + (j + 1) * cstep < ncols) tmem_ld8(trow + col0 + cbeg + (j + 1) * cstep, q[j + 1]);
 #pragma unroll
             for (int i = 0; i < 8; ++i) q[j][i] *= post;
 #pragma unroll
