@@ -1,2 +1,2 @@
 set -x
-timeout 300 python scripts/tc_cycles.py 2>&1 | tail -24
+timeout 120 python scripts/tc_cycles.py 2>&1 | tail -24
