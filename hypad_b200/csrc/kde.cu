@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(KDE_WARPS * 32, 8) kde_screened_kernel(const K
         int ncand = 0, myj = 0;
         float myest = -1.0f;
         {
+            // the distinct candidates first (lane c keeps the c-th): a single one needs no evaluation at all
             double seen0 = CUDART_NAN, seen1 = CUDART_NAN, seen2 = CUDART_NAN, seen3 = CUDART_NAN;
 #pragma unroll 1
             for (int q = 0; q < 4; ++q) {
@@ -340,6 +341,15 @@ __global__ void __launch_bounds__(KDE_WARPS * 32, 8) kde_screened_kernel(const K
                     seen2 = seen1;
                     seen1 = seen0;
                     seen0 = pj;
+                    if (lane == ncand) myj = j;
+                    ++ncand;
+                }
+            }
+            if (ncand > 1) {
+                const int ne = ncand < 32 ? ncand : 32;
+#pragma unroll 1
+                for (int c = 0; c < ne; ++c) {
+                    const double pj = P[__shfl_sync(0xffffffffu, myj, c)];
                     float part = 0.0f;
                     for (int k = lane; k < n; k += 32) {
                         const float r = (float)(P[k] - pj);
@@ -347,12 +357,10 @@ __global__ void __launch_bounds__(KDE_WARPS * 32, 8) kde_screened_kernel(const K
                     }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                    if (lane == ncand) {
-                        myj = j;
-                        myest = part;
-                    }
-                    ++ncand;
+                    if (lane == c) myest = part;
                 }
+            } else if (lane == 0) {
+                myest = 1.0f;  // the only candidate survives
             }
         }
         int bj = 0;
