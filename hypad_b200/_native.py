@@ -76,6 +76,7 @@ _SIGNATURES = {
     "hypad_point_error": (_int, [_vp, _vp, _int, _i64, _vp, _vp]),
     "hypad_area_error": (_int, [_vp, _vp, _int, _i64, _int, _vp, _vp]),
     "hypad_threshold_windows": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp, _int, _vp]),
+    "hypad_threshold_windows_range": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp, _int, _vp]),
     "hypad_threshold_windows_exhaustive": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp, _int, _vp]),
     "hypad_tc_probe_gemm": (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _vp]),
     "hypad_tc_probe_bench": (_int, [_int, _int, _int, _vp, _vp]),

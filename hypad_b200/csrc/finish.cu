@@ -338,6 +338,7 @@ struct TwArgs {
     const double* errors;
     int64_t len, window_size, step;
     int n_analysis, ddof, pad, max_runs, n_slices;
+    int64_t k0;             // index of the first analysis window handled (outputs are indexed from 0)
     double* stats;          // [n_analysis][4]
     double* runs;           // [n_analysis][max_runs][3]
     int32_t* n_runs;        // [n_analysis]
@@ -358,7 +359,7 @@ struct TwArgs {
 };
 
 __device__ __forceinline__ void tw_window(const TwArgs& a, int k, const double*& e, int64_t& n) {
-    const int64_t w0 = (int64_t)k * a.step;
+    const int64_t w0 = (int64_t)(a.k0 + k) * a.step;
     const int64_t w1 = w0 + a.window_size < a.len ? w0 + a.window_size : a.len;
     e = a.errors + w0;
     n = w1 - w0;
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(RB) tw_window_kernel(const TwArgs a) {
     __shared__ double sh[32];
     __shared__ unsigned long long s_quiet;
     const int k = blockIdx.x, tid = threadIdx.x;
-    const int64_t w0 = (int64_t)k * a.step, w1 = w0 + a.window_size < a.len ? w0 + a.window_size : a.len, n = w1 - w0;
+    const int64_t w0 = (int64_t)(a.k0 + k) * a.step, w1 = w0 + a.window_size < a.len ? w0 + a.window_size : a.len, n = w1 - w0;
     const double c = a.errors[a.len / 2];
     const int64_t bf0 = (w0 + TW_TILE - 1) / TW_TILE, bf1 = w1 / TW_TILE;  // blocks [bf0, bf1) lie fully inside
     double s1 = 0.0, s2 = 0.0;
@@ -648,7 +649,7 @@ __global__ void __launch_bounds__(TW_TILE) tw_events_work_kernel(const TwArgs a)
     for (int j = blockIdx.x; j < total; j += gridDim.x) {
         const longlong2 kb = a.work[j];
         const int k = (int)kb.x;
-        const int64_t w0 = (int64_t)k * a.step, w1 = w0 + a.window_size < a.len ? w0 + a.window_size : a.len;
+        const int64_t w0 = (int64_t)(a.k0 + k) * a.step, w1 = w0 + a.window_size < a.len ? w0 + a.window_size : a.len;
         const int64_t g0 = kb.y * TW_TILE > w0 ? kb.y * TW_TILE : w0, g1 = (kb.y + 1) * TW_TILE < w1 ? (kb.y + 1) * TW_TILE : w1;
         tw_events_tile(a, k, g0 - w0, (int)(g1 - g0), s_bits, s_dil, &s_below);
     }
@@ -659,7 +660,7 @@ __global__ void __launch_bounds__(TW_TILE) tw_runmax_work_kernel(const TwArgs a)
     for (int j = blockIdx.x; j < total; j += gridDim.x) {
         const longlong2 kb = a.work[j];
         const int k = (int)kb.x;
-        const int64_t w0 = (int64_t)k * a.step, w1 = w0 + a.window_size < a.len ? w0 + a.window_size : a.len;
+        const int64_t w0 = (int64_t)(a.k0 + k) * a.step, w1 = w0 + a.window_size < a.len ? w0 + a.window_size : a.len;
         const int64_t g = kb.y * TW_TILE + threadIdx.x;
         if (g >= w0 && g < w1) tw_runmax_elem(a, k, a.errors + w0, g - w0);
     }
@@ -835,12 +836,12 @@ int hypad_combine_scores(int mode, const double* critic_scores, const void* rec,
 }
 
 static int threshold_windows_impl(hypad_ctx* ctx, const double* errors, int64_t len, int64_t window_size, int64_t step,
-                                  int64_t n_analysis, int ddof, int anomaly_padding, double* stats, double* runs,
-                                  int32_t* n_runs, int max_runs, cudaStream_t stream, bool exhaustive) {
+                                  int64_t first_window, int64_t n_analysis, int ddof, int anomaly_padding, double* stats,
+                                  double* runs, int32_t* n_runs, int max_runs, cudaStream_t stream, bool exhaustive) {
     HYPAD_REQUIRE(ctx && errors && stats && runs && n_runs, "hypad_threshold_windows: NULL argument");
     HYPAD_REQUIRE(len >= 1 && window_size >= 1 && step >= 1 && n_analysis >= 1 && max_runs >= 1, "hypad_threshold_windows: bad shape");
     HYPAD_REQUIRE(n_analysis <= 65535, "hypad_threshold_windows: more than 65535 analysis windows");
-    HYPAD_REQUIRE((n_analysis - 1) * step < len, "hypad_threshold_windows: last window starts beyond the data");
+    HYPAD_REQUIRE(first_window >= 0 && (first_window + n_analysis - 1) * step < len, "hypad_threshold_windows: last window starts beyond the data");
     HYPAD_REQUIRE(anomaly_padding >= 0 && anomaly_padding <= TW_MAXPAD, "hypad_threshold_windows: padding %d outside 0..%d",
                   anomaly_padding, TW_MAXPAD);
     HYPAD_REQUIRE(ddof == 0 || ddof == 1, "hypad_threshold_windows: ddof must be 0 or 1");
@@ -848,6 +849,7 @@ static int threshold_windows_impl(hypad_ctx* ctx, const double* errors, int64_t 
     const int64_t wlen = window_size < len ? window_size : len;
     TwArgs a;
     a.errors = errors; a.len = len; a.window_size = window_size; a.step = step;
+    a.k0 = first_window;
     a.n_analysis = (int)n_analysis; a.ddof = ddof; a.pad = anomaly_padding; a.max_runs = max_runs;
     a.n_slices = (int)ceil_div(wlen, TW_CHUNK);
     a.stats = stats; a.runs = runs; a.n_runs = n_runs;
@@ -901,14 +903,21 @@ static int threshold_windows_impl(hypad_ctx* ctx, const double* errors, int64_t 
 int hypad_threshold_windows(hypad_ctx* ctx, const double* errors, int64_t len, int64_t window_size, int64_t step,
                             int64_t n_analysis, int ddof, int anomaly_padding, double* stats, double* runs,
                             int32_t* n_runs, int max_runs, void* stream_) {
-    return threshold_windows_impl(ctx, errors, len, window_size, step, n_analysis, ddof, anomaly_padding, stats, runs, n_runs,
+    return threshold_windows_impl(ctx, errors, len, window_size, step, 0, n_analysis, ddof, anomaly_padding, stats, runs, n_runs,
                                   max_runs, (cudaStream_t)stream_, false);
+}
+
+int hypad_threshold_windows_range(hypad_ctx* ctx, const double* errors, int64_t len, int64_t window_size, int64_t step,
+                                  int64_t first_window, int64_t n_analysis, int ddof, int anomaly_padding, double* stats,
+                                  double* runs, int32_t* n_runs, int max_runs, void* stream_) {
+    return threshold_windows_impl(ctx, errors, len, window_size, step, first_window, n_analysis, ddof, anomaly_padding, stats, runs,
+                                  n_runs, max_runs, (cudaStream_t)stream_, false);
 }
 
 int hypad_threshold_windows_exhaustive(hypad_ctx* ctx, const double* errors, int64_t len, int64_t window_size, int64_t step,
                                        int64_t n_analysis, int ddof, int anomaly_padding, double* stats, double* runs,
                                        int32_t* n_runs, int max_runs, void* stream_) {
-    return threshold_windows_impl(ctx, errors, len, window_size, step, n_analysis, ddof, anomaly_padding, stats, runs, n_runs,
+    return threshold_windows_impl(ctx, errors, len, window_size, step, 0, n_analysis, ddof, anomaly_padding, stats, runs, n_runs,
                                   max_runs, (cudaStream_t)stream_, true);
 }
 

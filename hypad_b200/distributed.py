@@ -6,8 +6,8 @@ timestep i needs the critic value of windows i-S+1 .. i.  Rank r 
     rank also owns the S-1 trailing timesteps),
   * recomputes the S-1 windows to the left of its range (the "halo": 0.01 % extra work at 1M windows/GPU),
   * runs the fused network + KDE arg-max on its range with no communication,
-and the per-timestep / per-window arrays (kmax f64, rec f32, unorm f32) are gathered once over NCCL
-(NVLink 5 / NVSwitch; <= 16 B per timestep).  The elementwise O(T) finish (quantile band, z-score, smoothing, combine)
+and the per-timestep / per-window arrays (kmax, rec, unorm, 12 B per timestep as fp32) are gathered in one NCCL all-gather
+(NVLink 5 / NVSwitch).  The elementwise O(T) finish (quantile band, z-score, smoothing, combine)
 is then run redundantly on every rank; the analysis windows of find_anomalies -- each a third of the signal, twenty-odd
 of them, the one part of the finish whose cost grows with the total length -- are dealt out to the ranks and their few
 runs gathered (a few KB).  There is no collective inside a kernel.
@@ -103,18 +103,19 @@ class ShardedScorer:
         t0, tc = timestep_range(first, count, n_windows, S, self.rank == self.world - 1)
         kmax_local = scoring.kde_argmax_overlap(fw["critic"], S, n_windows=n_windows, critic_offset=h0, t0=t0, t_count=tc)
         tcounts = [timestep_range(f, c, n_windows, S, r == self.world - 1)[1] for r, (f, c) in enumerate(ranges)]
-        kmax = gather_concat(kmax_local, tcounts, self.group)
-        # rec and unorm (fp32, per window) travel as one buffer.  (Issued asynchronously before the KDE kernel the gather
-        # only steals its SMs: measured 6 % slower at 2 GPUs.)
-        width = max(counts)
-        pair = fw["rec"].new_zeros(2 * width)
-        pair[:count] = fw["rec"][lead:]
-        pair[width:width + count] = fw["unorm"][lead:]
-        pair_flat = pair.new_empty(self.world * 2 * width)
-        dist.all_gather_into_tensor(pair_flat, pair, group=self.group)
-        pair_out = pair_flat.view(self.world, 2, width)
-        rec = _concat_rows(pair_out[:, 0, :], counts)
-        unorm = _concat_rows(pair_out[:, 1, :], counts)
+        # One collective for the three per-position arrays, 12 B per timestep: kmax is one of the fp32 critic values widened
+        # to float64, so it travels as fp32 without loss; rec and unorm are fp32 anyway.
+        width = max(tcounts)
+        pack = fw["rec"].new_zeros(3 * width)
+        pack[:tc] = kmax_local.float()
+        pack[width:width + count] = fw["rec"][lead:]
+        pack[2 * width:2 * width + count] = fw["unorm"][lead:]
+        flat = pack.new_empty(self.world * 3 * width)
+        dist.all_gather_into_tensor(flat, pack, group=self.group)
+        parts = flat.view(self.world, 3, width)
+        kmax = _concat_rows(parts[:, 0, :], tcounts).double()
+        rec = _concat_rows(parts[:, 1, :], counts)
+        unorm = _concat_rows(parts[:, 2, :], counts)
         cs = scoring.critic_zscore_smooth(kmax, math.trunc(n_windows * 0.01))
         final = scoring.combine(combination, cs[:n_windows], rec, unorm, n=n_windows)
         out = {"final": final, "kmax": kmax, "rec": rec, "unorm": unorm, "critic_scores": cs[:n_windows]}
@@ -128,8 +129,8 @@ class ShardedScorer:
                                anomaly_padding=50, ddof=0):
         """scoring.find_anomaly_intervals with the analysis windows dealt out to the ranks: rank r thresholds windows
         [r*per, (r+1)*per) of the (identical, gathered) score array, the packed per-window results are all-gathered and the
-        host tail (prune, score, merge) runs on every rank.  Window k of a sub-array that starts at k0*step is window k0+k of
-        the full array, so the kernels need no notion of a window subset and the result is bitwise the single-GPU one."""
+        host tail (prune, score, merge) runs on every rank.  The kernels work on the whole array with a first-window index, so
+        the block sums and the shift sample are the single-GPU ones and the result is bitwise the single-GPU one."""
         n = final.numel()
         wsize, step, count = scoring.analysis_windows(n, None, window_size_portion, None, window_step_size_portion)
         per = -(-count // self.world)
@@ -139,7 +140,7 @@ class ShardedScorer:
         blen = scoring.threshold_buffer_len(per, R)
         local = torch.zeros(blen, dtype=torch.float64, device=final.device)
         if kc > 0:
-            sub = scoring.threshold_windows_launch(final[k0 * step:], wsize, step, kc, ddof, anomaly_padding, R)
+            sub = scoring.threshold_windows_launch(final, wsize, step, kc, ddof, anomaly_padding, R, first_window=k0)
             # re-pack the kc-window buffer into the fixed per-window layout of `per` windows
             s_loc, r_loc, n_loc = scoring.threshold_buffer_len(kc, R), kc * 4, kc * R * 3
             local[: kc * 4] = sub[:r_loc]

@@ -250,8 +250,10 @@ def threshold_buffer_len(count, max_runs):
     return count * 4 + count * max_runs * 3 + (count + 1) // 2
 
 
-def threshold_windows_launch(errors, window_size, step, count, ddof, anomaly_padding, max_runs, out=None, exhaustive=False):
-    """Enqueues the per-window statistics / run kernels; returns the packed device buffer (no synchronisation)."""
+def threshold_windows_launch(errors, window_size, step, count, ddof, anomaly_padding, max_runs, out=None, exhaustive=False,
+                             first_window=0):
+    """Enqueues the per-window statistics / run kernels for windows [first_window, first_window + count); returns the packed
+    device buffer (no synchronisation)."""
     errors = _native.require_cuda(errors, "errors").reshape(-1).double().contiguous()
     dev = errors.device
     c = _ctx(errors)
@@ -259,9 +261,14 @@ def threshold_windows_launch(errors, window_size, step, count, ddof, anomaly_pad
     buf = torch.empty(threshold_buffer_len(count, max_runs), dtype=torch.float64, device=dev) if out is None else out
     base = buf.data_ptr()
     with torch.cuda.device(dev):
-        fn = c.lib.hypad_threshold_windows_exhaustive if exhaustive else c.lib.hypad_threshold_windows
-        check(fn(c.handle, ptr(errors), errors.shape[0], window_size, step, count, int(ddof), int(anomaly_padding), base,
-                 base + 8 * n_stats, base + 8 * (n_stats + n_runs_f), max_runs, c.stream()))
+        if first_window:
+            check(c.lib.hypad_threshold_windows_range(c.handle, ptr(errors), errors.shape[0], window_size, step, int(first_window), count,
+                                                      int(ddof), int(anomaly_padding), base, base + 8 * n_stats,
+                                                      base + 8 * (n_stats + n_runs_f), max_runs, c.stream()))
+        else:
+            fn = c.lib.hypad_threshold_windows_exhaustive if exhaustive else c.lib.hypad_threshold_windows
+            check(fn(c.handle, ptr(errors), errors.shape[0], window_size, step, count, int(ddof), int(anomaly_padding), base,
+                     base + 8 * n_stats, base + 8 * (n_stats + n_runs_f), max_runs, c.stream()))
     return buf
 
 

@@ -197,6 +197,12 @@ int hypad_area_error(const double* y, const void* y_hat, int y_hat_is_f32, int64
 int hypad_threshold_windows(hypad_ctx* ctx, const double* errors, int64_t len, int64_t window_size, int64_t step,
                             int64_t n_analysis, int ddof, int anomaly_padding, double* stats, double* runs,
                             int32_t* n_runs, int max_runs, void* stream);
+/* hypad_threshold_windows for the analysis windows [first_window, first_window + n_analysis) of the same array (outputs
+ * indexed from 0): what one rank computes when the windows are dealt out to several GPUs.  Bitwise the corresponding rows
+ * of the full call -- block sums and the shift sample are defined on the whole array. */
+int hypad_threshold_windows_range(hypad_ctx* ctx, const double* errors, int64_t len, int64_t window_size, int64_t step,
+                                  int64_t first_window, int64_t n_analysis, int ddof, int anomaly_padding, double* stats,
+                                  double* runs, int32_t* n_runs, int max_runs, void* stream);
 /* Same contract and results (statistics to the last few bits, runs exactly); every tile of every window is visited
  * element-wise with two-pass statistics: the in-library cross-check of hypad_threshold_windows, which reads the array
  * once (per-block sums and maxima) and visits only the blocks near anomalies and window edges. */

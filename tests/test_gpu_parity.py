@@ -529,3 +529,11 @@ def test_threshold_windows_block_path_equals_exhaustive(n, portion, pad, ddof, c
         np.testing.assert_allclose(got[0][k, :2], (w.mean(), w.std(ddof=ddof)), rtol=1e-12)
     np.testing.assert_allclose(got[0][:, :3], want[0][:, :3], rtol=1e-12)
     assert np.array_equal(got[0][:, 3], want[0][:, 3])
+    # a window range (what one rank computes when the windows are dealt out) is bitwise the same rows of the full call
+    for k0 in sorted(k for k in {1, count // 2, count - 1} if 0 < k < count):
+        kc = count - k0
+        host = scoring.threshold_windows_launch(dev_e, wsize, step, kc, ddof, pad, got[1].shape[1], first_window=k0).cpu().numpy()
+        st, ru, nr = scoring.threshold_windows_parse(host, kc, got[1].shape[1])
+        assert np.array_equal(st, got[0][k0:]) and np.array_equal(nr, got[2][k0:])
+        for k in range(kc):
+            assert np.array_equal(ru[k, :nr[k]], got[1][k0 + k, :nr[k]])
