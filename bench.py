@@ -193,7 +193,20 @@ def run_native(args):
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        # rank 0 prints exactly one JSON line: whatever the communicator set-up writes to file descriptor 1 (NCCL's version
+        # banner) goes to stderr instead; stdout is restored after the first collective
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     torch.manual_seed(0)
     enc, dec, cx = Encoder(S, 20), Decoder(S, 20, True), CriticX(S, 20)
