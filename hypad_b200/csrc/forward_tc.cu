@@ -14,16 +14,21 @@
 // weights at pack time, sa is 11 for activations bounded by 1 (LSTM outputs, tanh), 10 for the window itself (|x| < 63),
 // 8 for unbounded linear / LeakyReLU outputs (|a| < 255); leaving the range raises the context's sticky error flag.
 //
-// One persistent CTA per SM owns tiles of 128 windows (TMEM lane = window).  Warp roles:
+// One persistent CTA per SM owns tiles of 128 windows (TMEM lane = window), TWO tiles in flight: each has its own 64 KB
+// operand buffer and its own 256 TMEM columns, and while the epilogue warps work on one tile's accumulators the tensor pipe
+// runs the other tile's next pass -- the tensor work hides behind the activation math, which bounds the kernel.  Warp roles:
 //   warps 0-15 epilogue: warp w reads TMEM lanes 32*(w%4).. (its 32 windows) and every 4th 8-column chunk (w/4);
-//              gate / activation math in registers, then writes the next layer's A operand (hi and lo pieces) into shared
+//              gate / activation math in registers, then writes the next pass's A operand (hi and lo pieces) into shared
 //              memory in the UMMA K-major core-matrix layout, element (row r, feature k) at ((k/8)*128 + r)*16 B + (k%8)*2 B
-//   warp 16    weight producer: cp.async.bulk (TMA engine) of one <=16 KB weight stage (32 k x <=128 columns, hi+lo)
-//              per mbarrier slot, a ring of 5 slots running ahead across layers and tiles
-//   warp 17    MMA issuer: one thread issues the six tcgen05.mma per stage, tcgen05.commit frees the slot and, per
-//              layer, signals the epilogue
-// Activations never leave the SM: the A operand buffer (64 KB = 128 features x 128 windows x hi/lo) is overwritten in
-// place layer by layer (all MMAs of a layer retire before its epilogue runs).  Weights stream from L2.
+//   warp 16    weight producer: cp.async.bulk (TMA engine) of one <=16 KB weight stage (1-8 k-steps of 16 k x <=256
+//              columns, hi+lo) per mbarrier slot, a ring of 5 slots running ahead across passes and tiles
+//   warp 17    MMA issuer: one elected thread issues the three tcgen05.mma per k-step, tcgen05.commit frees the slot and,
+//              per pass and tile, signals the epilogue
+// A model is 11 passes (15 when the critic cannot ride along, see TcPass): an LSTM layer is a g|i pass (one N = 2 nu
+// contraction) and an o pass; the four CriticX layers ride along with the first four passes as a second small block.
+// Activations never leave the SM: a tile's operand buffer (64 KB = 128 features x 128 windows x hi/lo) is overwritten in
+// place pass by pass (all MMAs of a pass retire before its epilogue runs).  Weights (0.6 MB) stream from L2; biases, scales
+// and row-phase parameters are copied to shared memory once per kernel.
 #include <cuda_fp16.h>
 
 #include <vector>
@@ -44,7 +49,7 @@ constexpr int TC_TILE_COLS = 256;         // TMEM columns per tile slot
 constexpr int TC_STAGE_BYTES = 16384;     // one weight stage: kstage k-steps of 16 k x n columns x (hi + lo) x 2 B
 constexpr int TC_NSLOT = 5;
 constexpr int TC_RED_BYTES = TC_NSPLIT * TC_M * 2 * 8;  // row reductions of at most two fp64 values per row
-constexpr int TC_BIAS_BYTES = 9216;       // shared copy of every pass's biases and the Mobius bias (fp32 and fp64)
+constexpr int TC_BIAS_BYTES = 9216;       // shared copy of the small-parameter buffer: biases, Mobius bias, critic output layer, scales
 constexpr int TC_CRITIC_SHIFT = 8;        // sa of the critic's hidden activations (unbounded LeakyReLU outputs)
 constexpr int TC_CRITIC_K0 = 104;         // operand feature where the critic chain keeps its hidden state when it rides along
 
