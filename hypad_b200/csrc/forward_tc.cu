@@ -837,8 +837,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                     // ---- next step of this slot: the following pass of the tile, or the first pass of the slot's next tile
                     int pn = p + 1;
                     while (pn < T_COUNT && !((P.pass_mask >> pn) & 1u)) ++pn;
-                    if (pn < T_COUNT) hand_over(sl, t, pn);
-                    else if (t + TC_TILES < my_tiles) hand_over(sl, t + TC_TILES, p_first);
+                    if (pn < T_COUNT) {
+                        hand_over(sl, t, pn);
+                    } else if (t + TC_TILES < my_tiles) {
+                        has_x &= ~(1u << sl);  // a new tile: whatever window the buffer holds is the old tile's
+                        hand_over(sl, t + TC_TILES, p_first);
+                    }
                 }
             }
         if (dbg && blockIdx.x == 0 && tid == 0) {

@@ -537,3 +537,24 @@ def test_threshold_windows_block_path_equals_exhaustive(n, portion, pad, ddof, c
         assert np.array_equal(st, got[0][k0:]) and np.array_equal(nr, got[2][k0:])
         for k in range(kc):
             assert np.array_equal(ru[k, :nr[k]], got[1][k0 + k, :nr[k]])
+
+
+@pytest.mark.gpu
+def test_tensor_core_forward_many_tiles_per_cta_matches_ffma(hyp_scorer, cuda_device):
+    """More windows than 2 tiles x 148 SMs x 128: every CTA of the persistent tensor-core kernel walks through several tiles
+    per slot (operand buffers, TMEM columns, barrier phases and the window reload are reused), which the golden cases -- at
+    most one tile per CTA -- never exercise.  Checked against the independent FFMA kernel on the same signal."""
+    rng = np.random.default_rng(11)
+    T = 120000
+    sig = np.sin(2 * np.pi * np.arange(T) / 50.0) + 0.1 * rng.standard_normal(T)
+    sig[50000:50005] += 3.0
+    sig = torch.from_numpy(2 * (sig - sig.min()) / (sig.max() - sig.min()) - 1).to(cuda_device)
+    tc = hyp_scorer.forward(sig, True)
+    hyp_scorer.poll_error()
+    ff = hyp_scorer.forward(sig, True, ffma=True)
+    assert (tc["critic"] - ff["critic"]).abs().max().item() <= 1.5e-7
+    np.testing.assert_allclose(tc["unorm"].cpu().numpy(), ff["unorm"].cpu().numpy(), rtol=1e-6)
+    quantised_close(tc["rec"].cpu().numpy(), ff["rec"].cpu().numpy())
+    # and the tile boundaries are invisible: a window range starting inside the signal equals the same rows of the full run
+    part = hyp_scorer.forward(sig, True, first=40001, count=50000)
+    assert torch.equal(part["critic"], tc["critic"][40001:90001]) and torch.equal(part["rec"], tc["rec"][40001:90001])
