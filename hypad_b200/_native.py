@@ -58,6 +58,8 @@ _SIGNATURES = {
     "hypad_forward": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _int, ctypes.POINTER(hypad_forward_out), _vp]),
     "hypad_forward_ffma": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _int, ctypes.POINTER(hypad_forward_out), _vp]),
     "hypad_ctx_poll_error": (_int, [_vp]),
+    "hypad_segments_aggregate": (_int, [_vp, _vp, _i64, _vp, ctypes.c_double, _i64, _vp, _vp]),
+    "hypad_impute_minmax": (_int, [_vp, _vp, _i64, ctypes.c_double, ctypes.c_double, _vp, _vp]),
     "hypad_rowdiff_norm": (_int, [_vp, _int, _vp, _i64, _int, _vp, _vp]),
     "hypad_forward_debug_cycles": (_int, [_vp, _int, _vp]),
     "hypad_mobius_linear": (_int, [_vp, _vp, _i64, _int, _int, _vp, _vp, _int, _vp, _vp]),

@@ -1,15 +1,89 @@
-"""Drop-in for the window construction of utils/dataloader.py of the reference.
+"""Drop-in for utils/dataloader.py of the reference: preprocessing and window construction.
 
-`rolling_window_sequences` keeps the reference's signature (utils/dataloader.py:139-150) and return values; the window
-matrix is produced by the coalesced sm_100a gather kernel (`hypad_window_gather`).  The fused scoring pipeline never
-needs it -- windows are overlapping views of the signal -- so this exists for callers that want the materialised
-array.  CSV reading, interval aggregation, imputation and MinMax scaling (utils/dataloader.py:61-137) are the step
-before the path and stay in pandas/sklearn on the host.
+`SignalDataset` keeps the reference's constructor and attributes (utils/dataloader.py:61-97, 224-232).  The CSV is read on
+the host (pandas); interval aggregation, mean imputation and MinMax scaling to (-1, 1) (:83-89, :99-137 -- a Python loop
+with one pandas slice per segment in the reference) run on the device (`hypad_segments_aggregate`, `hypad_impute_minmax`),
+and the scaled signal stays there as `.signal` for the fused scoring path, which never materialises windows.
+`rolling_window_sequences` keeps the reference's signature (:139-150) and return values; the window matrix is produced by
+the coalesced sm_100a gather kernel (`hypad_window_gather`) for callers that want the materialised array.
+The YAHOO branch (scipy `detrend` + synthetic timestamps, :64-79) is not built.
 """
 import numpy as np
 import torch
 
+from .. import _native
 from .. import scoring as _sc
+from .._native import check, ptr
+
+
+def segment_starts(first, last, interval):
+    """The segment starts of the reference's loop (`while start_ts <= max_ts: ...; start_ts = end_ts`, :127-135): repeated
+    addition, so that non-integer intervals accumulate the same rounding."""
+    n = int(np.floor((last - first) / interval)) + 2
+    starts = np.cumsum(np.concatenate(([first], np.full(n, interval, dtype=np.result_type(first, interval)))))  # sequential adds
+    return starts[starts <= last]
+
+
+def preprocess_signal(timestamps, values, interval=21600, feature_range=(-1.0, 1.0), device=None):
+    """utils/dataloader.py:83-89 on the device: time_segments_aggregate(mean) -> SimpleImputer() -> MinMaxScaler(-1, 1).
+
+    timestamps, values: 1-D arrays (any order).  Returns (X, index): the scaled signal as a float64 device tensor (K,) and the
+    segment starts (K,) as a numpy array with the timestamps' dtype."""
+    ts = np.asarray(timestamps)
+    order = np.argsort(ts, kind="stable")  # the reference's sort_values is pandas' unstable quicksort: ties are arbitrary there
+    ts_sorted = ts[order]
+    index = segment_starts(ts_sorted[0], ts_sorted[-1], interval)
+    dev = _sc.cuda_device(device)
+    d_ts = torch.from_numpy(np.ascontiguousarray(ts_sorted, dtype=np.float64)).to(dev)
+    d_v = torch.from_numpy(np.ascontiguousarray(np.asarray(values, dtype=np.float64)[order])).to(dev)
+    d_start = torch.from_numpy(np.ascontiguousarray(index, dtype=np.float64)).to(dev)
+    K = index.shape[0]
+    agg = torch.empty(K, dtype=torch.float64, device=dev)
+    out = torch.empty(K, dtype=torch.float64, device=dev)
+    c = _native.default_context(dev)
+    with torch.cuda.device(dev):
+        check(c.lib.hypad_segments_aggregate(ptr(d_ts), ptr(d_v), d_ts.shape[0], ptr(d_start), float(interval), K, ptr(agg), c.stream()))
+        check(c.lib.hypad_impute_minmax(c.handle, ptr(agg), K, float(feature_range[0]), float(feature_range[1]), ptr(out), c.stream()))
+    return out, index
+
+
+class SignalDataset(torch.utils.data.Dataset):
+    """utils/dataloader.py:61-97, 224-232.  `.X` (N, window, 1), `.y`, `.X_index`, `.y_index`, `.index` as in the reference
+    (host arrays, built on first use); `.signal` is the scaled signal on the device -- what `WindowScorer.score(sliding=True)`
+    consumes."""
+
+    def __init__(self, path, interval=21600, windows_size=100, test=False, yahoo=None):
+        import pandas as pd
+
+        if yahoo:
+            raise NotImplementedError("hypad_b200: the YAHOO preprocessing branch (scipy detrend, utils/dataloader.py:64-79) is not built")
+        self.signal_df = pd.read_csv(path)
+        self.interval = interval
+        self.windows_size = windows_size
+        self.test = test
+        self.signal, self.index = preprocess_signal(self.signal_df["timestamp"].values, self.signal_df["value"].values, interval)
+        self._windows = None
+
+    def _build(self):
+        if self._windows is None:
+            X = self.signal.cpu().numpy().reshape(-1, 1)
+            self._windows = rolling_window_sequences(X, self.index, window_size=self.windows_size, target_size=1, step_size=1,
+                                                     target_column=0)
+        return self._windows
+
+    X = property(lambda self: self._build()[0])
+    y = property(lambda self: self._build()[1])
+    X_index = property(lambda self: self._build()[2])
+    y_index = property(lambda self: self._build()[3])
+
+    def __len__(self):
+        return max(0, self.signal.shape[0] - self.windows_size)
+
+    def __getitem__(self, idx):
+        x = torch.from_numpy(self.X[idx])
+        if self.test:
+            return x, self.index, self.y, self.y_index, self.X_index
+        return x
 
 
 def rolling_window_sequences(X, index, window_size, target_size, step_size, target_column, offset=0, drop=None, drop_windows=False):

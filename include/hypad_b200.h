@@ -128,6 +128,18 @@ int hypad_forward_debug_cycles(hypad_ctx* ctx, int enable, long long* h_out);
 int hypad_mobius_linear(hypad_ctx* ctx, const float* x, int64_t n, int in_features, int out_features,
                         const float* weight, const float* bias, int hyperbolic_bias, float* out, void* stream);
 
+/* ---- the step in front of the path: utils/dataloader.py:83-137 ------------------------------ */
+/* SignalDataset.time_segments_aggregate(method="mean"), utils/dataloader.py:99-137.  ts_sorted (n_rows) float64 timestamps
+ * in ascending order with their values; seg_start (n_segments): the segment starts the reference's loop produces
+ * (start, start+interval, ... by repeated addition, while <= the last timestamp).  Segment k takes the rows with
+ * seg_start[k] <= t <= seg_start[k] + interval - 1 (pandas label slicing is inclusive); out[k] = their NaN-skipping mean in
+ * numpy's summation order, NaN for an empty or all-NaN segment. */
+int hypad_segments_aggregate(const double* ts_sorted, const double* values, int64_t n_rows, const double* seg_start,
+                             double interval, int64_t n_segments, double* out, void* stream);
+/* sklearn SimpleImputer() (mean) then MinMaxScaler(feature_range=(lo, hi)) on one column, utils/dataloader.py:86-89:
+ * out = (isnan(x) ? mean(valid x) : x) * scale + (lo - min * scale), scale = (hi - lo) / (max - min) (1 for a constant column). */
+int hypad_impute_minmax(hypad_ctx* ctx, const double* x, int64_t n, double lo, double hi, double* out, void* stream);
+
 /* utils/anomaly_detection_utils.py:58-66: acosh(1 + 2|u-v|^2/((1-|u|^2)(1-|v|^2)) + 1e-7), fp32, per row. */
 int hypad_poincare_rowdist(const float* recons, const float* truth, int64_t n, int S, float* out, void* stream);
 /* np.linalg.norm(x, axis=1) on fp32 rows, utils/anomaly_detection_utils.py:342. */

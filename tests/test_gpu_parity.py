@@ -558,3 +558,52 @@ def test_tensor_core_forward_many_tiles_per_cta_matches_ffma(hyp_scorer, cuda_de
     # and the tile boundaries are invisible: a window range starting inside the signal equals the same rows of the full run
     part = hyp_scorer.forward(sig, True, first=40001, count=50000)
     assert torch.equal(part["critic"], tc["critic"][40001:90001]) and torch.equal(part["rec"], tc["rec"][40001:90001])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the step in front of the path: preprocessing on the device
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_preprocessing_on_device_vs_reference(cuda_device):
+    """utils/dataloader.py:83-137: the segment means are bit-identical to the reference's (same summation order), so are the
+    segment starts; the scaled signal follows sklearn's two roundings (x * scale + min_) -- bit-identical as well."""
+    from hypad_b200.utils.dataloader import preprocess_signal
+    from tests_preprocess_cases import cases
+
+    g = golden("preprocess.npz")
+    for name, (ts, vals, interval) in cases().items():
+        X, index = preprocess_signal(ts, vals, interval, device=cuda_device)
+        assert np.array_equal(index, g[name + "/index"]), name
+        assert X.dtype == torch.float64 and X.is_cuda
+        mine = X.cpu().numpy()
+        want = g[name + "/scaled"]
+        assert mine.shape == want.shape, name
+        assert np.abs(mine - want).max() <= 1e-15, (name, np.abs(mine - want).max())
+        o, _ = ho.preprocess_signal(ts, vals, interval)
+        assert np.array_equal(mine, o), (name, np.abs(mine - o).max())
+
+
+@pytest.mark.gpu
+def test_segments_aggregate_long_segments_vs_oracle(cuda_device):
+    """Segments longer than 128 rows exercise numpy's recursive pairwise split; a 200k-row signal in 100 segments and one of 3
+    rows per segment with NaNs, against the oracle, bit-exact."""
+    from hypad_b200 import _native
+    from hypad_b200._native import check, ptr
+    from hypad_b200.utils.dataloader import segment_starts
+
+    rng = np.random.default_rng(11)
+    for n, interval in ((200_000, 2000), (30_000, 3), (1000, 129)):
+        ts = np.arange(n, dtype=np.int64) * 1 + 7
+        v = rng.standard_normal(n) * 1e3
+        v[rng.integers(0, n, n // 50)] = np.nan
+        want, index = ho.time_segments_aggregate(ts, v, interval)
+        starts = segment_starts(ts[0], ts[-1], interval)
+        assert np.array_equal(starts, index)
+        c = _native.default_context(cuda_device)
+        d_ts = torch.from_numpy(ts.astype(np.float64)).to(cuda_device)
+        d_v = torch.from_numpy(v).to(cuda_device)
+        d_s = torch.from_numpy(starts.astype(np.float64)).to(cuda_device)
+        out = torch.empty(len(starts), dtype=torch.float64, device=cuda_device)
+        check(c.lib.hypad_segments_aggregate(ptr(d_ts), ptr(d_v), n, ptr(d_s), float(interval), len(starts), ptr(out), c.stream()))
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), want, equal_nan=True), (n, interval)
