@@ -60,6 +60,10 @@ _SIGNATURES = {
     "hypad_ctx_poll_error": (_int, [_vp]),
     "hypad_segments_aggregate": (_int, [_vp, _vp, _i64, _vp, ctypes.c_double, _i64, _vp, _vp]),
     "hypad_impute_minmax": (_int, [_vp, _vp, _i64, ctypes.c_double, ctypes.c_double, _vp, _vp]),
+    "hypad_detrend_linear": (_int, [_vp, _vp, _i64, _vp, _vp]),
+    "hypad_poincare_distance_pairwise": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp, _vp]),
+    "hypad_pairwise_sqdist": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp, _vp]),
+    "hypad_square_norm": (_int, [_vp, _i64, _int, _vp, _vp]),
     "hypad_rowdiff_norm": (_int, [_vp, _int, _vp, _i64, _int, _vp, _vp]),
     "hypad_forward_debug_cycles": (_int, [_vp, _int, _vp]),
     "hypad_mobius_linear": (_int, [_vp, _vp, _i64, _int, _int, _vp, _vp, _int, _vp, _vp]),

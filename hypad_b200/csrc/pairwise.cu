@@ -1,0 +1,156 @@
+// hyperspace/poincare_distance.py of the reference on the device (off the executed scoring path, used by
+// hyperspace/losses.py:154):
+//   square_norm(x)          :19-25   clamp(torch.norm(x, dim=-1)^2, min=1e-5)
+//   pairwise_distances(x,y) :28-48   clamp(|x_i|^2 + |y_j|^2 - 2 <x_i, y_j>, 1e-7, inf)
+//   poincare_distance(p,g)  :5-16    acosh(1 + 2 pairwise / ((1 - square_norm(p))_i (1 - square_norm(g))_j))
+// fp32 like the reference (torch.mm on fp32 inputs).  The N x M x D contraction runs on the fp32 FFMA pipe: the squared
+// distance is a difference of nearly equal numbers for close points, so the products must keep fp32 accuracy, and D is ~100
+// -- the kernel is bound by the N x M fp32 output (4 B per pair) and the FFMA pipe about equally; see DESIGN.md.
+#include "common.cuh"
+
+namespace hypad {
+
+constexpr int PW_TILE = 64;  // rows of x and rows of y per CTA tile
+constexpr int PW_K = 16;     // features per shared-memory stage
+
+// per row: sum of squares (fp32 value of the fp64 sum) and the clamped squared norm of square_norm()
+__global__ void pw_rownorm_kernel(const float* __restrict__ x, int64_t n, int D, float* __restrict__ sumsq, float* __restrict__ sqnorm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+        double s = 0.0;
+        for (int c = lane; c < D; c += 32) {
+            const float v = x[row * D + c];
+            s += (double)__fmul_rn(v, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            const float ss = (float)s;
+            if (sumsq) sumsq[row] = ss;
+            if (sqnorm) {
+                const float r = sqrtf(ss);  // torch.norm(...) ** 2
+                sqnorm[row] = fmaxf(__fmul_rn(r, r), 1e-5f);
+            }
+        }
+    }
+}
+
+// mode 0: poincare_distance, mode 1: pairwise_distances.  One CTA per 64 x 64 output tile (grid-stride), 256 threads, thread =
+// 4 x 4 outputs; operands staged k-major in shared memory 16 features at a time.
+__global__ void __launch_bounds__(256) pw_distance_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                          const float* __restrict__ xss, const float* __restrict__ yss,
+                                                          const float* __restrict__ xsq, const float* __restrict__ ysq, int64_t N,
+                                                          int64_t M, int D, int mode, float* __restrict__ out) {
+    __shared__ __align__(16) float As[PW_K][PW_TILE + 4];
+    __shared__ __align__(16) float Bs[PW_K][PW_TILE + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int lr = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;
+    const int64_t tiles_m = (M + PW_TILE - 1) / PW_TILE, tiles_n = (N + PW_TILE - 1) / PW_TILE;
+    for (int64_t tile = blockIdx.x; tile < tiles_n * tiles_m; tile += gridDim.x) {
+        const int64_t i0 = (tile / tiles_m) * PW_TILE, j0 = (tile % tiles_m) * PW_TILE;
+        float acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+        for (int k0 = 0; k0 < D; k0 += PW_K) {
+            const bool xr = i0 + lr < N, yr = j0 + lr < M;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = k0 + lk + q;
+                As[lk + q][lr] = (xr && k < D) ? x[(i0 + lr) * D + k] : 0.0f;
+                Bs[lk + q][lr] = (yr && k < D) ? y[(j0 + lr) * D + k] : 0.0f;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < PW_K; ++kk) {
+                const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+                const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int64_t i = i0 + ty * 4 + r;
+            if (i >= N) continue;
+            const float xn = xss[i];
+            const float a1 = mode == 0 ? __fsub_rn(1.0f, xsq[i]) : 0.0f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int64_t j = j0 + tx * 4 + c;
+                if (j >= M) continue;
+                // x_norm + y_norm - 2.0 * mm, clamped to [1e-7, inf)   (:45-48)
+                float d = __fsub_rn(__fadd_rn(xn, yss[j]), __fmul_rn(2.0f, acc[r][c]));
+                d = fmaxf(d, 1e-7f);
+                if (mode == 0) {
+                    const float den = __fmul_rn(a1, __fsub_rn(1.0f, ysq[j]));
+                    d = acoshf(__fadd_rn(1.0f, __fdiv_rn(__fmul_rn(2.0f, d), den)));  // :16
+                }
+                out[i * M + j] = d;
+            }
+        }
+    }
+}
+
+static int pairwise(hypad_ctx* ctx, const float* x, int64_t n, const float* y, int64_t m, int D, int mode, float* out, cudaStream_t stream) {
+    HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
+    int rc = ensure_workspace(ctx, (size_t)(2 * (n + m)) * sizeof(float));
+    if (rc != HYPAD_OK) return rc;
+    float* xss = (float*)ctx->workspace;
+    float* xsq = xss + n;
+    float* yss = xsq + n;
+    float* ysq = yss + m;
+    auto rows_grid = [](int64_t rows) { return (unsigned)(ceil_div(rows, 8) < kNumSMs * 8 ? ceil_div(rows, 8) : kNumSMs * 8); };
+    pw_rownorm_kernel<<<rows_grid(n), 256, 0, stream>>>(x, n, D, xss, xsq);
+    HYPAD_LAUNCH_CHECK();
+    if (y != x || m != n) {
+        pw_rownorm_kernel<<<rows_grid(m), 256, 0, stream>>>(y, m, D, yss, ysq);
+        HYPAD_LAUNCH_CHECK();
+    } else {
+        yss = xss, ysq = xsq;
+    }
+    const int64_t tiles = ceil_div(n, PW_TILE) * ceil_div(m, PW_TILE);
+    const unsigned grid = (unsigned)(tiles < (int64_t)kNumSMs * 16 ? tiles : (int64_t)kNumSMs * 16);
+    pw_distance_kernel<<<grid, 256, 0, stream>>>(x, y, xss, yss, xsq, ysq, n, m, D, mode, out);
+    HYPAD_LAUNCH_CHECK();
+    return HYPAD_OK;
+}
+
+}  // namespace hypad
+
+using namespace hypad;
+
+extern "C" {
+
+int hypad_poincare_distance_pairwise(hypad_ctx* ctx, const float* pred, int64_t n_pred, const float* gt, int64_t n_gt, int D, float* out,
+                                     void* stream) {
+    HYPAD_REQUIRE(ctx && pred && gt && out, "hypad_poincare_distance_pairwise: NULL argument");
+    HYPAD_REQUIRE(n_pred >= 0 && n_gt >= 0 && D >= 1, "hypad_poincare_distance_pairwise: bad shape");
+    if (n_pred == 0 || n_gt == 0) return HYPAD_OK;
+    return pairwise(ctx, pred, n_pred, gt, n_gt, D, 0, out, (cudaStream_t)stream);
+}
+
+int hypad_pairwise_sqdist(hypad_ctx* ctx, const float* x, int64_t n, const float* y, int64_t m, int D, float* out, void* stream) {
+    HYPAD_REQUIRE(ctx && x && y && out, "hypad_pairwise_sqdist: NULL argument");
+    HYPAD_REQUIRE(n >= 0 && m >= 0 && D >= 1, "hypad_pairwise_sqdist: bad shape");
+    if (n == 0 || m == 0) return HYPAD_OK;
+    return pairwise(ctx, x, n, y, m, D, 1, out, (cudaStream_t)stream);
+}
+
+int hypad_square_norm(const float* x, int64_t n, int D, float* out, void* stream) {
+    HYPAD_REQUIRE(x && out, "hypad_square_norm: NULL argument");
+    HYPAD_REQUIRE(n >= 0 && D >= 1, "hypad_square_norm: bad shape");
+    if (n == 0) return HYPAD_OK;
+    const unsigned grid = (unsigned)(ceil_div(n, 8) < kNumSMs * 8 ? ceil_div(n, 8) : kNumSMs * 8);
+    pw_rownorm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, D, nullptr, out);
+    HYPAD_LAUNCH_CHECK();
+    return HYPAD_OK;
+}
+
+}  // extern "C"

@@ -163,6 +163,50 @@ __global__ void impute_scale_kernel(const double* __restrict__ x, int64_t n, con
     }
 }
 
+// ---- scipy.signal.detrend(type="linear") of the YAHOO branch (utils/dataloader.py:36-38, :66): subtract the least-squares line
+// over t_i = (i + 1) / n.  Closed-form normal equations on centred abscissae (u_i = t_i - (n + 1) / (2 n), sum u_i^2 =
+// (n^2 - 1) / (12 n)); scipy solves the same 2-column problem with LAPACK gelsd, the two agree to a few ulps of max|v|.
+__global__ void __launch_bounds__(256) detrend_stats_kernel(const double* __restrict__ v, int64_t n, double* __restrict__ partial) {
+    __shared__ double sh[2][8];
+    const double dn = (double)n, ubar = (dn + 1.0) / (2.0 * dn);
+    double s = 0.0, suv = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = v[i];
+        s += x;
+        suv = fma((double)(i + 1) / dn - ubar, x, suv);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        suv += __shfl_xor_sync(0xffffffffu, suv, o);
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) sh[0][w] = s, sh[1][w] = suv;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < 8; ++q) s += sh[0][q], suv += sh[1][q];
+        partial[2 * blockIdx.x] = s;
+        partial[2 * blockIdx.x + 1] = suv;
+    }
+}
+
+// st: {slope, intercept} of the fitted line slope * t + intercept
+__global__ void detrend_final_kernel(const double* __restrict__ partial, int n_blocks, int64_t n, double* __restrict__ st) {
+    double s = 0.0, suv = 0.0;
+    for (int b = 0; b < n_blocks; ++b) s += partial[2 * b], suv += partial[2 * b + 1];
+    const double dn = (double)n, ubar = (dn + 1.0) / (2.0 * dn);
+    const double suu = (dn * dn - 1.0) / (12.0 * dn);
+    const double slope = n > 1 ? suv / suu : 0.0;  // one sample: the minimum-norm fit reproduces it, the residual is 0
+    st[0] = slope;
+    st[1] = s / dn - slope * ubar;
+}
+
+__global__ void detrend_apply_kernel(const double* __restrict__ v, int64_t n, const double* __restrict__ st, double* __restrict__ out) {
+    const double slope = st[0], icpt = st[1], dn = (double)n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = v[i] - fma(slope, (double)(i + 1) / dn, icpt);
+}
+
 }  // namespace hypad
 
 using namespace hypad;
@@ -194,6 +238,25 @@ int hypad_impute_minmax(hypad_ctx* ctx, const double* x, int64_t n, double lo, d
     column_stats_final_kernel<<<1, 1, 0, stream>>>(partial, blocks, lo, hi, st);
     HYPAD_LAUNCH_CHECK();
     impute_scale_kernel<<<blocks, 256, 0, stream>>>(x, n, st, out);
+    HYPAD_LAUNCH_CHECK();
+    return HYPAD_OK;
+}
+
+int hypad_detrend_linear(hypad_ctx* ctx, const double* x, int64_t n, double* out, void* stream_) {
+    HYPAD_REQUIRE(ctx && x && out, "hypad_detrend_linear: NULL argument");
+    HYPAD_REQUIRE(n >= 1, "hypad_detrend_linear: bad length");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
+    const int blocks = (int)((n + 256 * 8 - 1) / (256 * 8) < 592 ? (n + 256 * 8 - 1) / (256 * 8) : 592);
+    int rc = ensure_workspace(ctx, (size_t)(2 * blocks + 2) * sizeof(double));
+    if (rc != HYPAD_OK) return rc;
+    double* partial = (double*)ctx->workspace;
+    double* st = partial + 2 * blocks;
+    detrend_stats_kernel<<<blocks, 256, 0, stream>>>(x, n, partial);
+    HYPAD_LAUNCH_CHECK();
+    detrend_final_kernel<<<1, 1, 0, stream>>>(partial, blocks, n, st);
+    HYPAD_LAUNCH_CHECK();
+    detrend_apply_kernel<<<blocks, 256, 0, stream>>>(x, n, st, out);
     HYPAD_LAUNCH_CHECK();
     return HYPAD_OK;
 }

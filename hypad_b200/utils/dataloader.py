@@ -6,7 +6,8 @@ with one pandas slice per segment in the reference) run on the device (`hypad_se
 and the scaled signal stays there as `.signal` for the fused scoring path, which never materialises windows.
 `rolling_window_sequences` keeps the reference's signature (:139-150) and return values; the window matrix is produced by
 the coalesced sm_100a gather kernel (`hypad_window_gather`) for callers that want the materialised array.
-The YAHOO branch (scipy `detrend` + synthetic timestamps, :64-79) is not built.
+The YAHOO branch (:64-79, `yahoo_preprocess` :41-58) detrends on the device too (`hypad_detrend_linear`) and replaces the
+timestamps by the reference's one-per-second index starting 2012-11-24 (local time, like `datetime.timestamp`).
 """
 import numpy as np
 import torch
@@ -47,6 +48,58 @@ def preprocess_signal(timestamps, values, interval=21600, feature_range=(-1.0, 1
     return out, index
 
 
+def detrend_signal(values, device=None):
+    """scipy.signal.detrend(values) (type="linear") on the device, utils/dataloader.py:36-38.  Returns a float64 device tensor."""
+    dev = _sc.cuda_device(device)
+    v = torch.from_numpy(np.ascontiguousarray(np.asarray(values, dtype=np.float64))).to(dev)
+    if v.dim() != 1 or v.shape[0] < 1:
+        raise ValueError("hypad_b200: detrend_signal expects a non-empty 1-D signal")
+    out = torch.empty_like(v)
+    c = _native.default_context(dev)
+    with torch.cuda.device(dev):
+        check(c.lib.hypad_detrend_linear(c.handle, ptr(v), v.shape[0], ptr(out), c.stream()))
+    return out
+
+
+def yahoo_index(n):
+    """The synthetic timestamps of the YAHOO branch (:44-48, :67-75): one per second from 2012-11-24 00:00:00 to 2012-11-30
+    00:00:00 local time (518 401 of them), the first n.  Like the reference, a longer signal is an error (pandas refuses the
+    shorter column)."""
+    from datetime import datetime, timedelta
+
+    first, last = datetime(2012, 11, 24), datetime(2012, 11, 30)
+    total = int((last - first).total_seconds()) + 1
+    if n > total:
+        raise ValueError("Length of values (%d) does not match length of index (%d)" % (total, n))
+    b, e = first.timestamp(), last.timestamp()
+    if e - b == total - 1:  # no clock change inside the range: consecutive seconds
+        return b + np.arange(n, dtype=np.float64)
+    return np.array([(first + timedelta(seconds=i)).timestamp() for i in range(n)])
+
+
+def known_anomaly_runs(df):
+    """The (start, end) timestamp pairs `save_known_anomalies` collects (:14-33): one per run of is_anomaly == 1, last run
+    first (the reference prepends).  Files with an `anomaly` column instead (:19-21) are sorted by timestamp first."""
+    if "is_anomaly" not in df.columns:
+        df = df[["timestamp", "value", "anomaly"]].copy().sort_values(by=["timestamp"])
+        df.columns = ["timestamp", "value", "is_anomaly"]
+    flag = (df["is_anomaly"].values == 1).astype(np.int8)
+    ts = df["timestamp"].values
+    edges = np.flatnonzero(np.diff(np.concatenate(([0], flag, [0]))))
+    starts, ends = edges[0::2], edges[1::2] - 1
+    return df, np.stack([ts[starts], ts[ends]], axis=1)[::-1] if len(starts) else np.empty((0, 2))
+
+
+def yahoo_preprocess(df, device=None):
+    """utils/dataloader.py:41-58: detrended values and the synthetic per-second timestamps; returns df[["timestamp", "value"]]."""
+    df = df.copy()
+    df["value"] = detrend_signal(df["value"].values, device).cpu().numpy()
+    df["timestamp"] = yahoo_index(len(df))
+    if "is_anomaly" not in df.columns:
+        df = df[["timestamp", "value", "anomaly"]].copy().sort_values(by=["timestamp"])
+    return df[["timestamp", "value"]]
+
+
 class SignalDataset(torch.utils.data.Dataset):
     """utils/dataloader.py:61-97, 224-232.  `.X` (N, window, 1), `.y`, `.X_index`, `.y_index`, `.index` as in the reference
     (host arrays, built on first use); `.signal` is the scaled signal on the device -- what `WindowScorer.score(sliding=True)`
@@ -55,9 +108,13 @@ class SignalDataset(torch.utils.data.Dataset):
     def __init__(self, path, interval=21600, windows_size=100, test=False, yahoo=None):
         import pandas as pd
 
-        if yahoo:
-            raise NotImplementedError("hypad_b200: the YAHOO preprocessing branch (scipy detrend, utils/dataloader.py:64-79) is not built")
         self.signal_df = pd.read_csv(path)
+        if yahoo:
+            self.signal_df["value"] = detrend_signal(self.signal_df["value"].values).cpu().numpy()
+            self.signal_df["timestamp"] = yahoo_index(len(self.signal_df))
+            self.signal_df, runs = known_anomaly_runs(self.signal_df)  # :77, the side file the evaluation reads later
+            pd.DataFrame(runs, columns=["start", "end"]).to_csv(path[:-4] + "_known_anomalies.csv")
+            self.signal_df = self.signal_df[["timestamp", "value"]]
         self.interval = interval
         self.windows_size = windows_size
         self.test = test

@@ -140,6 +140,20 @@ int hypad_segments_aggregate(const double* ts_sorted, const double* values, int6
  * out = (isnan(x) ? mean(valid x) : x) * scale + (lo - min * scale), scale = (hi - lo) / (max - min) (1 for a constant column). */
 int hypad_impute_minmax(hypad_ctx* ctx, const double* x, int64_t n, double lo, double hi, double* out, void* stream);
 
+/* scipy.signal.detrend(type="linear") of the YAHOO branch, utils/dataloader.py:36-38 (_detrend_signal), called :66 and from
+ * yahoo_preprocess :42: out = x - (slope * t + intercept), least-squares line over t_i = (i + 1) / n.  out may alias x. */
+int hypad_detrend_linear(hypad_ctx* ctx, const double* x, int64_t n, double* out, void* stream);
+
+/* ---- hyperspace/poincare_distance.py (caller hyperspace/losses.py:154) ----------------------- */
+/* poincare_distance(pred, gt), :5-16: out (n_pred, n_gt) fp32 row-major,
+ * acosh(1 + 2 pairwise_distances(pred, gt)_ij / ((1 - square_norm(pred)_i) (1 - square_norm(gt)_j))). */
+int hypad_poincare_distance_pairwise(hypad_ctx* ctx, const float* pred, int64_t n_pred, const float* gt, int64_t n_gt, int D,
+                                     float* out, void* stream);
+/* pairwise_distances(x, y), :28-48: out (n, m) = clamp(|x_i|^2 + |y_j|^2 - 2 <x_i, y_j>, 1e-7, inf); pass y = x for y=None. */
+int hypad_pairwise_sqdist(hypad_ctx* ctx, const float* x, int64_t n, const float* y, int64_t m, int D, float* out, void* stream);
+/* square_norm(x), :19-25: clamp(torch.norm(x, dim=-1) ** 2, min=1e-5) per row. */
+int hypad_square_norm(const float* x, int64_t n, int D, float* out, void* stream);
+
 /* utils/anomaly_detection_utils.py:58-66: acosh(1 + 2|u-v|^2/((1-|u|^2)(1-|v|^2)) + 1e-7), fp32, per row. */
 int hypad_poincare_rowdist(const float* recons, const float* truth, int64_t n, int S, float* out, void* stream);
 /* np.linalg.norm(x, axis=1) on fp32 rows, utils/anomaly_detection_utils.py:342. */

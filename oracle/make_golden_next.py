@@ -1,0 +1,65 @@
+"""Generates the golden vectors of the SURVEY.md 8(f) rows by running the UNMODIFIED reference on the inputs of
+tests/tests_preprocess_cases.py:
+
+  tests/golden/preprocess.npz   SignalDataset.time_segments_aggregate (utils/dataloader.py:99-137), then the sklearn
+                                SimpleImputer / MinMaxScaler the dataset calls (:86-89); `yahoo/*`: yahoo_preprocess (:41-58)
+                                followed by the same chain at interval=1
+  tests/golden/pairwise.npz     hyperspace/poincare_distance.py: poincare_distance, pairwise_distances, square_norm
+
+Run in the build container only:   python oracle/make_golden_next.py
+TEST INFRASTRUCTURE ONLY.
+"""
+import os
+import sys
+
+os.environ["PYTORCH_JIT"] = "0"
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+import pandas as pd
+import torch
+
+from oracle import ref_harness as rh
+
+
+def main():
+    rh.bootstrap()
+    from sklearn.impute import SimpleImputer
+    from sklearn.preprocessing import MinMaxScaler
+    from tests_preprocess_cases import cases, pairwise_cases, yahoo_cases
+    from utils.dataloader import SignalDataset, yahoo_preprocess
+
+    def chain(df, interval):
+        X, index = SignalDataset.time_segments_aggregate(None, df, interval=interval, time_column="timestamp")
+        Xs = MinMaxScaler(feature_range=(-1, 1)).fit_transform(SimpleImputer().fit_transform(X))
+        return np.asarray(X[:, 0], dtype=np.float64), np.asarray(index), np.asarray(Xs[:, 0], dtype=np.float64)
+
+    g = {}
+    for name, (ts, vals, interval) in cases().items():
+        g[name + "/agg"], g[name + "/index"], g[name + "/scaled"] = chain(pd.DataFrame({"timestamp": ts, "value": vals}), interval)
+        print(name, g[name + "/agg"].shape, int(np.isnan(g[name + "/agg"]).sum()), "NaN segments")
+    for name, (vals, flag) in yahoo_cases().items():
+        df = yahoo_preprocess(pd.DataFrame({"timestamp": np.arange(1, len(vals) + 1), "value": vals, "is_anomaly": flag}))
+        g["yahoo/" + name + "/detrended"] = df["value"].values.astype(np.float64)
+        g["yahoo/" + name + "/timestamp"] = df["timestamp"].values.astype(np.float64)
+        _, g["yahoo/" + name + "/index"], g["yahoo/" + name + "/scaled"] = chain(df, 1)
+        print("yahoo", name, len(vals))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "preprocess.npz"), **g)
+
+    from hyperspace.poincare_distance import pairwise_distances, poincare_distance, square_norm
+
+    g = {}
+    for name, (p, q) in pairwise_cases().items():
+        tp, tq = torch.from_numpy(p), torch.from_numpy(q)
+        g[name + "/poincare"] = poincare_distance(tp, tq).numpy()
+        g[name + "/sqdist"] = pairwise_distances(tp, tq).numpy()
+        g[name + "/sqdist_self"] = pairwise_distances(tp).numpy()
+        g[name + "/square_norm"] = square_norm(tp).numpy()
+        print("pairwise", name, g[name + "/poincare"].shape)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "pairwise.npz"), **g)
+
+
+if __name__ == "__main__":
+    main()

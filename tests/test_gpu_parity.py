@@ -607,3 +607,67 @@ def test_segments_aggregate_long_segments_vs_oracle(cuda_device):
         check(c.lib.hypad_segments_aggregate(ptr(d_ts), ptr(d_v), n, ptr(d_s), float(interval), len(starts), ptr(out), c.stream()))
         torch.cuda.synchronize()
         assert np.array_equal(out.cpu().numpy(), want, equal_nan=True), (n, interval)
+
+
+@pytest.mark.gpu
+def test_yahoo_preprocessing_on_device_vs_reference(cuda_device, tmp_path):
+    """utils/dataloader.py:36-58, 64-79: the device detrend is a closed-form least-squares line, scipy's is LAPACK gelsd -- equal to
+    1e-12 of max|v| (a few fp64 ulps); timestamps exact; the scaled signal within 1e-13 (range 2)."""
+    import pandas as pd
+    from hypad_b200.utils import dataloader as dl
+    from tests_preprocess_cases import yahoo_cases
+
+    g = golden("preprocess.npz")
+    for name, (vals, flag) in yahoo_cases().items():
+        k = "yahoo/" + name
+        d = dl.detrend_signal(vals, cuda_device).cpu().numpy()
+        assert np.abs(d - g[k + "/detrended"]).max() <= 1e-12 * np.abs(vals).max(), name
+        ts = dl.yahoo_index(len(vals))
+        assert np.array_equal(ts - ts[0], g[k + "/timestamp"] - g[k + "/timestamp"][0]), name
+        df = dl.yahoo_preprocess(pd.DataFrame({"timestamp": np.arange(1, len(vals) + 1), "value": vals, "is_anomaly": flag}), cuda_device)
+        X, index = dl.preprocess_signal(df["timestamp"].values, df["value"].values, 1, device=cuda_device)
+        assert np.array_equal(index - index[0], g[k + "/index"] - g[k + "/index"][0]), name
+        assert np.abs(X.cpu().numpy() - g[k + "/scaled"]).max() <= 1e-13, name
+    # the dataset class, YAHOO flavour: file in, device signal + the known-anomalies side file out
+    vals, flag = yahoo_cases()["a1_like"]
+    path = str(tmp_path / "real_1.csv")
+    pd.DataFrame({"timestamp": np.arange(1, len(vals) + 1), "value": vals, "is_anomaly": flag}).to_csv(path, index=False)
+    ds = dl.SignalDataset(path, interval=1, windows_size=100, test=True, yahoo=True)
+    assert np.abs(ds.signal.cpu().numpy() - g["yahoo/a1_like/scaled"]).max() <= 1e-13
+    assert len(ds) == len(vals) - 100 and ds.X.shape == (len(vals) - 100, 100, 1)
+    runs = pd.read_csv(path[:-4] + "_known_anomalies.csv")
+    T = len(vals)
+    assert np.array_equal(runs[["start", "end"]].values - ds.index[0], [[T - 20, T - 19], [T // 3, T // 3 + 3]])
+
+
+@pytest.mark.gpu
+def test_pairwise_poincare_distance_vs_reference(cuda_device):
+    """hyperspace/poincare_distance.py:5-48 (fp32).  The reference's torch.mm sums the D products in MKL's order, the kernel in
+    ascending k: squared distances agree to a few fp32 ulps of |x|^2 + |y|^2, distances to 2e-4 relative where they are >= 0.09
+    (d acosh / d arg = 1 / sinh d amplifies the argument's ulps)."""
+    from hypad_b200.hyperspace.poincare_distance import pairwise_distances, poincare_distance, square_norm
+    from tests_preprocess_cases import pairwise_cases
+
+    g = golden("pairwise.npz")
+    for name, (p, q) in pairwise_cases().items():
+        tp, tq = torch.from_numpy(p).to(cuda_device), torch.from_numpy(q).to(cuda_device)
+        scale = (p.astype(np.float64) ** 2).sum(1)[:, None] + (q.astype(np.float64) ** 2).sum(1)[None, :]
+        sq = pairwise_distances(tp, tq).cpu().numpy()
+        assert sq.shape == g[name + "/sqdist"].shape
+        assert (np.abs(sq - g[name + "/sqdist"]) <= 2e-6 * scale + 1e-12).all(), name
+        sq_self = pairwise_distances(tp).cpu().numpy()
+        scale_self = (p.astype(np.float64) ** 2).sum(1)
+        assert (np.abs(sq_self - g[name + "/sqdist_self"]) <= 2e-6 * (scale_self[:, None] + scale_self[None, :]) + 1e-12).all(), name
+        np.testing.assert_allclose(square_norm(tp).cpu().numpy(), g[name + "/square_norm"], rtol=3e-7, atol=0)
+        d = poincare_distance(tp, tq).cpu().numpy()
+        np.testing.assert_allclose(d, g[name + "/poincare"], rtol=2e-4, atol=0, err_msg=name)
+        o = ho.poincare_distance(torch.from_numpy(p), torch.from_numpy(q)).numpy()
+        np.testing.assert_allclose(d, o, rtol=2e-4, atol=0, err_msg=name)
+    # a size that fills the machine: 4096 x 4096 pairs, D = 100, against the oracle on a sample of rows
+    rng = np.random.default_rng(3)
+    p = (rng.uniform(-1, 1, (4096, 100)) * 0.08).astype(np.float32)
+    q = (rng.uniform(-1, 1, (4096, 100)) * 0.08).astype(np.float32)
+    d = poincare_distance(torch.from_numpy(p).to(cuda_device), torch.from_numpy(q).to(cuda_device)).cpu().numpy()
+    rows = rng.integers(0, 4096, 64)
+    o = ho.poincare_distance(torch.from_numpy(p[rows]), torch.from_numpy(q)).numpy()
+    np.testing.assert_allclose(d[rows], o, rtol=2e-4, atol=0)

@@ -32,3 +32,32 @@ def cases():
     out["constant"] = (np.arange(100) * 5, np.full(100, 2.5), 5)
     out["one_segment"] = (np.arange(50), rng.standard_normal(50), 1000)
     return out
+
+
+def yahoo_cases():
+    """(values, is_anomaly) of YAHOO-shaped signals: trend + seasonality + noise, a few labelled runs."""
+    rng = np.random.default_rng(19)
+    out = {}
+    for name, T, slope in (("a1_like", 1420, 0.8), ("long", 20000, -0.003), ("tiny", 2, 1.0)):
+        t = np.arange(T)
+        v = 100.0 + slope * t + 20.0 * np.sin(t / 24.0 * 2 * np.pi) + 3.0 * rng.standard_normal(T)
+        flag = np.zeros(T, dtype=np.int64)
+        if T > 100:
+            flag[T // 3:T // 3 + 4] = 1
+            flag[T - 20:T - 18] = 1
+            v[flag == 1] += 80.0
+        out[name] = (v, flag)
+    return out
+
+
+def pairwise_cases():
+    """(pred, gt) fp32 point sets inside the unit ball; shapes off the 64-tile grid, D off the 16-feature stage."""
+    rng = np.random.default_rng(23)
+    out = {}
+    for name, n, m, d, r in (("square", 128, 128, 100, 0.6), ("ragged", 77, 201, 123, 0.9), ("thin", 1, 65, 7, 0.5), ("near_origin", 33, 40, 20, 1e-4)):
+        p = rng.standard_normal((n, d))
+        g = rng.standard_normal((m, d))
+        p = p / np.linalg.norm(p, axis=1, keepdims=True) * rng.uniform(0.05, 1.0, (n, 1)) * r
+        g = g / np.linalg.norm(g, axis=1, keepdims=True) * rng.uniform(0.05, 1.0, (m, 1)) * r
+        out[name] = (p.astype(np.float32), g.astype(np.float32))
+    return out
