@@ -19,6 +19,7 @@ _ALIASES = {
     "models.tadgan": "hypad_b200.models.tadgan",
     "hyperspace": "hypad_b200.hyperspace",
     "hyperspace.hyrnn_nets": "hypad_b200.hyperspace.hyrnn_nets",
+    "hyperspace.poincare_distance": "hypad_b200.hyperspace.poincare_distance",
     "utils": "hypad_b200.utils",
     "utils.anomaly_detection_utils": "hypad_b200.utils.anomaly_detection_utils",
     "utils.dataloader": "hypad_b200.utils.dataloader",
