@@ -5,9 +5,10 @@ work runs in hand-written sm_100a kernels through the C-ABI (hypad_b200/scoring.
 CPU tensors or CUDA tensors -- they are moved to the current CUDA device -- and the return types follow the
 reference (numpy arrays; a float64 torch tensor where the reference's mixed numpy/torch arithmetic produces one).
 A CUDA device is required: nothing here computes on the CPU except the bookkeeping on the handful of anomalous
-runs found per analysis window.
+runs found per analysis window and the evaluation of the detected intervals against the known ones
+(`contextual_confusion_matrix`, `compute_metrics`; SURVEY.md 8f rank 4 -- a few intervals per signal).
 
-Not provided (out of scope): plotting, contextual confusion matrix / metrics, dynamic threshold
+Not provided (out of scope): plotting, dynamic threshold
 search (`_find_threshold`, scipy fmin), `prune_false_positive`, `detect_anomaly`, `regression_errors`, `find_scores`.
 """
 import math
@@ -243,12 +244,82 @@ def _hyperbolic_rec_scores(recons_signal, true_signal, signal_shape, dev):
     return _sc.poincare_rowdist(r, t)
 
 
+def _pad(lst):
+    """utils/anomaly_detection_utils.py:602-603: closed intervals -> half-open."""
+    return [(part[0], part[1] + 1) for part in lst]
+
+
+def _overlap(expected, observed):
+    """utils/anomaly_detection_utils.py:301-304."""
+    return (expected[0] - observed[1]) * (expected[1] - observed[0]) < 0
+
+
+def _overlap_segment(expected, observed, start=None, end=None):
+    """utils/anomaly_detection_utils.py:579-599: tp = expected sequences hit by at least one observed one, fn = the others, fp =
+    observed sequences that hit nothing.  Returns (None, fp, fn, tp) like the reference (no true negatives for segments).
+    One (expected x observed) sign table instead of the nested loops; evaluation over a handful of intervals -- host work."""
+    ne, no = len(expected), len(observed)
+    if ne == 0 or no == 0:
+        return None, no, ne, 0
+    e = np.asarray([(x[0], x[1]) for x in expected], dtype=np.float64)
+    o = np.asarray([(x[0], x[1]) for x in observed], dtype=np.float64)
+    hit = np.sign(e[:, None, 0] - o[None, :, 1]) * np.sign(e[:, None, 1] - o[None, :, 0]) < 0
+    tp = int(hit.any(axis=1).sum())
+    return None, int(no - hit.any(axis=0).sum()), ne - tp, tp
+
+
+def contextual_confusion_matrix(expected, observed, data=None, start=None, end=None, weighted=True):
+    """utils/anomaly_detection_utils.py:606-655.  `weighted=True` calls `_weighted_segment` / `_contextual_partition`, which the
+    reference never defines (NameError there); only the overlap-segment algorithm its callers use (:100-105, :245) exists."""
+    if weighted:
+        raise NotImplementedError("hypad_b200: contextual_confusion_matrix(weighted=True) relies on _weighted_segment, which the "
+                                  "reference does not define either; its callers pass weighted=False")
+    if data is not None:
+        start = data["timestamp"].min()
+        end = data["timestamp"].max()
+    if not isinstance(expected, list):
+        expected = list(expected[["start", "end"]].itertuples(index=False))
+    if not isinstance(observed, list):
+        observed = list(observed[["start", "end"]].itertuples(index=False))
+    return _overlap_segment(_pad(expected), _pad(observed), start, end)
+
+
+def compute_metrics(known_anomalies, pred_anomalies):
+    """utils/anomaly_detection_utils.py:241-254: prints precision / recall / F1 / gmean of the overlap-segment counts; like the
+    reference it raises ZeroDivisionError when a denominator is empty (its callers swallow that).  Also returns the numbers."""
+    tn, fp, fn, tp = contextual_confusion_matrix(known_anomalies, pred_anomalies, weighted=False)
+    precision = tp / (tp + fp)
+    recall = tp / (tp + fn)
+    F1 = 2 * (precision * recall) / (precision + recall)
+    gmean = np.sqrt(precision * recall)
+    print("precision: {}, recall: {}".format(precision, recall))
+    print("f1_score: {}, gmean: {}".format(F1, gmean))
+    return {"precision": precision, "recall": recall, "f1": F1, "gmean": gmean}
+
+
+def _evaluate_and_record(intervals, known_anomalies, df, params, signal):
+    """The tail of the reference's univariate driver (:96-125): confusion counts against the known anomalies -- [0, 0, 0, 0]
+    whenever anything in the block raises, e.g. an empty denominator in compute_metrics -- and the optional results CSV."""
+    try:
+        pred_anomalies = pd.DataFrame(intervals, columns=["start", "end", "score"])
+        out = list(contextual_confusion_matrix(known_anomalies, pred_anomalies, data=df, weighted=False))
+        compute_metrics(known_anomalies, pred_anomalies)
+    except Exception:
+        out = [0, 0, 0, 0]
+    if getattr(params, "save_result", False):
+        file_place = "./results/{}".format(params.filename)
+        res = pd.read_csv(file_place) if os.path.isfile(file_place) else pd.DataFrame(columns=["signal", "tn", "fp", "fn", "tp"])
+        if params.signal not in list(res["signal"]):
+            res.loc[len(res)] = [signal] + out
+            res.to_csv(file_place, index=False)
+    return out
+
+
 def univariate_anomaly_detection(recons_signal, true_signal, params, combination, critic_score, path, read_path,
                                  rec_error_type="euclidean", true_index=None, known_anomalies=None, signal=None, signal_shape=None):
-    """utils/anomaly_detection_utils.py:21-126: scores -> find_anomalies -> `path + "anomalies.csv"`.
-
-    The metrics block of the reference (:100-110, swallowed exceptions) and `params.save_result` are evaluation
-    tooling and are not reproduced.  Returns the (K,3) interval array (the reference returns None)."""
+    """utils/anomaly_detection_utils.py:21-126: scores -> find_anomalies -> `path + "anomalies.csv"` -> confusion counts against
+    `known_anomalies` (and the results CSV when `params.save_result`).  Returns the (K,3) interval array (the reference returns
+    None); the confusion counts of the last call are kept in `univariate_anomaly_detection.last_counts`."""
     dev = _dev()
     if not params.hyperbolic:
         final_scores, true_index, _true, _pred = score_anomalies(true_signal, recons_signal, critic_score, true_index,
@@ -262,6 +333,12 @@ def univariate_anomaly_detection(recons_signal, true_signal, params, combination
         final = combine_scores(combination, critic_scores, rec.cpu(), recons_signal).reshape(-1)  # float64 torch tensor
     intervals = find_anomalies(final, true_index, window_size_portion=0.33, window_step_size_portion=0.1, fixed_threshold=True)
     pd.DataFrame(intervals, columns=["start", "end", "score"]).to_csv(path + "anomalies.csv")
+    univariate_anomaly_detection.last_counts = None
+    if known_anomalies is not None or getattr(params, "save_result", False):
+        df = None
+        if read_path and os.path.isfile(read_path):
+            df = pd.read_csv(read_path)  # only its timestamp range is read (:640-642), so the YAHOO detrend of :35-36 is not needed
+        univariate_anomaly_detection.last_counts = _evaluate_and_record(intervals, known_anomalies, df, params, signal)
     return intervals
 
 

@@ -5,6 +5,8 @@ tests/tests_preprocess_cases.py:
                                 SimpleImputer / MinMaxScaler the dataset calls (:86-89); `yahoo/*`: yahoo_preprocess (:41-58)
                                 followed by the same chain at interval=1
   tests/golden/pairwise.npz     hyperspace/poincare_distance.py: poincare_distance, pairwise_distances, square_norm
+  tests/golden/metrics.json     utils/anomaly_detection_utils.py: contextual_confusion_matrix(weighted=False) (:606-655) and the
+                                lines compute_metrics prints (:241-254) on seeded interval lists
 
 Run in the build container only:   python oracle/make_golden_next.py
 TEST INFRASTRUCTURE ONLY.
@@ -59,6 +61,33 @@ def main():
         g[name + "/square_norm"] = square_norm(tp).numpy()
         print("pairwise", name, g[name + "/poincare"].shape)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "pairwise.npz"), **g)
+
+    import contextlib
+    import io
+    import json
+
+    import utils.anomaly_detection_utils as adu
+    from tests_preprocess_cases import interval_cases
+
+    out = []
+    for expected, observed in interval_cases():
+        e = pd.DataFrame(expected, columns=["start", "end"])
+        o = pd.DataFrame([list(x) + [1.0] for x in observed], columns=["start", "end", "score"])
+        rec = {"expected": expected, "observed": observed, "counts": list(adu.contextual_confusion_matrix(e, o, weighted=False))}
+        rec["counts_lists"] = list(adu.contextual_confusion_matrix([tuple(x) for x in expected], [tuple(x) for x in observed], weighted=False))
+        buf = io.StringIO()
+        try:
+            with contextlib.redirect_stdout(buf):
+                adu.compute_metrics(e, o)
+            rec["printed"] = buf.getvalue()
+        except ZeroDivisionError:
+            rec["printed"] = None
+        rec["counts"] = [None if c is None else int(c) for c in rec["counts"]]
+        rec["counts_lists"] = [None if c is None else int(c) for c in rec["counts_lists"]]
+        out.append(rec)
+    with open(os.path.join(ROOT, "tests", "golden", "metrics.json"), "w") as f:
+        json.dump(out, f)
+    print("metrics", len(out), "cases,", sum(r["printed"] is None for r in out), "with an empty denominator")
 
 
 if __name__ == "__main__":

@@ -97,3 +97,38 @@ def test_numpy_order_sum_and_average_are_bitwise_numpy():
         w = rng.uniform(1, 500, n)
         assert _np_sum(list(v)) == float(np.add.reduce(v)), n
         assert _np_average(list(v), list(w)) == float(np.average(v, weights=w)), n
+
+
+def test_evaluation_tail_matches_reference_golden(capsys):
+    """contextual_confusion_matrix(weighted=False) / compute_metrics (utils/anomaly_detection_utils.py:241-254,
+    :579-655) against the reference's own outputs on seeded interval lists (tests/golden/metrics.json, oracle/make_golden_next.py)."""
+    import json
+    import os
+
+    import pandas as pd
+    from conftest import GOLDEN
+    from hypad_b200.utils import anomaly_detection_utils as adu
+
+    cases = json.load(open(os.path.join(GOLDEN, "metrics.json")))
+    assert len(cases) >= 30
+    for rec in cases:
+        e = pd.DataFrame(rec["expected"], columns=["start", "end"])
+        o = pd.DataFrame([list(x) + [1.0] for x in rec["observed"]], columns=["start", "end", "score"])
+        assert list(adu.contextual_confusion_matrix(e, o, weighted=False)) == rec["counts"], rec
+        as_lists = adu.contextual_confusion_matrix([tuple(x) for x in rec["expected"]], [tuple(x) for x in rec["observed"]], weighted=False)
+        assert list(as_lists) == rec["counts_lists"], rec
+        capsys.readouterr()
+        if rec["printed"] is None:
+            with pytest.raises(ZeroDivisionError):
+                adu.compute_metrics(e, o)
+        else:
+            m = adu.compute_metrics(e, o)
+            assert capsys.readouterr().out == rec["printed"]
+            assert 0.0 < m["f1"] <= 1.0
+        # the driver's tail: zeros whenever the metrics raise (the reference swallows the exception, :107-110)
+        class P:
+            save_result = False
+        want = [0, 0, 0, 0] if rec["printed"] is None else rec["counts"]
+        assert adu._evaluate_and_record(np.asarray([list(x) + [1.0] for x in rec["observed"]]).reshape(-1, 3), e, None, P, "s") == want
+    with pytest.raises(NotImplementedError):
+        adu.contextual_confusion_matrix([], [], weighted=True)

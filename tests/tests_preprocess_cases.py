@@ -61,3 +61,21 @@ def pairwise_cases():
         g = g / np.linalg.norm(g, axis=1, keepdims=True) * rng.uniform(0.05, 1.0, (m, 1)) * r
         out[name] = (p.astype(np.float32), g.astype(np.float32))
     return out
+
+
+def interval_cases():
+    """(expected, observed) lists of closed [start, end] timestamp intervals: random, touching, nested, duplicated, empty."""
+    rng = np.random.default_rng(31)
+    out = [([[10, 20]], [[21, 30]]),              # adjacent after padding: (10, 21) vs (21, 31) do not overlap
+           ([[10, 20]], [[20, 30]]),              # share one timestamp
+           ([[10, 50]], [[20, 25], [30, 35], [20, 25]]),  # nested, duplicated observed
+           ([[10, 20], [40, 50]], [[0, 100]]),    # one observed covers both
+           ([], [[1, 2]]), ([[1, 2]], []),
+           ([[5, 5]], [[5, 5]])]
+    for _ in range(25):
+        ne, no = rng.integers(0, 7), rng.integers(0, 9)
+        def draw(k):
+            s = np.sort(rng.integers(1_285_000_000, 1_285_000_000 + 21600 * 400, k))
+            return [[int(a), int(a + rng.integers(0, 21600 * 30))] for a in s]
+        out.append((draw(ne), draw(no)))
+    return out
