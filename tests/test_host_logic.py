@@ -132,3 +132,28 @@ def test_evaluation_tail_matches_reference_golden(capsys):
         assert adu._evaluate_and_record(np.asarray([list(x) + [1.0] for x in rec["observed"]]).reshape(-1, 3), e, None, P, "s") == want
     with pytest.raises(NotImplementedError):
         adu.contextual_confusion_matrix([], [], weighted=True)
+
+
+def test_preprocessing_host_helpers_match_reference_golden():
+    """The host side of utils/dataloader.py's preprocessing: segment starts (:127-135, repeated addition), the YAHOO per-second
+    index (:44-48) and the known-anomaly runs of save_known_anomalies (:14-33), against the reference's outputs."""
+    import pandas as pd
+    from hypad_b200.utils import dataloader as dl
+    from tests_preprocess_cases import cases, yahoo_cases
+
+    g = golden("preprocess.npz")
+    for name, (ts, _vals, interval) in cases().items():
+        s = np.sort(np.asarray(ts))
+        starts = dl.segment_starts(s[0], s[-1], interval)
+        assert np.array_equal(starts, g[name + "/index"]) and starts.dtype == g[name + "/index"].dtype, name
+    for name, (vals, flag) in yahoo_cases().items():
+        idx = dl.yahoo_index(len(vals))
+        want = g["yahoo/" + name + "/timestamp"]
+        assert np.array_equal(idx - idx[0], want - want[0]) and idx.dtype == np.float64
+        for col in ("is_anomaly", "anomaly"):
+            df = pd.DataFrame({"timestamp": 1000.0 + np.arange(len(vals)), "value": vals, col: flag})
+            _, runs = dl.known_anomaly_runs(df)
+            assert np.array_equal(np.asarray(runs, dtype=np.float64).reshape(-1, 2), g["yahoo/%s/known_%s" % (name, col)].reshape(-1, 2))
+    with pytest.raises(ValueError):
+        dl.yahoo_index(518402)
+    assert dl.yahoo_index(518401).shape == (518401,)
