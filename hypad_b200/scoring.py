@@ -470,12 +470,14 @@ class WindowScorer:
         return critic_zscore_smooth(kmax, math.trunc(n_windows * 0.01)), kmax
 
     def score(self, x, sliding=True, combination="uncertainty", rec_error_type="dtw", index=None, keep=(), multivariate=False,
-              lambda_rec=0.5):
+              lambda_rec=0.5, poll=True):
         """Per-position anomaly scores (+ intervals when `index` is given) for one signal.
 
         sliding=True : x is the scaled signal (T,), windows are x[n:n+S], n in [0, T-S)   (univariate configs)
         sliding=False: x is (N, S) materialised windows / multivariate rows.
         Hyperbolic models return one score per window (N,), Euclidean ones one per timestep (N+S-1,), like the reference.
+        poll=False leaves out the final synchronising error poll: a caller that enqueues many signals (sweep.SignalSweep) calls
+        `poll_error()` once after the last one.
         """
         keep = tuple(keep)
         need = keep if self.hyperbolic else tuple(set(keep) | {"eucl"})
@@ -541,5 +543,6 @@ class WindowScorer:
                 out["intervals"] = find_anomaly_intervals(final, index, 0.33, 0.1, anomaly_padding=50, ddof=ddof)
         # loud failure: pipeline protocol error, or an operand outside the tensor-core path's range.  Last, so that the
         # synchronisation it implies does not stall the launches above.
-        self.poll_error()
+        if poll:
+            self.poll_error()
         return out

@@ -1,0 +1,92 @@
+"""Bulk sweep: many signals, one TadGAN / HypAD model each, sharded BY SIGNAL across the GPUs of a node (SURVEY.md 8e-ii,
+BASELINE config 5).
+
+The reference scores one signal per process invocation (`python anomaly_detection.py -c cfg.yaml`, one trained model per signal:
+train.py:430-437 puts the signal name into the model path); a sweep over the 493 bundled NASA / NAB / YAHOO signals is a shell
+loop.  Here every rank takes the signals `assign_signals` deals it (greedy longest-first on the window count: no halo, no
+cross-GPU dependency), enqueues the whole scoring pipeline of all of them on its stream without synchronising in between,
+extracts the anomaly intervals once everything is queued, and the per-signal interval lists (a few rows each) are exchanged
+with one `all_gather_object` at the end.  No collective on the data path.
+"""
+import numpy as np
+import torch
+
+from . import scoring as _sc
+from ._native import HypadError
+
+
+def assign_signals(n_windows, world_size):
+    """Greedy longest-processing-time assignment: signals in descending window count (ties: lower signal id first), each to the
+    rank with the least work so far (ties: lower rank).  Returns one list of signal ids per rank, in scoring order."""
+    if world_size < 1:
+        raise ValueError("world_size must be >= 1")
+    order = sorted(range(len(n_windows)), key=lambda i: (-int(n_windows[i]), i))
+    load = [0] * world_size
+    out = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        out[r].append(i)
+        load[r] += int(n_windows[i])
+    return out
+
+
+class SignalSweep:
+    """Scores a list of univariate signals, each with its own scorer (or one shared scorer), on this rank's share.
+
+    scorers: a WindowScorer, or a callable `signal_id -> WindowScorer` (models are built / loaded lazily on the rank that needs
+    them).  With torch.distributed initialised the signals are dealt out over the ranks of `group`; otherwise this process
+    scores all of them."""
+
+    def __init__(self, scorers, group=None, window=100):
+        self.scorers = scorers if callable(scorers) else (lambda _i, s=scorers: s)
+        self.group = group
+        self.window = window
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.rank = torch.distributed.get_rank(group)
+            self.world = torch.distributed.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+
+    def plan(self, lengths):
+        """Signal ids per rank; signals too short to hold one window are scored by nobody (empty result)."""
+        n = [max(0, int(t) - self.window) for t in lengths]
+        plan = assign_signals(n, self.world)
+        return [[i for i in ids if n[i] > 0] for ids in plan]
+
+    def score_local(self, signals, indices, ids, combination="uncertainty", rec_error_type="dtw", keep_scores=False):
+        """Scores the signals `ids`; returns {id: {"intervals": (K,3) array[, "final": device tensor]}}.  Two phases so that the
+        device never waits for the host: (1) enqueue the pipeline of every signal up to its final scores, (2) extract intervals."""
+        queued = []
+        used = {}
+        for i in ids:
+            sc = self.scorers(i)
+            used[id(sc)] = sc
+            x = _sc._as_dev(signals[i], torch.float64, sc.device).reshape(-1)
+            out = sc.score(x, sliding=True, combination=combination, rec_error_type=rec_error_type, index=None, poll=False)
+            queued.append((i, sc, out["final"]))
+        res = {}
+        for i, sc, final in queued:
+            ddof = 1 if sc.hyperbolic else 0  # torch tensor (unbiased) vs ndarray
+            iv = _sc.find_anomaly_intervals(final, np.asarray(indices[i]), 0.33, 0.1, anomaly_padding=50, ddof=ddof)
+            res[i] = {"intervals": iv}
+            if keep_scores:
+                res[i]["final"] = final
+        for sc in used.values():
+            sc.poll_error()
+        return res
+
+    def run(self, signals, indices, combination="uncertainty", rec_error_type="dtw"):
+        """Every rank returns the full {signal id: (K,3) intervals} map (empty (0,3) array for signals without a window)."""
+        if len(signals) != len(indices):
+            raise HypadError("hypad_b200: %d signals but %d index arrays" % (len(signals), len(indices)))
+        plan = self.plan([len(s) for s in signals])
+        local = {i: r["intervals"] for i, r in self.score_local(signals, indices, plan[self.rank], combination, rec_error_type).items()}
+        if self.world > 1:
+            parts = [None] * self.world
+            torch.distributed.all_gather_object(parts, local, group=self.group)
+        else:
+            parts = [local]
+        merged = {}
+        for part in parts:
+            merged.update(part)
+        return {i: merged.get(i, np.empty((0, 3))) for i in range(len(signals))}

@@ -73,3 +73,71 @@ def test_shard_ranges_cover_exactly():
             assert max(c for _, c in r) - min(c for _, c in r) <= 1
             total_t = sum(hd.timestep_range(f, c, n, 100, i == world - 1)[1] for i, (f, c) in enumerate(r))
             assert total_t == n + 99
+
+
+# ---- bulk sweep: sharding by signal (BASELINE config 5) -----------------------------------------------------
+def bundled_length_multiset():
+    """A length multiset shaped like the bundled data (80 NASA-test, 46 NAB, 367 YAHOO signals), seeded."""
+    rng = np.random.default_rng(5)
+    return np.concatenate([rng.integers(2000, 8700, 80), rng.integers(1100, 22700, 46), rng.integers(1420, 1700, 367)]).tolist()
+
+
+def test_assign_signals_is_a_balanced_partition():
+    from hypad_b200.sweep import assign_signals
+
+    lengths = bundled_length_multiset()
+    n = [t - 100 for t in lengths]
+    for world in (1, 2, 4, 8):
+        plan = assign_signals(n, world)
+        assert sorted(i for ids in plan for i in ids) == list(range(len(n)))  # every signal exactly once
+        loads = [sum(n[i] for i in ids) for ids in plan]
+        assert max(loads) - min(loads) <= max(n)  # LPT: no rank is ahead by more than one signal
+        assert plan == assign_signals(n, world)  # deterministic
+        for ids in plan:
+            assert [n[i] for i in ids] == sorted((n[i] for i in ids), reverse=True)  # longest first on every rank
+    assert assign_signals([], 3) == [[], [], []]
+    assert assign_signals([7, 7, 7], 2) == [[0, 2], [1]]  # ties: lower id first, lower rank first
+    with pytest.raises(ValueError):
+        assign_signals([1], 0)
+
+
+def _sweep_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hypad_b200.sweep import SignalSweep
+
+    lengths = bundled_length_multiset()[:40] + [100, 37]  # two signals too short for a window
+    signals = [np.zeros(t) for t in lengths]
+    indices = [np.arange(t) for t in lengths]
+
+    class Sweep(SignalSweep):  # the device work replaced by a recognisable stand-in: the plumbing is what runs here
+        def score_local(self, signals, indices, ids, combination="uncertainty", rec_error_type="dtw", keep_scores=False):
+            self.scored = list(ids)
+            return {i: {"intervals": np.array([[i, len(signals[i]), self.rank]], dtype=np.float64)} for i in ids}
+
+    sw = Sweep(scorers=None)
+    res = sw.run(signals, indices)
+    plan = sw.plan(lengths)
+    ok = sw.scored == plan[rank] and sorted(res) == list(range(len(lengths)))
+    for r, ids in enumerate(plan):
+        for i in ids:
+            ok = ok and res[i].tolist() == [[i, lengths[i], r]]
+    ok = ok and res[40].shape == (0, 3) and res[41].shape == (0, 3) and not any(i in (40, 41) for ids in plan for i in ids)
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_signal_sweep_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sweep_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]

@@ -671,3 +671,54 @@ def test_pairwise_poincare_distance_vs_reference(cuda_device):
     rows = rng.integers(0, 4096, 64)
     o = ho.poincare_distance(torch.from_numpy(p[rows]), torch.from_numpy(q)).numpy()
     np.testing.assert_allclose(d[rows], o, rtol=2e-4, atol=0)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# bulk sweep (BASELINE config 5): many signals, one model each
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_signal_sweep_equals_per_signal_scoring(cuda_device):
+    """The sweep enqueues all signals before extracting any interval; results must be those of scoring each signal on its own
+    (bitwise: same kernels, same order per signal), and the golden case inside the sweep must still match the reference."""
+    from hypad_b200.models.tadgan import CriticX, Decoder, Encoder
+    from hypad_b200.scoring import WindowScorer
+    from hypad_b200.sweep import SignalSweep
+
+    g = golden("noisy1500_hyp_uncertainty.npz")
+    rng = np.random.default_rng(2)
+    signals, indices = [full_signal(g)], [g["index"]]
+    for T in (1420, 3000, 101, 100, 777, 2048):  # 101: a single window; 100: none
+        t = np.arange(T)
+        s = np.sin(2 * np.pi * t / 41.0) + 0.1 * rng.standard_normal(T)
+        if T > 500:
+            s[T // 2:T // 2 + 4] += 3
+        s = 2 * (s - s.min()) / (s.max() - s.min()) - 1
+        signals.append(s)
+        indices.append(1285027200 + 21600 * t)
+    scorers = {}
+
+    def scorer_of(i):
+        if i not in scorers:
+            if i == 0:
+                enc, dec, cx, _ = build_modules("weights_hyp_s100.npz", 100, True, cuda_device)
+            else:
+                torch.manual_seed(1000 + i)  # one model per signal, like the reference trains them (train.py:430-437)
+                enc, dec, cx = Encoder(100, 20).eval().to(cuda_device), Decoder(100, 20, True).eval().to(cuda_device), CriticX(100, 20).eval().to(cuda_device)
+            scorers[i] = WindowScorer(enc, dec, cx)
+        return scorers[i]
+
+    sw = SignalSweep(scorer_of)
+    res = sw.run(signals, indices)
+    assert sorted(res) == list(range(len(signals)))
+    assert res[4].shape == (0, 3)  # T == window: nothing to score
+    assert np.array_equal(res[0][:, :2], g["intervals"][:, :2])  # the reference's intervals for the golden case
+    np.testing.assert_allclose(res[0][:, 2], g["intervals"][:, 2], rtol=1e-4)
+    for i, (s, idx) in enumerate(zip(signals, indices)):
+        if len(s) <= 100:
+            continue
+        alone = scorer_of(i).score(torch.from_numpy(s).to(cuda_device), sliding=True, combination="uncertainty", index=idx)
+        assert np.array_equal(alone["intervals"], res[i]), i
+    local = sw.score_local(signals, indices, [1, 2], keep_scores=True)
+    for i in (1, 2):
+        alone = scorer_of(i).score(torch.from_numpy(signals[i]).to(cuda_device), sliding=True, combination="uncertainty")
+        assert torch.equal(alone["final"], local[i]["final"])
