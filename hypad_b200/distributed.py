@@ -19,6 +19,7 @@ import torch
 import torch.distributed as dist
 
 from . import scoring
+from ._native import HypadError
 
 
 def shard_ranges(n_windows, world_size):
@@ -72,11 +73,13 @@ def gather_concat(local, sizes, group=None):
 class ShardedScorer:
     """WindowScorer over torch.distributed.  Each rank holds only its slice of the signal (`local_slice`)."""
 
-    def __init__(self, scorer, group=None):
+    def __init__(self, scorer, group=None, rank=None, world=None):
+        """rank / world default to the process group's; passing both makes an object that plans and packs for that rank
+        without touching torch.distributed (tests replay all ranks of a sharded run on one GPU with it)."""
         self.scorer = scorer
         self.group = group
-        self.rank = dist.get_rank(group)
-        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
 
     def plan(self, n_windows):
         """(first, count, h0, sample_lo, sample_hi): owned windows, first halo window and the sample range
@@ -88,39 +91,91 @@ class ShardedScorer:
         # yields L-S windows, so the slice carries one sample beyond the last window.
         return first, count, h0, h0, first + count + S
 
-    def score_hyperbolic(self, local_slice, n_windows, combination="uncertainty", index=None):
-        """local_slice: samples [sample_lo, sample_hi) of the scaled signal (see plan()), on this rank's GPU.
-        Returns the full-length result on every rank."""
-        sc = self.scorer
-        S = sc.S
+    def plan_rows(self, n_rows):
+        """Multivariate rows (one row = one window, BASELINE config 4): (first, count, h0, row_lo, row_hi) -- the owned rows, the
+        first halo row and the row range [row_lo, row_hi) this rank needs resident.  The S-1 halo rows in front are recomputed
+        locally: the critic overlap aggregation of position i reads the critics of rows i-S+1 .. i."""
+        first, count = shard_ranges(n_rows, self.world)[self.rank]
+        h0 = halo_first(first, self.scorer.S)
+        return first, count, h0, h0, first + count
+
+    def pack_local(self, fw, n_windows):
+        """This rank's contribution to the gather, from its forward results `fw` (windows h0 .. first+count-1): one fp32 buffer
+        [kmax | rec | unorm], each part `width` long.  kmax is one of the fp32 critic values widened to float64, so it travels as
+        fp32 without loss; rec and unorm are fp32 anyway.  12 B per position."""
+        S = self.scorer.S
         ranges = shard_ranges(n_windows, self.world)
-        first, count, h0, lo, hi = self.plan(n_windows)
-        if local_slice.numel() != hi - lo:
-            raise ValueError("local slice has %d samples, plan() asks for %d" % (local_slice.numel(), hi - lo))
-        fw = sc.forward(local_slice, True)  # windows h0 .. first+count-1
+        first, count = ranges[self.rank]
+        h0 = halo_first(first, S)
         lead = first - h0
-        counts = [c for _, c in ranges]
         t0, tc = timestep_range(first, count, n_windows, S, self.rank == self.world - 1)
         kmax_local = scoring.kde_argmax_overlap(fw["critic"], S, n_windows=n_windows, critic_offset=h0, t0=t0, t_count=tc)
-        tcounts = [timestep_range(f, c, n_windows, S, r == self.world - 1)[1] for r, (f, c) in enumerate(ranges)]
-        # One collective for the three per-position arrays, 12 B per timestep: kmax is one of the fp32 critic values widened
-        # to float64, so it travels as fp32 without loss; rec and unorm are fp32 anyway.
-        width = max(tcounts)
+        width = self.gather_width(n_windows)
         pack = fw["rec"].new_zeros(3 * width)
         pack[:tc] = kmax_local.float()
         pack[width:width + count] = fw["rec"][lead:]
         pack[2 * width:2 * width + count] = fw["unorm"][lead:]
-        flat = pack.new_empty(self.world * 3 * width)
-        dist.all_gather_into_tensor(flat, pack, group=self.group)
-        parts = flat.view(self.world, 3, width)
-        kmax = _concat_rows(parts[:, 0, :], tcounts).double()
-        rec = _concat_rows(parts[:, 1, :], counts)
-        unorm = _concat_rows(parts[:, 2, :], counts)
+        return pack
+
+    def gather_width(self, n_windows):
+        ranges = shard_ranges(n_windows, self.world)
+        return max(timestep_range(f, c, n_windows, self.scorer.S, r == self.world - 1)[1] for r, (f, c) in enumerate(ranges))
+
+    def unpack_gathered(self, flat, n_windows):
+        """flat: the world's packs back to back -> (kmax float64 (n+S-1,), rec fp32 (n,), unorm fp32 (n,))."""
+        S = self.scorer.S
+        ranges = shard_ranges(n_windows, self.world)
+        counts = [c for _, c in ranges]
+        tcounts = [timestep_range(f, c, n_windows, S, r == self.world - 1)[1] for r, (f, c) in enumerate(ranges)]
+        parts = flat.view(self.world, 3, self.gather_width(n_windows))
+        return _concat_rows(parts[:, 0, :], tcounts).double(), _concat_rows(parts[:, 1, :], counts), _concat_rows(parts[:, 2, :], counts)
+
+    def finish(self, kmax, rec, unorm, n_windows, combination, multivariate=False):
+        """The O(T) finish every rank repeats on the gathered arrays.  multivariate: rec goes through zscore / clip(0) + 1 over
+        ALL rows first (utils/anomaly_detection_utils.py:177-178) -- a global statistic, hence after the gather."""
+        if multivariate:
+            rec = scoring.zscore_clip(rec)
         cs = scoring.critic_zscore_smooth(kmax, math.trunc(n_windows * 0.01))
         final = scoring.combine(combination, cs[:n_windows], rec, unorm, n=n_windows)
-        out = {"final": final, "kmax": kmax, "rec": rec, "unorm": unorm, "critic_scores": cs[:n_windows]}
+        return {"final": final, "kmax": kmax, "rec": rec, "unorm": unorm, "critic_scores": cs[:n_windows]}
+
+    def _gather(self, pack):
+        flat = pack.new_empty(self.world * pack.numel())
+        dist.all_gather_into_tensor(flat, pack, group=self.group)
+        return flat
+
+    def score_hyperbolic(self, local_slice, n_windows, combination="uncertainty", index=None):
+        """local_slice: samples [sample_lo, sample_hi) of the scaled signal (see plan()), on this rank's GPU.
+        Returns the full-length result on every rank."""
+        sc = self.scorer
+        first, count, h0, lo, hi = self.plan(n_windows)
+        if local_slice.numel() != hi - lo:
+            raise ValueError("local slice has %d samples, plan() asks for %d" % (local_slice.numel(), hi - lo))
+        fw = sc.forward(local_slice, True)  # windows h0 .. first+count-1
+        # One collective for the three per-position arrays
+        kmax, rec, unorm = self.unpack_gathered(self._gather(self.pack_local(fw, n_windows)), n_windows)
+        out = self.finish(kmax, rec, unorm, n_windows, combination)
         if index is not None:
-            out["intervals"] = self.find_anomaly_intervals(final, index, 0.33, 0.1, anomaly_padding=50, ddof=1)
+            out["intervals"] = self.find_anomaly_intervals(out["final"], index, 0.33, 0.1, anomaly_padding=50, ddof=1)
+        return out
+
+    def score_multivariate(self, local_rows, n_rows, combination="mult", index=None):
+        """BASELINE config 4: (N, C) rows sharded by contiguous row range.  local_rows: rows [row_lo, row_hi) of plan_rows() on
+        this rank's GPU, shape (row_hi - row_lo, C).  Hyperbolic models (the Euclidean multivariate score is a float64 row norm;
+        score it unsharded with WindowScorer.score).  Returns the full-length result on every rank; equals
+        `WindowScorer.score(rows, sliding=False, multivariate=True)` bit for bit."""
+        sc = self.scorer
+        if not sc.hyperbolic:
+            raise HypadError("hypad_b200: ShardedScorer.score_multivariate needs a hyperbolic model")
+        first, count, h0, lo, hi = self.plan_rows(n_rows)
+        if local_rows.dim() != 2 or local_rows.shape[0] != hi - lo:
+            raise ValueError("local rows have shape %s, plan_rows() asks for %d rows" % (tuple(local_rows.shape), hi - lo))
+        fw = sc.forward(local_rows, False)  # rows h0 .. first+count-1
+        kmax, rec, unorm = self.unpack_gathered(self._gather(self.pack_local(fw, n_rows)), n_rows)
+        out = self.finish(kmax, rec, unorm, n_rows, combination, multivariate=True)
+        if index is not None:
+            out["intervals"] = self.find_anomaly_intervals(out["final"], index, 0.2, 0.1, anomaly_padding=200, ddof=0)
+        sc.poll_error()
         return out
 
     MAX_RUNS = 64  # per analysis window in the gathered buffer; more (never seen) -> every rank redoes all windows

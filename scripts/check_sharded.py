@@ -40,6 +40,22 @@ def main():
         if rank == 0:
             print("%s: world=%d sharded == single-GPU: %s" % (case, world, bool(t.item())))
         ok = ok and bool(t.item())
+    # BASELINE config 4: multivariate rows (S = C = 123) sharded by row range
+    enc, dec, cx, _ = build_modules("weights_hyp_s123.npz", 123, True, dev)
+    scorer = WindowScorer(enc, dec, cx)
+    rows = np.random.default_rng(33).uniform(-1, 1, (4000, 123))
+    rows[1900:1910] *= 3
+    index = 1353715200.0 + np.arange(4000)
+    sh = ShardedScorer(scorer)
+    first, count, h0, lo, hi = sh.plan_rows(4000)
+    out = sh.score_multivariate(torch.from_numpy(rows[lo:hi].copy()).to(dev), 4000, "mult", index=index)
+    ref = scorer.score(torch.from_numpy(rows).to(dev), False, "mult", index=index, multivariate=True)
+    same = all(torch.equal(out[k], ref[k]) for k in ("final", "kmax", "rec")) and np.array_equal(out["intervals"], ref["intervals"])
+    t = torch.tensor([int(same)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("multivariate rows S=123: world=%d sharded == single-GPU: %s" % (world, bool(t.item())))
+    ok = ok and bool(t.item())
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

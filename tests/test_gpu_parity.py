@@ -722,3 +722,54 @@ def test_signal_sweep_equals_per_signal_scoring(cuda_device):
     for i in (1, 2):
         alone = scorer_of(i).score(torch.from_numpy(signals[i]).to(cuda_device), sliding=True, combination="uncertainty")
         assert torch.equal(alone["final"], local[i]["final"])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# sharding by window / row range, every rank replayed on this one GPU (the NCCL run itself: tests/test_gpu_sharded.py)
+# ------------------------------------------------------------------------------------------------------------
+def replay_sharded(scorer, x, n, world, sliding, combination, multivariate):
+    """What `world` ranks compute, one after the other on this GPU: each rank's slice (with its halo) through pack_local, the
+    packs laid back to back like all_gather_into_tensor does, then unpack + finish."""
+    from hypad_b200.distributed import ShardedScorer
+
+    packs = []
+    for r in range(world):
+        sh = ShardedScorer(scorer, rank=r, world=world)
+        first, count, h0, lo, hi = sh.plan(n) if sliding else sh.plan_rows(n)
+        assert hi - lo == (count + first - h0 + (scorer.S if sliding else 0))
+        fw = scorer.forward(x[lo:hi].contiguous(), sliding)
+        packs.append(sh.pack_local(fw, n))
+    kmax, rec, unorm = sh.unpack_gathered(torch.cat(packs), n)
+    return sh.finish(kmax, rec, unorm, n, combination, multivariate=multivariate)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_rows_multivariate_equal_unsharded(world, cuda_device):
+    """BASELINE config 4: rows sharded by contiguous range with an S-1 row halo; the z-score of the reconstruction error is a
+    global statistic and is taken after the gather -- bitwise the unsharded result."""
+    from hypad_b200.scoring import WindowScorer
+
+    enc, dec, cx, _ = build_modules("weights_hyp_s123.npz", 123, True, cuda_device)
+    scorer = WindowScorer(enc, dec, cx)
+    rng = np.random.default_rng(33)
+    rows = rng.uniform(-1, 1, (2500, 123))
+    rows[1200:1210] *= 3
+    x = torch.from_numpy(rows).to(cuda_device)
+    ref = scorer.score(x, False, "mult", multivariate=True)
+    out = replay_sharded(scorer, x, 2500, world, False, "mult", True)
+    for k in ("final", "kmax", "rec"):
+        assert torch.equal(out[k], ref[k]), k
+    assert torch.equal(out["critic_scores"], ref["critic_scores"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 5])
+def test_sharded_windows_univariate_equal_unsharded(world, hyp_scorer, cuda_device):
+    g = golden("noisy1500_hyp_uncertainty.npz")
+    x = dev_signal(g, cuda_device)
+    n = x.shape[0] - 100
+    ref = hyp_scorer.score(x, True, "uncertainty")
+    out = replay_sharded(hyp_scorer, x, n, world, True, "uncertainty", False)
+    for k in ("final", "kmax", "rec", "unorm"):
+        assert torch.equal(out[k], ref[k]), k
