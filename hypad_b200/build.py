@@ -57,10 +57,12 @@ def build(force=False, verbose=False):
         out, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, out.decode(errors="replace")))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    tmp = LIB + ".tmp.%d" % os.getpid()  # linked aside and renamed: a reader never sees a half-written library
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs]
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if out.returncode != 0:
         raise RuntimeError("link failed:\n%s" % out.stdout.decode(errors="replace"))
+    os.replace(tmp, LIB)
     with open(stamp, "w") as fh:
         fh.write(fp)
     return LIB

@@ -5,13 +5,13 @@
 //   poincare_distance(p,g)  :5-16    acosh(1 + 2 pairwise / ((1 - square_norm(p))_i (1 - square_norm(g))_j))
 // fp32 like the reference (torch.mm on fp32 inputs).  The N x M x D contraction runs on the fp32 FFMA pipe: the squared
 // distance is a difference of nearly equal numbers for close points, so the products must keep fp32 accuracy, and D is ~100
-// -- the kernel is bound by the N x M fp32 output (4 B per pair) and the FFMA pipe about equally; see DESIGN.md.
+// -- the kernel is bound by the FFMA pipe (200 FLOP per pair) with the N x M fp32 output (4 B per pair) close behind; see DESIGN.md.
 #include "common.cuh"
 
 namespace hypad {
 
-constexpr int PW_TILE = 64;  // rows of x and rows of y per CTA tile
-constexpr int PW_K = 16;     // features per shared-memory stage
+constexpr int PW_TILE = 128;  // rows of x and rows of y per CTA tile
+constexpr int PW_K = 16;      // features per shared-memory stage
 
 // per row: sum of squares (fp32 value of the fp64 sum) and the clamped squared norm of square_norm()
 __global__ void pw_rownorm_kernel(const float* __restrict__ x, int64_t n, int D, float* __restrict__ sumsq, float* __restrict__ sqnorm) {
@@ -36,54 +36,61 @@ __global__ void pw_rownorm_kernel(const float* __restrict__ x, int64_t n, int D,
     }
 }
 
-// mode 0: poincare_distance, mode 1: pairwise_distances.  One CTA per 64 x 64 output tile (grid-stride), 256 threads, thread =
-// 4 x 4 outputs; operands staged k-major in shared memory 16 features at a time.
-__global__ void __launch_bounds__(256) pw_distance_kernel(const float* __restrict__ x, const float* __restrict__ y,
-                                                          const float* __restrict__ xss, const float* __restrict__ yss,
-                                                          const float* __restrict__ xsq, const float* __restrict__ ysq, int64_t N,
-                                                          int64_t M, int D, int mode, float* __restrict__ out) {
+// mode 0: poincare_distance, mode 1: pairwise_distances.  One CTA per 128 x 128 output tile (grid-stride), 256 threads, thread =
+// 8 x 8 outputs (rows ty*4 + {0..3} and 64 + ty*4 + {0..3}, columns likewise with tx: every shared-memory read is a conflict-free
+// LDS.128, 4 of them per 64 FFMA, and 16 neighbouring threads store 64 consecutive floats); operands staged k-major in shared
+// memory 16 features at a time.
+__global__ void __launch_bounds__(256, 2) pw_distance_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                             const float* __restrict__ xss, const float* __restrict__ yss,
+                                                             const float* __restrict__ xsq, const float* __restrict__ ysq, int64_t N,
+                                                             int64_t M, int D, int mode, float* __restrict__ out) {
     __shared__ __align__(16) float As[PW_K][PW_TILE + 4];
     __shared__ __align__(16) float Bs[PW_K][PW_TILE + 4];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int lr = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;
+    const int lr = threadIdx.x >> 1, lk = (threadIdx.x & 1) * 8;  // staging: row lr, features lk .. lk+7 of the stage
     const int64_t tiles_m = (M + PW_TILE - 1) / PW_TILE, tiles_n = (N + PW_TILE - 1) / PW_TILE;
     for (int64_t tile = blockIdx.x; tile < tiles_n * tiles_m; tile += gridDim.x) {
         const int64_t i0 = (tile / tiles_m) * PW_TILE, j0 = (tile % tiles_m) * PW_TILE;
-        float acc[4][4];
+        float acc[8][8];
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < 8; ++r)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+            for (int c = 0; c < 8; ++c) acc[r][c] = 0.0f;
+        const bool xr = i0 + lr < N, yr = j0 + lr < M;
+        const float* xrow = x + (i0 + lr) * D;
+        const float* yrow = y + (j0 + lr) * D;
         for (int k0 = 0; k0 < D; k0 += PW_K) {
-            const bool xr = i0 + lr < N, yr = j0 + lr < M;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 8; ++q) {
                 const int k = k0 + lk + q;
-                As[lk + q][lr] = (xr && k < D) ? x[(i0 + lr) * D + k] : 0.0f;
-                Bs[lk + q][lr] = (yr && k < D) ? y[(j0 + lr) * D + k] : 0.0f;
+                As[lk + q][lr] = (xr && k < D) ? xrow[k] : 0.0f;
+                Bs[lk + q][lr] = (yr && k < D) ? yrow[k] : 0.0f;
             }
             __syncthreads();
 #pragma unroll
             for (int kk = 0; kk < PW_K; ++kk) {
-                const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-                const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+                const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+                const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+                const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                for (int r = 0; r < 4; ++r)
+                for (int r = 0; r < 8; ++r)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+                    for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
             }
             __syncthreads();
         }
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int64_t i = i0 + ty * 4 + r;
+        for (int r = 0; r < 8; ++r) {
+            const int64_t i = i0 + (r >> 2) * 64 + ty * 4 + (r & 3);
             if (i >= N) continue;
             const float xn = xss[i];
             const float a1 = mode == 0 ? __fsub_rn(1.0f, xsq[i]) : 0.0f;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int64_t j = j0 + tx * 4 + c;
+            for (int c = 0; c < 8; ++c) {
+                const int64_t j = j0 + (c >> 2) * 64 + tx * 4 + (c & 3);
                 if (j >= M) continue;
                 // x_norm + y_norm - 2.0 * mm, clamped to [1e-7, inf)   (:45-48)
                 float d = __fsub_rn(__fadd_rn(xn, yss[j]), __fmul_rn(2.0f, acc[r][c]));
