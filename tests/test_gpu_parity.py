@@ -578,9 +578,16 @@ def test_preprocessing_on_device_vs_reference(cuda_device):
         mine = X.cpu().numpy()
         want = g[name + "/scaled"]
         assert mine.shape == want.shape, name
-        assert np.abs(mine - want).max() <= 1e-15, (name, np.abs(mine - want).max())
         o, _ = ho.preprocess_signal(ts, vals, interval)
-        assert np.array_equal(mine, o), (name, np.abs(mine - o).max())
+        if np.isnan(g[name + "/agg"]).any():
+            # the imputed value is the mean of the valid segments: the device folds per-CTA partial sums, numpy sums pairwise --
+            # an ulp apart at most, which the scaling carries into the imputed positions only
+            bad = np.isnan(g[name + "/agg"])
+            assert np.array_equal(mine[~bad], want[~bad]), name
+            assert np.abs(mine - want).max() <= 2e-15 and np.abs(mine - o).max() <= 2e-15, (name, np.abs(mine - want).max())
+        else:
+            assert np.abs(mine - want).max() <= 1e-15, (name, np.abs(mine - want).max())
+            assert np.array_equal(mine, o), (name, np.abs(mine - o).max())
 
 
 @pytest.mark.gpu
