@@ -178,10 +178,13 @@ _default_ctx = {}
 
 
 def default_context(device):
-    """A per-device context for the stateless entry points (workspace only)."""
+    """A context (workspace only) for the stateless entry points: one per device AND per current stream, because calls on one
+    context must be issued on one stream at a time (the workspace is shared) -- pipelines running side by side on different
+    streams (sweep.SignalSweep) each get their own."""
     device = torch.device(device)
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    ctx = _default_ctx.get(idx)
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
+    ctx = _default_ctx.get(key)
     if ctx is None:
-        ctx = _default_ctx[idx] = Context(torch.device("cuda", idx))
+        ctx = _default_ctx[key] = Context(torch.device("cuda", idx))
     return ctx

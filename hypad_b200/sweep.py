@@ -37,10 +37,15 @@ class SignalSweep:
     them).  With torch.distributed initialised the signals are dealt out over the ranks of `group`; otherwise this process
     scores all of them."""
 
-    def __init__(self, scorers, group=None, window=100):
+    def __init__(self, scorers, group=None, window=100, streams=1):
+        """streams > 1 deals a rank's signals out over that many CUDA streams so that the small kernels of short signals overlap
+        on the device; only with one scorer per signal (a scorer's packed weights and workspace serve one stream at a time)."""
+        self.shared = not callable(scorers)
         self.scorers = scorers if callable(scorers) else (lambda _i, s=scorers: s)
         self.group = group
         self.window = window
+        self.n_streams = 1 if self.shared else max(1, int(streams))
+        self._streams = None
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.rank = torch.distributed.get_rank(group)
             self.world = torch.distributed.get_world_size(group)
@@ -58,19 +63,33 @@ class SignalSweep:
         device never waits for the host: (1) enqueue the pipeline of every signal up to its final scores, (2) extract intervals."""
         queued = []
         used = {}
-        for i in ids:
-            sc = self.scorers(i)
-            used[id(sc)] = sc
-            x = _sc._as_dev(signals[i], torch.float64, sc.device).reshape(-1)
-            out = sc.score(x, sliding=True, combination=combination, rec_error_type=rec_error_type, index=None, poll=False)
-            queued.append((i, sc, out["final"]))
+        if self.n_streams > 1 and self._streams is None:
+            self._streams = [torch.cuda.Stream() for _ in range(self.n_streams)]
+        lanes = self._streams if self.n_streams > 1 else [torch.cuda.current_stream()]
+        if self.n_streams > 1:
+            start = torch.cuda.Event()
+            start.record()
+            for st in lanes:
+                st.wait_event(start)  # the side streams start after whatever the caller queued
+        for k, i in enumerate(ids):
+            lane = lanes[k % len(lanes)]
+            with torch.cuda.stream(lane):
+                sc = self.scorers(i)  # inside the lane: a scorer built on demand packs its weights on the stream that uses them
+                used[id(sc)] = sc
+                x = _sc._as_dev(signals[i], torch.float64, sc.device).reshape(-1)
+                out = sc.score(x, sliding=True, combination=combination, rec_error_type=rec_error_type, index=None, poll=False)
+            queued.append((i, sc, out["final"], lane))
         res = {}
-        for i, sc, final in queued:
+        for i, sc, final, lane in queued:
             ddof = 1 if sc.hyperbolic else 0  # SURVEY.md 0.5: torch tensor (unbiased) vs ndarray
-            iv = _sc.find_anomaly_intervals(final, np.asarray(indices[i]), 0.33, 0.1, anomaly_padding=50, ddof=ddof)
+            with torch.cuda.stream(lane):
+                iv = _sc.find_anomaly_intervals(final, np.asarray(indices[i]), 0.33, 0.1, anomaly_padding=50, ddof=ddof)
             res[i] = {"intervals": iv}
             if keep_scores:
                 res[i]["final"] = final
+        if self.n_streams > 1:
+            for st in lanes:
+                torch.cuda.current_stream().wait_stream(st)
         for sc in used.values():
             sc.poll_error()
         return res

@@ -89,7 +89,10 @@ def main():
     scorers = [model(1000 + i, 100, True) for i in range(len(lengths))]
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build
-    for label, sw in (("cfg5_sweep_one_model_per_signal", SignalSweep(lambda i: scorers[i])), ("cfg5_sweep_shared_weights", SignalSweep(scorers[0]))):
+    for label, sw in (("cfg5_sweep_one_model_per_signal", SignalSweep(lambda i: scorers[i])),
+                      ("cfg5_sweep_one_model_per_signal_4_streams", SignalSweep(lambda i: scorers[i], streams=4)),
+                      ("cfg5_sweep_one_model_per_signal_8_streams", SignalSweep(lambda i: scorers[i], streams=8)),
+                      ("cfg5_sweep_shared_weights", SignalSweep(scorers[0]))):
         out = sw.run(signals, indices)
         t = wall(lambda: sw.run(signals, indices), 3, warm=1)
         res[label] = {"signals": len(lengths), "windows": total, "ms": t * 1e3, "windows_per_s": total / t,

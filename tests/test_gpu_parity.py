@@ -725,6 +725,12 @@ def test_signal_sweep_equals_per_signal_scoring(cuda_device):
             continue
         alone = scorer_of(i).score(torch.from_numpy(s).to(cuda_device), sliding=True, combination="uncertainty", index=idx)
         assert np.array_equal(alone["intervals"], res[i]), i
+    # the same sweep over three streams (fresh scorers, built inside their lanes): identical results
+    first_pass = dict(scorers)
+    scorers.clear()
+    res3 = SignalSweep(scorer_of, streams=3).run(signals, indices)
+    assert all(np.array_equal(res3[i], res[i]) for i in res)
+    assert all(scorers[i] is not first_pass[i] for i in scorers)
     local = sw.score_local(signals, indices, [1, 2], keep_scores=True)
     for i in (1, 2):
         alone = scorer_of(i).score(torch.from_numpy(signals[i]).to(cuda_device), sliding=True, combination="uncertainty")
