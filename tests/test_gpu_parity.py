@@ -694,7 +694,7 @@ def test_signal_sweep_equals_per_signal_scoring(cuda_device):
     g = golden("noisy1500_hyp_uncertainty.npz")
     rng = np.random.default_rng(2)
     signals, indices = [full_signal(g)], [g["index"]]
-    for T in (1420, 3000, 101, 100, 777, 2048):  # 101: a single window; 100: none
+    for T in (1420, 3000, 130, 100, 777, 2048):  # 130: thirty windows; 100: none
         t = np.arange(T)
         s = np.sin(2 * np.pi * t / 41.0) + 0.1 * rng.standard_normal(T)
         if T > 500:
@@ -786,3 +786,23 @@ def test_sharded_windows_univariate_equal_unsharded(world, hyp_scorer, cuda_devi
     out = replay_sharded(hyp_scorer, x, n, world, True, "uncertainty", False)
     for k in ("final", "kmax", "rec", "unorm"):
         assert torch.equal(out[k], ref[k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T", [101, 102, 105])
+def test_signals_of_a_few_windows_vs_oracle(T, hyp_scorer, cuda_device):
+    """One, two and five windows: the critic values under every timestep coincide or nearly so, the smoothing window is 0 -- the
+    reference's scores are NaN and it finds no interval; the device path must say the same instead of tripping over the sizes."""
+    from conftest import weights
+
+    t = np.arange(T)
+    s = np.sin(2 * np.pi * t / 41.0)
+    s = 2 * (s - s.min()) / (s.max() - s.min()) - 1
+    idx = 1285027200 + 21600 * t
+    W = ho.rolling_window_sequences(s[:, None], idx, 100)[0][:, :, 0]
+    want = ho.univariate_scores(W, weights("weights_hyp_s100.npz"), True, "uncertainty", index=idx)
+    out = hyp_scorer.score(torch.from_numpy(s).to(cuda_device), True, "uncertainty", index=idx)
+    final = out["final"].cpu().numpy()
+    assert final.shape == want["final"].shape
+    assert np.array_equal(np.isnan(final), np.isnan(want["final"]))
+    assert np.asarray(out["intervals"]).reshape(-1, 3).shape[0] == len(want["intervals"]) == 0
