@@ -94,3 +94,41 @@ def test_reference_init_is_reproduced_by_the_mirror_modules():
         assert sorted(mine) == sorted(ref)
         for k in ref:
             assert np.array_equal(mine[k].numpy(), ref[k].numpy()), k
+
+
+def test_argument_validation_needs_no_device():
+    """Bad arguments are refused before any CUDA call: EINVAL and a message naming the entry point, with or without a GPU."""
+    from hypad_b200 import _native
+
+    lib = _native.load_library()
+    one = ctypes.c_void_p(8)  # never dereferenced: validation rejects the call first
+    assert lib.hypad_segments_aggregate(None, one, 10, one, 1.0, 5, one, None) != 0
+    assert b"hypad_segments_aggregate" in lib.hypad_last_error()
+    assert lib.hypad_segments_aggregate(one, one, 10, one, 0.0, 5, one, None) != 0  # interval must be positive
+    assert lib.hypad_impute_minmax(None, one, 10, -1.0, 1.0, one, None) != 0
+    assert lib.hypad_detrend_linear(None, one, 10, one, None) != 0
+    assert lib.hypad_square_norm(None, 4, 3, one, None) != 0
+    assert b"hypad_square_norm" in lib.hypad_last_error()
+    assert lib.hypad_square_norm(one, 4, 0, one, None) != 0  # D >= 1
+    assert lib.hypad_poincare_distance_pairwise(None, one, 4, one, 4, 3, one, None) != 0
+    assert lib.hypad_pairwise_sqdist(None, one, 4, one, 4, 3, one, None) != 0
+
+
+def test_no_cpu_fallback_in_the_new_mirrors():
+    import numpy as np
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from hypad_b200 import HypadError
+    from hypad_b200.hyperspace.poincare_distance import pairwise_distances, poincare_distance, square_norm
+    from hypad_b200.utils import dataloader as dl
+
+    x = torch.zeros(4, 8)
+    for fn in (lambda: poincare_distance(x, x), lambda: pairwise_distances(x), lambda: square_norm(x)):
+        with pytest.raises(HypadError):
+            fn()
+    with pytest.raises(HypadError):
+        dl.preprocess_signal(np.arange(10), np.zeros(10), 1)
+    with pytest.raises(HypadError):
+        dl.detrend_signal(np.zeros(10))
