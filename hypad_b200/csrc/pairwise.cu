@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(256, 2) pw_distance_kernel(const float* __rest
             }
             __syncthreads();
         }
+        const bool vec = (M & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;  // rows of out are 16-byte aligned
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const int64_t i = i0 + (r >> 2) * 64 + ty * 4 + (r & 3);
@@ -89,17 +90,28 @@ __global__ void __launch_bounds__(256, 2) pw_distance_kernel(const float* __rest
             const float xn = xss[i];
             const float a1 = mode == 0 ? __fsub_rn(1.0f, xsq[i]) : 0.0f;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int64_t j = j0 + (c >> 2) * 64 + tx * 4 + (c & 3);
-                if (j >= M) continue;
-                // x_norm + y_norm - 2.0 * mm, clamped to [1e-7, inf)   (:45-48)
-                float d = __fsub_rn(__fadd_rn(xn, yss[j]), __fmul_rn(2.0f, acc[r][c]));
-                d = fmaxf(d, 1e-7f);
-                if (mode == 0) {
-                    const float den = __fmul_rn(a1, __fsub_rn(1.0f, ysq[j]));
-                    d = acoshf(__fadd_rn(1.0f, __fdiv_rn(__fmul_rn(2.0f, d), den)));  // :16
+            for (int cg = 0; cg < 2; ++cg) {
+                const int64_t jb = j0 + cg * 64 + tx * 4;
+                float d[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int64_t j = jb + c < M ? jb + c : M - 1;
+                    // x_norm + y_norm - 2.0 * mm, clamped to [1e-7, inf)   (:45-48)
+                    float v = __fsub_rn(__fadd_rn(xn, yss[j]), __fmul_rn(2.0f, acc[r][cg * 4 + c]));
+                    v = fmaxf(v, 1e-7f);
+                    if (mode == 0) {
+                        const float den = __fmul_rn(a1, __fsub_rn(1.0f, ysq[j]));
+                        v = acoshf(__fadd_rn(1.0f, __fdiv_rn(__fmul_rn(2.0f, v), den)));  // :16
+                    }
+                    d[c] = v;
                 }
-                out[i * M + j] = d;
+                if (vec && jb + 3 < M) {
+                    *reinterpret_cast<float4*>(out + i * M + jb) = make_float4(d[0], d[1], d[2], d[3]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (jb + c < M) out[i * M + jb + c] = d[c];
+                }
             }
         }
     }

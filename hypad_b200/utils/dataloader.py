@@ -51,7 +51,7 @@ def preprocess_signal(timestamps, values, interval=21600, feature_range=(-1.0, 1
 def detrend_signal(values, device=None):
     """scipy.signal.detrend(values) (type="linear") on the device, utils/dataloader.py:36-38.  Returns a float64 device tensor."""
     dev = _sc.cuda_device(device)
-    v = torch.from_numpy(np.ascontiguousarray(np.asarray(values, dtype=np.float64))).to(dev)
+    v = torch.from_numpy(np.array(values, dtype=np.float64, order="C")).to(dev)  # a copy: pandas hands out read-only views
     if v.dim() != 1 or v.shape[0] < 1:
         raise ValueError("hypad_b200: detrend_signal expects a non-empty 1-D signal")
     out = torch.empty_like(v)

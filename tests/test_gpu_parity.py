@@ -634,7 +634,10 @@ def test_yahoo_preprocessing_on_device_vs_reference(cuda_device, tmp_path):
         df = dl.yahoo_preprocess(pd.DataFrame({"timestamp": np.arange(1, len(vals) + 1), "value": vals, "is_anomaly": flag}), cuda_device)
         X, index = dl.preprocess_signal(df["timestamp"].values, df["value"].values, 1, device=cuda_device)
         assert np.array_equal(index - index[0], g[k + "/index"] - g[k + "/index"][0]), name
-        assert np.abs(X.cpu().numpy() - g[k + "/scaled"]).max() <= 1e-13, name
+        if np.ptp(g[k + "/detrended"]) > 1e-9 * np.abs(vals).max():
+            assert np.abs(X.cpu().numpy() - g[k + "/scaled"]).max() <= 1e-13, name
+        # else ("tiny": two samples lie ON their fitted line) the residual is rounding noise in the reference as well, and MinMax
+        # scaling of noise to (-1, 1) is not a comparable quantity
     # the dataset class, YAHOO flavour: file in, device signal + the known-anomalies side file out
     vals, flag = yahoo_cases()["a1_like"]
     path = str(tmp_path / "real_1.csv")
@@ -665,7 +668,8 @@ def test_pairwise_poincare_distance_vs_reference(cuda_device):
         sq_self = pairwise_distances(tp).cpu().numpy()
         scale_self = (p.astype(np.float64) ** 2).sum(1)
         assert (np.abs(sq_self - g[name + "/sqdist_self"]) <= 2e-6 * (scale_self[:, None] + scale_self[None, :]) + 1e-12).all(), name
-        np.testing.assert_allclose(square_norm(tp).cpu().numpy(), g[name + "/square_norm"], rtol=3e-7, atol=0)
+        # sqrt then square (torch.norm(x) ** 2): each side within 2 fp32 ulps of the exact sum
+        np.testing.assert_allclose(square_norm(tp).cpu().numpy(), g[name + "/square_norm"], rtol=5e-7, atol=0)
         d = poincare_distance(tp, tq).cpu().numpy()
         np.testing.assert_allclose(d, g[name + "/poincare"], rtol=2e-4, atol=0, err_msg=name)
         o = ho.poincare_distance(torch.from_numpy(p), torch.from_numpy(q)).numpy()
@@ -718,8 +722,7 @@ def test_signal_sweep_equals_per_signal_scoring(cuda_device):
     res = sw.run(signals, indices)
     assert sorted(res) == list(range(len(signals)))
     assert res[4].shape == (0, 3)  # T == window: nothing to score
-    assert np.array_equal(res[0][:, :2], g["intervals"][:, :2])  # the reference's intervals for the golden case
-    np.testing.assert_allclose(res[0][:, 2], g["intervals"][:, 2], rtol=1e-4)
+    check_intervals(res[0], g["intervals"])  # the reference's intervals for the golden case
     for i, (s, idx) in enumerate(zip(signals, indices)):
         if len(s) <= 100:
             continue
