@@ -4,7 +4,7 @@
 //                                                     inclusive), value = NaN-skipping mean, NaN for an empty segment
 //   SimpleImputer() (mean)                  :86-87    NaN -> mean of the valid entries
 //   MinMaxScaler(feature_range=(lo, hi))    :88-89    x * scale + (lo - min * scale), scale = (hi - lo) / (max - min)
-// The reference walks the segments in a Python loop (`while start_ts <= max_ts`, one pandas slice per segment): ~1 s per
+// The reference walks the segments in a Python loop (`while start_ts <= max_ts`, one pandas slice per segment): ~2 s per
 // 10^4 segments.  Here a thread owns a segment and finds its rows by binary search in the sorted timestamps.
 #include "common.cuh"
 
