@@ -38,11 +38,29 @@ class PackedNet:
         self.S = self.latent = self.critic_dim = None
         self.hyperbolic = False
 
+    def _param_slots(self, mods):
+        """[(owner module, parameter name)] in sorted-name order per top-level module, cached: walking the module trees on every
+        forward call cost more host time than the launch itself on short signals.  The cache is valid while every module of the
+        walk still has the same children (a replaced sub-module or top-level module rebuilds it); a replaced Parameter object
+        is picked up because the slot is read through its owner each time."""
+        shape = tuple(id(m) for m in mods)
+        cached = getattr(self, "_slots", None)
+        if cached is not None and cached[0] == shape and all(tuple(map(id, mod._modules.values())) == kids for mod, kids in cached[1]):
+            return cached[2]
+        walk, slots = [], []
+        for m in mods:
+            if m is None:
+                continue
+            named = dict(m.named_modules())
+            walk.extend((mod, tuple(map(id, mod._modules.values()))) for mod in named.values())
+            for full, _p in sorted(m.named_parameters()):
+                owner, _, leaf = full.rpartition(".")
+                slots.append((named[owner], leaf))
+        self._slots = (shape, walk, slots)
+        return slots
+
     def ensure(self, encoder, decoder, critic_x):
-        params = []
-        for m in (encoder, decoder, critic_x):
-            if m is not None:
-                params.extend(p for _, p in sorted(m.named_parameters()))
+        params = [owner._parameters[name] for owner, name in self._param_slots((encoder, decoder, critic_x))]
         key = tuple((p.data_ptr(), p._version, p.dtype, p.device) for p in params)
         if key == self.key:
             return self

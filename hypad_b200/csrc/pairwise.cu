@@ -36,6 +36,17 @@ __global__ void pw_rownorm_kernel(const float* __restrict__ x, int64_t n, int D,
     }
 }
 
+// One output from its dot product, in the reference's operation order.  Not inlined: the kernel calls it for each of a thread's 64
+// outputs, and 64 inlined copies of acoshf pushed the epilogue out of the instruction cache (ncu: `no_instruction` was the top
+// stall of the first version).
+__device__ __noinline__ float pw_finish(float dot, float xn, float yn, float one_minus_xsq, float one_minus_ysq, int mode) {
+    // x_norm + y_norm - 2.0 * mm, clamped to [1e-7, inf)   (:45-48)
+    float v = __fsub_rn(__fadd_rn(xn, yn), __fmul_rn(2.0f, dot));
+    v = fmaxf(v, 1e-7f);
+    if (mode == 0) v = acoshf(__fadd_rn(1.0f, __fdiv_rn(__fmul_rn(2.0f, v), __fmul_rn(one_minus_xsq, one_minus_ysq))));  // :16
+    return v;
+}
+
 // mode 0: poincare_distance, mode 1: pairwise_distances.  One CTA per 128 x 128 output tile (grid-stride), 256 threads, thread =
 // 8 x 8 outputs (rows ty*4 + {0..3} and 64 + ty*4 + {0..3}, columns likewise with tx: every shared-memory read is a conflict-free
 // LDS.128, 4 of them per 64 FFMA, and 16 neighbouring threads store 64 consecutive floats); operands staged k-major in shared
@@ -83,6 +94,15 @@ __global__ void __launch_bounds__(256, 2) pw_distance_kernel(const float* __rest
             __syncthreads();
         }
         const bool vec = (M & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;  // rows of out are 16-byte aligned
+        // the 8 columns' norms once per tile (clamped index: lanes beyond M compute a value nobody stores)
+        float yn[8], yq[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int64_t j = j0 + (c >> 2) * 64 + tx * 4 + (c & 3);
+            const int64_t jc = j < M ? j : M - 1;
+            yn[c] = yss[jc];
+            yq[c] = mode == 0 ? __fsub_rn(1.0f, ysq[jc]) : 0.0f;
+        }
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const int64_t i = i0 + (r >> 2) * 64 + ty * 4 + (r & 3);
@@ -94,17 +114,7 @@ __global__ void __launch_bounds__(256, 2) pw_distance_kernel(const float* __rest
                 const int64_t jb = j0 + cg * 64 + tx * 4;
                 float d[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int64_t j = jb + c < M ? jb + c : M - 1;
-                    // x_norm + y_norm - 2.0 * mm, clamped to [1e-7, inf)   (:45-48)
-                    float v = __fsub_rn(__fadd_rn(xn, yss[j]), __fmul_rn(2.0f, acc[r][cg * 4 + c]));
-                    v = fmaxf(v, 1e-7f);
-                    if (mode == 0) {
-                        const float den = __fmul_rn(a1, __fsub_rn(1.0f, ysq[j]));
-                        v = acoshf(__fadd_rn(1.0f, __fdiv_rn(__fmul_rn(2.0f, v), den)));  // :16
-                    }
-                    d[c] = v;
-                }
+                for (int c = 0; c < 4; ++c) d[c] = pw_finish(acc[r][cg * 4 + c], xn, yn[cg * 4 + c], a1, yq[cg * 4 + c], mode);
                 if (vec && jb + 3 < M) {
                     *reinterpret_cast<float4*>(out + i * M + jb) = make_float4(d[0], d[1], d[2], d[3]);
                 } else {
