@@ -60,31 +60,57 @@ class SignalSweep:
 
     def score_local(self, signals, indices, ids, combination="uncertainty", rec_error_type="dtw", keep_scores=False):
         """Scores the signals `ids`; returns {id: {"intervals": (K,3) array[, "final": device tensor]}}.  Two phases so that the
-        device never waits for the host: (1) enqueue the pipeline of every signal up to its final scores, (2) extract intervals."""
+        device never waits for the host: (1) enqueue the pipeline of every signal -- scores, the thresholding kernels of
+        find_anomalies and the copy of their packed result to pinned host memory -- without a synchronisation, (2) one
+        synchronisation, then the host bookkeeping (prune, score, merge of the few runs) per signal."""
         queued = []
         used = {}
         if self.n_streams > 1 and self._streams is None:
             self._streams = [torch.cuda.Stream() for _ in range(self.n_streams)]
         lanes = self._streams if self.n_streams > 1 else [torch.cuda.current_stream()]
+        # one upload for all host-resident signals of this rank (a pageable copy per signal would stall the host once each)
+        resident = {}
+        host_ids = [i for i in ids if not (isinstance(signals[i], torch.Tensor) and signals[i].is_cuda)]
+        if host_ids:
+            flat = np.concatenate([np.asarray(signals[i], dtype=np.float64).reshape(-1) for i in host_ids])
+            big = torch.from_numpy(flat).pin_memory().to(_sc.cuda_device(), non_blocking=True)
+            off = 0
+            for i in host_ids:
+                n = int(np.asarray(signals[i]).size)
+                resident[i] = big[off:off + n]
+                off += n
         if self.n_streams > 1:
             start = torch.cuda.Event()
             start.record()
             for st in lanes:
                 st.wait_event(start)  # the side streams start after whatever the caller queued
+        MAX_RUNS = 64
         for k, i in enumerate(ids):
             lane = lanes[k % len(lanes)]
             with torch.cuda.stream(lane):
                 sc = self.scorers(i)  # inside the lane: a scorer built on demand packs its weights on the stream that uses them
                 used[id(sc)] = sc
-                x = _sc._as_dev(signals[i], torch.float64, sc.device).reshape(-1)
+                x = resident[i] if i in resident else _sc._as_dev(signals[i], torch.float64, sc.device).reshape(-1)
                 out = sc.score(x, sliding=True, combination=combination, rec_error_type=rec_error_type, index=None, poll=False)
-            queued.append((i, sc, out["final"], lane))
+                final = out["final"]
+                # find_anomalies' device part queued right behind the scores, its packed result on its way to pinned host
+                # memory: no host synchronisation per signal
+                ddof = 1 if sc.hyperbolic else 0  # SURVEY.md 0.5: torch tensor (unbiased) vs ndarray
+                wsize, step, count = _sc.analysis_windows(final.numel(), None, 0.33, None, 0.1)
+                buf = _sc.threshold_windows_launch(final, wsize, step, count, ddof, 50, MAX_RUNS)
+                host = torch.empty(buf.shape, dtype=buf.dtype, pin_memory=True)
+                host.copy_(buf, non_blocking=True)
+            queued.append((i, final, lane, ddof, (wsize, step, count), host, buf))
+        for st in lanes:
+            st.synchronize()
         res = {}
-        for i, sc, final, lane in queued:
-            ddof = 1 if sc.hyperbolic else 0  # SURVEY.md 0.5: torch tensor (unbiased) vs ndarray
-            with torch.cuda.stream(lane):
-                iv = _sc.find_anomaly_intervals(final, np.asarray(indices[i]), 0.33, 0.1, anomaly_padding=50, ddof=ddof)
-            res[i] = {"intervals": iv}
+        for i, final, lane, ddof, (wsize, step, count), host, _buf in queued:
+            stats, runs, nr = _sc.threshold_windows_parse(host.numpy(), count, MAX_RUNS)
+            if nr.max(initial=0) > MAX_RUNS:  # more runs in one analysis window than the buffer holds (never seen): the one-by-one path
+                with torch.cuda.stream(lane):
+                    stats, runs, nr = _sc.threshold_windows(final, wsize, step, count, ddof, 50, max_runs=int(nr.max()) + 16)
+            merged = _sc.intervals_from_runs(stats, runs, nr, step, 0.1)
+            res[i] = {"intervals": _sc.intervals_to_index(merged, np.asarray(indices[i]))}
             if keep_scores:
                 res[i]["final"] = final
         if self.n_streams > 1:
