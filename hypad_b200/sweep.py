@@ -46,6 +46,7 @@ class SignalSweep:
         self.window = window
         self.n_streams = 1 if self.shared else max(1, int(streams))
         self._streams = None
+        self._host_buf = None
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.rank = torch.distributed.get_rank(group)
             self.world = torch.distributed.get_world_size(group)
@@ -79,12 +80,27 @@ class SignalSweep:
                 n = int(np.asarray(signals[i]).size)
                 resident[i] = big[off:off + n]
                 off += n
+        # one device buffer for the packed thresholding results of all signals and one pinned host buffer to receive it: a single
+        # device-to-host copy per rank (a pinned allocation and a small copy per signal cost more than the kernels)
+        MAX_RUNS = 64
+        S = self.window
+        slot = {}
+        total = 0
+        for i in ids:
+            T = int(np.asarray(signals[i].shape).prod()) if hasattr(signals[i], "shape") else len(signals[i])
+            # hyperbolic models score T-S windows, Euclidean ones T-1 timesteps: room for the larger layout
+            need = max(_sc.threshold_buffer_len(_sc.analysis_windows(n, None, 0.33, None, 0.1)[2], MAX_RUNS) for n in (T - S, T - 1))
+            slot[i] = (total, need)
+            total += need
+        dev = _sc.cuda_device()
+        dev_buf = torch.empty(max(total, 1), dtype=torch.float64, device=dev)
+        if self._host_buf is None or self._host_buf.numel() < total:
+            self._host_buf = torch.empty(max(total, 1), dtype=torch.float64, pin_memory=True)
         if self.n_streams > 1:
             start = torch.cuda.Event()
             start.record()
             for st in lanes:
                 st.wait_event(start)  # the side streams start after whatever the caller queued
-        MAX_RUNS = 64
         for k, i in enumerate(ids):
             lane = lanes[k % len(lanes)]
             with torch.cuda.stream(lane):
@@ -93,29 +109,32 @@ class SignalSweep:
                 x = resident[i] if i in resident else _sc._as_dev(signals[i], torch.float64, sc.device).reshape(-1)
                 out = sc.score(x, sliding=True, combination=combination, rec_error_type=rec_error_type, index=None, poll=False)
                 final = out["final"]
-                # find_anomalies' device part queued right behind the scores, its packed result on its way to pinned host
-                # memory: no host synchronisation per signal
+                # find_anomalies' device part queued right behind the scores: no host synchronisation per signal
                 ddof = 1 if sc.hyperbolic else 0  # torch tensor (unbiased) vs ndarray
                 wsize, step, count = _sc.analysis_windows(final.numel(), None, 0.33, None, 0.1)
-                buf = _sc.threshold_windows_launch(final, wsize, step, count, ddof, 50, MAX_RUNS)
-                host = torch.empty(buf.shape, dtype=buf.dtype, pin_memory=True)
-                host.copy_(buf, non_blocking=True)
-            queued.append((i, final, lane, ddof, (wsize, step, count), host, buf))
-        for st in lanes:
-            st.synchronize()
+                off, room = slot[i]
+                used_len = _sc.threshold_buffer_len(count, MAX_RUNS)
+                if used_len > room:
+                    raise HypadError("hypad_b200: signal %d yields %d scores, neither T-window nor T-1" % (i, final.numel()))
+                _sc.threshold_windows_launch(final, wsize, step, count, ddof, 50, MAX_RUNS, out=dev_buf[off:off + used_len])
+            queued.append((i, final, lane, ddof, (wsize, step, count), off, used_len))
+        cur = torch.cuda.current_stream()
+        if self.n_streams > 1:
+            for st in lanes:
+                cur.wait_stream(st)
+        host_buf = self._host_buf[:max(total, 1)]
+        host_buf.copy_(dev_buf, non_blocking=True)
+        cur.synchronize()
+        host_np = host_buf.numpy()
         res = {}
-        for i, final, lane, ddof, (wsize, step, count), host, _buf in queued:
-            stats, runs, nr = _sc.threshold_windows_parse(host.numpy(), count, MAX_RUNS)
+        for i, final, lane, ddof, (wsize, step, count), off, used_len in queued:
+            stats, runs, nr = _sc.threshold_windows_parse(host_np[off:off + used_len], count, MAX_RUNS)
             if nr.max(initial=0) > MAX_RUNS:  # more runs in one analysis window than the buffer holds (never seen): the one-by-one path
-                with torch.cuda.stream(lane):
-                    stats, runs, nr = _sc.threshold_windows(final, wsize, step, count, ddof, 50, max_runs=int(nr.max()) + 16)
+                stats, runs, nr = _sc.threshold_windows(final, wsize, step, count, ddof, 50, max_runs=int(nr.max()) + 16)
             merged = _sc.intervals_from_runs(stats, runs, nr, step, 0.1)
             res[i] = {"intervals": _sc.intervals_to_index(merged, np.asarray(indices[i]))}
             if keep_scores:
                 res[i]["final"] = final
-        if self.n_streams > 1:
-            for st in lanes:
-                torch.cuda.current_stream().wait_stream(st)
         for sc in used.values():
             sc.poll_error()
         return res
