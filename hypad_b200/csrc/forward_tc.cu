@@ -862,20 +862,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
 // ------------------------------------------------------------------------------------------------------------
 // One CTA per pass: sw = the largest power of two that keeps max|w| 2^sw below 2^15; scale[0] = 2^sw,
 // scale[1] = 2^-(sa+sw) (what the epilogue multiplies the accumulators by).
-__global__ void tc_wscale_kernel(const ColSrc* __restrict__ cols, int ncols, int in_shift, float* __restrict__ scale) {
-    __shared__ float smax[256];
+__global__ void __launch_bounds__(1024) tc_wscale_kernel(const ColSrc* __restrict__ cols, int ncols, int in_shift, float* __restrict__ scale) {
+    // a warp per column (32 warps, <= 8 columns each): the first version walked the <= 256 columns one after the other with the
+    // whole CTA, 46 us per pass -- 0.9 ms per model, three times what scoring a short signal costs.  A maximum does not depend on
+    // the order, so the scales are bit for bit the same.
+    __shared__ float smax[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     float m = 0.0f;
-    for (int cc = 0; cc < ncols; ++cc) {
+    for (int cc = warp; cc < ncols; cc += nwarps) {
         const ColSrc s = cols[cc];
         if (s.w == nullptr) continue;
-        for (int k = threadIdx.x; k < s.K; k += blockDim.x) m = fmaxf(m, fabsf(s.w[(size_t)s.row * s.K + k]));
+        for (int k = lane; k < s.K; k += 32) m = fmaxf(m, fabsf(s.w[(size_t)s.row * s.K + k]));
     }
-    smax[threadIdx.x] = m;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) smax[warp] = m;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) smax[threadIdx.x] = fmaxf(smax[threadIdx.x], smax[threadIdx.x + o]);
-        __syncthreads();
-    }
+    if (threadIdx.x == 0)
+        for (int w = 1; w < nwarps; ++w) smax[0] = fmaxf(smax[0], smax[w]);
     if (threadIdx.x == 0) {
         int e = 0;
         int sw = 11;
@@ -1083,7 +1087,7 @@ int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
         const TcPass& p = prog.pass[i];
         const int total = p.k16 * 16 * p.n;
         float* scale = small + prog.post_off + 4 * i;
-        tc_wscale_kernel<<<1, 256, 0, stream>>>((const ColSrc*)ctx->workspace + start[i], p.n, p.in_shift, scale);
+        tc_wscale_kernel<<<1, 1024, 0, stream>>>((const ColSrc*)ctx->workspace + start[i], p.n, p.in_shift, scale);
         HYPAD_LAUNCH_CHECK();
         pack_tc_kernel<<<(total + 255) / 256, 256, 0, stream>>>((const ColSrc*)ctx->workspace + start[i], p.k16, 1, p.n,
                                                                reinterpret_cast<__half*>(ctx->tc_packed + p.w_off), small + p.b_off, scale,
@@ -1091,7 +1095,7 @@ int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream) {
         HYPAD_LAUNCH_CHECK();
         if (p.n2) {
             const int total2 = p.k2_n * 16 * p.n2;
-            tc_wscale_kernel<<<1, 256, 0, stream>>>((const ColSrc*)ctx->workspace + start2[i], p.n2, p.in_shift2, scale + 2);
+            tc_wscale_kernel<<<1, 1024, 0, stream>>>((const ColSrc*)ctx->workspace + start2[i], p.n2, p.in_shift2, scale + 2);
             HYPAD_LAUNCH_CHECK();
             pack_tc_kernel<<<(total2 + 255) / 256, 256, 0, stream>>>((const ColSrc*)ctx->workspace + start2[i], p.k2_n, 1, p.n2,
                                                                     reinterpret_cast<__half*>(ctx->tc_packed + p.w_off2), small + p.b_off2,
