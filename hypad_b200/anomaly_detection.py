@@ -4,8 +4,10 @@ Same signature.  Instead of looping over DataLoader batches of 64 windows with f
 per batch (anomaly_detection.py:67-113), all windows of the dataset go through the fused sm_100a pipeline in one
 call; the same artefacts are written to `path` (recons_signal.pt, gt_signal.pt, critic_score.pt, true_index.pt,
 eucl_recons.pt, real_hyper.pt, critic_scores.pickle, anomalies.csv; anomaly_detection.py:116-131,
-utils/anomaly_detection_utils.py:97-98, :234-235).  Ground-truth loading and the metrics printout are evaluation
-tooling and are skipped.
+utils/anomaly_detection_utils.py:97-98, :234-235).  Ground-truth loading (`utils.data.load_anomalies`: S3 / bundled label
+files, anomaly_detection.py:136-150) is not reproduced; with the labels in hand the evaluation itself is available as
+`utils.anomaly_detection_utils.contextual_confusion_matrix` / `compute_metrics`, or through the `known_anomalies` argument of
+`univariate_anomaly_detection`.
 """
 import os
 import pickle

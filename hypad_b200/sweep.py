@@ -15,6 +15,11 @@ from . import scoring as _sc
 from ._native import HypadError
 
 
+def _n_samples(signal):
+    """Samples of one univariate signal given as (T,), (T, 1) or (1, T) array, tensor or list."""
+    return int(np.prod(np.shape(signal), dtype=np.int64))
+
+
 def assign_signals(n_windows, world_size):
     """Greedy longest-processing-time assignment: signals in descending window count (ties: lower signal id first), each to the
     rank with the least work so far (ties: lower rank).  Returns one list of signal ids per rank, in scoring order."""
@@ -77,7 +82,7 @@ class SignalSweep:
             big = torch.from_numpy(flat).pin_memory().to(_sc.cuda_device(), non_blocking=True)
             off = 0
             for i in host_ids:
-                n = int(np.asarray(signals[i]).size)
+                n = _n_samples(signals[i])
                 resident[i] = big[off:off + n]
                 off += n
         # one device buffer for the packed thresholding results of all signals and one pinned host buffer to receive it: a single
@@ -87,7 +92,7 @@ class SignalSweep:
         slot = {}
         total = 0
         for i in ids:
-            T = int(np.asarray(signals[i].shape).prod()) if hasattr(signals[i], "shape") else len(signals[i])
+            T = _n_samples(signals[i])
             # hyperbolic models score T-S windows, Euclidean ones T-1 timesteps: room for the larger layout
             need = max(_sc.threshold_buffer_len(_sc.analysis_windows(n, None, 0.33, None, 0.1)[2], MAX_RUNS) for n in (T - S, T - 1))
             slot[i] = (total, need)
@@ -143,7 +148,7 @@ class SignalSweep:
         """Every rank returns the full {signal id: (K,3) intervals} map (empty (0,3) array for signals without a window)."""
         if len(signals) != len(indices):
             raise HypadError("hypad_b200: %d signals but %d index arrays" % (len(signals), len(indices)))
-        plan = self.plan([len(s) for s in signals])
+        plan = self.plan([_n_samples(s) for s in signals])
         local = {i: r["intervals"] for i, r in self.score_local(signals, indices, plan[self.rank], combination, rec_error_type).items()}
         if self.world > 1:
             parts = [None] * self.world
