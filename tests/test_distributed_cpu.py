@@ -141,3 +141,40 @@ def test_signal_sweep_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(res) == [(0, True), (1, True)]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("n,S,rows", [(2500, 123, True), (1400, 100, False), (130, 100, False), (7, 3, True)])
+def test_pack_layout_round_trips(world, n, S, rows):
+    """The gather layout of ShardedScorer ([kmax | rec | unorm] per rank, `width` each) for every rank of a run, on CPU tensors:
+    packs built the way pack_local lays them out, concatenated like all_gather_into_tensor, must unpack to the global arrays --
+    for window sharding (sample ranges with S extra samples) and row sharding (multivariate, config 4)."""
+    from hypad_b200 import distributed as hd
+
+    class FakeScorer:
+        pass
+
+    fs = FakeScorer()
+    fs.S = S
+    kmax_g = torch.arange(n + S - 1, dtype=torch.float32) * 0.25 + 1
+    rec_g = torch.arange(n, dtype=torch.float32) + 1000
+    unorm_g = torch.arange(n, dtype=torch.float32) + 5000
+    ranges = hd.shard_ranges(n, world)
+    packs, covered = [], 0
+    for r in range(world):
+        sh = hd.ShardedScorer(fs, rank=r, world=world)
+        first, count, h0, lo, hi = sh.plan_rows(n) if rows else sh.plan(n)
+        assert (first, count) == ranges[r] and h0 == max(0, first - (S - 1)) and lo == h0
+        assert hi == first + count + (0 if rows else S)
+        covered += count
+        width = sh.gather_width(n)
+        t0, tc = hd.timestep_range(first, count, n, S, r == world - 1)
+        pack = torch.zeros(3 * width)
+        pack[:tc] = kmax_g[t0:t0 + tc]
+        pack[width:width + count] = rec_g[first:first + count]
+        pack[2 * width:2 * width + count] = unorm_g[first:first + count]
+        packs.append(pack)
+    assert covered == n
+    kmax, rec, unorm = sh.unpack_gathered(torch.cat(packs), n)
+    assert kmax.dtype == torch.float64 and torch.equal(kmax, kmax_g.double())
+    assert torch.equal(rec, rec_g) and torch.equal(unorm, unorm_g)
