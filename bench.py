@@ -19,7 +19,6 @@ per-timestep arrays are gathered once over NCCL and the O(T) finish runs on ever
 """
 import argparse
 import json
-import math
 import os
 import statistics
 import subprocess

@@ -9,7 +9,6 @@ files, anomaly_detection.py:136-150) is not reproduced; with the labels in hand 
 `utils.anomaly_detection_utils.contextual_confusion_matrix` / `compute_metrics`, or through the `known_anomalies` argument of
 `univariate_anomaly_detection`.
 """
-import os
 import pickle
 
 import numpy as np

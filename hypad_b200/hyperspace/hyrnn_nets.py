@@ -17,7 +17,6 @@ import torch
 import torch.nn
 
 from .. import _native
-from .._native import HypadError
 
 
 def _expmap0_cpu(u):

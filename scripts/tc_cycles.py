@@ -1,7 +1,7 @@
 """Prints the per-role cycle breakdown of forward_tc_kernel (CTA 0) on the bench workload."""
 import ctypes, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from bench import make_signal
 from hypad_b200 import _native, scoring
 from hypad_b200.models.tadgan import Encoder, Decoder, CriticX

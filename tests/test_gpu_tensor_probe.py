@@ -1,7 +1,6 @@
 """Measurement, on the B200, of what a tcgen05 (TF32, TMEM accumulator) contraction does to the numbers:
 layout/descriptor correctness on exactly representable inputs, then the error of 1xTF32 / 3xTF32 / 6-term split
 products against an fp64 product, next to the error of the fp32 FFMA order the fused kernel uses."""
-import ctypes
 
 import numpy as np
 import pytest
