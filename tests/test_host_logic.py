@@ -157,3 +157,25 @@ def test_preprocessing_host_helpers_match_reference_golden():
     with pytest.raises(ValueError):
         dl.yahoo_index(518402)
     assert dl.yahoo_index(518401).shape == (518401,)
+
+
+def test_segment_starts_equal_the_repeated_addition_loop():
+    """utils/dataloader.py:127-135: `while start_ts <= max_ts: ...; start_ts = end_ts` with end_ts = start_ts + interval.  For
+    float timestamps / intervals the k-th start is the k-fold rounded sum, not first + k * interval; segment_starts must give the
+    former."""
+    from hypad_b200.utils.dataloader import segment_starts
+
+    rng = np.random.default_rng(41)
+    cases = [(0, 0, 1), (5, 5, 3), (0, 99, 1), (0, 100, 7), (1285027200, 1285027200 + 21600 * 999, 21600)]
+    for _ in range(40):
+        first = float(rng.uniform(-1e3, 1.4e9))
+        span = float(rng.uniform(0, 5e4))
+        cases.append((first, first + span, float(rng.uniform(0.05, 977.3))))
+        cases.append((np.float64(first), np.float64(first + span), int(rng.integers(1, 500))))
+    for first, last, interval in cases:
+        want, s = [], first
+        while s <= last:
+            want.append(s)
+            s = s + interval
+        got = segment_starts(first, last, interval)
+        assert len(got) == len(want) and all(a == b for a, b in zip(got.tolist(), want)), (first, last, interval)
