@@ -132,3 +132,44 @@ def test_no_cpu_fallback_in_the_new_mirrors():
         dl.preprocess_signal(np.arange(10), np.zeros(10), 1)
     with pytest.raises(HypadError):
         dl.detrend_signal(np.zeros(10))
+
+
+C_CLIENT = r"""
+#include <stdio.h>
+#include <string.h>
+#include "hypad_b200.h"
+
+int main(void) {
+    float out[4];
+    if (hypad_abi_version() != 1) return 1;
+    if (hypad_square_norm(NULL, 4, 3, out, NULL) == 0) return 2;
+    if (strstr(hypad_last_error(), "hypad_square_norm") == NULL) return 3;
+    if (hypad_segments_aggregate(NULL, NULL, 0, NULL, 1.0, 0, NULL, NULL) == 0) return 4;
+    if (hypad_forward(NULL, NULL, 1, 0, 1, NULL, 15, NULL, NULL) == 0) return 5;
+    printf("c client ok\n");
+    return 0;
+}
+"""
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """The drop-in boundary is a C ABI: include/hypad_b200.h must compile as strict C99 (no C++ in the signatures) and a C
+    program must link against the library and call into it -- here only entry points that answer without a device."""
+    import shutil
+    import subprocess
+
+    from hypad_b200 import _native
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    _native.load_library()
+    src = tmp_path / "client.c"
+    src.write_text(C_CLIENT)
+    exe = tmp_path / "client"
+    libdir = os.path.join(ROOT, "hypad_b200")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+           os.path.join(libdir, "libhypad_b200.so"), "-Wl,-rpath," + libdir]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "c client ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
