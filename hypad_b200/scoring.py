@@ -420,6 +420,9 @@ class WindowScorer:
         if sliding:
             x = x.reshape(-1).contiguous()
             return x, x.shape[0] - self.S, 1
+        if x.dim() < 2 or x.shape[0] == 0:
+            raise HypadError("hypad_b200: no windows to score (windows must be a non-empty (N, %d) array, got shape %s)"
+                             % (self.S, tuple(x.shape)))
         x = x.reshape(x.shape[0], -1).contiguous()
         if x.shape[1] != self.S:
             raise HypadError("hypad_b200: windows have %d samples, the model expects %d" % (x.shape[1], self.S))

@@ -809,3 +809,22 @@ def test_signals_of_a_few_windows_vs_oracle(T, hyp_scorer, cuda_device):
     assert final.shape == want["final"].shape
     assert np.array_equal(np.isnan(final), np.isnan(want["final"]))
     assert np.asarray(out["intervals"]).reshape(-1, 3).shape[0] == len(want["intervals"]) == 0
+
+
+@pytest.mark.gpu
+def test_empty_and_misshaped_inputs_fail_loudly(hyp_scorer, cuda_device):
+    """No window to score (the reference's dataset yields an empty array there and its loop never runs) and rows of the wrong
+    width: an error that names the problem, never an empty or garbage result."""
+    from hypad_b200._native import HypadError
+
+    for T in (0, 50, 100):
+        with pytest.raises(HypadError, match="no windows"):
+            hyp_scorer.score(torch.zeros(T, dtype=torch.float64, device=cuda_device), True, "uncertainty")
+    with pytest.raises(HypadError, match="no windows"):
+        hyp_scorer.forward(torch.zeros((0, 100), dtype=torch.float32, device=cuda_device), False)
+    with pytest.raises(HypadError, match="expects 100"):
+        hyp_scorer.forward(torch.zeros((5, 99), dtype=torch.float32, device=cuda_device), False)
+    with pytest.raises(HypadError, match="CUDA tensor"):
+        hyp_scorer.forward(torch.zeros(300, dtype=torch.float64), True)
+    one = torch.sin(torch.arange(101, dtype=torch.float64, device=cuda_device) / 7.0) * 0.9
+    assert hyp_scorer.score(one, True, "uncertainty")["final"].shape == (1,)  # the smallest input that does have a window
