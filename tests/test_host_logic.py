@@ -179,3 +179,41 @@ def test_segment_starts_equal_the_repeated_addition_loop():
             s = s + interval
         got = segment_starts(first, last, interval)
         assert len(got) == len(want) and all(a == b for a, b in zip(got.tolist(), want)), (first, last, interval)
+
+
+def test_overlap_segment_counts_equal_the_nested_loops():
+    """_overlap_segment as one sign table against the counting rule spelled out with loops (utils/anomaly_detection_utils.py:
+    579-599: an expected sequence is a hit when any observed one overlaps it; an observed one is a false positive when it overlaps
+    none), on random closed intervals with duplicates, nesting, shared end points and float end points."""
+    from hypad_b200.utils import anomaly_detection_utils as adu
+
+    def naive(expected, observed):
+        hit_obs = [False] * len(observed)
+        tp = fn = 0
+        for e in expected:
+            found = False
+            for j, o in enumerate(observed):
+                if (e[0] - o[1]) * (e[1] - o[0]) < 0:
+                    found = True
+                    hit_obs[j] = True
+            tp += found
+            fn += not found
+        return None, hit_obs.count(False), fn, tp
+
+    rng = np.random.default_rng(43)
+    for trial in range(300):
+        ne, no = int(rng.integers(0, 8)), int(rng.integers(0, 10))
+        scale = 50 if trial % 2 else 1_400_000_000
+        def draw(k):
+            out = []
+            for _ in range(k):
+                a = int(rng.integers(0, 60)) + scale
+                out.append((a, a + int(rng.integers(0, 12))))
+            return out
+        expected, observed = draw(ne), draw(no)
+        if observed and trial % 3 == 0:
+            observed.append(observed[0])  # a duplicate
+        if trial % 5 == 0:
+            expected = [(float(a) + 0.5, float(b) + 0.5) for a, b in expected]
+        pe, po = adu._pad(expected), adu._pad(observed)
+        assert adu._overlap_segment(pe, po) == naive(pe, po), (expected, observed)
