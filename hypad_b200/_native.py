@@ -15,6 +15,8 @@ LIB_PATH = os.path.join(_HERE, "libhypad_b200.so")
 
 STAGE_ENCODER, STAGE_DECODER, STAGE_MOBIUS_X, STAGE_CRITIC = 1, 2, 4, 8
 STAGE_ALL = 15
+ABI_VERSION = 2
+STATS_F32 = 16  # HYPAD_STATS_F32: OR-ed into the ddof argument of the thresholding entry points
 
 COMBINE_MODES = {"mult": 0, "uncertainty": 1, "sum": 2, "critic": 3, "critic_uncertainty": 4, "sum_uncertainty": 5,
                  "rec": 6, "rec_uncertainty": 7, "euclidean_sum": 8}
@@ -58,6 +60,8 @@ _SIGNATURES = {
     "hypad_forward": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _int, ctypes.POINTER(hypad_forward_out), _vp]),
     "hypad_forward_ffma": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _int, ctypes.POINTER(hypad_forward_out), _vp]),
     "hypad_ctx_poll_error": (_int, [_vp]),
+    "hypad_ctx_set_strict_range": (_int, [_vp, _int]),
+    "hypad_ctx_range_fallbacks": (ctypes.c_int64, [_vp]),
     "hypad_segments_aggregate": (_int, [_vp, _vp, _i64, _vp, ctypes.c_double, _i64, _vp, _vp]),
     "hypad_impute_minmax": (_int, [_vp, _vp, _i64, ctypes.c_double, ctypes.c_double, _vp, _vp]),
     "hypad_detrend_linear": (_int, [_vp, _vp, _i64, _vp, _vp]),
@@ -110,7 +114,7 @@ def load_library():
                 fn = getattr(lib, name)  # AttributeError if the header and the library disagree
                 fn.restype = res
                 fn.argtypes = args
-            if lib.hypad_abi_version() != 1:
+            if lib.hypad_abi_version() != ABI_VERSION:
                 raise HypadError("hypad_b200: ABI version mismatch")
             _lib = lib
     return _lib

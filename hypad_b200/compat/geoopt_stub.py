@@ -26,7 +26,21 @@ class ManifoldTensor(torch.Tensor):
     pass
 
 
-def _rebuild(data, manifold, requires_grad):
+def _rebuild(*args):
+    """geoopt.tensor._rebuild_manifold_parameter.  geoopt 0.5.0 pickles a ManifoldParameter as
+    `_rebuild_manifold_parameter(*tensor_rebuild_args, cls, manifold, requires_grad)`, the leading arguments being those of
+    `torch._utils._rebuild_tensor_v2` (storage, offset, size, stride, requires_grad, hooks[, metadata]); this stub's own
+    pickles (and those of the oracle's shim) carry `(data, manifold, requires_grad)`.  Both layouts are accepted; the class named
+    in the pickle is replaced by the stub's, the manifold object is kept as an attribute and otherwise ignored."""
+    if len(args) == 3 and isinstance(args[0], torch.Tensor):
+        data, manifold, requires_grad = args
+    else:
+        if len(args) < 7:
+            raise TypeError("geoopt stub: unknown ManifoldParameter pickle layout (%d arguments)" % len(args))
+        from torch._utils import _rebuild_tensor_v2
+
+        data = _rebuild_tensor_v2(*args[:-3])
+        manifold, requires_grad = args[-2], args[-1]
     return ManifoldParameter(data, manifold=manifold, requires_grad=requires_grad)
 
 

@@ -38,7 +38,7 @@ int ensure_workspace(hypad_ctx* ctx, size_t bytes) {
 }
 
 int launch_forward(const hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_t row_stride, const float* z_in,
-                   int stages, const hypad_forward_out* out, cudaStream_t stream);
+                   int stages, const hypad_forward_out* out, cudaStream_t stream, const int* guard);
 int launch_forward_tc(const hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_t row_stride, const float* z_in,
                       int stages, const hypad_forward_out* out, cudaStream_t stream);
 int pack_tc(hypad_ctx* ctx, const hypad_weights* w, cudaStream_t stream);
@@ -302,15 +302,27 @@ int hypad_forward(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_
     int rc = check_forward_args(ctx, x, n, row_stride, z_in, stages, out);
     if (rc != HYPAD_OK || n == 0) return rc;
     HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
-    return launch_forward_tc(ctx, x, x_is_f64, n, row_stride, z_in, stages, out, (cudaStream_t)stream);
+    rc = launch_forward_tc(ctx, x, x_is_f64, n, row_stride, z_in, stages, out, (cudaStream_t)stream);
+    if (rc != HYPAD_OK || ctx->strict_range) return rc;
+    // Range fallback, decided on the device: the FFMA kernel is queued behind the tensor-core kernel and returns at once unless
+    // that kernel raised the range flag, in which case it recomputes every output of the call (no operand limits there).
+    return launch_forward(ctx, x, x_is_f64, n, row_stride, z_in, stages, out, (cudaStream_t)stream, ctx->tc_error);
 }
+
+int hypad_ctx_set_strict_range(hypad_ctx* ctx, int strict) {
+    HYPAD_REQUIRE(ctx != nullptr, "hypad_ctx_set_strict_range: NULL context");
+    ctx->strict_range = strict != 0;
+    return HYPAD_OK;
+}
+
+int64_t hypad_ctx_range_fallbacks(hypad_ctx* ctx) { return ctx ? (int64_t)ctx->range_fallbacks : 0; }
 
 int hypad_forward_ffma(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_t row_stride, const float* z_in,
                        int stages, const hypad_forward_out* out, void* stream) {
     int rc = check_forward_args(ctx, x, n, row_stride, z_in, stages, out);
     if (rc != HYPAD_OK || n == 0) return rc;
     HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
-    return launch_forward(ctx, x, x_is_f64, n, row_stride, z_in, stages, out, (cudaStream_t)stream);
+    return launch_forward(ctx, x, x_is_f64, n, row_stride, z_in, stages, out, (cudaStream_t)stream, nullptr);
 }
 
 int hypad_forward_debug_cycles(hypad_ctx* ctx, int enable, long long* h_out) {
@@ -335,15 +347,19 @@ int hypad_ctx_poll_error(hypad_ctx* ctx) {
     HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
     int flag = 0;
     HYPAD_CUDA_TRY(cudaMemcpy(&flag, ctx->tc_error, sizeof(int), cudaMemcpyDeviceToHost));
-    if (flag == 2) {
+    if (flag & 1) {
+        set_error("forward_tc_kernel: a barrier wait timed out (pipeline protocol error)");
+        return HYPAD_ECUDA;
+    }
+    if (flag & 2) {  // strict mode (or a call still in flight when polled): the outputs of that call are saturated
         set_error("forward_tc_kernel: an activation left the range of the scaled fp16 operand split (|x| < 63, linear / critic "
                   "activations < 255); results of that call are invalid -- use hypad_forward_ffma for such data");
         HYPAD_CUDA_TRY(cudaMemset(ctx->tc_error, 0, sizeof(int)));
         return HYPAD_EINVAL;
     }
-    if (flag) {
-        set_error("forward_tc_kernel: a barrier wait timed out (pipeline protocol error)");
-        return HYPAD_ECUDA;
+    if (flag & 4) {  // the guarded FFMA kernel redid the call: valid results, slower path -- reported, not an error
+        ctx->range_fallbacks += 1;
+        HYPAD_CUDA_TRY(cudaMemset(ctx->tc_error, 0, sizeof(int)));
     }
     return HYPAD_OK;
 }

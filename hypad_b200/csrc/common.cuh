@@ -118,7 +118,9 @@ struct hypad_ctx {
     unsigned char* tc_packed;   // TF32-split weight stages followed by the small-parameter block
     size_t tc_bytes;
     size_t tc_small_off;
-    int* tc_error;              // device flag raised when a barrier wait times out
+    int* tc_error;              // device flags: 1 barrier wait timed out, 2 operand range left, 4 range fallback served the call
+    bool strict_range;          // hypad_forward raises on a range violation instead of falling back to the FFMA kernel
+    long long range_fallbacks;  // polls that found a call served by the fallback
     long long* tc_debug;        // optional device cycle counters (hypad_forward_debug_cycles)
     unsigned char tc_prog_storage[2048];
 };

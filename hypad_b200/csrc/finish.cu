@@ -316,7 +316,10 @@ __global__ void combine_kernel(int mode, const double* __restrict__ c, const TR*
             case 4: o = cv * uv; break;                                  // critic_uncertainty
             case 5: o = (0.5 * cv) * uv + (0.5 * rv) * uv; break;        // sum_uncertainty
             case 6: o = rv; break;                                       // rec
-            case 7: o = rv * uv; break;                                  // rec_uncertainty
+            case 7:                                                      // rec_uncertainty: an fp32 tensor times the fp32 norms stays fp32
+                if (sizeof(TR) == 4) o = (double)__fmul_rn((float)rv, (float)uv);
+                else o = rv * uv;
+                break;
             default: o = (1.0 - lambda_rec) * (cv - 1.0) + lambda_rec * (rv - 1.0); break;  // score_anomalies "sum"
         }
         out[i] = o;
@@ -338,6 +341,7 @@ struct TwArgs {
     const double* errors;
     int64_t len, window_size, step;
     int n_analysis, ddof, pad, max_runs, n_slices;
+    int stats_f32;          // mean / std / threshold rounded to fp32 and combined in fp32 (find_anomalies on an fp32 torch tensor)
     int64_t k0;             // index of the first analysis window handled (outputs are indexed from 0)
     double* stats;          // [n_analysis][4]
     double* runs;           // [n_analysis][max_runs][3]
@@ -397,11 +401,17 @@ __global__ void __launch_bounds__(32) tw_final_kernel(const TwArgs a, int mode) 
         if (lane == 0) a.mean[k] = acc / (double)n;
     } else {
         if (lane == 0) {
-            const double mean = a.mean[k];
-            const double sd = sqrt(acc / (double)(n - a.ddof));
+            double mean = a.mean[k];
+            double sd = sqrt(acc / (double)(n - a.ddof));
+            double thr = mean + 4.0 * sd;  // _fixed_threshold, k = 4 (:1098-1114)
+            if (a.stats_f32) {
+                mean = (double)(float)mean;
+                sd = (double)(float)sd;
+                thr = (double)__fadd_rn((float)mean, __fmul_rn(4.0f, (float)sd));
+            }
             a.stats[k * 4 + 0] = mean;
             a.stats[k * 4 + 1] = sd;
-            a.stats[k * 4 + 2] = mean + 4.0 * sd;  // _fixed_threshold, k = 4 (:1098-1114)
+            a.stats[k * 4 + 2] = thr;
             a.cnt[k * 2] = 0;
             a.cnt[k * 2 + 1] = 0;
             a.below[k] = 0ull;
@@ -602,7 +612,12 @@ __global__ void __launch_bounds__(RB) tw_window_kernel(const TwArgs a) {
     const double dm = s1 / (double)n;                   // mean - c
     double var = (s2 - s1 * dm) / (double)(n - a.ddof);  // sum((x-mean)^2) = sum((x-c)^2) - n (mean-c)^2
     var = var > 0.0 ? var : 0.0;
-    const double mean = c + dm, sd = sqrt(var), thr = mean + 4.0 * sd;  // _fixed_threshold, k = 4 (:1098-1114)
+    double mean = c + dm, sd = sqrt(var), thr = mean + 4.0 * sd;  // _fixed_threshold, k = 4 (:1098-1114)
+    if (a.stats_f32) {  // torch fp32 tensor: errors.mean(), errors.std() and mean + 4 * std are fp32 values
+        mean = (double)(float)mean;
+        sd = (double)(float)sd;
+        thr = (double)__fadd_rn((float)mean, __fmul_rn(4.0f, (float)sd));
+    }
     if (tid == 0) {
         a.stats[k * 4 + 0] = mean;
         a.stats[k * 4 + 1] = sd;
@@ -844,13 +859,16 @@ static int threshold_windows_impl(hypad_ctx* ctx, const double* errors, int64_t 
     HYPAD_REQUIRE(first_window >= 0 && (first_window + n_analysis - 1) * step < len, "hypad_threshold_windows: last window starts beyond the data");
     HYPAD_REQUIRE(anomaly_padding >= 0 && anomaly_padding <= TW_MAXPAD, "hypad_threshold_windows: padding %d outside 0..%d",
                   anomaly_padding, TW_MAXPAD);
-    HYPAD_REQUIRE(ddof == 0 || ddof == 1, "hypad_threshold_windows: ddof must be 0 or 1");
+    const int stats_f32 = (ddof & HYPAD_STATS_F32) ? 1 : 0;
+    ddof &= ~HYPAD_STATS_F32;
+    HYPAD_REQUIRE(ddof == 0 || ddof == 1, "hypad_threshold_windows: ddof must be 0 or 1 (optionally | HYPAD_STATS_F32)");
     HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
     const int64_t wlen = window_size < len ? window_size : len;
     TwArgs a;
     a.errors = errors; a.len = len; a.window_size = window_size; a.step = step;
     a.k0 = first_window;
     a.n_analysis = (int)n_analysis; a.ddof = ddof; a.pad = anomaly_padding; a.max_runs = max_runs;
+    a.stats_f32 = stats_f32;
     a.n_slices = (int)ceil_div(wlen, TW_CHUNK);
     a.stats = stats; a.runs = runs; a.n_runs = n_runs;
     const size_t na = (size_t)n_analysis, mr = (size_t)max_runs;

@@ -49,6 +49,7 @@ struct FwdParams {
     int32_t want_rowstats;   // rec and/or unorm are produced
     hypad_forward_out out;
     NetProgram prog;
+    const int* guard;        // when set: the kernel only works if (*guard & 2), i.e. the tensor-core kernel left its operand range
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) forward_kernel(const __grid_const
     double* red = reinterpret_cast<double*>(sW);  // row phases reuse the (idle) weight stage: 3*2*64 doubles = 3 KB
     int pass_parity = 0;
 
+    if (P.guard != nullptr && !(*P.guard & 2)) return;  // range fallback of hypad_forward: nothing to redo
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int tm = (warp & 1) * 4 + (lane >> 3);
@@ -455,10 +457,17 @@ size_t forward_smem_bytes(int S8) {
     return (size_t)(S8 + 2 * ACT_ROWS) * LDM * sizeof(float) + (2 * WSTAGE_FLOATS + 2 * BIAS_FLOATS) * sizeof(float);
 }
 
+// range flag (2) -> fallback-served flag (4), after the guarded FFMA kernel has redone the call's outputs
+__global__ void range_fallback_done_kernel(int* flag) {
+    const int f = *flag;
+    if (f & 2) *flag = (f & ~2) | 4;
+}
+
 int launch_forward(const hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_t row_stride, const float* z_in,
-                   int stages, const hypad_forward_out* out, cudaStream_t stream) {
+                   int stages, const hypad_forward_out* out, cudaStream_t stream, const int* guard) {
     FwdParams P;
     memset(&P, 0, sizeof(P));
+    P.guard = guard;
     P.x = x;
     P.z_in = z_in;
     P.packed = ctx->packed;
@@ -502,6 +511,10 @@ int launch_forward(const hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n,
     const int64_t grid = ntiles < (int64_t)sms * per_sm ? ntiles : (int64_t)sms * per_sm;
     forward_kernel<<<(unsigned)grid, NTHREADS, smem, stream>>>(P);
     HYPAD_LAUNCH_CHECK();
+    if (guard != nullptr) {
+        range_fallback_done_kernel<<<1, 1, 0, stream>>>(const_cast<int*>(guard));
+        HYPAD_LAUNCH_CHECK();
+    }
     return HYPAD_OK;
 }
 

@@ -157,6 +157,7 @@ class ShardedScorer:
         out = self.finish(kmax, rec, unorm, n_windows, combination)
         if index is not None:
             out["intervals"] = self.find_anomaly_intervals(out["final"], index, 0.33, 0.1, anomaly_padding=50, ddof=1)
+        sc.poll_error()  # after the collectives, so that every rank still reaches them
         return out
 
     def score_multivariate(self, local_rows, n_rows, combination="mult", index=None):

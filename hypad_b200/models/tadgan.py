@@ -44,6 +44,17 @@ def _forward(net, x, z_in, stages, n, **outs):
                                                 net.ctx.stream()))
 
 
+def poll_error(*modules):
+    """Synchronises and raises if a kernel launched by one of these modules' forward() reported an error (include/hypad_b200.h,
+    hypad_ctx_poll_error).  forward() itself never synchronises -- the reference's `.cpu()` after every batch
+    (anomaly_detection.py:90-95) is where a caller naturally places this.  An operand outside the tensor-core kernel's range is
+    not an error: that call was redone by the FFMA kernel on the device."""
+    for m in modules:
+        kw = {"encoder": m} if isinstance(m, Encoder) else {"decoder": m} if isinstance(m, Decoder) else {"critic_x": m}
+        net = _weights.packed_net(**kw)
+        _native.check(net.ctx.lib.hypad_ctx_poll_error(net.ctx.handle))
+
+
 class Encoder(nn.Module):
     """BiLSTM(signal_shape -> 2x50, sequence length 1) + Linear(100 -> latent): models/tadgan.py:10-27."""
 

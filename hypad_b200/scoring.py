@@ -326,28 +326,39 @@ def _np_sum(vals):
 
 
 def _np_average(values, weights):
-    """np.average(values, weights=weights) (:1297): (v*w).sum() / w.sum(), bit for bit, without numpy's per-call cost."""
-    return _ieee_div(_np_sum([v * w for v, w in zip(values, weights)]), _np_sum(weights))
+    """np.average(values, weights=weights) (:1297): (v*w).sum() / w.sum(), bit for bit, without numpy's per-call cost.
+    Like numpy it refuses a zero weight sum (merged runs of one position each: end - start == 0)."""
+    scl = _np_sum(weights)
+    if scl == 0.0:
+        raise ZeroDivisionError("Weights sum to zero, can't be normalized")
+    return _ieee_div(_np_sum([v * w for v, w in zip(values, weights)]), scl)
 
 
-def intervals_from_runs(stats, runs, n_runs, step, min_percent):
+def _f32(x):
+    return float(np.float32(x))
+
+
+def intervals_from_runs(stats, runs, n_runs, step, min_percent, f32=False):
     """Host tail of find_anomalies on the few runs per window: prune (:1203-1237), score (:1240-1269), merge (:1272-1313).
-    Plain Python floats: the arrays hold a handful of values per window and numpy's per-call overhead would dominate."""
+    Plain Python floats: the arrays hold a handful of values per window and numpy's per-call overhead would dominate.
+    f32: the scores came as a float32 torch tensor, so `(max - threshold) / (mean + std)` is single-precision arithmetic."""
     stats, n_runs = np.asarray(stats).tolist(), np.asarray(n_runs).tolist()
     sequences = []
     for k in range(len(stats)):
         mean, std, thr, max_below = stats[k]
         rk = runs[k][: int(n_runs[k])].tolist()
         rows = [(max_below, -1.0, -1.0)] + [(r[2], r[0], r[1]) for r in rk]
-        rows.sort(key=lambda t: -t[0])  # descending by max error, stable
+        # descending by max error, stable, NaN last (pandas sort_values(ascending=False), :1224)
+        rows.sort(key=lambda t: (t[0] != t[0], -t[0] if t[0] == t[0] else 0.0))
         last = -1  # the last position whose drop to the next maximum is not "too small" (increase < min_percent is False)
         for i in range(len(rows) - 1):
             if not (_ieee_div(rows[i][0] - rows[i + 1][0], rows[i][0]) < min_percent):
                 last = i
-        denom = mean + std
+        denom = _f32(mean + std) if f32 else mean + std
         shift = k * step
         for m, s, e in rows[: last + 1]:
-            sequences.append([s + shift, e + shift, _ieee_div(m - thr, denom)])
+            score = _f32(_ieee_div(_f32(m - thr), denom)) if f32 else _ieee_div(m - thr, denom)
+            sequences.append([s + shift, e + shift, score])
     if not sequences:
         return []
     sequences.sort(key=lambda s: s[0])
@@ -378,13 +389,36 @@ def intervals_to_index(merged, index):
 
 
 def find_anomaly_intervals(errors, index, window_size_portion=None, window_step_size_portion=None, window_size=None,
-                           window_step_size=None, min_percent=0.1, anomaly_padding=50, ddof=0):
-    """find_anomalies(..., fixed_threshold=True) on a device array; returns (K,3) float64 [index[start], index[end], score]."""
+                           window_step_size=None, min_percent=0.1, anomaly_padding=50, ddof=0, stats_f32=False):
+    """find_anomalies(..., fixed_threshold=True) on a device array; returns (K,3) float64 [index[start], index[end], score].
+    stats_f32: the reference would be handed a float32 torch tensor (statistics, threshold and scores in single precision)."""
     n = errors.numel()
     wsize, step, count = analysis_windows(n, window_size, window_size_portion, window_step_size, window_step_size_portion)
-    stats, runs, n_runs = threshold_windows(errors, wsize, step, count, ddof, anomaly_padding)
-    merged = intervals_from_runs(stats, runs, n_runs, step, min_percent)
+    stats, runs, n_runs = threshold_windows(errors, wsize, step, count, ddof | (_native.STATS_F32 if stats_f32 else 0), anomaly_padding)
+    merged = intervals_from_runs(stats, runs, n_runs, step, min_percent, f32=stats_f32)
     return intervals_to_index(merged, index)
+
+
+def univariate_hyperbolic_semantics(combination):
+    """What reaches find_anomalies on the reference's univariate hyperbolic path (utils/anomaly_detection_utils.py:54-94), where
+    the critic scores are a float64 ndarray, the reconstruction scores a float32 torch tensor and the norms a float32 ndarray:
+      mult, uncertainty        float64 torch tensor  -> unbiased std (ddof 1)              (:340, :343)
+      critic, critic_uncertainty  float64 ndarray    -> ddof 0                             (:345, :349)
+      rec, rec_uncertainty     float32 torch tensor  -> ddof 1, single-precision statistics (:356, :360)
+      sum, sum_uncertainty     `ndarray + tensor` raises TypeError in the reference (:338, :352-355); so does this path.
+    Returns (ddof, stats_f32)."""
+    if combination in ("mult", "uncertainty"):
+        return 1, False
+    if combination in ("critic", "critic_uncertainty"):
+        return 0, False
+    if combination in ("rec", "rec_uncertainty"):
+        return 1, True
+    if combination in ("sum", "sum_uncertainty"):
+        raise TypeError("combination %r adds a float64 ndarray and a float32 torch tensor on the univariate hyperbolic path; the "
+                        "reference raises here too (utils/anomaly_detection_utils.py:338, :352-355: 'Concatenation operation is "
+                        "not implemented for NumPy arrays'); it is defined for multivariate scoring, where both are ndarrays"
+                        % (combination,))
+    raise ValueError("unknown combination %r" % (combination,))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -462,9 +496,25 @@ class WindowScorer:
         return res
 
     def poll_error(self):
-        """Synchronises and raises if the forward kernel reported an error: a bounded barrier wait timed out, or an
-        operand left the range of the scaled fp16 split (|x| < 63; see include/hypad_b200.h, hypad_forward)."""
+        """Synchronises and raises if the forward kernel reported an error (a bounded barrier wait timed out; in strict mode an
+        operand outside the range of the scaled fp16 split, |x| < 63 -- include/hypad_b200.h, hypad_forward).  A call that left the
+        range was redone by the FFMA kernel on the device: valid results, warned about once per scorer and counted in
+        `range_fallbacks`."""
         check(self.net.ctx.lib.hypad_ctx_poll_error(self.net.ctx.handle))
+        n = self.range_fallbacks
+        if n and not getattr(self, "_warned_fallback", False):
+            import warnings
+
+            self._warned_fallback = True
+            warnings.warn("hypad_b200: an operand left the tensor-core kernel's range (|x| < 63, linear activations < 255); the "
+                          "call was served by the FFMA kernel instead (valid results, about 5x slower)", RuntimeWarning, stacklevel=2)
+
+    @property
+    def range_fallbacks(self):
+        return int(self.net.ctx.lib.hypad_ctx_range_fallbacks(self.net.ctx.handle))
+
+    def set_strict_range(self, strict=True):
+        check(self.net.ctx.lib.hypad_ctx_set_strict_range(self.net.ctx.handle, int(bool(strict))))
 
     # -- scoring -------------------------------------------------------------------------------------------
     def critic_scores(self, critic, n_windows):
@@ -483,6 +533,9 @@ class WindowScorer:
         `poll_error()` once after the last one.
         """
         keep = tuple(keep)
+        stats_f32 = False
+        if self.hyperbolic and not multivariate:
+            univariate_hyperbolic_semantics(combination)  # unknown / undefined combinations fail before any work is queued
         need = keep if self.hyperbolic else tuple(set(keep) | {"eucl"})
         fw = self.forward(x, sliding, need)
         n, S = fw["critic"].shape[0], self.S
@@ -500,8 +553,8 @@ class WindowScorer:
                 out["kmax"], out["critic_scores_full"] = kmax, cs_full
                 cs = cs_full[:n]
             out["critic_scores"] = cs
+            ddof, stats_f32 = (0, False) if multivariate else univariate_hyperbolic_semantics(combination)
             final = combine(combination, cs, rec, fw["unorm"], n=n)
-            ddof = 0 if multivariate else 1  # torch tensor (unbiased) vs ndarray
         elif multivariate:
             # utils/anomaly_detection_utils.py:153-213, Euclidean branch: one score per row
             if sliding:
@@ -543,7 +596,8 @@ class WindowScorer:
             if multivariate:
                 out["intervals"] = find_anomaly_intervals(final, index, 0.2, 0.1, anomaly_padding=200, ddof=ddof)
             else:
-                out["intervals"] = find_anomaly_intervals(final, index, 0.33, 0.1, anomaly_padding=50, ddof=ddof)
+                out["intervals"] = find_anomaly_intervals(final, index, 0.33, 0.1, anomaly_padding=50, ddof=ddof,
+                                                          stats_f32=stats_f32)
         # loud failure: pipeline protocol error, or an operand outside the tensor-core path's range.  Last, so that the
         # synchronisation it implies does not stall the launches above.
         if poll:

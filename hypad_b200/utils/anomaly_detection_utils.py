@@ -70,12 +70,24 @@ def compute_critic_scores(rec_scores, critic_score, true_signal, params, path):
 
 
 def combine_scores(combination, critic_scores=[], rec_scores=[], recons_signal=[]):
-    """utils/anomaly_detection_utils.py:336-362.  Returns a float64 torch tensor when rec_scores is a tensor (as the
-    reference's numpy-times-tensor arithmetic does), else a float64 ndarray."""
+    """utils/anomaly_detection_utils.py:336-362, including what the reference's mixed numpy / torch arithmetic makes of the
+    operand types (critic_scores float64 ndarray, recons_signal float32 ndarray, rec_scores a float32 torch tensor on the
+    univariate path and a float64 ndarray on the multivariate one):
+      mult, uncertainty     -> float64 torch tensor when rec_scores is a tensor, else float64 ndarray
+      critic                -> critic_scores itself;  critic_uncertainty -> float64 ndarray
+      rec                   -> rec_scores itself;     rec_uncertainty -> float32 tensor (fp32 product) / float64 ndarray
+      sum, sum_uncertainty  -> TypeError when rec_scores is a tensor (`ndarray + Tensor`, :338 / :352-355), else float64 ndarray."""
     if combination not in _sc.HYPERBOLIC_COMBINATIONS:
         raise UnboundLocalError("local variable 'final_scores' referenced before assignment")  # what the reference raises
-    dev = _dev()
     want_tensor = isinstance(rec_scores, torch.Tensor)
+    if want_tensor and combination in ("sum", "sum_uncertainty"):
+        raise TypeError("Concatenation operation is not implemented for NumPy arrays, use np.concatenate() instead. Please do "
+                        "not rely on this error; it may not be given on all Python implementations.")
+    if combination == "critic":
+        return critic_scores
+    if combination == "rec":
+        return rec_scores
+    dev = _dev()
     c = _sc._as_dev(critic_scores, torch.float64, dev) if combination in _sc._NEEDS_CRITIC else None
     r = None
     if combination not in ("critic", "critic_uncertainty"):
@@ -91,6 +103,10 @@ def combine_scores(combination, critic_scores=[], rec_scores=[], recons_signal=[
         n_u = r.shape[0] if r is not None else c.shape[0]
         u = u[:n_u]
     out = _sc.combine(combination, c, r, u)
+    if combination == "critic_uncertainty":
+        return _np(out)
+    if combination == "rec_uncertainty" and want_tensor and rec_scores.dtype == torch.float32:
+        return out.float().cpu()  # the kernel formed the product in fp32; the widened copy narrows back without loss
     return out.cpu() if want_tensor else _np(out)
 
 
@@ -229,9 +245,10 @@ def find_anomalies(errors, index, z_range=(0, 10), window_size=None, window_size
     if lower_threshold:
         raise NotImplementedError("hypad_b200: lower_threshold=True is not used by the reference's callers")
     ddof = 1 if isinstance(errors, torch.Tensor) else 0
+    f32 = isinstance(errors, torch.Tensor) and errors.dtype == torch.float32  # fp32 tensor: fp32 mean / std / threshold / scores
     e = _sc._as_dev(errors, torch.float64, _dev()).reshape(-1)
     return _sc.find_anomaly_intervals(e, index, window_size_portion, window_step_size_portion, window_size, window_step_size,
-                                      min_percent, anomaly_padding, ddof)
+                                      min_percent, anomaly_padding, ddof, stats_f32=f32)
 
 
 # ---- orchestration ----------------------------------------------------------------------------------------------
@@ -330,9 +347,12 @@ def univariate_anomaly_detection(recons_signal, true_signal, params, combination
         critic_scores = []
         if combination in _sc._NEEDS_CRITIC:
             critic_scores = compute_critic_scores(rec, critic_score, np.asarray(true_signal), params, path)
-        final = combine_scores(combination, critic_scores, rec.cpu(), recons_signal).reshape(-1)  # float64 torch tensor
+        final = combine_scores(combination, critic_scores, rec.cpu(), recons_signal).reshape(-1)  # types as in the reference
     intervals = find_anomalies(final, true_index, window_size_portion=0.33, window_step_size_portion=0.1, fixed_threshold=True)
-    pd.DataFrame(intervals, columns=["start", "end", "score"]).to_csv(path + "anomalies.csv")
+    if len(intervals):
+        # :96-98 sits in a try block: with no interval the reference's find_anomalies returns a shape-(0,) array, the DataFrame
+        # constructor raises, the except swallows it and no anomalies.csv is written
+        pd.DataFrame(intervals, columns=["start", "end", "score"]).to_csv(path + "anomalies.csv")
     univariate_anomaly_detection.last_counts = None
     if known_anomalies is not None or getattr(params, "save_result", False):
         df = None

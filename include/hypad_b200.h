@@ -33,7 +33,11 @@ extern "C" {
 #define HYPAD_ENOMEM (-3)   /* workspace allocation failed */
 #define HYPAD_ESTATE (-4)   /* weights not packed / context misuse */
 
-#define HYPAD_ABI_VERSION 1
+#define HYPAD_ABI_VERSION 2
+/* OR-ed into the `ddof` argument of hypad_threshold_windows*: mean, std and threshold are rounded to single precision and
+ * the threshold is formed in single precision -- what find_anomalies does when handed a float32 torch tensor
+ * (combination "rec" / "rec_uncertainty" of the univariate hyperbolic path, utils/anomaly_detection_utils.py:356-360). */
+#define HYPAD_STATS_F32 16
 
 typedef struct hypad_ctx hypad_ctx;
 
@@ -101,9 +105,12 @@ int hypad_pack_weights(hypad_ctx* ctx, const hypad_weights* w, void* stream);
  *   z_in        : when HYPAD_STAGE_ENCODER is not requested and HYPAD_STAGE_DECODER is, the latent
  *                 input (N, latent) fp32 of Decoder.forward; else NULL.
  * Contractions run on the tensor cores on a scaled hi/lo fp16 split of both operands (fp32-class accuracy,
- * csrc/forward_tc.cu).  Operand range: |x| < 63, linear-layer / LeakyReLU activations < 255, weights of any
- * magnitude (scaled per layer at pack time); a value outside raises the context's sticky error, reported by
- * hypad_ctx_poll_error -- hypad_forward_ffma has no such limit.
+ * csrc/forward_tc.cu).  Operand range of that kernel: |x| < 63, linear-layer / LeakyReLU activations < 255, weights of
+ * any magnitude (scaled per layer at pack time).  A call that leaves the range is redone, on the device and without a host
+ * round trip, by the FFMA kernel of hypad_forward_ffma, which is queued behind the tensor-core kernel and returns at once
+ * unless that kernel raised its range flag: the results are valid either way, hypad_ctx_poll_error counts such calls
+ * (hypad_ctx_range_fallbacks).  With hypad_ctx_set_strict_range(ctx, 1) there is no fallback: the violation raises the
+ * context's sticky error and hypad_ctx_poll_error reports it.
  */
 int hypad_forward(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_t row_stride,
                   const float* z_in, int stages, const hypad_forward_out* out, void* stream);
@@ -112,8 +119,12 @@ int hypad_forward(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_
 int hypad_forward_ffma(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_t row_stride,
                        const float* z_in, int stages, const hypad_forward_out* out, void* stream);
 /* Synchronises with the device and reports a sticky error raised inside hypad_forward's kernel (a bounded
- * barrier wait that timed out).  0 = healthy. */
+ * barrier wait that timed out; in strict mode an operand outside the range).  0 = healthy. */
 int hypad_ctx_poll_error(hypad_ctx* ctx);
+/* strict != 0: hypad_forward does not fall back to the FFMA kernel on a range violation, it reports it (see hypad_forward). */
+int hypad_ctx_set_strict_range(hypad_ctx* ctx, int strict);
+/* Number of hypad_ctx_poll_error calls that found a hypad_forward call served by the FFMA fallback since the context was made. */
+int64_t hypad_ctx_range_fallbacks(hypad_ctx* ctx);
 /* Diagnostic: enable/disable per-role cycle counters of hypad_forward's kernel (CTA 0) and read them back into
  * h_out (host, HYPAD_DEBUG_SLOTS values): [0] epilogue total, [1] epilogue waiting for accumulators, [2] MMA warp waiting
  * for operands, [3] MMA warp waiting for weights, [4] producer waiting for free slots, [5] operand (re)load + hand-over,
@@ -194,7 +205,9 @@ int hypad_zscore_clip(hypad_ctx* ctx, const void* x, int x_is_f32, int64_t len, 
 
 /* utils/anomaly_detection_utils.py:336-362 combine_scores on device arrays (float64 result of length n).
  * mode: 0 mult, 1 uncertainty, 2 sum, 3 critic, 4 critic_uncertainty, 5 sum_uncertainty, 6 rec, 7 rec_uncertainty,
- *       8 euclidean "sum" of score_anomalies (:558, lambda_rec) .  rec may be fp32 (rec_is_f32) or fp64. */
+ *       8 euclidean "sum" of score_anomalies (:558, lambda_rec) .  rec may be fp32 (rec_is_f32) or fp64.  Every mode is
+ * evaluated in float64 on the widened inputs, as numpy does with the reference's float64 critic scores -- except mode 7
+ * with an fp32 rec, which is the fp32 product of an fp32 torch tensor and the fp32 norms (:360). */
 int hypad_combine_scores(int mode, const double* critic_scores, const void* rec, int rec_is_f32, const float* unorm,
                          double lambda_rec, int64_t n, double* out, void* stream);
 

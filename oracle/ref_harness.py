@@ -150,8 +150,9 @@ def run_univariate(values, timestamps, hyperbolic, combination, rec_error="dtw",
         if hyperbolic:
             cap["eucl_recons"] = np.asarray(torch.load(p + "eucl_recons.pt", weights_only=False))
             cap["real_hyper"] = np.asarray(torch.load(p + "real_hyper.pt", weights_only=False))
-        with open(p + "critic_scores.pickle", "rb") as fh:
-            cap["critic_scores"] = np.asarray(pickle.load(fh))
+        if os.path.exists(p + "critic_scores.pickle"):  # absent for combination in (rec, rec_uncertainty): :68-82
+            with open(p + "critic_scores.pickle", "rb") as fh:
+                cap["critic_scores"] = np.asarray(pickle.load(fh))
         for ret in ("point", "area", "dtw"):
             if os.path.exists(p + ret + ".pickle"):
                 with open(p + ret + ".pickle", "rb") as fh:

@@ -52,6 +52,29 @@ def full_signal(g):
     return sig
 
 
+def long_signal(T, seed=0):
+    """BASELINE config 3's generator (bench.py:make_signal): sine + a 5-sample burst every 50,000 steps, MinMax to [-1, 1] the
+    way sklearn does it (utils/dataloader.py:88-89); float64 (T,)."""
+    from oracle import hypad_oracle as ho
+
+    t = np.arange(T, dtype=np.float64)
+    s = np.sin(2 * np.pi * t / 50.0)
+    rng = np.random.default_rng(seed)
+    for k in range(25000, T, 50000):
+        s[k:k + 5] += rng.uniform(2, 4)
+    return ho.minmax_scale(s)
+
+
+def long_golden_signal(g):
+    """Scaled signal of tests/golden/cfg3_long300k.npz as the reference's dataset produced it (its CSV round trip moves some
+    samples by an ulp against long_signal()); the last sample, which is in no window, comes from the generator."""
+    sig = g["signal"].copy()
+    gen = long_signal(sig.shape[0])
+    assert np.abs(gen[:-1] - sig[:-1]).max() <= 4e-16
+    sig[-1] = gen[-1]
+    return sig
+
+
 @pytest.fixture(scope="session")
 def cuda_device():
     import torch

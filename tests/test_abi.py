@@ -28,7 +28,7 @@ def test_library_is_built_and_exports_the_header():
         assert hasattr(lib, s), "library does not export %s" % s
     assert sorted(_native.EXPORTED_SYMBOLS) == syms, "ctypes binding and header disagree"
     lib.hypad_abi_version.restype = ctypes.c_int
-    assert lib.hypad_abi_version() == 1
+    assert lib.hypad_abi_version() == 2
 
 
 def test_ctx_create_fails_loudly_without_cuda():
@@ -141,7 +141,7 @@ C_CLIENT = r"""
 
 int main(void) {
     float out[4];
-    if (hypad_abi_version() != 1) return 1;
+    if (hypad_abi_version() != HYPAD_ABI_VERSION) return 1;
     if (hypad_square_norm(NULL, 4, 3, out, NULL) == 0) return 2;
     if (strstr(hypad_last_error(), "hypad_square_norm") == NULL) return 3;
     if (hypad_segments_aggregate(NULL, NULL, 0, NULL, 1.0, 0, NULL, NULL) == 0) return 4;

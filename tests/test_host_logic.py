@@ -217,3 +217,53 @@ def test_overlap_segment_counts_equal_the_nested_loops():
             expected = [(float(a) + 0.5, float(b) + 0.5) for a, b in expected]
         pe, po = adu._pad(expected), adu._pad(observed)
         assert adu._overlap_segment(pe, po) == naive(pe, po), (expected, observed)
+
+
+def test_merge_tail_degenerate_inputs_follow_numpy_and_pandas():
+    """merged runs of one position each have weights (end - start) that sum to zero -- np.average raises
+    ZeroDivisionError (utils/anomaly_detection_utils.py:1297; recorded from the reference in tests/golden/pieces_r2.npz) and so
+    must the host tail; a NaN run maximum sorts LAST in the reference's `sort_values(ascending=False)` (:1224)."""
+    from hypad_b200 import scoring
+
+    assert str(golden("pieces_r2.npz")["merge_zero_weights"]).startswith("ZeroDivisionError")
+    # two single-position runs next to each other in one window: merged group, both weights 0
+    stats = np.asarray([[1.0, 0.5, 3.0, 2.0]])
+    runs = np.zeros((1, 2, 3))
+    runs[0, 0] = (5, 5, 9.0)
+    runs[0, 1] = (6, 6, 8.0)
+    with pytest.raises(ZeroDivisionError):
+        scoring.intervals_from_runs(stats, runs, np.asarray([2]), 10, 0.1)
+    with pytest.raises(ZeroDivisionError):
+        ho._merge_sequences([(5, 5, 1.0), (6, 6, 2.0)])
+    # NaN maximum: pandas puts it last, so the prune sees [9, 2 (max_below), nan]; (2 - nan) / 2 < 0.1 is False, hence the last
+    # "not too small" position is 1 and the reference keeps the 9-run AND the max_below pseudo row (start = stop = -1, :1192)
+    import pandas as pd
+
+    order = pd.DataFrame({"max_error": [2.0, 9.0, np.nan]}).sort_values("max_error", ascending=False)["max_error"].tolist()
+    assert order[:2] == [9.0, 2.0] and np.isnan(order[2])
+    runs[0, 0] = (5, 9, 9.0)
+    runs[0, 1] = (40, 44, np.nan)
+    got = scoring.intervals_from_runs(stats, runs, np.asarray([2]), 10, 0.1)
+    assert [g[:2] for g in got] == [[-1.0, -1.0], [5.0, 9.0]]
+    np.testing.assert_allclose([g[2] for g in got], [(2.0 - 3.0) / 1.5, (9.0 - 3.0) / 1.5])
+
+
+def test_fp32_statistics_interval_scores_follow_the_oracle():
+    """find_anomalies on a float32 torch tensor (combination rec / rec_uncertainty): mean, std, threshold and the interval
+    scores are single-precision; host tail with f32=True against the oracle's torch-based restatement and the reference's own
+    result (tests/golden/pieces_r2.npz)."""
+    from hypad_b200 import scoring
+
+    p = golden("pieces_r2.npz")
+    e32, idx = p["fa32_errors"], p["fa32_index"]
+    e = e32.astype(np.float64)
+    wsize, step, count = scoring.analysis_windows(len(e), None, 0.33, None, 0.1)
+    stats, runs, n_runs = numpy_threshold_windows(e, wsize, step, count, 1, 50)
+    # what the kernel does with HYPAD_STATS_F32: round mean / std, form the threshold in fp32
+    stats[:, 0] = stats[:, 0].astype(np.float32)
+    stats[:, 1] = stats[:, 1].astype(np.float32)
+    stats[:, 2] = (stats[:, 0].astype(np.float32) + np.float32(4) * stats[:, 1].astype(np.float32)).astype(np.float32)
+    merged = scoring.intervals_from_runs(stats, runs, n_runs, step, 0.1, f32=True)
+    mine = np.asarray([[idx[int(s)], idx[int(t)], sc] for s, t, sc in merged], dtype=np.float64).reshape(-1, 3)
+    assert np.array_equal(mine[:, :2], p["fa32_uni"][:, :2])
+    np.testing.assert_allclose(mine[:, 2], p["fa32_uni"][:, 2], rtol=2e-6)
