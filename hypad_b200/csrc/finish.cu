@@ -226,58 +226,159 @@ __global__ void zscore_clip_kernel(const T* __restrict__ x, int64_t len, const d
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// centred rolling mean through a two-level fp64 prefix sum
+// centred rolling mean (pandas rolling(window, center=True, min_periods).mean()) through a two-level prefix sum.
+// pandas keeps a Kahan-compensated running sum and, when every value in the window is the same, returns that value itself
+// (roll_mean / calc_mean in pandas/_libs/window/aggregations.pyx: num_consecutive_same_value >= nobs).  Both matter to the
+// thresholding downstream: a flat stretch of the signal gives a flat stretch of scores, and a residue of a few ulps there
+// decides whether `errors > mean + 4 std` holds on a window whose std is itself a few ulps.  So the prefix sums are carried as
+// unevaluated (hi, lo) pairs (error-free TwoSum: the window sum is the correctly rounded difference of two exact prefixes up
+// to ~1e-32 of their magnitude) and a max-scan carries the index of the last position whose value differs from its
+// predecessor, which answers "is the window constant" in O(1).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int SCAN_CHUNK = 2048;  // elements per CTA (256 threads x 8)
 
-__global__ void __launch_bounds__(256) scan_local_kernel(const double* __restrict__ x, int64_t len, double* __restrict__ pre,
-                                                         double* __restrict__ totals) {
-    __shared__ double sh[256];
-    const int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK + threadIdx.x * 8;
-    double v[8];
-    double run = 0.0;
+struct dd {
+    double hi, lo;
+};
+__device__ __forceinline__ dd dd_add(dd a, dd b) {
+    const double s = __dadd_rn(a.hi, b.hi), bb = __dadd_rn(s, -a.hi);
+    double e = __dadd_rn(__dadd_rn(a.hi, -__dadd_rn(s, -bb)), __dadd_rn(b.hi, -bb));  // TwoSum error term
+    e = __dadd_rn(e, __dadd_rn(a.lo, b.lo));
+    dd r;
+    r.hi = __dadd_rn(s, e);
+    r.lo = __dadd_rn(e, -__dadd_rn(r.hi, -s));
+    return r;
+}
+__device__ __forceinline__ dd dd_add(dd a, double b) {
+    dd t;
+    t.hi = b;
+    t.lo = 0.0;
+    return dd_add(a, t);
+}
+
+struct ScanBufs {
+    double* pre_hi;      // [len] chunk-local inclusive prefix
+    double* pre_lo;
+    long long* lc;       // [len] chunk-local index of the last value change at or before i (-1: none in this chunk so far)
+    double* tot_hi;      // [nchunks] chunk totals -> exclusive prefix of the totals
+    double* tot_lo;
+    long long* tot_lc;   // [nchunks] last change inside the chunk -> last change before the chunk
+};
+
+__global__ void __launch_bounds__(256) scan_local_kernel(const double* __restrict__ x, int64_t len, ScanBufs sb) {
+    __shared__ double sh_hi[256], sh_lo[256];
+    __shared__ long long sh_lc[256];
+    const int tid = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK + tid * 8;
+    dd v[8];
+    long long c[8];
+    dd run;
+    run.hi = run.lo = 0.0;
+    long long last = -1;
+    double prev = base > 0 && base - 1 < len ? x[base - 1] : 0.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        v[k] = base + k < len ? x[base + k] : 0.0;
-        run += v[k];
+        const int64_t i = base + k;
+        const double xv = i < len ? x[i] : 0.0;
+        run = dd_add(run, xv);
         v[k] = run;
+        if (i < len && (i == 0 || xv != prev)) last = i;
+        c[k] = last;
+        prev = xv;
     }
-    sh[threadIdx.x] = run;
+    sh_hi[tid] = run.hi;
+    sh_lo[tid] = run.lo;
+    sh_lc[tid] = last;
     __syncthreads();
-    for (int o = 1; o < 256; o <<= 1) {  // Hillis-Steele inclusive scan of the thread sums
-        double t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0.0;
+    for (int o = 1; o < 256; o <<= 1) {  // Hillis-Steele inclusive scan of the thread sums / last changes
+        dd t;
+        t.hi = t.lo = 0.0;
+        long long l = -1;
+        if (tid >= o) {
+            t.hi = sh_hi[tid - o];
+            t.lo = sh_lo[tid - o];
+            l = sh_lc[tid - o];
+        }
         __syncthreads();
-        sh[threadIdx.x] += t;
+        if (tid >= o) {
+            dd m;
+            m.hi = sh_hi[tid];
+            m.lo = sh_lo[tid];
+            m = dd_add(t, m);
+            sh_hi[tid] = m.hi;
+            sh_lo[tid] = m.lo;
+            sh_lc[tid] = l > sh_lc[tid] ? l : sh_lc[tid];
+        }
         __syncthreads();
     }
-    const double off = threadIdx.x ? sh[threadIdx.x - 1] : 0.0;
+    dd off;
+    off.hi = tid ? sh_hi[tid - 1] : 0.0;
+    off.lo = tid ? sh_lo[tid - 1] : 0.0;
+    const long long loff = tid ? sh_lc[tid - 1] : -1;
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-        if (base + k < len) pre[base + k] = v[k] + off;
-    if (threadIdx.x == 255) totals[blockIdx.x] = sh[255];
+        if (base + k < len) {
+            const dd r = dd_add(off, v[k]);
+            sb.pre_hi[base + k] = r.hi;
+            sb.pre_lo[base + k] = r.lo;
+            sb.lc[base + k] = c[k] > loff ? c[k] : loff;
+        }
+    if (tid == 255) {
+        sb.tot_hi[blockIdx.x] = sh_hi[255];
+        sb.tot_lo[blockIdx.x] = sh_lo[255];
+        sb.tot_lc[blockIdx.x] = sh_lc[255];
+    }
 }
 // exclusive scan of the chunk totals in place (one warp, contiguous segments per lane)
-__global__ void __launch_bounds__(32) scan_totals_kernel(double* totals, int64_t nchunks) {
+__global__ void __launch_bounds__(32) scan_totals_kernel(ScanBufs sb, int64_t nchunks) {
     const int lane = threadIdx.x;
     const int64_t per = (nchunks + 31) / 32;
     const int64_t b = lane * per, e = b + per < nchunks ? b + per : nchunks;
-    double s = 0.0;
-    for (int64_t i = b; i < e; ++i) s += totals[i];
-    double incl = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    double run = incl - s;
+    dd s;
+    s.hi = s.lo = 0.0;
+    long long l = -1;
     for (int64_t i = b; i < e; ++i) {
-        const double t = totals[i];
-        totals[i] = run;
-        run += t;
+        dd t;
+        t.hi = sb.tot_hi[i];
+        t.lo = sb.tot_lo[i];
+        s = dd_add(s, t);
+        l = sb.tot_lc[i] > l ? sb.tot_lc[i] : l;
+    }
+    dd run;  // exclusive prefix over the lanes
+    run.hi = run.lo = 0.0;
+    long long lrun = -1;
+    for (int src = 0; src < 31; ++src) {
+        dd t;
+        t.hi = __shfl_sync(0xffffffffu, s.hi, src);
+        t.lo = __shfl_sync(0xffffffffu, s.lo, src);
+        const long long tl = __shfl_sync(0xffffffffu, l, src);
+        if (lane > src) {
+            run = dd_add(run, t);
+            lrun = tl > lrun ? tl : lrun;
+        }
+    }
+    for (int64_t i = b; i < e; ++i) {
+        dd t;
+        t.hi = sb.tot_hi[i];
+        t.lo = sb.tot_lo[i];
+        const long long tl = sb.tot_lc[i];
+        sb.tot_hi[i] = run.hi;
+        sb.tot_lo[i] = run.lo;
+        sb.tot_lc[i] = lrun;
+        run = dd_add(run, t);
+        lrun = tl > lrun ? tl : lrun;
     }
 }
-__global__ void rolling_mean_kernel(const double* __restrict__ pre, const double* __restrict__ offs, int64_t len, int64_t window,
-                                    int64_t min_periods, double* __restrict__ out) {
+__device__ __forceinline__ dd scan_prefix(const ScanBufs& sb, int64_t i) {  // exact-ish sum of x[0..i]
+    dd p, o;
+    p.hi = sb.pre_hi[i];
+    p.lo = sb.pre_lo[i];
+    o.hi = sb.tot_hi[i / SCAN_CHUNK];
+    o.lo = sb.tot_lo[i / SCAN_CHUNK];
+    return dd_add(o, p);
+}
+__global__ void rolling_mean_kernel(const double* __restrict__ x, ScanBufs sb, int64_t len, int64_t window, int64_t min_periods,
+                                    double* __restrict__ out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t back = window / 2, fwd = (window - 1) / 2;
     const int64_t need = min_periods > 1 ? min_periods : 1;
@@ -290,9 +391,19 @@ __global__ void rolling_mean_kernel(const double* __restrict__ pre, const double
             out[i] = nan("");
             continue;
         }
-        const double hi = pre[b - 1] + offs[(b - 1) / SCAN_CHUNK];
-        const double lo = a > 0 ? pre[a - 1] + offs[(a - 1) / SCAN_CHUNK] : 0.0;
-        out[i] = (hi - lo) / (double)cnt;
+        const long long lc = sb.lc[b - 1], lo_c = sb.tot_lc[(b - 1) / SCAN_CHUNK];
+        if ((lc > lo_c ? lc : lo_c) <= a) {  // x[a..b-1] all equal: pandas returns the value, not sum / count
+            out[i] = x[b - 1];
+            continue;
+        }
+        dd s = scan_prefix(sb, b - 1);
+        if (a > 0) {
+            dd l = scan_prefix(sb, a - 1);
+            l.hi = -l.hi;
+            l.lo = -l.lo;
+            s = dd_add(s, l);
+        }
+        out[i] = s.hi / (double)cnt;
     }
 }
 
@@ -539,16 +650,21 @@ __global__ void __launch_bounds__(TW_TILE) tw_runmax_kernel(const TwArgs a) {
 
 // ---------------------------------------------------------------------------------------------------------
 // The product path reads the array ONCE.  The analysis windows overlap ten-fold and nearly all of their elements are far
-// from any anomaly, so per aligned block of TW_TILE elements the kernel below keeps sum(x-c), sum((x-c)^2) and the maximum
-// (c = a sample of the data, against cancellation); a window's statistics are the sums of its inner blocks plus its two
-// ragged edges, and a block whose own and neighbouring maxima are all below the window's threshold cannot touch a run:
-// it contributes its maximum to max_below and nothing else.  Only the remaining (window, block) pairs -- the blocks near
+// from any anomaly, so per aligned block of TW_TILE elements the kernel below keeps sum(x-c_b), sum((x-c_b)^2) and the maximum,
+// centred on the block's own first element c_b; a window's statistics are the sums of its inner blocks plus its two ragged
+// edges, and a block whose own and neighbouring maxima are all below the window's threshold cannot touch a run: it
+// contributes its maximum to max_below and nothing else.  Only the remaining (window, block) pairs -- the blocks near
 // anomalies and the window edges -- go through the element-wise tile code above, from a work list.
+// The local centres are what makes flat stretches come out right: there every difference is exactly 0 (or a few ulps), the
+// window mean is its first element plus an exactly-small correction, and the variance is the sum of squared deviations from
+// THAT mean with no cancellation -- a constant window gets mean = the value, std = 0, threshold = the value, nothing above it,
+// like numpy's two-pass mean / std do (a far-away centre left a residue of ~1e-16 in the mean with the variance clamped to 0,
+// i.e. a threshold below the constant and one run spanning the whole window).
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RB) tw_blocks_kernel(const TwArgs a) {
     __shared__ double sh[32];
     const int64_t b = blockIdx.x, i0 = b * TW_TILE, i1 = i0 + TW_TILE < a.len ? i0 + TW_TILE : a.len;
-    const double c = a.errors[a.len / 2];
+    const double c = a.errors[i0];
     double s1 = 0.0, s2 = 0.0;
     unsigned long long m = 0ull;
     for (int64_t i = i0 + threadIdx.x; i < i1; i += RB) {
@@ -582,37 +698,37 @@ __global__ void __launch_bounds__(RB) tw_window_kernel(const TwArgs a) {
     __shared__ unsigned long long s_quiet;
     const int k = blockIdx.x, tid = threadIdx.x;
     const int64_t w0 = (int64_t)(a.k0 + k) * a.step, w1 = w0 + a.window_size < a.len ? w0 + a.window_size : a.len, n = w1 - w0;
-    const double c = a.errors[a.len / 2];
+    const double c0 = a.errors[w0];  // the window's own centre
     const int64_t bf0 = (w0 + TW_TILE - 1) / TW_TILE, bf1 = w1 / TW_TILE;  // blocks [bf0, bf1) lie fully inside
-    double s1 = 0.0, s2 = 0.0;
-    if (bf0 < bf1) {
-        for (int64_t b = bf0 + tid; b < bf1; b += RB) {
-            s1 += a.bsum1[b];
-            s2 += a.bsum2[b];
-        }
-        for (int64_t i = w0 + tid; i < bf0 * TW_TILE; i += RB) {
-            const double d = a.errors[i] - c;
-            s1 += d;
-            s2 += d * d;
-        }
-        for (int64_t i = bf1 * TW_TILE + tid; i < w1; i += RB) {
-            const double d = a.errors[i] - c;
-            s1 += d;
-            s2 += d * d;
-        }
-    } else {
-        for (int64_t i = w0 + tid; i < w1; i += RB) {
-            const double d = a.errors[i] - c;
-            s1 += d;
-            s2 += d * d;
-        }
-    }
+    const bool blocks = bf0 < bf1;
+    const int64_t e0 = blocks ? bf0 * TW_TILE : w1, e1 = blocks ? bf1 * TW_TILE : w1;  // ragged edges [w0, e0) and [e1, w1)
+    // mean = c0 + sum(x - c0) / n, with sum over a block = TW_TILE (c_b - c0) + sum(x - c_b)
+    double s1 = 0.0;
+    if (blocks)
+        for (int64_t b = bf0 + tid; b < bf1; b += RB) s1 += (double)TW_TILE * (a.errors[b * TW_TILE] - c0) + a.bsum1[b];
+    for (int64_t i = w0 + tid; i < e0; i += RB) s1 += a.errors[i] - c0;
+    for (int64_t i = e1 + tid; i < w1; i += RB) s1 += a.errors[i] - c0;
     s1 = block_sum(s1, sh);
+    const double dm = s1 / (double)n;  // mean - c0
+    // sum((x - mean)^2); over a block, with e = c_b - mean: sum((x-c_b)^2) + 2 e sum(x-c_b) + TW_TILE e^2
+    double s2 = 0.0;
+    if (blocks)
+        for (int64_t b = bf0 + tid; b < bf1; b += RB) {
+            const double e = (a.errors[b * TW_TILE] - c0) - dm;
+            s2 += a.bsum2[b] + 2.0 * e * a.bsum1[b] + (double)TW_TILE * e * e;
+        }
+    for (int64_t i = w0 + tid; i < e0; i += RB) {
+        const double d = (a.errors[i] - c0) - dm;
+        s2 += d * d;
+    }
+    for (int64_t i = e1 + tid; i < w1; i += RB) {
+        const double d = (a.errors[i] - c0) - dm;
+        s2 += d * d;
+    }
     s2 = block_sum(s2, sh);
-    const double dm = s1 / (double)n;                   // mean - c
-    double var = (s2 - s1 * dm) / (double)(n - a.ddof);  // sum((x-mean)^2) = sum((x-c)^2) - n (mean-c)^2
+    double var = s2 / (double)(n - a.ddof);
     var = var > 0.0 ? var : 0.0;
-    double mean = c + dm, sd = sqrt(var), thr = mean + 4.0 * sd;  // _fixed_threshold, k = 4 (:1098-1114)
+    double mean = c0 + dm, sd = sqrt(var), thr = mean + 4.0 * sd;  // _fixed_threshold, k = 4 (:1098-1114)
     if (a.stats_f32) {  // torch fp32 tensor: errors.mean(), errors.std() and mean + 4 * std are fp32 values
         mean = (double)(float)mean;
         sd = (double)(float)sd;
@@ -729,21 +845,29 @@ static unsigned ew_grid(int64_t n) {
 // workspace layout helpers -------------------------------------------------------------------------------
 static inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
+static size_t rolling_ws_bytes(int64_t len) {
+    return 3 * align256((size_t)len * 8) + 3 * align256((size_t)ceil_div(len, SCAN_CHUNK) * 8);
+}
 static int rolling_mean(hypad_ctx* ctx, const double* x, int64_t len, int64_t window, int64_t min_periods, double* out,
                         char* ws, cudaStream_t stream) {
-    // ws: pre[len] | totals[nchunks]
+    // ws: pre_hi[len] | pre_lo[len] | lc[len] | tot_hi[nchunks] | tot_lo[nchunks] | tot_lc[nchunks]
     const int64_t nchunks = ceil_div(len, SCAN_CHUNK);
-    double* pre = (double*)ws;
-    double* totals = (double*)(ws + align256((size_t)len * 8));
-    scan_local_kernel<<<(unsigned)nchunks, 256, 0, stream>>>(x, len, pre, totals);
+    const size_t la = align256((size_t)len * 8), ca = align256((size_t)nchunks * 8);
+    ScanBufs sb;
+    sb.pre_hi = (double*)ws;
+    sb.pre_lo = (double*)(ws + la);
+    sb.lc = (long long*)(ws + 2 * la);
+    sb.tot_hi = (double*)(ws + 3 * la);
+    sb.tot_lo = (double*)(ws + 3 * la + ca);
+    sb.tot_lc = (long long*)(ws + 3 * la + 2 * ca);
+    scan_local_kernel<<<(unsigned)nchunks, 256, 0, stream>>>(x, len, sb);
     HYPAD_LAUNCH_CHECK();
-    scan_totals_kernel<<<1, 32, 0, stream>>>(totals, nchunks);
+    scan_totals_kernel<<<1, 32, 0, stream>>>(sb, nchunks);
     HYPAD_LAUNCH_CHECK();
-    rolling_mean_kernel<<<ew_grid(len), 256, 0, stream>>>(pre, totals, len, window, min_periods, out);
+    rolling_mean_kernel<<<ew_grid(len), 256, 0, stream>>>(x, sb, len, window, min_periods, out);
     HYPAD_LAUNCH_CHECK();
     return HYPAD_OK;
 }
-static size_t rolling_ws_bytes(int64_t len) { return align256((size_t)len * 8) + align256((size_t)ceil_div(len, SCAN_CHUNK) * 8); }
 
 }  // namespace hypad
 
