@@ -132,15 +132,21 @@ def cpu_reference_step(sig, sd, sample_T):
     return time.perf_counter() - t0, windows.shape[0]
 
 
+CPU_SAMPLE_T = 40000  # timesteps of the workload signal the CPU arm scores per step (cpu_baseline and --impl reference alike)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
 
-    sig = make_signal(max(args.timesteps, 8640))
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; this arm runs on rank 0 alone and may use the whole host
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sig = make_signal(max(args.timesteps, CPU_SAMPLE_T))
     sd = reference_weights()
-    sample_T = 8640 if (args.steps + args.warmup) <= 20 else 2260
+    sample_T = min(CPU_SAMPLE_T, sig.shape[0])
     for _ in range(args.warmup):
         cpu_reference_step(sig, sd, sample_T)
     times, nwin = [], 0
@@ -149,13 +155,16 @@ def run_reference(args):
         times.append(dt)
     total = sum(times)
     value = nwin * args.steps / total
-    cores = torch.get_num_threads()
-    sample = "first %d timesteps (%d windows) of the workload signal per step; reference's CPU path " \
-             "(torch CPU per-64 batches + scipy gaussian_kde per timestep), oracle port" % (sample_T, nwin)
+    sample = "first %d timesteps (%d windows) of the workload signal per step; reference's CPU path (torch CPU per-64 batches + " \
+             "scipy gaussian_kde per timestep), oracle literal port; torch intra-op threads = %d" % (sample_T, nwin, torch.get_num_threads())
+    cfg = workload_config(args)
+    cfg["workload"] += " -- CPU arm: each step scores the first %d timesteps (%d windows) of that signal" % (sample_T, nwin)
+    cfg["cpu_sample_timesteps"] = sample_T
+    cfg["cpu_threads"] = torch.get_num_threads()
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
                              "host_cpus": os.cpu_count()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -311,19 +320,36 @@ def run_native(args):
                     "fp32_simt_peak_tflops": simt_peak, "speedup_vs_fp32_simt_peak": achieved / simt_peak,
                     "algorithmic_flop_per_window": FLOP_PER_WINDOW_HYP, "windows_per_launch": n_local,
                     "avg_launch_ms": fw_ms}
+        kde_pairs = 4950 * (n_local + S - 1)
+        kde_rate = kde_pairs / (kde_ms / 1e3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "profiles", "peaks.json")))
+        except Exception:
+            pass
+        ex2_peak = (peaks.get("mufu_ex2_f32") or {}).get("value") or 148 * 16 * sm_mhz * 1e6 / 1e12
+        roofline_kde = {"kernel": "kde_screened_kernel (scipy gaussian_kde arg-max per timestep: S(S-1)/2 = 4950 Gaussian pair "
+                                  "kernels, one exp each)",
+                        "bound": "sfu (MUFU.EX2)", "achieved": kde_rate, "peak": ex2_peak, "unit": "T pair-kernels/s",
+                        "frac": kde_rate / ex2_peak,
+                        "peak_source": "measured on the box (scripts/measure_peaks.py -> profiles/peaks.json)" if peaks
+                        else "computed: 148 SM x 16 MUFU/clk x SM clock (profiles/peaks.json missing)",
+                        "pair_kernels_per_launch": kde_pairs, "avg_launch_ms": kde_ms, "traffic": None,
+                        "note": "HBM traffic is the 4 B critic value per window in and 8 B per timestep out; the kernel is bound by "
+                                "the special-function pipe (one ex2 per pair) and the instructions around it"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": workload_config(args), "clocks": clocks,
                 "e2e": {"value": n_windows * args.steps / (e2e_ms / 1e3), "unit": UNIT,
                         "h2d_bytes_per_step": int(host_slice.numel() * 8), "d2h_bytes_per_step": int(n_windows * 8),
                         "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": int(launches), "roofline": roofline,
+                "gpu_launches": int(launches), "roofline": roofline, "roofline_kde": roofline_kde,
                 "kernels_ms": {"forward_tc_kernel": fw_ms, "kde_screened_kernel": kde_ms, "step_total": ms_per_step},
                 "kde": {"pair_evals_per_timestep": 4950, "timesteps_per_launch": n_local + S - 1,
                         "gpair_evals_per_s": 4950 * (n_local + S - 1) / (kde_ms / 1e3) / 1e9}}
         if world == 1 and not args.no_cpu_baseline:
             sd = reference_weights()
-            cpu_T = min(40000, sig.shape[0])
+            cpu_T = min(CPU_SAMPLE_T, sig.shape[0])
             dt, nwin = cpu_reference_step(sig, sd, cpu_T)
             line["cpu_baseline"] = {"value": nwin / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                     "host_cpus": os.cpu_count(),

@@ -257,6 +257,13 @@ int hypad_tc_probe_gemm(const float* A, const float* B, float* D, int K, int N, 
  * until retired, h_out2[1] = cycles spent issuing.  mode 0 same accumulator, 1 rotating accumulators, 2 alternating operands. */
 int hypad_tc_probe_bench(int N, int reps, int mode, long long* h_out2, void* stream);
 
+/* Diagnostic (not on the product path): one launch of a pipe-rate micro-benchmark filling every SM with `ctas_per_sm` CTAs
+ * of 1024 threads, each running 8 independent chains of `iters` instructions.  kind 0 FP32 FFMA, 1 FP64 DFMA, 2 MUFU.EX2
+ * (ex2.approx.ftz.f32), 3 MUFU.EX2 packed (ex2.approx.f16x2), 4 SHFL.IDX.  *instr_per_launch = thread-level instructions
+ * issued; the caller times the launch (scripts/measure_peaks.py -> profiles/peaks.json, the denominators SURVEY.md 8(d)
+ * asks to be measured on the box). */
+int hypad_peak_probe(int kind, int iters, int ctas_per_sm, float* sink, long long* instr_per_launch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
