@@ -130,6 +130,7 @@ int hypad_ctx_destroy(hypad_ctx* ctx) {
     if (ctx->tc_packed) cudaFree(ctx->tc_packed);
     if (ctx->tc_error) cudaFree(ctx->tc_error);
     if (ctx->tc_debug) cudaFree(ctx->tc_debug);
+    if (ctx->fin_state) cudaFree(ctx->fin_state);
     delete ctx;
     return HYPAD_OK;
 }

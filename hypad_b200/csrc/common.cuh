@@ -123,6 +123,7 @@ struct hypad_ctx {
     long long range_fallbacks;  // polls that found a call served by the fallback
     long long* tc_debug;        // optional device cycle counters (hypad_forward_debug_cycles)
     unsigned char tc_prog_storage[2048];
+    void* fin_state;            // device: state of the staged statistics (critic_stats.cu), allocated on first use
 };
 
 namespace hypad {

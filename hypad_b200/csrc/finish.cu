@@ -3,10 +3,16 @@
 // score combination (:336-362, :554-570) and the per-window statistics / run extraction of find_anomalies
 // (:1098-1166).  All results stay on the device; scalars travel through a small block of the workspace.
 #include "common.cuh"
+#include "dd.cuh"
 
 namespace hypad {
 
 constexpr int RB = 256;  // threads of the reduction kernels
+
+// critic_stats.cu
+int ensure_fin_state(hypad_ctx* ctx);
+double* fin_scalars(hypad_ctx* ctx);
+double* fin_local_record(hypad_ctx* ctx);
 
 __device__ __forceinline__ double block_sum(double v, double* sh) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -30,9 +36,6 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 template <typename T>
 __device__ __forceinline__ double ld(const T* p, int64_t i) { return (double)p[i]; }
 
-// ---------------------------------------------------------------------------------------------------------
-// order statistics by radix select on order-preserving 64-bit keys (4 ranks at once)
-// ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long dkey(double x) {
     unsigned long long b = (unsigned long long)__double_as_longlong(x);
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
@@ -42,182 +45,10 @@ __device__ __forceinline__ double dunkey(unsigned long long k) {
     return __longlong_as_double((long long)b);
 }
 
-constexpr int NQ = 4;  // simultaneous ranks
-
-struct SelectState {  // lives in the workspace
-    unsigned long long prefix[NQ];
-    long long rank[NQ];
-    unsigned int hist[8][NQ][256];
-};
-
-__global__ void select_init_kernel(SelectState* st, long long r0, long long r1, long long r2, long long r3) {
-    const int t = threadIdx.x + blockIdx.x * blockDim.x;
-    unsigned int* h = &st->hist[0][0][0];
-    for (int e = t; e < 8 * NQ * 256; e += gridDim.x * blockDim.x) h[e] = 0;
-    if (t == 0) {
-        st->prefix[0] = st->prefix[1] = st->prefix[2] = st->prefix[3] = 0ull;
-        st->rank[0] = r0; st->rank[1] = r1; st->rank[2] = r2; st->rank[3] = r3;
-    }
-}
-
-// pass p handles bits [56-8p, 64-8p): histogram of the digit among keys whose higher bits equal prefix[q]
-__global__ void __launch_bounds__(RB) select_hist_kernel(const double* __restrict__ x, int64_t len, int pass, SelectState* st) {
-    __shared__ unsigned int sh[NQ][256];
-    for (int e = threadIdx.x; e < NQ * 256; e += blockDim.x) (&sh[0][0])[e] = 0;
-    __syncthreads();
-    const int shift = 56 - 8 * pass;
-    unsigned long long pre[NQ];
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) pre[q] = st->prefix[q];
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
-        const unsigned long long k = dkey(x[i]);
-        const unsigned long long hi = pass == 0 ? 0ull : (k >> (shift + 8));
-        const unsigned int digit = (unsigned int)((k >> shift) & 255ull);
-#pragma unroll
-        for (int q = 0; q < NQ; ++q)
-            if (hi == pre[q]) atomicAdd(&sh[q][digit], 1u);
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < NQ * 256; e += blockDim.x) {
-        const unsigned int c = (&sh[0][0])[e];
-        if (c) atomicAdd(&st->hist[pass][0][0] + e, c);
-    }
-}
-
-// one block of NQ warps: locate the digit holding rank[q], extend the prefix
-__global__ void __launch_bounds__(NQ * 32) select_pick_kernel(int pass, SelectState* st) {
-    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned int* h = st->hist[pass][q];
-    unsigned int c[8];
-    unsigned int s = 0;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        c[t] = h[lane * 8 + t];
-        s += c[t];
-    }
-    unsigned int incl = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    const long long rank = st->rank[q];
-    const long long before = (long long)incl - s;
-    const bool mine = rank >= before && rank < (long long)incl;
-    if (mine) {
-        long long acc = before;
-        int digit = 0;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            if (rank >= acc && rank < acc + c[t]) {
-                digit = lane * 8 + t;
-                st->rank[q] = rank - acc;
-                break;
-            }
-            acc += c[t];
-        }
-        st->prefix[q] = (st->prefix[q] << 8) | (unsigned long long)digit;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// _compute_critic_score scalars:  s[0]=q25 s[1]=q75 s[2]=mean(all) s[3]=mean(in band) s[4]=std(all, ddof 0)
-// ---------------------------------------------------------------------------------------------------------
-__global__ void quantile_finish_kernel(const SelectState* st, double g25, double g75, double* s) {
-    // numpy _lerp: a + (b-a)*t, and b - (b-a)*(1-t) when t >= 0.5
-    const double a0 = dunkey(st->prefix[0]), b0 = dunkey(st->prefix[1]);
-    const double a1 = dunkey(st->prefix[2]), b1 = dunkey(st->prefix[3]);
-    const double d0 = b0 - a0, d1 = b1 - a1;
-    s[0] = g25 >= 0.5 ? b0 - d0 * (1.0 - g25) : a0 + d0 * g25;
-    s[1] = g75 >= 0.5 ? b1 - d1 * (1.0 - g75) : a1 + d1 * g75;
-}
-
-// partial[b*3 + {0,1,2}] = sum(x), sum(x in band), count(in band)
-__global__ void __launch_bounds__(RB) band_partial_kernel(const double* __restrict__ x, int64_t len, const double* s,
-                                                          double* __restrict__ partial) {
-    __shared__ double sh[32];
-    const double lo = s[0], hi = s[1];
-    double a = 0.0, b = 0.0, c = 0.0;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
-        const double v = x[i];
-        a += v;
-        if (v >= lo && v <= hi) {
-            b += v;
-            c += 1.0;
-        }
-    }
-    a = block_sum(a, sh);
-    b = block_sum(b, sh);
-    c = block_sum(c, sh);
-    if (threadIdx.x == 0) {
-        partial[blockIdx.x * 3 + 0] = a;
-        partial[blockIdx.x * 3 + 1] = b;
-        partial[blockIdx.x * 3 + 2] = c;
-    }
-}
-__global__ void __launch_bounds__(RB) band_final_kernel(const double* __restrict__ partial, int nblocks, int64_t len, double* s) {
-    __shared__ double sh[32];
-    double a = 0.0, b = 0.0, c = 0.0;
-    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) {
-        a += partial[i * 3];
-        b += partial[i * 3 + 1];
-        c += partial[i * 3 + 2];
-    }
-    a = block_sum(a, sh);
-    b = block_sum(b, sh);
-    c = block_sum(c, sh);
-    if (threadIdx.x == 0) {
-        s[2] = a / (double)len;
-        s[3] = b / c;
-    }
-}
-// generic: partial[b] = sum (x - *center)^2
-template <typename T>
-__global__ void __launch_bounds__(RB) sqdev_partial_kernel(const T* __restrict__ x, int64_t len, const double* center,
-                                                           double* __restrict__ partial) {
-    __shared__ double sh[32];
-    const double m = *center;
-    double a = 0.0;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
-        const double d = ld(x, i) - m;
-        a += d * d;
-    }
-    a = block_sum(a, sh);
-    if (threadIdx.x == 0) partial[blockIdx.x] = a;
-}
-template <typename T>
-__global__ void __launch_bounds__(RB) sum_partial_kernel(const T* __restrict__ x, int64_t len, double* __restrict__ partial) {
-    __shared__ double sh[32];
-    double a = 0.0;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) a += ld(x, i);
-    a = block_sum(a, sh);
-    if (threadIdx.x == 0) partial[blockIdx.x] = a;
-}
-// *dst = f(sum(partial)) with f = mean (mode 0) or sqrt(sum / (len - ddof)) (mode 1)
-__global__ void __launch_bounds__(RB) scalar_final_kernel(const double* __restrict__ partial, int nblocks, int64_t len, int ddof,
-                                                          int mode, double* dst) {
-    __shared__ double sh[32];
-    double a = 0.0;
-    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) a += partial[i];
-    a = block_sum(a, sh);
-    if (threadIdx.x == 0) *dst = mode == 0 ? a / (double)len : sqrt(a / (double)(len - ddof));
-}
-
-// z = |x - s[3]| / s[4] + 1
-__global__ void critic_z_kernel(const double* __restrict__ x, int64_t len, const double* s, double* __restrict__ z) {
-    const double mu = s[3], sd = s[4];
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) z[i] = fabs((x[i] - mu) / sd) + 1.0;
-}
-
-// out = clip((x - s[0]) / s[1], 0) + 1
+// out = clip((x - s[5]) / s[6], 0) + 1   (the scalars of critic_stats.cu)
 template <typename T>
 __global__ void zscore_clip_kernel(const T* __restrict__ x, int64_t len, const double* s, double* __restrict__ out) {
-    const double mu = s[0], sd = s[1];
+    const double mu = s[5], sd = s[6];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
         const double z = (ld(x, i) - mu) / sd;
@@ -237,25 +68,6 @@ __global__ void zscore_clip_kernel(const T* __restrict__ x, int64_t len, const d
 // ---------------------------------------------------------------------------------------------------------
 constexpr int SCAN_CHUNK = 2048;  // elements per CTA (256 threads x 8)
 
-struct dd {
-    double hi, lo;
-};
-__device__ __forceinline__ dd dd_add(dd a, dd b) {
-    const double s = __dadd_rn(a.hi, b.hi), bb = __dadd_rn(s, -a.hi);
-    double e = __dadd_rn(__dadd_rn(a.hi, -__dadd_rn(s, -bb)), __dadd_rn(b.hi, -bb));  // TwoSum error term
-    e = __dadd_rn(e, __dadd_rn(a.lo, b.lo));
-    dd r;
-    r.hi = __dadd_rn(s, e);
-    r.lo = __dadd_rn(e, -__dadd_rn(r.hi, -s));
-    return r;
-}
-__device__ __forceinline__ dd dd_add(dd a, double b) {
-    dd t;
-    t.hi = b;
-    t.lo = 0.0;
-    return dd_add(a, t);
-}
-
 struct ScanBufs {
     double* pre_hi;      // [len] chunk-local inclusive prefix
     double* pre_lo;
@@ -265,7 +77,15 @@ struct ScanBufs {
     long long* tot_lc;   // [nchunks] last change inside the chunk -> last change before the chunk
 };
 
-__global__ void __launch_bounds__(256) scan_local_kernel(const double* __restrict__ x, int64_t len, ScanBufs sb) {
+// the scanned value: x itself, or the critic z-score |x - s[3]| / s[4] + 1 (:322-325) taken on the fly
+template <bool Z>
+__device__ __forceinline__ double scan_value(const double* __restrict__ x, int64_t i, double mu, double sd) {
+    return Z ? fabs((x[i] - mu) / sd) + 1.0 : x[i];
+}
+
+template <bool Z>
+__global__ void __launch_bounds__(256) scan_local_kernel(const double* __restrict__ x, int64_t len, ScanBufs sb, const double* scal) {
+    const double mu = Z ? scal[3] : 0.0, sd = Z ? scal[4] : 1.0;
     __shared__ double sh_hi[256], sh_lo[256];
     __shared__ long long sh_lc[256];
     const int tid = threadIdx.x;
@@ -275,11 +95,11 @@ __global__ void __launch_bounds__(256) scan_local_kernel(const double* __restric
     dd run;
     run.hi = run.lo = 0.0;
     long long last = -1;
-    double prev = base > 0 && base - 1 < len ? x[base - 1] : 0.0;
+    double prev = base > 0 && base - 1 < len ? scan_value<Z>(x, base - 1, mu, sd) : 0.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int64_t i = base + k;
-        const double xv = i < len ? x[i] : 0.0;
+        const double xv = i < len ? scan_value<Z>(x, i, mu, sd) : 0.0;
         run = dd_add(run, xv);
         v[k] = run;
         if (i < len && (i == 0 || xv != prev)) last = i;
@@ -377,33 +197,35 @@ __device__ __forceinline__ dd scan_prefix(const ScanBufs& sb, int64_t i) {  // e
     o.lo = sb.tot_lo[i / SCAN_CHUNK];
     return dd_add(o, p);
 }
-__global__ void rolling_mean_kernel(const double* __restrict__ x, ScanBufs sb, int64_t len, int64_t window, int64_t min_periods,
-                                    double* __restrict__ out) {
+// x / sb cover the global positions [ext0, ext0 + ext_len) of an array of n_total positions; output for the `count` positions
+// from p0 on (the caller guarantees that their windows, clipped to [0, n_total), lie inside the covered range).
+template <bool Z>
+__global__ void rolling_mean_kernel(const double* __restrict__ x, ScanBufs sb, const double* scal, int64_t ext0, int64_t n_total,
+                                    int64_t p0, int64_t count, int64_t window, int64_t min_periods, double* __restrict__ out) {
+    const double mu = Z ? scal[3] : 0.0, sd = Z ? scal[4] : 1.0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t back = window / 2, fwd = (window - 1) / 2;
     const int64_t need = min_periods > 1 ? min_periods : 1;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) {
+        const int64_t i = p0 + j;
         int64_t a = i - back, b = i + fwd + 1;
         if (a < 0) a = 0;
-        if (b > len) b = len;
+        if (b > n_total) b = n_total;
         const int64_t cnt = b - a;
         if (window <= 0 || cnt < need) {
-            out[i] = nan("");
+            out[j] = nan("");
             continue;
         }
+        a -= ext0;
+        b -= ext0;
         const long long lc = sb.lc[b - 1], lo_c = sb.tot_lc[(b - 1) / SCAN_CHUNK];
         if ((lc > lo_c ? lc : lo_c) <= a) {  // x[a..b-1] all equal: pandas returns the value, not sum / count
-            out[i] = x[b - 1];
+            out[j] = scan_value<Z>(x, b - 1, mu, sd);
             continue;
         }
         dd s = scan_prefix(sb, b - 1);
-        if (a > 0) {
-            dd l = scan_prefix(sb, a - 1);
-            l.hi = -l.hi;
-            l.lo = -l.lo;
-            s = dd_add(s, l);
-        }
-        out[i] = s.hi / (double)cnt;
+        if (a > 0) s = dd_add(s, dd_neg(scan_prefix(sb, a - 1)));
+        out[j] = s.hi / (double)cnt;
     }
 }
 
@@ -848,11 +670,13 @@ static inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 static size_t rolling_ws_bytes(int64_t len) {
     return 3 * align256((size_t)len * 8) + 3 * align256((size_t)ceil_div(len, SCAN_CHUNK) * 8);
 }
-static int rolling_mean(hypad_ctx* ctx, const double* x, int64_t len, int64_t window, int64_t min_periods, double* out,
-                        char* ws, cudaStream_t stream) {
+// x covers global positions [ext0, ext0 + ext_len) of n_total; out[j] = smoothed value at position p0 + j, j < count.
+// zscore: smooth the critic z-score of x (scalars of critic_stats.cu) instead of x.
+static int rolling_mean(hypad_ctx* ctx, const double* x, int64_t ext_len, int64_t ext0, int64_t n_total, int64_t p0, int64_t count,
+                        int64_t window, int64_t min_periods, bool zscore, double* out, char* ws, cudaStream_t stream) {
     // ws: pre_hi[len] | pre_lo[len] | lc[len] | tot_hi[nchunks] | tot_lo[nchunks] | tot_lc[nchunks]
-    const int64_t nchunks = ceil_div(len, SCAN_CHUNK);
-    const size_t la = align256((size_t)len * 8), ca = align256((size_t)nchunks * 8);
+    const int64_t nchunks = ceil_div(ext_len, SCAN_CHUNK);
+    const size_t la = align256((size_t)ext_len * 8), ca = align256((size_t)nchunks * 8);
     ScanBufs sb;
     sb.pre_hi = (double*)ws;
     sb.pre_lo = (double*)(ws + la);
@@ -860,11 +684,14 @@ static int rolling_mean(hypad_ctx* ctx, const double* x, int64_t len, int64_t wi
     sb.tot_hi = (double*)(ws + 3 * la);
     sb.tot_lo = (double*)(ws + 3 * la + ca);
     sb.tot_lc = (long long*)(ws + 3 * la + 2 * ca);
-    scan_local_kernel<<<(unsigned)nchunks, 256, 0, stream>>>(x, len, sb);
+    const double* scal = zscore ? fin_scalars(ctx) : nullptr;
+    if (zscore) scan_local_kernel<true><<<(unsigned)nchunks, 256, 0, stream>>>(x, ext_len, sb, scal);
+    else scan_local_kernel<false><<<(unsigned)nchunks, 256, 0, stream>>>(x, ext_len, sb, scal);
     HYPAD_LAUNCH_CHECK();
     scan_totals_kernel<<<1, 32, 0, stream>>>(sb, nchunks);
     HYPAD_LAUNCH_CHECK();
-    rolling_mean_kernel<<<ew_grid(len), 256, 0, stream>>>(x, sb, len, window, min_periods, out);
+    if (zscore) rolling_mean_kernel<true><<<ew_grid(count), 256, 0, stream>>>(x, sb, scal, ext0, n_total, p0, count, window, min_periods, out);
+    else rolling_mean_kernel<false><<<ew_grid(count), 256, 0, stream>>>(x, sb, scal, ext0, n_total, p0, count, window, min_periods, out);
     HYPAD_LAUNCH_CHECK();
     return HYPAD_OK;
 }
@@ -883,77 +710,68 @@ int hypad_rolling_mean_centered(hypad_ctx* ctx, const double* x, int64_t len, in
     HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
     int rc = ensure_workspace(ctx, rolling_ws_bytes(len));
     if (rc != HYPAD_OK) return rc;
-    return rolling_mean(ctx, x, len, window, min_periods, out, (char*)ctx->workspace, (cudaStream_t)stream);
+    return rolling_mean(ctx, x, len, 0, len, 0, len, window, min_periods, false, out, (char*)ctx->workspace, (cudaStream_t)stream);
+}
+
+int hypad_critic_smooth_shard(hypad_ctx* ctx, const double* kmax_ext, int64_t ext_len, int64_t ext0, int64_t n_total, int64_t p0,
+                              int64_t count, int64_t smooth_window, double* out, void* stream) {
+    HYPAD_REQUIRE(ctx && ctx->fin_state && kmax_ext && out, "hypad_critic_smooth_shard: NULL argument (hypad_stats_* first)");
+    HYPAD_REQUIRE(ext_len >= 1 && ext0 >= 0 && ext0 + ext_len <= n_total && p0 >= ext0 && count >= 0 && p0 + count <= ext0 + ext_len,
+                  "hypad_critic_smooth_shard: the slice [%lld, %lld) does not hold the positions [%lld, %lld)", (long long)ext0,
+                  (long long)(ext0 + ext_len), (long long)p0, (long long)(p0 + count));
+    if (count == 0) return HYPAD_OK;
+    if (smooth_window > 0) {
+        const int64_t need_lo = p0 - smooth_window / 2 > 0 ? p0 - smooth_window / 2 : 0;
+        const int64_t hi = p0 + count - 1 + (smooth_window - 1) / 2 + 1, need_hi = hi < n_total ? hi : n_total;
+        HYPAD_REQUIRE(ext0 <= need_lo && ext0 + ext_len >= need_hi, "hypad_critic_smooth_shard: the slice lacks the smoothing halo "
+                      "(needs [%lld, %lld), holds [%lld, %lld))", (long long)need_lo, (long long)need_hi, (long long)ext0,
+                      (long long)(ext0 + ext_len));
+    }
+    HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
+    int rc = ensure_workspace(ctx, rolling_ws_bytes(ext_len));
+    if (rc != HYPAD_OK) return rc;
+    return rolling_mean(ctx, kmax_ext, ext_len, ext0, n_total, p0, count, smooth_window, smooth_window / 2, true, out,
+                        (char*)ctx->workspace, (cudaStream_t)stream);
 }
 
 int hypad_critic_zscore_smooth(hypad_ctx* ctx, const double* kmax, int64_t len, int64_t smooth_window, double* out,
-                               void* stream_) {
+                               void* stream) {
     HYPAD_REQUIRE(ctx && kmax && out, "hypad_critic_zscore_smooth: NULL argument");
     HYPAD_REQUIRE(len >= 1, "hypad_critic_zscore_smooth: len < 1");
-    cudaStream_t stream = (cudaStream_t)stream_;
-    HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
-    const unsigned rg = red_grid(len);
-    // workspace: scalars[8] | SelectState | partial[3*rg] | z[len] | rolling scratch
-    const size_t o_state = 256, o_part = o_state + align256(sizeof(SelectState)), o_z = o_part + align256((size_t)rg * 3 * 8);
-    const size_t o_roll = o_z + align256((size_t)len * 8);
-    int rc = ensure_workspace(ctx, o_roll + rolling_ws_bytes(len));
+    // the one-rank chain of the staged statistics (critic_stats.cu); arbitrary doubles: 64-bit keys
+    int rc = hypad_stats_select_begin(ctx, len, 0, stream);
     if (rc != HYPAD_OK) return rc;
-    char* ws = (char*)ctx->workspace;
-    double* s = (double*)ws;
-    SelectState* st = (SelectState*)(ws + o_state);
-    double* partial = (double*)(ws + o_part);
-    double* z = (double*)(ws + o_z);
-    // np.quantile(method='linear'): virtual index q*(n-1); neighbours floor / floor+1 (clipped)
-    const double v25 = 0.25 * (double)(len - 1), v75 = 0.75 * (double)(len - 1);
-    const long long f25 = (long long)v25, f75 = (long long)v75;
-    const long long c25 = f25 + 1 < len ? f25 + 1 : len - 1, c75 = f75 + 1 < len ? f75 + 1 : len - 1;
-    select_init_kernel<<<8, 256, 0, stream>>>(st, f25, c25, f75, c75);
-    HYPAD_LAUNCH_CHECK();
-    for (int p = 0; p < 8; ++p) {
-        select_hist_kernel<<<rg, RB, 0, stream>>>(kmax, len, p, st);
-        HYPAD_LAUNCH_CHECK();
-        select_pick_kernel<<<1, NQ * 32, 0, stream>>>(p, st);
-        HYPAD_LAUNCH_CHECK();
+    uint32_t* hist = (uint32_t*)fin_local_record(ctx);
+    for (int p = 0; p < hypad_stats_select_passes(0); ++p) {
+        if ((rc = hypad_stats_select_hist(ctx, kmax, len, p, hist, stream)) != HYPAD_OK) return rc;
+        if ((rc = hypad_stats_select_pick(ctx, hist, 1, p, stream)) != HYPAD_OK) return rc;
     }
-    quantile_finish_kernel<<<1, 1, 0, stream>>>(st, v25 - (double)f25, v75 - (double)f75, s);
-    HYPAD_LAUNCH_CHECK();
-    band_partial_kernel<<<rg, RB, 0, stream>>>(kmax, len, s, partial);
-    HYPAD_LAUNCH_CHECK();
-    band_final_kernel<<<1, RB, 0, stream>>>(partial, (int)rg, len, s);
-    HYPAD_LAUNCH_CHECK();
-    sqdev_partial_kernel<double><<<rg, RB, 0, stream>>>(kmax, len, s + 2, partial);
-    HYPAD_LAUNCH_CHECK();
-    scalar_final_kernel<<<1, RB, 0, stream>>>(partial, (int)rg, len, 0, 1, s + 4);
-    HYPAD_LAUNCH_CHECK();
-    critic_z_kernel<<<ew_grid(len), 256, 0, stream>>>(kmax, len, s, z);
-    HYPAD_LAUNCH_CHECK();
-    return rolling_mean(ctx, z, len, smooth_window, smooth_window / 2, out, ws + o_roll, stream);
+    double* rec = fin_local_record(ctx);
+    if ((rc = hypad_stats_moments_partial(ctx, kmax, 0, len, 1, rec, stream)) != HYPAD_OK) return rc;
+    if ((rc = hypad_stats_moments_final(ctx, rec, 1, len, 1, 0, stream)) != HYPAD_OK) return rc;
+    return hypad_critic_smooth_shard(ctx, kmax, len, 0, len, 0, len, smooth_window, out, stream);
 }
 
-int hypad_zscore_clip(hypad_ctx* ctx, const void* x, int x_is_f32, int64_t len, double* out, void* stream_) {
-    HYPAD_REQUIRE(ctx && x && out, "hypad_zscore_clip: NULL argument");
-    HYPAD_REQUIRE(len >= 1, "hypad_zscore_clip: len < 1");
+int hypad_zscore_clip_apply(hypad_ctx* ctx, const void* x, int x_is_f32, int64_t len, double* out, void* stream_) {
+    HYPAD_REQUIRE(ctx && ctx->fin_state && out && (x || len == 0) && len >= 0, "hypad_zscore_clip_apply: bad argument");
+    if (len == 0) return HYPAD_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
-    const unsigned rg = red_grid(len);
-    int rc = ensure_workspace(ctx, 256 + align256((size_t)rg * 8));
-    if (rc != HYPAD_OK) return rc;
-    double* s = (double*)ctx->workspace;
-    double* partial = (double*)((char*)ctx->workspace + 256);
-    if (x_is_f32) sum_partial_kernel<float><<<rg, RB, 0, stream>>>((const float*)x, len, partial);
-    else sum_partial_kernel<double><<<rg, RB, 0, stream>>>((const double*)x, len, partial);
-    HYPAD_LAUNCH_CHECK();
-    scalar_final_kernel<<<1, RB, 0, stream>>>(partial, (int)rg, len, 0, 0, s);
-    HYPAD_LAUNCH_CHECK();
-    if (x_is_f32) sqdev_partial_kernel<float><<<rg, RB, 0, stream>>>((const float*)x, len, s, partial);
-    else sqdev_partial_kernel<double><<<rg, RB, 0, stream>>>((const double*)x, len, s, partial);
-    HYPAD_LAUNCH_CHECK();
-    scalar_final_kernel<<<1, RB, 0, stream>>>(partial, (int)rg, len, 0, 1, s + 1);
-    HYPAD_LAUNCH_CHECK();
-    if (x_is_f32) zscore_clip_kernel<float><<<ew_grid(len), 256, 0, stream>>>((const float*)x, len, s, out);
-    else zscore_clip_kernel<double><<<ew_grid(len), 256, 0, stream>>>((const double*)x, len, s, out);
+    if (x_is_f32) zscore_clip_kernel<float><<<ew_grid(len), 256, 0, stream>>>((const float*)x, len, fin_scalars(ctx), out);
+    else zscore_clip_kernel<double><<<ew_grid(len), 256, 0, stream>>>((const double*)x, len, fin_scalars(ctx), out);
     HYPAD_LAUNCH_CHECK();
     return HYPAD_OK;
+}
+
+int hypad_zscore_clip(hypad_ctx* ctx, const void* x, int x_is_f32, int64_t len, double* out, void* stream) {
+    HYPAD_REQUIRE(ctx && x && out, "hypad_zscore_clip: NULL argument");
+    HYPAD_REQUIRE(len >= 1, "hypad_zscore_clip: len < 1");
+    int rc = ensure_fin_state(ctx);
+    if (rc != HYPAD_OK) return rc;
+    double* rec = fin_local_record(ctx);
+    if ((rc = hypad_stats_moments_partial(ctx, x, x_is_f32, len, 0, rec, stream)) != HYPAD_OK) return rc;
+    if ((rc = hypad_stats_moments_final(ctx, rec, 1, len, 0, 0, stream)) != HYPAD_OK) return rc;
+    return hypad_zscore_clip_apply(ctx, x, x_is_f32, len, out, stream);
 }
 
 int hypad_combine_scores(int mode, const double* critic_scores, const void* rec, int rec_is_f32, const float* unorm,

@@ -1,16 +1,23 @@
-"""Sharding of one signal's windows across GPUs: one process per GPU, a single gather at the end.
+"""Sharding of one signal's windows across GPUs: one process per GPU, small exchanges between the stages of the finish.
 
-The scoring path is embarrassingly parallel per window; the only coupling is the overlap aggregation, where
-timestep i needs the critic value of windows i-S+1 .. i.  Rank r therefore
-  * owns the contiguous window range [first, first+count) and the timesteps with the same indices (the last
-    rank also owns the S-1 trailing timesteps),
-  * recomputes the S-1 windows to the left of its range (the "halo": 0.01 % extra work at 1M windows/GPU),
-  * runs the fused network + KDE arg-max on its range with no communication,
-and the per-timestep / per-window arrays (kmax, rec, unorm, 12 B per timestep as fp32) are gathered in one NCCL all-gather
-(NVLink 5 / NVSwitch).  The elementwise O(T) finish (quantile band, z-score, smoothing, combine)
-is then run redundantly on every rank; the analysis windows of find_anomalies -- each a third of the signal, twenty-odd
-of them, the one part of the finish whose cost grows with the total length -- are dealt out to the ranks and their few
-runs gathered (a few KB).  There is no collective inside a kernel.
+The scoring path is embarrassingly parallel per window; the couplings are
+  * the overlap aggregation, where timestep i needs the critic value of windows i-S+1 .. i: rank r owns the contiguous window
+    range [first, first+count) and the timesteps with the same indices (the last rank also the S-1 trailing ones) and
+    recomputes the S-1 windows to the left of its range (the "halo": 0.01 % extra work at 1M windows/GPU);
+  * the global statistics of the finish -- the 25 % / 75 % quantiles, band mean and std of the KDE selections
+    (utils/anomaly_detection_utils.py:319-325), the z-score moments of the multivariate reconstruction error (:177) -- taken
+    in stages (csrc/critic_stats.cu): every rank reduces its slice to a small record (a digit histogram of the radix select,
+    a few (hi, lo) partial sums), the records are all-gathered (NCCL over NVLink 5 / NVSwitch, a few KB) and every rank folds
+    them in rank order.  Three histogram exchanges and one for the sums;
+  * the smoothing (:326-331), a centred rolling mean of 1 % of the signal: the first and last window/2 selections of every
+    rank ride on the first histogram exchange and give the neighbours their halo;
+  * find_anomalies (:1363-1472), whose analysis windows each span a third of the signal: the per-window final scores
+    (8 B per window) are all-gathered once, the twenty-odd analysis windows dealt out to the ranks and their few runs gathered
+    (a few KB).
+Every rank keeps and returns ITS slice of the per-window results (`final_local`, ...); nothing O(total length) is computed
+twice.  The partial sums are carried as unevaluated double pairs (csrc/dd.cuh), so the statistics do not depend on how many
+ranks took part: a sharded run equals the single-GPU run bit for bit (tests/test_gpu_parity.py, scripts/check_sharded.py).
+There is no collective inside a kernel.
 """
 import math
 
@@ -55,6 +62,14 @@ def _all_gather_padded(local, width, group=None, async_op=False):
     return out.view(world, width), work
 
 
+def _pad_to(local, width):
+    if local.shape[0] == width:
+        return local.contiguous()
+    buf = local.new_zeros(width)
+    buf[: local.shape[0]] = local
+    return buf
+
+
 def _concat_rows(out, sizes):
     """Rows of a padded gather result cut to their true lengths and concatenated (a view when nothing was padded)."""
     if all(s == out.shape[1] for s in sizes):
@@ -70,16 +85,33 @@ def gather_concat(local, sizes, group=None):
     return _concat_rows(out, sizes)
 
 
+class TorchComm:
+    """The stage exchange over torch.distributed: all_gather_into_tensor of one flat device buffer per rank."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def all_gather(self, buf):
+        flat = buf.reshape(-1)
+        out = flat.new_empty(self.world * flat.numel())
+        dist.all_gather_into_tensor(out, flat, group=self.group)
+        return out.view(self.world, -1)
+
+
 class ShardedScorer:
     """WindowScorer over torch.distributed.  Each rank holds only its slice of the signal (`local_slice`)."""
 
-    def __init__(self, scorer, group=None, rank=None, world=None):
+    def __init__(self, scorer, group=None, rank=None, world=None, comm=None):
         """rank / world default to the process group's; passing both makes an object that plans and packs for that rank
-        without touching torch.distributed (tests replay all ranks of a sharded run on one GPU with it)."""
+        without touching torch.distributed; `comm` (rank, world, all_gather) then carries the stage exchanges -- tests replay all
+        ranks of a sharded run on one GPU, one thread per rank, with it."""
         self.scorer = scorer
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
+        self.comm = comm if comm is not None else (TorchComm(group) if rank is None else None)
 
     def plan(self, n_windows):
         """(first, count, h0, sample_lo, sample_hi): owned windows, first halo window and the sample range
@@ -99,71 +131,65 @@ class ShardedScorer:
         h0 = halo_first(first, self.scorer.S)
         return first, count, h0, h0, first + count
 
-    def pack_local(self, fw, n_windows):
-        """This rank's contribution to the gather, from its forward results `fw` (windows h0 .. first+count-1): one fp32 buffer
-        [kmax | rec | unorm], each part `width` long.  kmax is one of the fp32 critic values widened to float64, so it travels as
-        fp32 without loss; rec and unorm are fp32 anyway.  12 B per position."""
+    def position_ranges(self, n_windows):
+        """[(first position, count)] of every rank in the kmax array (n_windows + S - 1 positions)."""
         S = self.scorer.S
-        ranges = shard_ranges(n_windows, self.world)
-        first, count = ranges[self.rank]
-        h0 = halo_first(first, S)
-        lead = first - h0
-        t0, tc = timestep_range(first, count, n_windows, S, self.rank == self.world - 1)
-        kmax_local = scoring.kde_argmax_overlap(fw["critic"], S, n_windows=n_windows, critic_offset=h0, t0=t0, t_count=tc)
-        width = self.gather_width(n_windows)
-        pack = fw["rec"].new_zeros(3 * width)
-        pack[:tc] = kmax_local.float()
-        pack[width:width + count] = fw["rec"][lead:]
-        pack[2 * width:2 * width + count] = fw["unorm"][lead:]
-        return pack
+        return [timestep_range(f, c, n_windows, S, r == self.world - 1) for r, (f, c) in enumerate(shard_ranges(n_windows, self.world))]
 
-    def gather_width(self, n_windows):
-        ranges = shard_ranges(n_windows, self.world)
-        return max(timestep_range(f, c, n_windows, self.scorer.S, r == self.world - 1)[1] for r, (f, c) in enumerate(ranges))
+    def _gather_windows(self, local, n_windows):
+        """Per-window array of the own windows -> the full array on every rank (one all-gather)."""
+        counts = [c for _, c in shard_ranges(n_windows, self.world)]
+        g = self.comm.all_gather(_pad_to(local, max(counts)))
+        return _concat_rows(g, counts)
 
-    def unpack_gathered(self, flat, n_windows):
-        """flat: the world's packs back to back -> (kmax float64 (n+S-1,), rec fp32 (n,), unorm fp32 (n,))."""
-        S = self.scorer.S
-        ranges = shard_ranges(n_windows, self.world)
-        counts = [c for _, c in ranges]
-        tcounts = [timestep_range(f, c, n_windows, S, r == self.world - 1)[1] for r, (f, c) in enumerate(ranges)]
-        parts = flat.view(self.world, 3, self.gather_width(n_windows))
-        return _concat_rows(parts[:, 0, :], tcounts).double(), _concat_rows(parts[:, 1, :], counts), _concat_rows(parts[:, 2, :], counts)
+    def _score(self, fw, n, combination, index, multivariate, portion, padding, ddof):
+        sc, S = self.scorer, self.scorer.S
+        first, count = shard_ranges(n, self.world)[self.rank]
+        lead = first - halo_first(first, S)
+        ranges = self.position_ranges(n)
+        t0, tc = ranges[self.rank]
+        kmax = scoring.kde_argmax_overlap(fw["critic"], S, n_windows=n, critic_offset=halo_first(first, S), t0=t0, t_count=tc)
+        rec, unorm = fw["rec"][lead:], fw["unorm"][lead:]
+        if multivariate:  # utils/anomaly_detection_utils.py:177-178: a statistic of ALL rows
+            rec = scoring.zscore_clip_staged(rec, n, self.comm)
+        cs = scoring.critic_scores_staged(kmax, ranges, n + S - 1, math.trunc(n * 0.01), self.comm)
+        final = scoring.combine(combination, cs[:count], rec, unorm, n=count)
+        out = {"first": first, "count": count, "final_local": final, "kmax_local": kmax, "rec_local": rec, "unorm_local": unorm,
+               "critic_scores_local": cs[:count]}
+        if index is not None:
+            out["final"] = self._gather_windows(final, n)
+            out["intervals"] = self.find_anomaly_intervals(out["final"], index, portion, 0.1, anomaly_padding=padding, ddof=ddof)
+        sc.poll_error()  # after the collectives, so that every rank still reaches them
+        return out
 
-    def finish(self, kmax, rec, unorm, n_windows, combination, multivariate=False):
-        """The O(T) finish every rank repeats on the gathered arrays.  multivariate: rec goes through zscore / clip(0) + 1 over
-        ALL rows first (utils/anomaly_detection_utils.py:177-178) -- a global statistic, hence after the gather."""
-        if multivariate:
-            rec = scoring.zscore_clip(rec)
-        cs = scoring.critic_zscore_smooth(kmax, math.trunc(n_windows * 0.01))
-        final = scoring.combine(combination, cs[:n_windows], rec, unorm, n=n_windows)
-        return {"final": final, "kmax": kmax, "rec": rec, "unorm": unorm, "critic_scores": cs[:n_windows]}
-
-    def _gather(self, pack):
-        flat = pack.new_empty(self.world * pack.numel())
-        dist.all_gather_into_tensor(flat, pack, group=self.group)
-        return flat
+    def gather_full(self, out, n):
+        """The full-length arrays of a sharded result on every rank (tests, callers that want them): final, kmax, rec, unorm."""
+        res = dict(out)
+        if "final" not in res:
+            res["final"] = self._gather_windows(out["final_local"], n)
+        res["rec"] = self._gather_windows(out["rec_local"], n)
+        res["unorm"] = self._gather_windows(out["unorm_local"], n)
+        res["critic_scores"] = self._gather_windows(out["critic_scores_local"], n)
+        pc = [c for _, c in self.position_ranges(n)]
+        res["kmax"] = _concat_rows(self.comm.all_gather(_pad_to(out["kmax_local"], max(pc))), pc)
+        return res
 
     def score_hyperbolic(self, local_slice, n_windows, combination="uncertainty", index=None):
         """local_slice: samples [sample_lo, sample_hi) of the scaled signal (see plan()), on this rank's GPU.
-        Returns the full-length result on every rank."""
-        sc = self.scorer
+        Returns this rank's slice of the per-window results (`final_local`, `kmax_local`, `rec_local`, `unorm_local`,
+        `critic_scores_local`, with `first` / `count`); when `index` is given also the gathered `final` and the intervals, the
+        same on every rank."""
         first, count, h0, lo, hi = self.plan(n_windows)
         if local_slice.numel() != hi - lo:
             raise ValueError("local slice has %d samples, plan() asks for %d" % (local_slice.numel(), hi - lo))
-        fw = sc.forward(local_slice, True)  # windows h0 .. first+count-1
-        # One collective for the three per-position arrays
-        kmax, rec, unorm = self.unpack_gathered(self._gather(self.pack_local(fw, n_windows)), n_windows)
-        out = self.finish(kmax, rec, unorm, n_windows, combination)
-        if index is not None:
-            out["intervals"] = self.find_anomaly_intervals(out["final"], index, 0.33, 0.1, anomaly_padding=50, ddof=1)
-        sc.poll_error()  # after the collectives, so that every rank still reaches them
-        return out
+        fw = self.scorer.forward(local_slice, True)  # windows h0 .. first+count-1
+        scoring.univariate_hyperbolic_semantics(combination)
+        return self._score(fw, n_windows, combination, index, False, 0.33, 50, 1)
 
     def score_multivariate(self, local_rows, n_rows, combination="mult", index=None):
         """BASELINE config 4: (N, C) rows sharded by contiguous row range.  local_rows: rows [row_lo, row_hi) of plan_rows() on
         this rank's GPU, shape (row_hi - row_lo, C).  Hyperbolic models (the Euclidean multivariate score is a float64 row norm;
-        score it unsharded with WindowScorer.score).  Returns the full-length result on every rank; equals
+        score it unsharded with WindowScorer.score).  Same result layout as score_hyperbolic; equals
         `WindowScorer.score(rows, sliding=False, multivariate=True)` bit for bit."""
         sc = self.scorer
         if not sc.hyperbolic:
@@ -172,12 +198,7 @@ class ShardedScorer:
         if local_rows.dim() != 2 or local_rows.shape[0] != hi - lo:
             raise ValueError("local rows have shape %s, plan_rows() asks for %d rows" % (tuple(local_rows.shape), hi - lo))
         fw = sc.forward(local_rows, False)  # rows h0 .. first+count-1
-        kmax, rec, unorm = self.unpack_gathered(self._gather(self.pack_local(fw, n_rows)), n_rows)
-        out = self.finish(kmax, rec, unorm, n_rows, combination, multivariate=True)
-        if index is not None:
-            out["intervals"] = self.find_anomaly_intervals(out["final"], index, 0.2, 0.1, anomaly_padding=200, ddof=0)
-        sc.poll_error()
-        return out
+        return self._score(fw, n_rows, combination, index, True, 0.2, 200, 0)
 
     MAX_RUNS = 64  # per analysis window in the gathered buffer; more (never seen) -> every rank redoes all windows
 
@@ -202,9 +223,7 @@ class ShardedScorer:
             local[: kc * 4] = sub[:r_loc]
             local[per * 4: per * 4 + n_loc] = sub[r_loc:r_loc + n_loc]
             local[per * 4 + per * R * 3: per * 4 + per * R * 3 + (kc + 1) // 2] = sub[r_loc + n_loc:s_loc]
-        parts = [torch.empty_like(local) for _ in range(self.world)]
-        dist.all_gather(parts, local, group=self.group)
-        host = torch.stack(parts).cpu().numpy()
+        host = self.comm.all_gather(local).cpu().numpy()
         stats, runs, n_runs = [], [], []
         for r in range(self.world):
             rk0 = min(r * per, count)

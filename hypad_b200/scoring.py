@@ -122,6 +122,138 @@ def critic_zscore_smooth(kmax, smooth_window):
     return out
 
 
+class LocalComm:
+    """The exchange of a world of one: a stage's record is handed straight to the next stage."""
+    rank, world = 0, 1
+
+    def all_gather(self, buf):
+        return buf.view(1, -1)
+
+
+def _record_buffer(dev, *parts):
+    """One uint8 device buffer holding the named parts back to back (8-byte aligned): [(name, dtype, numel)] ->
+    (buffer, {name: view}, {name: (byte offset, byte length)})."""
+    off, spans = 0, {}
+    for name, dtype, numel in parts:
+        nbytes = numel * torch.empty(0, dtype=dtype).element_size()
+        spans[name] = (off, nbytes, dtype)
+        off += (nbytes + 7) // 8 * 8
+    buf = torch.empty(max(off, 8), dtype=torch.uint8, device=dev)
+    views = {name: buf[o:o + n].view(dt) for name, (o, n, dt) in spans.items()}
+    return buf, views, spans
+
+
+def _halo_from_strips(strips, ranges, rank, need_left, need_right):
+    """strips: (world, 2, H) -- every rank's first and last min(len, H) values, right-/left-aligned as stored by
+    critic_scores_staged; ranges: [(p0, len)] per rank.  Returns (left, right): the `need_left` values before this rank's
+    positions and the `need_right` values after them, walking outwards over as many ranks as it takes."""
+    H = strips.shape[2]
+    left, right = [], []
+    got, r = 0, rank - 1
+    while got < need_left and r >= 0:
+        ln = min(ranges[r][1], H)
+        take = min(ln, need_left - got)
+        if take:
+            left.insert(0, strips[r, 1, H - take:])  # the rank's last `take` values (its strip is right-aligned)
+        got += take
+        if ranges[r][1] > H and got < need_left:
+            raise HypadError("hypad_b200: smoothing halo reaches beyond a neighbour's strip")
+        r -= 1
+    got, r = 0, rank + 1
+    while got < need_right and r < len(ranges):
+        ln = min(ranges[r][1], H)
+        take = min(ln, need_right - got)
+        if take:
+            right.append(strips[r, 0, :take])  # the rank's first `take` values (left-aligned)
+        got += take
+        if ranges[r][1] > H and got < need_right:
+            raise HypadError("hypad_b200: smoothing halo reaches beyond a neighbour's strip")
+        r += 1
+    return left, right
+
+
+def critic_scores_staged(kmax_local, ranges, n_total, smooth_window, comm=None, keys_f32=True):
+    """_compute_critic_score (:307-333) for this rank's positions of a kmax array sharded by contiguous range.
+
+    kmax_local: float64 device tensor, the positions ranges[comm.rank] = (p0, len) of the n_total-long array.
+    Stages (critic_stats.cu) with one small all-gather between them: digit histograms of the radix select (3 passes on
+    fp32-representable values) with the smoothing halo riding on the first, then the partial sums of mean / std.
+    Returns the smoothed z-scores of the own positions (len,)."""
+    comm = comm or LocalComm()
+    kmax_local = _native.require_cuda(kmax_local, "kmax").double().contiguous()
+    dev = kmax_local.device
+    c = _ctx(kmax_local)
+    lib, h, st = c.lib, c.handle, c.stream
+    p0, ln = ranges[comm.rank]
+    if kmax_local.shape[0] != ln:
+        raise HypadError("hypad_b200: kmax slice has %d positions, the plan says %d" % (kmax_local.shape[0], ln))
+    w = int(smooth_window)
+    back, fwd = (w // 2, (w - 1) // 2) if w > 0 else (0, 0)
+    H = back if comm.world > 1 else 0
+    HW = 8192  # HYPAD_SELECT_HIST_WORDS
+    with torch.cuda.device(dev):
+        check(lib.hypad_stats_select_begin(h, int(n_total), int(keys_f32), st()))
+        strips = None
+        for p in range(lib.hypad_stats_select_passes(int(keys_f32))):
+            parts = [("hist", torch.int32, HW)]
+            if p == 0 and H:
+                parts.append(("strips", torch.float64, 2 * H))
+            buf, v, spans = _record_buffer(dev, *parts)
+            check(lib.hypad_stats_select_hist(h, ptr(kmax_local), ln, p, ptr(v["hist"]), st()))
+            if p == 0 and H:
+                k = min(ln, H)
+                v["strips"].zero_()
+                if k:
+                    v["strips"][:k] = kmax_local[:k]             # first values, left-aligned
+                    v["strips"][2 * H - k:] = kmax_local[ln - k:]  # last values, right-aligned
+            g = comm.all_gather(buf)
+            if p == 0 and H:
+                o, n, _ = spans["strips"]
+                strips = g[:, o:o + n].contiguous().view(torch.float64).view(comm.world, 2, H)
+            if comm.world > 1:
+                hists = g[:, :HW * 4].contiguous()
+            else:
+                hists = g
+            check(lib.hypad_stats_select_pick(h, ptr(hists), comm.world, p, st()))
+        rec = torch.empty(8, dtype=torch.float64, device=dev)
+        check(lib.hypad_stats_moments_partial(h, ptr(kmax_local), 0, ln, 1, ptr(rec), st()))
+        recs = comm.all_gather(rec.view(torch.uint8)).contiguous()
+        check(lib.hypad_stats_moments_final(h, ptr(recs), comm.world, int(n_total), 1, 0, st()))
+        # the slice with its smoothing halo
+        lo, hi = max(p0 - back, 0), min(p0 + ln + fwd, n_total)
+        if comm.world > 1 and ln and (lo < p0 or hi > p0 + ln):
+            left, right = _halo_from_strips(strips, ranges, comm.rank, p0 - lo, hi - (p0 + ln))
+            ext = torch.cat(left + [kmax_local] + right)
+        else:
+            ext, lo, hi = kmax_local, p0, p0 + ln
+        out = torch.empty(ln, dtype=torch.float64, device=dev)
+        if ln:
+            if ext.shape[0] != hi - lo:
+                raise HypadError("hypad_b200: assembled %d positions of kmax, expected %d" % (ext.shape[0], hi - lo))
+            check(lib.hypad_critic_smooth_shard(h, ptr(ext), ext.shape[0], lo, int(n_total), p0, ln, w, ptr(out), st()))
+    return out
+
+
+def zscore_clip_staged(x_local, n_total, comm=None):
+    """stats.zscore + clip(0) + 1 (:177-178, :523-524) of an array sharded over the ranks: mean / std of ALL rows from the
+    ranks' partial sums, applied to the local rows."""
+    comm = comm or LocalComm()
+    x_local = _native.require_cuda(x_local, "x")
+    if x_local.dtype not in (torch.float32, torch.float64):
+        x_local = x_local.double()
+    x_local = x_local.contiguous()
+    c = _ctx(x_local)
+    out = torch.empty(x_local.shape, dtype=torch.float64, device=x_local.device)
+    f32 = int(x_local.dtype == torch.float32)
+    with torch.cuda.device(x_local.device):
+        rec = torch.empty(8, dtype=torch.float64, device=x_local.device)
+        check(c.lib.hypad_stats_moments_partial(c.handle, ptr(x_local), f32, x_local.numel(), 0, ptr(rec), c.stream()))
+        recs = comm.all_gather(rec.view(torch.uint8)).contiguous()
+        check(c.lib.hypad_stats_moments_final(c.handle, ptr(recs), comm.world, int(n_total), 0, 0, c.stream()))
+        check(c.lib.hypad_zscore_clip_apply(c.handle, ptr(x_local), f32, x_local.numel(), ptr(out), c.stream()))
+    return out
+
+
 def rolling_mean_centered(x, window, min_periods=None):
     x = _native.require_cuda(x, "x").double().contiguous()
     out = torch.empty_like(x)
@@ -520,7 +652,9 @@ class WindowScorer:
     def critic_scores(self, critic, n_windows):
         """final_critic_scores (:365-404): KDE arg-max overlap aggregation + quantile-band z-score + smoothing."""
         kmax = kde_argmax_overlap(critic, self.S)
-        return critic_zscore_smooth(kmax, math.trunc(n_windows * 0.01)), kmax
+        total = kmax.shape[0]
+        # kmax holds fp32 critic values widened to float64: 32-bit keys, three select passes
+        return critic_scores_staged(kmax, [(0, total)], total, math.trunc(n_windows * 0.01)), kmax
 
     def score(self, x, sliding=True, combination="uncertainty", rec_error_type="dtw", index=None, keep=(), multivariate=False,
               lambda_rec=0.5, poll=True):

@@ -249,6 +249,39 @@ int hypad_threshold_windows_exhaustive(hypad_ctx* ctx, const double* errors, int
                             int64_t n_analysis, int ddof, int anomaly_padding, double* stats, double* runs,
                             int32_t* n_runs, int max_runs, void* stream);
 
+/* ---- staged global statistics: one GPU's slice per call, a small record exchanged between stages -------------------------
+ * The reference computes its statistics on whole arrays (np.quantile / mean / std in _compute_critic_score,
+ * utils/anomaly_detection_utils.py:307-333; stats.zscore at :177 and :523).  When a signal's windows are sharded over
+ * several GPUs each stage below works on the local slice and leaves a record the caller all-gathers (rank order) before
+ * the next stage; with one GPU the records are passed straight on (hypad_critic_zscore_smooth / hypad_zscore_clip do that).
+ * The state between stages lives in the context: one chain at a time per context, in stream order. */
+#define HYPAD_SELECT_HIST_WORDS 8192 /* uint32 words of one rank's histogram record (4 order statistics x 2048 bins) */
+#define HYPAD_MOMENTS_RECORD_DOUBLES 8
+/* Number of radix-select passes: 3 when the values are fp32-representable (32-bit keys), else 6. */
+int hypad_stats_select_passes(int keys_f32);
+/* Starts the selection of the four order statistics around the 25 % / 75 % quantiles of n_total values. */
+int hypad_stats_select_begin(hypad_ctx* ctx, int64_t n_total, int keys_f32, void* stream);
+/* hist[HYPAD_SELECT_HIST_WORDS] = this slice's digit histogram of pass `pass` (zeroed first). */
+int hypad_stats_select_hist(hypad_ctx* ctx, const double* x, int64_t len, int pass, uint32_t* hist, void* stream);
+/* hists: `world` records back to back.  After the last pass the quantiles are known to the later stages. */
+int hypad_stats_select_pick(hypad_ctx* ctx, const uint32_t* hists, int world, int pass, void* stream);
+/* record[8] = (hi, lo) pairs of sum x, sum x^2, and -- band != 0 -- sum / count of the x inside [q25, q75]. */
+int hypad_stats_moments_partial(hypad_ctx* ctx, const void* x, int x_is_f32, int64_t len, int band, double* record,
+                                void* stream);
+/* records: `world` records back to back.  band != 0: critic mean (in band) and std (all, ddof 0) for
+ * hypad_critic_smooth_shard; band == 0: mean and std (ddof) for hypad_zscore_clip_apply. */
+int hypad_stats_moments_final(hypad_ctx* ctx, const double* records, int world, int64_t n_total, int band, int ddof,
+                              void* stream);
+/* host8[0..7] = q25, q75, mean(all), mean(in band), std(all), z-score mean, z-score std, 0 (synchronises; diagnostics). */
+int hypad_stats_read(hypad_ctx* ctx, double* host8, void* stream);
+/* :322-331 on a slice: kmax_ext holds the global positions [ext0, ext0 + ext_len) of n_total; out[j] = rolling mean
+ * (window smooth_window, centred, min_periods window/2) of |x - mean_band| / std + 1 at position p0 + j, j < count.  The slice
+ * must hold the smoothing halo: positions p0 - window/2 .. p0 + count - 1 + (window-1)/2, clipped to [0, n_total). */
+int hypad_critic_smooth_shard(hypad_ctx* ctx, const double* kmax_ext, int64_t ext_len, int64_t ext0, int64_t n_total, int64_t p0,
+                              int64_t count, int64_t smooth_window, double* out, void* stream);
+/* out = clip((x - mean) / std, 0) + 1 with the mean / std of hypad_stats_moments_final(band = 0). */
+int hypad_zscore_clip_apply(hypad_ctx* ctx, const void* x, int x_is_f32, int64_t len, double* out, void* stream);
+
 /* Diagnostic (not on the product path): D (128,N) = A (128,K) B(N,K)^T on the tcgen05 tensor cores with the fp32
  * operands split into `pieces` TF32 parts and `terms` partial products accumulated in TMEM: (1,1) plain TF32,
  * (2,3) 3xTF32, (3,6) six-term split.  Used to measure whether a tensor-core contraction can hold score parity. */

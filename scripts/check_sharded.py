@@ -22,18 +22,25 @@ def main():
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for case in ("cfg1_hyp_uncertainty.npz", "noisy1500_hyp_uncertainty.npz", "edge_n300_hyp.npz"):
-        g = golden(case)
+    for case in ("cfg1_hyp_uncertainty.npz", "noisy1500_hyp_uncertainty.npz", "edge_n300_hyp.npz", "long200k"):
         enc, dec, cx, _ = build_modules("weights_hyp_s100.npz", 100, True, dev)
         scorer = WindowScorer(enc, dec, cx)
-        sig = full_signal(g)
+        if case == "long200k":  # the staged statistics at a size where halos and quantile ranks cross rank boundaries
+            from conftest import long_signal
+
+            sig = long_signal(200000)
+            g = {"index": np.arange(200000)}
+        else:
+            g = golden(case)
+            sig = full_signal(g)
         n = sig.shape[0] - 100
         sh = ShardedScorer(scorer)
         first, count, h0, lo, hi = sh.plan(n)
         local_slice = torch.from_numpy(sig[lo:hi].copy()).to(dev)
-        out = sh.score_hyperbolic(local_slice, n, "uncertainty", index=g["index"])
+        out = sh.gather_full(sh.score_hyperbolic(local_slice, n, "uncertainty", index=g["index"]), n)
         ref = scorer.score(torch.from_numpy(sig).to(dev), True, "uncertainty", index=g["index"])
-        same = all(torch.equal(out[k], ref[k]) for k in ("final", "kmax", "rec", "unorm"))
+        same = all(torch.equal(out[k], ref[k]) for k in ("final", "kmax", "rec", "unorm", "critic_scores"))
+        same = same and torch.equal(out["final_local"], ref["final"][out["first"]:out["first"] + out["count"]])
         same = same and out["intervals"].shape == ref["intervals"].shape and np.array_equal(out["intervals"], ref["intervals"])
         t = torch.tensor([int(same)], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
@@ -48,7 +55,7 @@ def main():
     index = 1353715200.0 + np.arange(4000)
     sh = ShardedScorer(scorer)
     first, count, h0, lo, hi = sh.plan_rows(4000)
-    out = sh.score_multivariate(torch.from_numpy(rows[lo:hi].copy()).to(dev), 4000, "mult", index=index)
+    out = sh.gather_full(sh.score_multivariate(torch.from_numpy(rows[lo:hi].copy()).to(dev), 4000, "mult", index=index), 4000)
     ref = scorer.score(torch.from_numpy(rows).to(dev), False, "mult", index=index, multivariate=True)
     same = all(torch.equal(out[k], ref[k]) for k in ("final", "kmax", "rec")) and np.array_equal(out["intervals"], ref["intervals"])
     t = torch.tensor([int(same)], device=dev)

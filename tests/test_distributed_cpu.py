@@ -145,10 +145,10 @@ def test_signal_sweep_world2():
 
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 @pytest.mark.parametrize("n,S,rows", [(2500, 123, True), (1400, 100, False), (130, 100, False), (7, 3, True)])
-def test_pack_layout_round_trips(world, n, S, rows):
-    """The gather layout of ShardedScorer ([kmax | rec | unorm] per rank, `width` each) for every rank of a run, on CPU tensors:
-    packs built the way pack_local lays them out, concatenated like all_gather_into_tensor, must unpack to the global arrays --
-    for window sharding (sample ranges with S extra samples) and row sharding (multivariate, config 4)."""
+def test_plan_and_gather_layout_round_trip(world, n, S, rows):
+    """The plan of every rank of a run (owned windows, halo, resident samples / rows, owned positions of the kmax array) and the
+    layout of the padded all-gathers that put the ranks' slices back together (ShardedScorer.gather_full), on CPU tensors with
+    a stand-in for the exchange: slices cut the way the ranks hold them must come back as the global arrays."""
     from hypad_b200 import distributed as hd
 
     class FakeScorer:
@@ -156,25 +156,66 @@ def test_pack_layout_round_trips(world, n, S, rows):
 
     fs = FakeScorer()
     fs.S = S
-    kmax_g = torch.arange(n + S - 1, dtype=torch.float32) * 0.25 + 1
+    kmax_g = torch.arange(n + S - 1, dtype=torch.float64) * 0.25 + 1
     rec_g = torch.arange(n, dtype=torch.float32) + 1000
-    unorm_g = torch.arange(n, dtype=torch.float32) + 5000
+    fin_g = torch.arange(n, dtype=torch.float64) + 5000
     ranges = hd.shard_ranges(n, world)
-    packs, covered = [], 0
+    slots = {}
+
+    class Comm:
+        def __init__(self, rank):
+            self.rank, self.world = rank, world
+
+        def all_gather(self, buf):  # every rank's buffer for this call was deposited beforehand
+            return torch.stack(slots[(buf.dtype, buf.numel())])
+
+    shs, outs, covered, pos = [], [], 0, 0
     for r in range(world):
-        sh = hd.ShardedScorer(fs, rank=r, world=world)
+        sh = hd.ShardedScorer(fs, rank=r, world=world, comm=Comm(r))
         first, count, h0, lo, hi = sh.plan_rows(n) if rows else sh.plan(n)
         assert (first, count) == ranges[r] and h0 == max(0, first - (S - 1)) and lo == h0
         assert hi == first + count + (0 if rows else S)
         covered += count
-        width = sh.gather_width(n)
-        t0, tc = hd.timestep_range(first, count, n, S, r == world - 1)
-        pack = torch.zeros(3 * width)
-        pack[:tc] = kmax_g[t0:t0 + tc]
-        pack[width:width + count] = rec_g[first:first + count]
-        pack[2 * width:2 * width + count] = unorm_g[first:first + count]
-        packs.append(pack)
-    assert covered == n
-    kmax, rec, unorm = sh.unpack_gathered(torch.cat(packs), n)
-    assert kmax.dtype == torch.float64 and torch.equal(kmax, kmax_g.double())
-    assert torch.equal(rec, rec_g) and torch.equal(unorm, unorm_g)
+        t0, tc = sh.position_ranges(n)[r]
+        assert t0 == pos and tc == count + (S - 1 if r == world - 1 else 0)
+        pos += tc
+        outs.append({"final_local": fin_g[first:first + count], "rec_local": rec_g[first:first + count],
+                     "unorm_local": rec_g[first:first + count] * 2, "critic_scores_local": fin_g[first:first + count] * 3,
+                     "kmax_local": kmax_g[t0:t0 + tc]})
+        shs.append(sh)
+    assert covered == n and pos == n + S - 1
+    wmax = max(c for _, c in ranges)
+    pmax = max(c for _, c in shs[0].position_ranges(n))
+    # one array at a time: the stand-in hands back what all ranks would have contributed to this call
+    for r in range(world):
+        for key, width, want in (("final_local", wmax, fin_g), ("rec_local", wmax, rec_g), ("kmax_local", pmax, kmax_g)):
+            slots[(outs[0][key].dtype, width)] = [hd._pad_to(outs[q][key], width) for q in range(world)]
+            if key == "kmax_local":
+                got = hd._concat_rows(shs[r].comm.all_gather(hd._pad_to(outs[r][key], width)), [c for _, c in shs[r].position_ranges(n)])
+            else:
+                got = shs[r]._gather_windows(outs[r][key], n)
+            assert torch.equal(got, want), (r, key)
+
+
+def test_halo_from_strips_walks_over_short_neighbours():
+    """The smoothing halo is cut from the neighbours' edge strips; a neighbour shorter than the halo hands over all it has and
+    the walk goes on to the next rank (hypad_b200.scoring._halo_from_strips)."""
+    from hypad_b200.scoring import _halo_from_strips
+
+    full = torch.arange(40, dtype=torch.float64)
+    for lens, H in (([10, 10, 10, 10], 4), ([17, 2, 1, 20], 5), ([3, 3, 3, 31], 6), ([40], 3), ([0, 20, 0, 20], 4)):
+        ranges, p = [], 0
+        for ln in lens:
+            ranges.append((p, ln))
+            p += ln
+        strips = torch.zeros(len(lens), 2, H, dtype=torch.float64)
+        for r, (p0, ln) in enumerate(ranges):
+            k = min(ln, H)
+            if k:
+                strips[r, 0, :k] = full[p0:p0 + k]
+                strips[r, 1, H - k:] = full[p0 + ln - k:p0 + ln]
+        for r, (p0, ln) in enumerate(ranges):
+            nl, nr = min(H, p0), min(H, 40 - (p0 + ln))
+            left, right = _halo_from_strips(strips, ranges, r, nl, nr)
+            got = torch.cat(left + [full[p0:p0 + ln]] + right)
+            assert torch.equal(got, full[p0 - nl:p0 + ln + nr]), (lens, r)

@@ -873,20 +873,83 @@ def test_signal_sweep_equals_per_signal_scoring(cuda_device):
 # ------------------------------------------------------------------------------------------------------------
 # sharding by window / row range, every rank replayed on this one GPU (the NCCL run itself: tests/test_gpu_sharded.py)
 # ------------------------------------------------------------------------------------------------------------
-def replay_sharded(scorer, x, n, world, sliding, combination, multivariate):
-    """What `world` ranks compute, one after the other on this GPU: each rank's slice (with its halo) through pack_local, the
-    packs laid back to back like all_gather_into_tensor does, then unpack + finish."""
+class ThreadComm:
+    """The stage exchange of a sharded run replayed on one GPU: one thread (and one CUDA stream, hence one library context) per
+    rank; all_gather hands every rank the stack of all ranks' buffers."""
+
+    def __init__(self, world):
+        import threading
+
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.slots = [None] * world
+
+    def for_rank(self, rank):
+        outer = self
+
+        class Comm:
+            world = outer.world
+
+            def all_gather(self, buf):
+                ev = torch.cuda.Event()
+                ev.record()
+                outer.slots[rank] = (buf.reshape(-1), ev)
+                outer.barrier.wait()
+                for _, e in outer.slots:
+                    torch.cuda.current_stream().wait_event(e)
+                out = torch.stack([b for b, _ in outer.slots])
+                torch.cuda.current_stream().synchronize()
+                outer.barrier.wait()
+                return out
+
+        c = Comm()
+        c.rank = rank
+        return c
+
+
+def replay_sharded(scorer, x, n, world, sliding, combination, multivariate, index=None):
+    """What `world` ranks compute, replayed on this GPU: each rank's slice (with its halo) through the fused network one after
+    the other, then the staged finish of all ranks side by side (threads standing in for the processes, ThreadComm for NCCL).
+    Returns rank 0's result with the full-length arrays gathered."""
+    import threading
+
     from hypad_b200.distributed import ShardedScorer
 
-    packs = []
+    tc = ThreadComm(world)
+    shs, fws = [], []
     for r in range(world):
-        sh = ShardedScorer(scorer, rank=r, world=world)
+        sh = ShardedScorer(scorer, rank=r, world=world, comm=tc.for_rank(r))
         first, count, h0, lo, hi = sh.plan(n) if sliding else sh.plan_rows(n)
         assert hi - lo == (count + first - h0 + (scorer.S if sliding else 0))
-        fw = scorer.forward(x[lo:hi].contiguous(), sliding)
-        packs.append(sh.pack_local(fw, n))
-    kmax, rec, unorm = sh.unpack_gathered(torch.cat(packs), n)
-    return sh.finish(kmax, rec, unorm, n, combination, multivariate=multivariate)
+        fws.append(scorer.forward(x[lo:hi].contiguous(), sliding))
+        shs.append(sh)
+    scorer.poll_error()
+    torch.cuda.synchronize()
+    results, errors = [None] * world, []
+
+    def run(r):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                out = shs[r]._score(fws[r], n, combination, index, multivariate, 0.2 if multivariate else 0.33,
+                                    200 if multivariate else 50, 0 if multivariate else 1)
+                results[r] = shs[r].gather_full(out, n)
+                torch.cuda.current_stream().synchronize()
+        except BaseException as e:  # noqa: BLE001 -- surfaced below; the barrier must not be left waiting
+            errors.append(e)
+            tc.barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    for r in range(1, world):
+        for k in ("final", "kmax", "rec", "unorm", "critic_scores"):
+            assert torch.equal(results[r][k], results[0][k]), (r, k)
+        if index is not None:
+            assert np.array_equal(results[r]["intervals"], results[0]["intervals"])
+    return results[0]
 
 
 @pytest.mark.gpu
@@ -915,10 +978,35 @@ def test_sharded_windows_univariate_equal_unsharded(world, hyp_scorer, cuda_devi
     g = golden("noisy1500_hyp_uncertainty.npz")
     x = dev_signal(g, cuda_device)
     n = x.shape[0] - 100
-    ref = hyp_scorer.score(x, True, "uncertainty")
-    out = replay_sharded(hyp_scorer, x, n, world, True, "uncertainty", False)
-    for k in ("final", "kmax", "rec", "unorm"):
+    ref = hyp_scorer.score(x, True, "uncertainty", index=g["index"])
+    out = replay_sharded(hyp_scorer, x, n, world, True, "uncertainty", False, index=g["index"])
+    for k in ("final", "kmax", "rec", "unorm", "critic_scores"):
         assert torch.equal(out[k], ref[k]), k
+    assert np.array_equal(out["intervals"], ref["intervals"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,T", [(8, 60000), (3, 200000)])
+def test_sharded_long_signal_staged_statistics_equal_unsharded(world, T, hyp_scorer, cuda_device):
+    """The staged statistics at a size where they matter: the smoothing window (1 % of the windows) needs a halo of hundreds of
+    positions from the neighbours, the quantile ranks fall inside other ranks' slices, and the partial sums of eight ranks
+    must round to the single-GPU mean / std."""
+    from conftest import long_signal
+
+    sig = long_signal(T)
+    sig[T // 3: T // 3 + 4000] = sig[T // 3]  # a flat stretch across a rank boundary region
+    x = torch.from_numpy(sig).to(cuda_device)
+    n = T - 100
+    index = np.arange(T)
+    ref = hyp_scorer.score(x, True, "uncertainty", index=index)
+    out = replay_sharded(hyp_scorer, x, n, world, True, "uncertainty", False, index=index)
+    for k in ("kmax", "rec", "unorm", "critic_scores", "final"):
+        assert torch.equal(out[k], ref[k]), k
+    assert np.array_equal(out["intervals"], ref["intervals"]) and len(ref["intervals"]) >= 1
+    # and the statistics themselves against numpy on the gathered selections
+    km = ref["kmax"].cpu().numpy()
+    want = ho.compute_critic_score(km, math.trunc(n * 0.01))[:n]
+    np.testing.assert_allclose(ref["critic_scores"].cpu().numpy(), want, rtol=1e-11, atol=0)
 
 
 @pytest.mark.gpu
