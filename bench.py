@@ -246,11 +246,11 @@ def run_native(args):
         return scorer.score(x, True, "uncertainty", index=index)
 
     def step_e2e():
-        x = host_slice.to(dev, non_blocking=True)
-        out = step(x)
-        host_final.copy_(out["final_local"] if distributed else out["final"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return out
+        # the public call with HOST buffers: pinned signal in, pinned scores out (upload in chunks under the network,
+        # download under the interval extraction); returns when the scores are in host_final and the intervals are known
+        if distributed:
+            return sharded.score_hyperbolic(host_slice, n_windows, "uncertainty", index=index, out_host=host_final)
+        return scorer.score(host_slice, True, "uncertainty", index=index, out_host=host_final)
 
     def barrier():
         if distributed:

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(NQ * 32) sel_pick_kernel(const unsigned int* _
 
 // Local partial sums: out[0..1] sum x, [2..3] sum x^2, [4..5] sum of the x inside [lo, hi], [6] their count -- (hi, lo) pairs.
 // band: lo / hi come from st->s[0..1]; without it only the first two sums are taken (zscore moments).
-// The last CTA to finish folds the per-CTA records in CTA order (a fixed order: the result does not depend on scheduling).
+// The last CTA to finish folds the per-CTA records in a fixed pattern (the result does not depend on scheduling).
 template <typename T>
 __global__ void __launch_bounds__(RB) moments_partial_kernel(const T* __restrict__ x, int64_t len, int band, FinState* st,
                                                              double* __restrict__ scratch, double* __restrict__ out) {
@@ -220,20 +220,24 @@ __global__ void __launch_bounds__(RB) moments_partial_kernel(const T* __restrict
     __syncthreads();
     if (!last_cta) return;
     __threadfence();
-    if (threadIdx.x < 4) {  // thread t folds quantity t over the CTAs, in order
-        const int t = threadIdx.x;
+    const int t = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (t < 4) {  // warp t folds quantity t over the CTAs: lane-strided partial sums, then a fixed shuffle tree
         dd acc = dd_make(0.0);
-        for (unsigned int b = 0; b < gridDim.x; ++b) {
-            const volatile double* r = scratch + (size_t)b * 8;
-            acc = dd_add(acc, t < 3 ? dd_make(r[2 * t], r[2 * t + 1]) : dd_make(r[6]));
+        for (unsigned int b = lane; b < gridDim.x; b += 32) {
+            const double* r = scratch + (size_t)b * 8;
+            acc = dd_add(acc, t < 3 ? dd_make(__ldcg(r + 2 * t), __ldcg(r + 2 * t + 1)) : dd_make(__ldcg(r + 6)));
         }
-        if (t < 3) {
-            out[2 * t] = acc.hi;
-            out[2 * t + 1] = acc.lo;
-        } else {
-            out[6] = acc.hi;
-            out[7] = 0.0;
-            st->ticket = 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc = dd_add(acc, dd_shfl_xor(acc, o));
+        if (lane == 0) {
+            if (t < 3) {
+                out[2 * t] = acc.hi;
+                out[2 * t + 1] = acc.lo;
+            } else {
+                out[6] = acc.hi;
+                out[7] = 0.0;
+                st->ticket = 0u;
+            }
         }
     }
 }

@@ -1,0 +1,135 @@
+// Host tail of find_anomalies on the few runs per analysis window the device kernels extracted: prune (_prune_anomalies,
+// utils/anomaly_detection_utils.py:1203-1237), score (_compute_scores :1240-1269) and merge (_merge_sequences :1272-1313).
+// Plain C++ on the host -- the reference does this part on the host too, on a handful of rows per window; synthetic noise
+// (BASELINE config 4 at 8M rows) produces tens of thousands of runs, where an interpreter loop costs more than the kernels.
+// Arithmetic follows numpy / pandas to the bit: descending stable sort with NaN last, float64 (or float32) scores,
+// np.average as (v * w).sum() / w.sum() with numpy's pairwise summation order.
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace hypad {
+
+// numpy's pairwise_sum (umath loops): plain loop below 8, eight interleaved accumulators up to 128, halves above
+static double np_pairwise_sum_host(const double* a, int64_t n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int64_t i = 0; i < n; ++i) res += a[i];
+        return res;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        int64_t i = 8;
+        for (; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i];
+        return res;
+    }
+    int64_t n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_pairwise_sum_host(a, n2) + np_pairwise_sum_host(a + n2, n - n2);
+}
+
+struct Row {
+    double m, s, e;
+};
+struct Seq {
+    double s, e, score;
+};
+
+}  // namespace hypad
+
+using namespace hypad;
+
+extern "C" int hypad_intervals_from_runs(const double* stats, const double* runs, const int32_t* n_runs, int64_t count,
+                                         int64_t max_runs, int64_t step, double min_percent, int f32, double* out, int64_t cap,
+                                         int64_t* n_out) {
+    HYPAD_REQUIRE(stats && runs && n_runs && n_out && count >= 0 && max_runs >= 1 && (out || cap == 0), "hypad_intervals_from_runs: bad argument");
+    std::vector<Seq> seqs;
+    std::vector<Row> rows;
+    for (int64_t k = 0; k < count; ++k) {
+        const double mean = stats[k * 4 + 0], sd = stats[k * 4 + 1], thr = stats[k * 4 + 2], max_below = stats[k * 4 + 3];
+        const int64_t nr = n_runs[k];
+        HYPAD_REQUIRE(nr >= 0 && nr <= max_runs, "hypad_intervals_from_runs: window %lld has %lld runs, room for %lld", (long long)k,
+                      (long long)nr, (long long)max_runs);
+        rows.clear();
+        rows.push_back({max_below, -1.0, -1.0});
+        for (int64_t r = 0; r < nr; ++r) {
+            const double* p = runs + ((size_t)k * max_runs + r) * 3;
+            rows.push_back({p[2], p[0], p[1]});
+        }
+        // descending by max error, stable, NaN last (pandas sort_values(ascending=False), :1224)
+        std::stable_sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) {
+            const bool an = a.m != a.m, bn = b.m != b.m;
+            if (an || bn) return !an && bn;
+            return a.m > b.m;
+        });
+        // the last position whose drop to the next maximum is not "too small" (increase < min_percent is False)
+        int64_t last = -1;
+        for (size_t i = 0; i + 1 < rows.size(); ++i)
+            if (!((rows[i].m - rows[i + 1].m) / rows[i].m < min_percent)) last = (int64_t)i;
+        const double denom = f32 ? (double)(float)(mean + sd) : mean + sd;
+        const double shift = (double)(k * step);
+        for (int64_t i = 0; i <= last; ++i) {
+            const double d = rows[i].m - thr;
+            const double score = f32 ? (double)(float)((double)(float)d / denom) : d / denom;
+            seqs.push_back({rows[i].s + shift, rows[i].e + shift, score});
+        }
+    }
+    int64_t n = 0;
+    auto emit = [&](double s, double e, double sc) {
+        if (n < cap) {
+            out[n * 3 + 0] = s;
+            out[n * 3 + 1] = e;
+            out[n * 3 + 2] = sc;
+        }
+        ++n;
+    };
+    if (!seqs.empty()) {
+        std::stable_sort(seqs.begin(), seqs.end(), [](const Seq& a, const Seq& b) { return a.s < b.s; });
+        std::vector<double> score, weights, prod;
+        Seq cur = seqs[0];
+        score.assign(1, cur.score);
+        weights.assign(1, cur.e - cur.s);
+        bool grouped = false;
+        auto close = [&]() -> int {
+            if (grouped) {  // np.average(score, weights=weights)
+                const double scl = np_pairwise_sum_host(weights.data(), (int64_t)weights.size());
+                if (scl == 0.0) {
+                    set_error("Weights sum to zero, can't be normalized");
+                    return HYPAD_EZERODIV;
+                }
+                prod.resize(score.size());
+                for (size_t i = 0; i < score.size(); ++i) prod[i] = score[i] * weights[i];
+                cur.score = np_pairwise_sum_host(prod.data(), (int64_t)prod.size()) / scl;
+            }
+            emit(cur.s, cur.e, cur.score);
+            return HYPAD_OK;
+        };
+        for (size_t i = 1; i < seqs.size(); ++i) {
+            const Seq& q = seqs[i];
+            if (q.s <= cur.e + 1) {
+                score.push_back(q.score);
+                weights.push_back(q.e - q.s);
+                cur.e = q.e > cur.e ? q.e : cur.e;
+                grouped = true;
+            } else {
+                const int rc = close();
+                if (rc != HYPAD_OK) return rc;
+                cur = q;
+                score.assign(1, q.score);
+                weights.assign(1, q.e - q.s);
+                grouped = false;
+            }
+        }
+        const int rc = close();
+        if (rc != HYPAD_OK) return rc;
+    }
+    *n_out = n;
+    return HYPAD_OK;
+}

@@ -142,7 +142,7 @@ class ShardedScorer:
         g = self.comm.all_gather(_pad_to(local, max(counts)))
         return _concat_rows(g, counts)
 
-    def _score(self, fw, n, combination, index, multivariate, portion, padding, ddof):
+    def _score(self, fw, n, combination, index, multivariate, portion, padding, ddof, out_host=None):
         sc, S = self.scorer, self.scorer.S
         first, count = shard_ranges(n, self.world)[self.rank]
         lead = first - halo_first(first, S)
@@ -156,9 +156,13 @@ class ShardedScorer:
         final = scoring.combine(combination, cs[:count], rec, unorm, n=count)
         out = {"first": first, "count": count, "final_local": final, "kmax_local": kmax, "rec_local": rec, "unorm_local": unorm,
                "critic_scores_local": cs[:count]}
+        if out_host is not None:  # this rank's scores travel to its host while the interval extraction still runs
+            scoring.download_async(sc, final, out_host)
         if index is not None:
             out["final"] = self._gather_windows(final, n)
             out["intervals"] = self.find_anomaly_intervals(out["final"], index, portion, 0.1, anomaly_padding=padding, ddof=ddof)
+        if out_host is not None:
+            sc._down_stream.synchronize()
         sc.poll_error()  # after the collectives, so that every rank still reaches them
         return out
 
@@ -174,17 +178,22 @@ class ShardedScorer:
         res["kmax"] = _concat_rows(self.comm.all_gather(_pad_to(out["kmax_local"], max(pc))), pc)
         return res
 
-    def score_hyperbolic(self, local_slice, n_windows, combination="uncertainty", index=None):
-        """local_slice: samples [sample_lo, sample_hi) of the scaled signal (see plan()), on this rank's GPU.
+    def score_hyperbolic(self, local_slice, n_windows, combination="uncertainty", index=None, out_host=None):
+        """local_slice: samples [sample_lo, sample_hi) of the scaled signal (see plan()), on this rank's GPU -- or in pinned host
+        memory: then it is uploaded chunk by chunk under the network (WindowScorer.forward_from_host).  out_host: pinned float64
+        host tensor that receives `final_local`.
         Returns this rank's slice of the per-window results (`final_local`, `kmax_local`, `rec_local`, `unorm_local`,
         `critic_scores_local`, with `first` / `count`); when `index` is given also the gathered `final` and the intervals, the
         same on every rank."""
         first, count, h0, lo, hi = self.plan(n_windows)
         if local_slice.numel() != hi - lo:
             raise ValueError("local slice has %d samples, plan() asks for %d" % (local_slice.numel(), hi - lo))
-        fw = self.scorer.forward(local_slice, True)  # windows h0 .. first+count-1
         scoring.univariate_hyperbolic_semantics(combination)
-        return self._score(fw, n_windows, combination, index, False, 0.33, 50, 1)
+        if local_slice.is_cuda:
+            fw = self.scorer.forward(local_slice, True)  # windows h0 .. first+count-1
+        else:
+            fw = self.scorer.forward_from_host(local_slice)
+        return self._score(fw, n_windows, combination, index, False, 0.33, 50, 1, out_host=out_host)
 
     def score_multivariate(self, local_rows, n_rows, combination="mult", index=None):
         """BASELINE config 4: (N, C) rows sharded by contiguous row range.  local_rows: rows [row_lo, row_hi) of plan_rows() on
@@ -200,41 +209,43 @@ class ShardedScorer:
         fw = sc.forward(local_rows, False)  # rows h0 .. first+count-1
         return self._score(fw, n_rows, combination, index, True, 0.2, 200, 0)
 
-    MAX_RUNS = 64  # per analysis window in the gathered buffer; more (never seen) -> every rank redoes all windows
+    max_runs = 64  # room per analysis window in the gathered buffer; grown (on every rank alike) when a window holds more runs
 
     def find_anomaly_intervals(self, final, index, window_size_portion, window_step_size_portion, min_percent=0.1,
                                anomaly_padding=50, ddof=0):
         """scoring.find_anomaly_intervals with the analysis windows dealt out to the ranks: rank r thresholds windows
         [r*per, (r+1)*per) of the (identical, gathered) score array, the packed per-window results are all-gathered and the
         host tail (prune, score, merge) runs on every rank.  The kernels work on the whole array with a first-window index, so
-        the block sums and the shift sample are the single-GPU ones and the result is bitwise the single-GPU one."""
+        the block sums are the single-GPU ones and the result is bitwise the single-GPU one."""
         n = final.numel()
         wsize, step, count = scoring.analysis_windows(n, None, window_size_portion, None, window_step_size_portion)
         per = -(-count // self.world)
         k0 = min(self.rank * per, count)
         kc = max(0, min(per, count - k0))
-        R = self.MAX_RUNS
-        blen = scoring.threshold_buffer_len(per, R)
-        local = torch.zeros(blen, dtype=torch.float64, device=final.device)
-        if kc > 0:
-            sub = scoring.threshold_windows_launch(final, wsize, step, kc, ddof, anomaly_padding, R, first_window=k0)
-            # re-pack the kc-window buffer into the fixed per-window layout of `per` windows
-            s_loc, r_loc, n_loc = scoring.threshold_buffer_len(kc, R), kc * 4, kc * R * 3
-            local[: kc * 4] = sub[:r_loc]
-            local[per * 4: per * 4 + n_loc] = sub[r_loc:r_loc + n_loc]
-            local[per * 4 + per * R * 3: per * 4 + per * R * 3 + (kc + 1) // 2] = sub[r_loc + n_loc:s_loc]
-        host = self.comm.all_gather(local).cpu().numpy()
-        stats, runs, n_runs = [], [], []
-        for r in range(self.world):
-            rk0 = min(r * per, count)
-            rkc = max(0, min(per, count - rk0))
-            st, ru, nr = scoring.threshold_windows_parse(host[r], per, R)
-            stats.append(st[:rkc])
-            runs.append(ru[:rkc])
-            n_runs.append(nr[:rkc])
-        stats, runs, n_runs = np.concatenate(stats), np.concatenate(runs), np.concatenate(n_runs)
-        if n_runs.max(initial=0) > R:  # same decision on every rank: the gathered counts are identical
-            return scoring.find_anomaly_intervals(final, index, window_size_portion, window_step_size_portion,
-                                                  min_percent=min_percent, anomaly_padding=anomaly_padding, ddof=ddof)
+        while True:
+            R = self.max_runs
+            blen = scoring.threshold_buffer_len(per, R)
+            local = torch.zeros(blen, dtype=torch.float64, device=final.device)
+            if kc > 0:
+                sub = scoring.threshold_windows_launch(final, wsize, step, kc, ddof, anomaly_padding, R, first_window=k0)
+                # re-pack the kc-window buffer into the fixed per-window layout of `per` windows
+                s_loc, r_loc, n_loc = scoring.threshold_buffer_len(kc, R), kc * 4, kc * R * 3
+                local[: kc * 4] = sub[:r_loc]
+                local[per * 4: per * 4 + n_loc] = sub[r_loc:r_loc + n_loc]
+                local[per * 4 + per * R * 3: per * 4 + per * R * 3 + (kc + 1) // 2] = sub[r_loc + n_loc:s_loc]
+            host = self.comm.all_gather(local).cpu().numpy()
+            stats, runs, n_runs = [], [], []
+            for r in range(self.world):
+                rk0 = min(r * per, count)
+                rkc = max(0, min(per, count - rk0))
+                st, ru, nr = scoring.threshold_windows_parse(host[r], per, R)
+                stats.append(st[:rkc])
+                runs.append(ru[:rkc])
+                n_runs.append(nr[:rkc])
+            stats, runs, n_runs = np.concatenate(stats), np.concatenate(runs), np.concatenate(n_runs)
+            most = int(n_runs.max(initial=0))
+            if most <= R:
+                break
+            self.max_runs = most * 3 // 2 + 16  # the same decision on every rank: the gathered counts are identical
         merged = scoring.intervals_from_runs(stats, runs, n_runs, step, min_percent)
         return scoring.intervals_to_index(merged, index)

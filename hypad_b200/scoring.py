@@ -5,6 +5,7 @@ output with torch (plumbing) and enqueues hand-written sm_100a kernels on the cu
 `WindowScorer` chains them into what anomaly_detection.py:67-155 + utils/anomaly_detection_utils.py:21-94 of the
 reference compute for one signal, without ever materialising the (N, S) window matrix for univariate signals.
 """
+import ctypes
 import math
 
 import numpy as np
@@ -411,16 +412,22 @@ def threshold_windows_parse(host, count, max_runs):
     return host[:n_stats].reshape(count, 4), host[n_stats:n_stats + n_runs_f].reshape(count, max_runs, 3), nr
 
 
-def threshold_windows(errors, window_size, step, count, ddof, anomaly_padding, max_runs=64, exhaustive=False):
+_RUNS_HINT = {"max": 64}  # the largest run count of a window seen so far: noisy inputs then get room on the first try
+
+
+def threshold_windows(errors, window_size, step, count, ddof, anomaly_padding, max_runs=None, exhaustive=False):
     """Per analysis window: (mean, std, threshold, max_below) and the padded above-threshold runs.
     One device buffer holds the three outputs so that a single device-to-host copy (one synchronisation) brings them back."""
+    if max_runs is None:
+        max_runs = _RUNS_HINT["max"]
     while True:
         host = threshold_windows_launch(errors, window_size, step, count, ddof, anomaly_padding, max_runs,
                                         exhaustive=exhaustive).cpu().numpy()
         stats, runs, nr = threshold_windows_parse(host, count, max_runs)
         if nr.max(initial=0) <= max_runs:
             return stats, runs, nr
-        max_runs = int(nr.max()) + 16
+        max_runs = int(nr.max()) * 3 // 2 + 16
+        _RUNS_HINT["max"] = max(_RUNS_HINT["max"], min(max_runs, 4096))
 
 
 def _ieee_div(a, b):
@@ -471,9 +478,29 @@ def _f32(x):
 
 
 def intervals_from_runs(stats, runs, n_runs, step, min_percent, f32=False):
-    """Host tail of find_anomalies on the few runs per window: prune (:1203-1237), score (:1240-1269), merge (:1272-1313).
-    Plain Python floats: the arrays hold a handful of values per window and numpy's per-call overhead would dominate.
-    f32: the scores came as a float32 torch tensor, so `(max - threshold) / (mean + std)` is single-precision arithmetic."""
+    """Host tail of find_anomalies on the few runs per window: prune (:1203-1237), score (:1240-1269), merge (:1272-1313), in
+    the library's host code (csrc/host_tail.cu; noise can produce tens of thousands of runs, see there).
+    f32: the scores came as a float32 torch tensor, so `(max - threshold) / (mean + std)` is single-precision arithmetic.
+    Returns [[start, end, score], ...]."""
+    stats = np.ascontiguousarray(stats, dtype=np.float64).reshape(-1, 4)
+    count = stats.shape[0]
+    runs = np.ascontiguousarray(runs, dtype=np.float64).reshape(count, -1, 3)
+    n_runs = np.ascontiguousarray(n_runs, dtype=np.int32).reshape(-1)
+    max_runs = runs.shape[1]
+    lib = _native.load_library()
+    cap = int(n_runs.sum()) + count + 1
+    out = np.empty((cap, 3), dtype=np.float64)
+    n_out = ctypes.c_int64(0)
+    rc = lib.hypad_intervals_from_runs(stats.ctypes.data, runs.ctypes.data, n_runs.ctypes.data, count, max(max_runs, 1), int(step),
+                                       float(min_percent), int(bool(f32)), out.ctypes.data, cap, ctypes.byref(n_out))
+    if rc == -4:
+        raise ZeroDivisionError("Weights sum to zero, can't be normalized")
+    check(rc)
+    return out[: n_out.value].tolist()
+
+
+def intervals_from_runs_py(stats, runs, n_runs, step, min_percent, f32=False):
+    """The same tail in plain Python floats (the cross-check of the library's host code in tests/test_host_logic.py)."""
     stats, n_runs = np.asarray(stats).tolist(), np.asarray(n_runs).tolist()
     sequences = []
     for k in range(len(stats)):
@@ -561,6 +588,18 @@ HYPERBOLIC_COMBINATIONS = ("mult", "uncertainty", "sum", "sum_uncertainty", "cri
 _NEEDS_CRITIC = ("mult", "uncertainty", "sum", "sum_uncertainty", "critic", "critic_uncertainty")
 
 
+def download_async(owner, src, out_host):
+    """src (device) -> out_host (pinned) on owner's side stream, ordered after the work queued so far on the current stream."""
+    if getattr(owner, "_down_stream", None) is None:
+        owner._down_stream = torch.cuda.Stream(device=src.device)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(src.device))
+    owner._down_stream.wait_event(ev)
+    with torch.cuda.stream(owner._down_stream):
+        out_host[: src.numel()].copy_(src, non_blocking=True)
+    src.record_stream(owner._down_stream)
+
+
 class WindowScorer:
     """Scores every window of a signal with a (random-init or trained) TadGAN / HypAD model on one B200.
 
@@ -594,27 +633,26 @@ class WindowScorer:
             raise HypadError("hypad_b200: windows have %d samples, the model expects %d" % (x.shape[1], self.S))
         return x, x.shape[0], self.S
 
-    def forward(self, x, sliding, keep=(), first=0, count=None, ffma=False):
+    def forward(self, x, sliding, keep=(), first=0, count=None, ffma=False, into=None, into_offset=0):
         """Runs the fused network over windows [first, first+count).  Returns dict of device tensors:
         critic (n,) always; rec, unorm (n,) when hyperbolic; plus any of z/eucl/hyper/hyper_x named in `keep`.
-        ffma=True runs the FFMA cross-check kernel instead of the tensor-core product path."""
+        ffma=True runs the FFMA cross-check kernel instead of the tensor-core product path.
+        into: a result dict of an earlier call sized for more windows; this call writes its rows from `into_offset` on
+        (forward_from_host scores a signal chunk by chunk into one set of arrays)."""
         self.net.ensure(self.encoder, self.decoder, self.critic_x)
         x, n_all, stride = self._input(x, sliding)
         count = n_all - first if count is None else count
         if count <= 0:
             raise HypadError("hypad_b200: no windows to score (signal shorter than the window?)")
         dev, S = x.device, self.S
-        res = {"critic": torch.empty(count, dtype=torch.float32, device=dev)}
-        if self.hyperbolic:
-            res["rec"] = torch.empty(count, dtype=torch.float32, device=dev)
-            res["unorm"] = torch.empty(count, dtype=torch.float32, device=dev)
-        widths = {"z": self.net.latent, "eucl": S, "hyper": S, "hyper_x": S}
-        for name in keep:
-            if name in ("hyper", "hyper_x") and not self.hyperbolic:
-                continue
-            res[name] = torch.empty((count, widths[name]), dtype=torch.float32, device=dev)
+        if into is None:
+            res = self._alloc_results(count, keep, dev)
+            views = res
+        else:
+            res = into
+            views = {k: v[into_offset:into_offset + count] for k, v in into.items() if not k.startswith("_")}
         out = _native.hypad_forward_out()
-        for name, t in res.items():
+        for name, t in views.items():
             setattr(out, name, t.data_ptr())
         stages = _native.STAGE_ENCODER | _native.STAGE_DECODER | _native.STAGE_CRITIC
         if self.hyperbolic:
@@ -624,7 +662,65 @@ class WindowScorer:
         with torch.cuda.device(dev):
             check(fn(self.net.ctx.handle, base, int(x.dtype == torch.float64), count, stride, None, stages, out,
                      self.net.ctx.stream()))
-        res["_x"], res["_n"], res["_stride"] = x, n_all, stride
+        if into is None:
+            res["_x"], res["_n"], res["_stride"] = x, n_all, stride
+        return res
+
+    def _alloc_results(self, count, keep, dev):
+        S = self.S
+        res = {"critic": torch.empty(count, dtype=torch.float32, device=dev)}
+        if self.hyperbolic:
+            res["rec"] = torch.empty(count, dtype=torch.float32, device=dev)
+            res["unorm"] = torch.empty(count, dtype=torch.float32, device=dev)
+        widths = {"z": self.net.latent, "eucl": S, "hyper": S, "hyper_x": S}
+        for name in keep:
+            if name in ("hyper", "hyper_x") and not self.hyperbolic:
+                continue
+            res[name] = torch.empty((count, widths[name]), dtype=torch.float32, device=dev)
+        return res
+
+    UPLOAD_CHUNKS = (0.08, 0.25, 0.67)  # fractions of the windows per upload / launch: a short first chunk starts the GPU early
+
+    def forward_from_host(self, host_signal, keep=()):
+        """forward() of a sliding-window signal that lives in (pinned) host memory: the signal is uploaded in a few chunks on a
+        copy stream and the fused kernel is launched per chunk as its samples arrive, so that all but the first upload is
+        hidden behind the network.  Same results as forward(host_signal.to(device), True): every window is computed by the
+        same code from the same samples."""
+        if host_signal.is_cuda:
+            return self.forward(host_signal, True, keep)
+        dev, S = self.device, self.S
+        T = host_signal.numel()
+        n = T - S
+        if n <= 0:
+            raise HypadError("hypad_b200: no windows to score (signal shorter than the window?)")
+        host_signal = host_signal.reshape(-1)
+        if host_signal.dtype not in (torch.float32, torch.float64):
+            host_signal = host_signal.double()
+        x = torch.empty(T, dtype=host_signal.dtype, device=dev)
+        if n < 200000:  # short signals: one copy, one launch
+            x.copy_(host_signal, non_blocking=True)
+            return self.forward(x, True, keep)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        self._copy_stream.wait_stream(main)  # x was allocated on the main stream
+        bounds, acc = [0], 0.0
+        for f in self.UPLOAD_CHUNKS[:-1]:
+            acc += f
+            bounds.append(int(n * acc) // 64 * 64)  # whole 64-window tiles per launch
+        bounds.append(n)
+        res = self._alloc_results(n, keep, dev)
+        up = 0
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            hi = T if b == n else b + S  # samples the windows [a, b) read: [a, b + S - 1]; the last chunk takes the tail
+            with torch.cuda.stream(self._copy_stream):
+                x[up:hi].copy_(host_signal[up:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            up = hi
+            main.wait_event(ev)
+            self.forward(x, True, keep, first=a, count=b - a, into=res, into_offset=a)
+        res["_x"], res["_n"], res["_stride"] = x, n, 1
         return res
 
     def poll_error(self):
@@ -657,7 +753,7 @@ class WindowScorer:
         return critic_scores_staged(kmax, [(0, total)], total, math.trunc(n_windows * 0.01)), kmax
 
     def score(self, x, sliding=True, combination="uncertainty", rec_error_type="dtw", index=None, keep=(), multivariate=False,
-              lambda_rec=0.5, poll=True):
+              lambda_rec=0.5, poll=True, out_host=None):
         """Per-position anomaly scores (+ intervals when `index` is given) for one signal.
 
         sliding=True : x is the scaled signal (T,), windows are x[n:n+S], n in [0, T-S)   (univariate configs)
@@ -665,13 +761,19 @@ class WindowScorer:
         Hyperbolic models return one score per window (N,), Euclidean ones one per timestep (N+S-1,), like the reference.
         poll=False leaves out the final synchronising error poll: a caller that enqueues many signals (sweep.SignalSweep) calls
         `poll_error()` once after the last one.
+        x may be a pinned host tensor when sliding (uploaded chunk by chunk under the network, forward_from_host); out_host, a
+        pinned float64 host tensor, receives the final scores on a side stream while the interval extraction still runs (the
+        call returns after both are done).
         """
         keep = tuple(keep)
         stats_f32 = False
         if self.hyperbolic and not multivariate:
             univariate_hyperbolic_semantics(combination)  # unknown / undefined combinations fail before any work is queued
         need = keep if self.hyperbolic else tuple(set(keep) | {"eucl"})
-        fw = self.forward(x, sliding, need)
+        if sliding and isinstance(x, torch.Tensor) and not x.is_cuda:
+            fw = self.forward_from_host(x, need)
+        else:
+            fw = self.forward(x, sliding, need)
         n, S = fw["critic"].shape[0], self.S
         out = {k: v for k, v in fw.items() if not k.startswith("_")}
         if self.hyperbolic:
@@ -726,6 +828,8 @@ class WindowScorer:
             out.update(kmax=kmax, critic_scores=cs, rec=rec, pred=pred, true=true, errors=errors)
             ddof = 0
         out["final"] = final
+        if out_host is not None:
+            download_async(self, final, out_host)
         if index is not None:
             if multivariate:
                 out["intervals"] = find_anomaly_intervals(final, index, 0.2, 0.1, anomaly_padding=200, ddof=ddof)
@@ -734,6 +838,8 @@ class WindowScorer:
                                                           stats_f32=stats_f32)
         # loud failure: pipeline protocol error, or an operand outside the tensor-core path's range.  Last, so that the
         # synchronisation it implies does not stall the launches above.
+        if out_host is not None:
+            self._down_stream.synchronize()
         if poll:
             self.poll_error()
         return out

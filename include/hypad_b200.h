@@ -31,6 +31,7 @@ extern "C" {
 #define HYPAD_EINVAL (-1)   /* bad argument */
 #define HYPAD_ECUDA (-2)    /* CUDA runtime error (message in hypad_last_error) */
 #define HYPAD_ENOMEM (-3)   /* workspace allocation failed */
+#define HYPAD_EZERODIV (-4) /* np.average's "Weights sum to zero" (merged runs of one position each), as the reference raises */
 #define HYPAD_ESTATE (-4)   /* weights not packed / context misuse */
 
 #define HYPAD_ABI_VERSION 2
@@ -248,6 +249,13 @@ int hypad_threshold_windows_range(hypad_ctx* ctx, const double* errors, int64_t 
 int hypad_threshold_windows_exhaustive(hypad_ctx* ctx, const double* errors, int64_t len, int64_t window_size, int64_t step,
                             int64_t n_analysis, int ddof, int anomaly_padding, double* stats, double* runs,
                             int32_t* n_runs, int max_runs, void* stream);
+
+/* Host tail of find_anomalies on the outputs of hypad_threshold_windows (host pointers, no device work): prune
+ * (utils/anomaly_detection_utils.py:1203-1237), score (:1240-1269) and merge (:1272-1313) with numpy's / pandas' arithmetic.
+ * out receives up to `cap` (start, end, score) triples in positions of the scored array, *n_out their number (call again with
+ * more room when it exceeds cap).  f32: the scores were a float32 tensor (single-precision interval scores). */
+int hypad_intervals_from_runs(const double* stats, const double* runs, const int32_t* n_runs, int64_t count, int64_t max_runs,
+                              int64_t step, double min_percent, int f32, double* out, int64_t cap, int64_t* n_out);
 
 /* ---- staged global statistics: one GPU's slice per call, a small record exchanged between stages -------------------------
  * The reference computes its statistics on whole arrays (np.quantile / mean / std in _compute_critic_score,

@@ -986,6 +986,25 @@ def test_sharded_windows_univariate_equal_unsharded(world, hyp_scorer, cuda_devi
 
 
 @pytest.mark.gpu
+def test_host_buffer_call_equals_device_call(hyp_scorer, cuda_device):
+    """The end-to-end form of the call: pinned host signal in (uploaded in chunks under the fused kernel, one launch per chunk),
+    pinned host scores out (downloaded under the interval extraction).  Bitwise the device-resident call."""
+    from conftest import long_signal
+
+    for T in (5000, 260000):
+        sig = long_signal(T)
+        index = np.arange(T)
+        ref = hyp_scorer.score(torch.from_numpy(sig).to(cuda_device), True, "uncertainty", index=index)
+        host = torch.from_numpy(sig).pin_memory()
+        out_host = torch.full((T - 100,), -1.0, dtype=torch.float64).pin_memory()
+        out = hyp_scorer.score(host, True, "uncertainty", index=index, out_host=out_host)
+        for k in ("critic", "rec", "unorm", "kmax", "final"):
+            assert torch.equal(out[k], ref[k]), (T, k)
+        assert torch.equal(out_host, ref["final"].cpu())
+        assert np.array_equal(out["intervals"], ref["intervals"])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("world,T", [(8, 60000), (3, 200000)])
 def test_sharded_long_signal_staged_statistics_equal_unsharded(world, T, hyp_scorer, cuda_device):
     """The staged statistics at a size where they matter: the smoothing window (1 % of the windows) needs a halo of hundreds of

@@ -267,3 +267,31 @@ def test_fp32_statistics_interval_scores_follow_the_oracle():
     mine = np.asarray([[idx[int(s)], idx[int(t)], sc] for s, t, sc in merged], dtype=np.float64).reshape(-1, 3)
     assert np.array_equal(mine[:, :2], p["fa32_uni"][:, :2])
     np.testing.assert_allclose(mine[:, 2], p["fa32_uni"][:, 2], rtol=2e-6)
+
+
+def test_library_host_tail_equals_the_python_restatement():
+    """hypad_intervals_from_runs (csrc/host_tail.cu, what the product path calls) against the plain-Python tail, bit for bit, on
+    random windows: ties, NaN maxima, merged groups of more than 128 members (numpy's pairwise summation recursion), float32."""
+    from hypad_b200 import scoring
+
+    rng = np.random.default_rng(5)
+    for trial in range(120):
+        count, R, step = int(rng.integers(1, 12)), int(rng.integers(1, 40)), int(rng.integers(1, 50))
+        if trial % 10 == 0:
+            count, R, step = 30, 300, 3  # dense overlapping runs: groups of hundreds of members
+        stats = np.c_[rng.normal(1, .1, count), rng.uniform(0.1, 1, count), rng.normal(3, .2, count), rng.normal(2.5, .3, count)]
+        nr = rng.integers(0, R + 1, count).astype(np.int32)
+        runs = np.zeros((count, R, 3))
+        for k in range(count):
+            st = np.sort(rng.integers(0, 500, nr[k]))
+            runs[k, :nr[k], 0] = st
+            runs[k, :nr[k], 1] = st + rng.integers(1, 30, nr[k])
+            runs[k, :nr[k], 2] = np.round(rng.normal(3.5, .5, nr[k]), 1)  # rounded: equal maxima do occur
+            if rng.random() < 0.1 and nr[k]:
+                runs[k, 0, 2] = np.nan
+        for f32 in (False, True):
+            a = scoring.intervals_from_runs(stats, runs, nr, step, 0.1, f32=f32)
+            b = scoring.intervals_from_runs_py(stats, runs, nr, step, 0.1, f32=f32)
+            assert len(a) == len(b), (trial, len(a), len(b))
+            for x, y in zip(a, b):
+                assert all((p == q) or (p != p and q != q) for p, q in zip(x, map(float, y))), (trial, x, y)
