@@ -50,6 +50,7 @@ constexpr int TC_STAGE_BYTES = 16384;     // one weight stage: kstage k-steps of
 constexpr int TC_NSLOT = 5;
 constexpr int TC_RED_BYTES = TC_NSPLIT * TC_M * 2 * 8;  // row reductions of at most two fp64 values per row
 constexpr int TC_BIAS_BYTES = 9216;       // shared copy of the small-parameter buffer: biases, Mobius bias, critic output layer, scales
+constexpr int TC_XS_FLOATS = 240;         // per tile slot: the 128 + S - 1 samples a tile of sliding windows covers (S <= 113), as fp32
 constexpr int TC_CRITIC_SHIFT = 8;        // sa of the critic's hidden activations (unbounded LeakyReLU outputs)
 constexpr int TC_CRITIC_K0 = 104;         // operand feature where the critic chain keeps its hidden state when it rides along
 
@@ -308,12 +309,45 @@ __device__ __forceinline__ void load_rows_to_act(unsigned char* act, const T* __
     const int r = t & (TC_M - 1);
     const bool live = w0 + r < n;
     const T* row = x + (w0 + r) * stride;
+    // a thread owns at most four 8-feature chunks (width16 <= 128): all of its loads are issued before the first conversion,
+    // so the tile costs one trip to L2 / HBM instead of one per chunk
+    float v[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = (t >> 7) + j * TC_NSPLIT;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = 8 * c + e;
+            v[j][e] = (live && k < width) ? (float)row[k] : 0.0f;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = (t >> 7) + j * TC_NSPLIT;
+        if (c < width16 / 8) {
+            check_range8(v[j], sc, error_flag);
+            store_act8(act, r, 8 * c, v[j], sc);
+        }
+    }
+}
+
+// Sliding windows (row stride 1): a tile's 128 windows cover 128 + S - 1 consecutive samples, each read by up to S windows and
+// by two passes (the encoder's first layer and the Mobius layer of the window itself).  They are fetched from global memory
+// ONCE per tile into shared memory as fp32 (one load per thread, one L2 latency) and the operand rows are cut from there:
+// lane r of a warp reads xs[r + k], consecutive words, no bank conflict.
+template <typename T>
+__device__ __forceinline__ void stage_samples(float* xs, const T* __restrict__ x, int64_t w0, int64_t n_samples, int count, int t) {
+    for (int i = t; i < count; i += TC_EPI_THREADS) xs[i] = w0 + i < n_samples ? (float)x[w0 + i] : 0.0f;
+}
+__device__ __forceinline__ void staged_rows_to_act(unsigned char* act, const float* xs, bool live, int width, int width16, int t, float sc,
+                                                   int* error_flag) {
+    const int r = t & (TC_M - 1);
     for (int c = t >> 7; c < width16 / 8; c += TC_NSPLIT) {
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int k = 8 * c + e;
-            v[e] = (live && k < width) ? (float)row[k] : 0.0f;
+            v[e] = (live && k < width) ? xs[r + k] : 0.0f;
         }
         check_range8(v, sc, error_flag);
         store_act8(act, r, 8 * c, v, sc);
@@ -485,6 +519,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
     float* sbias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(red) + TC_RED_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(sbias) + TC_BIAS_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_NSLOT + 2 * TC_TILES);
+    float* xs_base = reinterpret_cast<float*>(tmem_slot + 4);         // TC_TILES x TC_XS_FLOATS staged samples
     const uint32_t bar_full = s_u32(bars), bar_empty = s_u32(bars + TC_NSLOT);
     const uint32_t bar_acc = s_u32(bars + 2 * TC_NSLOT), bar_a = s_u32(bars + 2 * TC_NSLOT + TC_TILES);  // one per tile slot
 
@@ -653,6 +688,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
         const float* __restrict__ small = P.small;
         uint32_t acc_par = 0;   // bit sl = parity of slot sl's next accumulator hand-over
         uint32_t has_x = 0;     // bit sl = slot sl's A operand buffer currently holds the window tile
+        uint32_t staged = 0;    // bit sl = slot sl's samples of the current tile are in shared memory
+        const bool stage_x = P.row_stride == 1 && TC_M + S - 1 <= TC_XS_FLOATS;
         float sq_mr0 = 0.0f, sq_mr1 = 0.0f;  // squared norm of the reconstruction's hyperbolic point, per slot
         bool ok = true;
         long long dbg_wait = 0, dbg_xload = 0;
@@ -670,7 +707,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
             const float sc = __int_as_float((127 + ps.in_shift) << 23);
             if (ps.needs_x && !((has_x >> sl) & 1u)) {
                 epi_bar();  // every column split of every row is done writing the previous layer's output
-                if (P.x_is_f64) load_rows_to_act<double>(act, (const double*)P.x, w0, P.n, P.row_stride, S, S16, tid, sc, P.error_flag);
+                if (stage_x) {
+                    float* xs = xs_base + sl * TC_XS_FLOATS;
+                    if (!((staged >> sl) & 1u)) {
+                        // window w reads samples [w, w + S): the n windows of this call cover n + S - 1 samples
+                        if (P.x_is_f64) stage_samples<double>(xs, (const double*)P.x, w0, P.n + S - 1, TC_M + S - 1, tid);
+                        else stage_samples<float>(xs, (const float*)P.x, w0, P.n + S - 1, TC_M + S - 1, tid);
+                        staged |= 1u << sl;
+                        epi_bar();
+                    }
+                    staged_rows_to_act(act, xs, w0 + (tid & (TC_M - 1)) < P.n, S, S16, tid, sc, P.error_flag);
+                } else if (P.x_is_f64) load_rows_to_act<double>(act, (const double*)P.x, w0, P.n, P.row_stride, S, S16, tid, sc, P.error_flag);
                 else load_rows_to_act<float>(act, (const float*)P.x, w0, P.n, P.row_stride, S, S16, tid, sc, P.error_flag);
                 has_x |= 1u << sl;
             } else if (p == T_D0 && !(P.stages & HYPAD_STAGE_ENCODER)) {
@@ -841,6 +888,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) forward_tc_kernel(const __grid_
                         hand_over(sl, t, pn);
                     } else if (t + TC_TILES < my_tiles) {
                         has_x &= ~(1u << sl);  // a new tile: whatever window the buffer holds is the old tile's
+                        staged &= ~(1u << sl);
                         hand_over(sl, t + TC_TILES, p_first);
                     }
                 }
@@ -925,7 +973,8 @@ static inline int round8i(int v) { return (v + 7) / 8 * 8; }
 static inline int round16i(int v) { return (v + 15) / 16 * 16; }
 
 size_t forward_tc_smem_bytes() {
-    return (size_t)TC_TILES * TC_ACT_BYTES + (size_t)TC_NSLOT * TC_STAGE_BYTES + TC_RED_BYTES + TC_BIAS_BYTES + (2 * TC_NSLOT + 2 * TC_TILES) * 8 + 16;
+    return (size_t)TC_TILES * TC_ACT_BYTES + (size_t)TC_NSLOT * TC_STAGE_BYTES + TC_RED_BYTES + TC_BIAS_BYTES + (2 * TC_NSLOT + 2 * TC_TILES) * 8 + 16 +
+           (size_t)TC_TILES * TC_XS_FLOATS * 4;
 }
 
 // Builds the tensor-core program and packs the weights (called from hypad_pack_weights).

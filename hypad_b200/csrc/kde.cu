@@ -62,6 +62,20 @@ __device__ __forceinline__ int load_points(const KdeArgs& a, int64_t i, int lane
     return n;
 }
 
+// The raw fp32 points of timestep i (0 beyond n): issued one iteration ahead, so the global-load latency hides behind the
+// previous timestep's kernel evaluations.
+__device__ __forceinline__ int fetch_points(const KdeArgs& a, int64_t i, int lane, float (&f)[4]) {
+    const int64_t hi = i < a.n_windows - 1 ? i : a.n_windows - 1;
+    const int64_t lo = i - a.S + 1 > 0 ? i - a.S + 1 : 0;
+    const int n = (int)(hi - lo + 1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int j = lane + 32 * q;
+        f[q] = j < n ? a.critic[hi - j - a.critic_offset] : 0.0f;
+    }
+    return n;
+}
+
 // mean / ddof-1 variance of the warp's points (fp64)
 __device__ __forceinline__ void point_stats(const double (&v)[4], int n, int lane, double& mean, double& var) {
     double s = 0.0;
@@ -161,7 +175,74 @@ __global__ void __launch_bounds__(KDE_WARPS * 32) kde_exhaustive_kernel(const Kd
     }
 }
 
-__global__ void __launch_bounds__(KDE_WARPS * 32, 8) kde_screened_kernel(const KdeArgs a) {
+// fp32 screening densities of up to 32 Q points, lane l owning points l, l + 32, ... (d[q], a sentinel far away where the
+// timestep has no point).  K(a, b) = K(b, a): every unordered pair is evaluated ONCE and credited to both points.  Step s pairs
+// the lane's Q points with the Q points of lane l + s (read from shared memory, where every group of 32 is stored twice back to
+// back so that the rotated read is a constant offset from a per-lane base): Q^2 kernel values per step for Q loads and Q
+// shuffles -- the values go to the lane's own sums, and into Q running sums that are handed from lane l + 1 to lane l after
+// every step, so that they travel with the partner index; after 15 steps lane l holds the complete sums of lane l + 16's points.
+// Steps 1..15 cover every unordered pair of lanes once, step 16 pairs l with l + 16 from both sides (own sums only).
+// The special-function pipe (one MUFU.EX2 per pair) shares its issue path with shared-memory loads and shuffles: with one
+// point per lane and step every pair cost one of each and the three pipes took turns (61 % XU, 60 % LSU busy); a Q x Q
+// register tile amortises the load and the shuffle over Q pairs.
+template <int Q>
+__device__ __forceinline__ void screen_pairs(const float (&d)[4], const float* D, int lane, float (&e32)[4]) {
+    const unsigned full = 0xffffffffu;
+    const int nxt = (lane + 1) & 31;
+    float e[Q], R[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        e[q] = 1.f;  // the point's own kernel value
+        R[q] = 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+        for (int p = q + 1; p < Q; ++p) {  // the lane's own points against each other
+            const float r = d[p] - d[q];
+            const float val = ex2_approx(-(r * r));
+            e[q] += val;
+            e[p] += val;
+        }
+    const float* base = D + lane;
+#pragma unroll
+    for (int s = 1; s < 16; ++s) {
+        float y[Q];
+#pragma unroll
+        for (int p = 0; p < Q; ++p) y[p] = base[64 * p + s];
+#pragma unroll
+        for (int p = 0; p < Q; ++p) {
+            float acc = R[p];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const float r = y[p] - d[q];
+                const float val = ex2_approx(-(r * r));
+                e[q] += val;
+                acc += val;
+            }
+            R[p] = __shfl_sync(full, acc, nxt);
+        }
+    }
+    {
+        float y[Q];
+#pragma unroll
+        for (int p = 0; p < Q; ++p) y[p] = base[64 * p + 16];
+#pragma unroll
+        for (int p = 0; p < Q; ++p) {
+            // after 15 hand-overs lane l holds the sums of lane l + 16's points: its owner fetches them
+            e[p] += __shfl_sync(full, R[p], (lane + 16) & 31);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const float r = y[p] - d[q];
+                e[q] += ex2_approx(-(r * r));
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) e32[q] = e[q];
+}
+
+__global__ void __launch_bounds__(KDE_WARPS * 32, 6) kde_screened_kernel(const KdeArgs a) {
     __shared__ double sP[KDE_WARPS][KDE_MAXPTS];
     __shared__ float sD[KDE_WARPS][2 * KDE_MAXPTS];
     __shared__ double sScott[KDE_MAXPTS + 1];
@@ -173,10 +254,18 @@ __global__ void __launch_bounds__(KDE_WARPS * 32, 8) kde_screened_kernel(const K
     // exp(-r^2/2) = 2^(-(s r)^2) with s = sqrt(log2(e)/2): the scale is folded into the stored values, so one kernel
     // evaluation is FADD, FMUL (negated), MUFU.EX2, FADD
     const double kScale = 0.8493218002880191;
+    float nf[4];
+    int nn = 0;
+    {
+        const int64_t it0 = (int64_t)blockIdx.x * KDE_WARPS + warp;
+        if (it0 < a.t_count) nn = fetch_points(a, a.t0 + it0, lane, nf);
+    }
     for (int64_t it = (int64_t)blockIdx.x * KDE_WARPS + warp; it < a.t_count; it += stride) {
-        const int64_t i = a.t0 + it;
         double v[4];
-        const int n = load_points(a, i, lane, v);
+        const int n = nn;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = (double)nf[q];
+        if (it + stride < a.t_count) nn = fetch_points(a, a.t0 + it + stride, lane, nf);
         if (n == 1) {
             if (lane == 0) a.out[it] = v[0];
             continue;
@@ -191,69 +280,32 @@ __global__ void __launch_bounds__(KDE_WARPS * 32, 8) kde_screened_kernel(const K
         const double rcho = 1.0 / cho;
         const double dscale = kScale * rcho;
         float d[4];
+        const float kFar = 1e18f;  // sentinel for the slots beyond n: 2^-(1e36) = 0 against every real point
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int j = lane + 32 * q;
-            d[q] = (float)((v[q] - mean) * dscale);
+            d[q] = j < n ? (float)((v[q] - mean) * dscale) : kFar;
             if (j < n) P[j] = v[q] * rcho;  // scipy divides; a last-bit difference of the scaled points cannot change the arg-max
         }
-        // ---- fp32 screening: all n^2 kernel values with ex2.approx -------------------------------------
+        // ---- fp32 screening: every unordered pair once, with ex2.approx ----------------------------------
         float e32[4] = {0.f, 0.f, 0.f, 0.f};
-        if (n == 100) {
-            // The interior case of the reference's window length.  K(a,b) = K(b,a): every unordered pair is evaluated ONCE and
-            // credited to both points.  Points 0..95 form three groups of 32 (lane l owns point l of each group).  For a pair of
-            // groups (X, Y), step s pairs x_l with y_(l+s): the value goes to lane l's own sum for x_l, and into a running sum R
-            // that is handed from lane l+1 to lane l before every step, so that after 32 steps it has collected all 32
-            // contributions of one y and one more rotation delivers it to its owner -- one shuffle instead of one MUFU.EX2.
-            // Inside a group, steps 1..15 cover every unordered pair once and step 16 pairs l with l+16 from both sides.
-            // The groups are stored twice back to back so that the rotated read is a constant offset from a per-lane base.
+        const int Q = n == 100 ? 3 : (n + 31) >> 5;  // n = 100: three full groups, the last four points separately
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
+        for (int q = 0; q < 4; ++q)
+            if (q < Q) {
                 D[64 * q + lane] = d[q];
                 D[64 * q + 32 + lane] = d[q];
             }
-            if (lane < 4) D[192 + lane] = d[3];
-            __syncwarp();
+        if (n == 100 && lane < 4) D[192 + lane] = d[3];
+        __syncwarp();
+        if (Q == 3) screen_pairs<3>(d, D, lane, e32);
+        else if (Q == 4) screen_pairs<4>(d, D, lane, e32);
+        else if (Q == 2) screen_pairs<2>(d, D, lane, e32);
+        else screen_pairs<1>(d, D, lane, e32);
+        if (n == 100) {
+            // the interior case of the reference's window length: the last 4 points against the 96 (credited to both sides)
+            // and against each other
             const unsigned full = 0xffffffffu;
-            const int nxt = (lane + 1) & 31;
-            float e[3] = {1.f, 1.f, 1.f};  // the point's own kernel value
-#pragma unroll
-            for (int X = 0; X < 3; ++X) {
-                {   // inside group X: the running sum is handed on after every step
-                    const float* px = D + 64 * X + lane;
-                    float R = 0.f;
-#pragma unroll
-                    for (int s = 1; s < 16; ++s) {
-                        const float r = px[s] - d[X];
-                        const float val = ex2_approx(-(r * r));
-                        e[X] += val;
-                        R = __shfl_sync(full, R + val, nxt);
-                    }
-                    e[X] += __shfl_sync(full, R, (lane + 16) & 31);  // after 15 hand-overs lane l holds the sum of point l+16
-                    const float r = px[16] - d[X];
-                    e[X] += ex2_approx(-(r * r));
-                }
-#pragma unroll
-                for (int Y = X + 1; Y < 3; ++Y) {
-                    const float* py = D + 64 * Y + lane;
-                    float R = 0.f;
-#pragma unroll
-                    for (int s0 = 0; s0 < 32; s0 += 8) {
-                        float y[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) y[u] = py[s0 + u];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const float r = y[u] - d[X];
-                            const float val = ex2_approx(-(r * r));
-                            e[X] += val;
-                            R = __shfl_sync(full, R + val, nxt);
-                        }
-                    }
-                    e[Y] += R;  // 32 hand-overs: back at the owner
-                }
-            }
-            // the last 4 points against the 96 (credited to both sides) and against each other
             float L[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -263,7 +315,7 @@ __global__ void __launch_bounds__(KDE_WARPS * 32, 8) kde_screened_kernel(const K
                 for (int q = 0; q < 3; ++q) {
                     const float r = dt - d[q];
                     const float val = ex2_approx(-(r * r));
-                    e[q] += val;
+                    e32[q] += val;
                     L[t] += val;
                 }
             }
@@ -273,27 +325,20 @@ __global__ void __launch_bounds__(KDE_WARPS * 32, 8) kde_screened_kernel(const K
 #pragma unroll
                 for (int t = 0; t < 4; ++t) L[t] += (lane >> 2) == t ? val : 0.f;
             }
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) L[t] += __shfl_xor_sync(full, L[t], o);
-                if (lane == t) e32[3] = L[t];
-            }
-            e32[0] = e[0];
-            e32[1] = e[1];
-            e32[2] = e[2];
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (lane + 32 * q < n) D[lane + 32 * q] = d[q];
-            __syncwarp();
-            for (int k = 0; k < n; ++k) {
-                const float dk = D[k];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float r = dk - d[q];
-                    e32[q] += ex2_approx(-(r * r));
-                }
+            // four warp sums for six shuffles: lanes trade halves (16), then quarters (8) of the four partial sums and finish the
+            // one they are left with; lane l ends up with the total of point 96 + ((l >> 3) & 3)
+            {
+                const bool up16 = lane & 16, up8 = lane & 8;
+                const float s0 = __shfl_xor_sync(full, up16 ? L[0] : L[2], 16), s1 = __shfl_xor_sync(full, up16 ? L[1] : L[3], 16);
+                const float a0 = (up16 ? L[2] : L[0]) + s0, a1 = (up16 ? L[3] : L[1]) + s1;  // sums of points (2|0) and (3|1)
+                const float s2 = __shfl_xor_sync(full, up8 ? a0 : a1, 8);
+                float tot = (up8 ? a1 : a0) + s2;
+                tot += __shfl_xor_sync(full, tot, 4);
+                tot += __shfl_xor_sync(full, tot, 2);
+                tot += __shfl_xor_sync(full, tot, 1);
+                // lane bits (16, 8) -> point: (0,0) 0, (0,1) 1, (1,0) 2, (1,1) 3; lane t < 4 fetches point t's total
+                const float mine = __shfl_sync(full, tot, ((lane & 2) << 3) | ((lane & 1) << 3));
+                e32[3] = lane < 4 ? mine : 0.f;
             }
         }
         float m32 = 0.f;
@@ -325,7 +370,25 @@ __global__ void __launch_bounds__(KDE_WARPS * 32, 8) kde_screened_kernel(const K
         // Lane c keeps the c-th distinct candidate; more than 32 of them (a flat-topped density) fall back to fp64 for all.
         int ncand = 0, myj = 0;
         float myest = -1.0f;
+        // Usually every candidate carries the same value: one candidate, or exact repeats of it (periodic and plateau signals
+        // put the same critic value under a timestep more than once).  Equal values have bitwise equal densities and the first
+        // index wins: decided without evaluating anything.
+        bool all_same = false;
+        int first_j = 0;
         {
+            const int f0 = cands[0] ? __ffs(cands[0]) - 1 : cands[1] ? 31 + __ffs(cands[1]) : cands[2] ? 63 + __ffs(cands[2]) : 95 + __ffs(cands[3]);
+            first_j = f0;
+            double v0 = 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if ((f0 >> 5) == q) v0 = v[q];
+            v0 = __shfl_sync(0xffffffffu, v0, f0 & 31);
+            bool differs = false;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) differs |= ((cands[q] >> lane) & 1u) && v[q] != v0;
+            all_same = !__any_sync(0xffffffffu, differs);
+        }
+        if (!all_same) {
             // the distinct candidates first (lane c keeps the c-th): a single one needs no evaluation at all
             double seen0 = CUDART_NAN, seen1 = CUDART_NAN, seen2 = CUDART_NAN, seen3 = CUDART_NAN;
 #pragma unroll 1
@@ -363,10 +426,10 @@ __global__ void __launch_bounds__(KDE_WARPS * 32, 8) kde_screened_kernel(const K
                 myest = 1.0f;  // the only candidate survives
             }
         }
-        int bj = 0;
+        int bj = first_j;
         unsigned keep[4] = {cands[0], cands[1], cands[2], cands[3]};
-        bool decided = false;
-        if (ncand <= 32) {
+        bool decided = all_same;
+        if (!all_same && ncand <= 32) {
             const float m2 = warp_max(myest);
             unsigned surv = __ballot_sync(0xffffffffu, lane < ncand && myest >= m2 * (1.0f - 1e-5f));
             if (__popc(surv) == 1) {
@@ -453,7 +516,7 @@ static int launch_kde(K kernel, const float* critic, int64_t critic_offset, int6
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t want = ceil_div(t_count, KDE_WARPS);
-    const int64_t cap = (int64_t)sms * 8;  // 8 CTAs of 4 warps per SM, grid-stride beyond
+    const int64_t cap = (int64_t)sms * 6;  // 6 CTAs of 4 warps per SM (80 registers), grid-stride beyond
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     kernel<<<grid, KDE_WARPS * 32, 0, stream>>>(a);
     HYPAD_LAUNCH_CHECK();
