@@ -90,6 +90,7 @@ _SIGNATURES = {
     "hypad_threshold_windows_exhaustive": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp, _int, _vp]),
     "hypad_tc_probe_gemm": (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _vp]),
     "hypad_tc_probe_bench": (_int, [_int, _int, _int, _vp, _vp]),
+    "hypad_critic_scores": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp]),
     "hypad_stats_select_passes": (_int, [_int]),
     "hypad_stats_select_begin": (_int, [_vp, _i64, _int, _vp]),
     "hypad_stats_select_hist": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),

@@ -130,22 +130,30 @@ __global__ void __launch_bounds__(RB) sel_hist_kernel(const double* __restrict__
     }
 }
 
-// One CTA of NQ warps: sum the ranks' histograms, locate the digit holding rank[q], extend the prefix; after the last pass
-// turn the four order statistics into the two quantiles (numpy's _lerp).
-__global__ void __launch_bounds__(NQ * 32) sel_pick_kernel(const unsigned int* __restrict__ hists, int world, int pass, FinState* st) {
-    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// One CTA, 256 threads per order statistic: sum the ranks' histograms (8 consecutive bins per thread), locate the digit holding
+// rank[q] with a block-wide prefix sum, extend the prefix; after the last pass turn the four order statistics into the two
+// quantiles (numpy's _lerp).
+__global__ void __launch_bounds__(NQ * 256) sel_pick_kernel(const unsigned int* __restrict__ hists, int world, int pass, FinState* st) {
+    __shared__ long long wsum[NQ][8];
+    const int q = threadIdx.x >> 8, t = threadIdx.x & 255, lane = threadIdx.x & 31, w = t >> 5;
     int shift, width;
     sel_digit(st->key_bits, pass, &shift, &width);
-    const int bins = 1 << width, per = bins / 32;
+    const int bins = 1 << width;  // 1024 or 2048
     const int src = st->rep[q];
     const long long rank = st->rank[q];
     const unsigned long long prefix = st->prefix[q];
-    __syncthreads();  // every warp has read its inputs before any warp updates the state
+    long long c[8];
     long long s = 0;
-    for (int t = 0; t < per; ++t) {
-        long long c = 0;
-        for (int r = 0; r < world; ++r) c += hists[((size_t)r * NQ + src) * SEL_BINS + lane * per + t];
-        s += c;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c[k] = 0;
+    if (t * 8 < bins) {
+        for (int r = 0; r < world; ++r) {
+            const uint4* p = reinterpret_cast<const uint4*>(hists + ((size_t)r * NQ + src) * SEL_BINS + t * 8);
+            const uint4 a = p[0], b = p[1];
+            c[0] += a.x; c[1] += a.y; c[2] += a.z; c[3] += a.w; c[4] += b.x; c[5] += b.y; c[6] += b.z; c[7] += b.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += c[k];
     }
     long long incl = s;
 #pragma unroll
@@ -153,18 +161,19 @@ __global__ void __launch_bounds__(NQ * 32) sel_pick_kernel(const unsigned int* _
         const long long v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += v;
     }
-    const long long before = incl - s;
-    if (rank >= before && rank < incl) {
+    if (lane == 31) wsum[q][w] = incl;
+    __syncthreads();  // also: every thread has read the state before any thread updates it
+    long long before = incl - s;
+    for (int k = 0; k < w; ++k) before += wsum[q][k];
+    if (rank >= before && rank < before + s) {
         long long acc = before;
-        for (int t = 0; t < per; ++t) {
-            long long c = 0;
-            for (int r = 0; r < world; ++r) c += hists[((size_t)r * NQ + src) * SEL_BINS + lane * per + t];
-            if (rank < acc + c) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (rank >= acc && rank < acc + c[k]) {
                 st->rank[q] = rank - acc;
-                st->prefix[q] = (prefix << width) | (unsigned long long)(lane * per + t);
-                break;
+                st->prefix[q] = (prefix << width) | (unsigned long long)(t * 8 + k);
             }
-            acc += c;
+            acc += c[k];
         }
     }
     __syncthreads();
@@ -328,7 +337,7 @@ int hypad_stats_select_hist(hypad_ctx* ctx, const double* x, int64_t len, int pa
 int hypad_stats_select_pick(hypad_ctx* ctx, const uint32_t* hists, int world, int pass, void* stream) {
     HYPAD_REQUIRE(ctx && ctx->fin_state && hists && world >= 1 && pass >= 0 && pass < 6, "hypad_stats_select_pick: bad argument");
     HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
-    sel_pick_kernel<<<1, NQ * 32, 0, (cudaStream_t)stream>>>(hists, world, pass, fin_state(ctx));
+    sel_pick_kernel<<<1, NQ * 256, 0, (cudaStream_t)stream>>>(hists, world, pass, fin_state(ctx));
     HYPAD_LAUNCH_CHECK();
     return HYPAD_OK;
 }

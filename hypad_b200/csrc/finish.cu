@@ -734,15 +734,15 @@ int hypad_critic_smooth_shard(hypad_ctx* ctx, const double* kmax_ext, int64_t ex
                         (char*)ctx->workspace, (cudaStream_t)stream);
 }
 
-int hypad_critic_zscore_smooth(hypad_ctx* ctx, const double* kmax, int64_t len, int64_t smooth_window, double* out,
-                               void* stream) {
-    HYPAD_REQUIRE(ctx && kmax && out, "hypad_critic_zscore_smooth: NULL argument");
-    HYPAD_REQUIRE(len >= 1, "hypad_critic_zscore_smooth: len < 1");
-    // the one-rank chain of the staged statistics (critic_stats.cu); arbitrary doubles: 64-bit keys
-    int rc = hypad_stats_select_begin(ctx, len, 0, stream);
+int hypad_critic_scores(hypad_ctx* ctx, const double* kmax, int64_t len, int64_t smooth_window, int keys_f32, double* out,
+                        void* stream) {
+    HYPAD_REQUIRE(ctx && kmax && out, "hypad_critic_scores: NULL argument");
+    HYPAD_REQUIRE(len >= 1, "hypad_critic_scores: len < 1");
+    // the one-rank chain of the staged statistics (critic_stats.cu)
+    int rc = hypad_stats_select_begin(ctx, len, keys_f32, stream);
     if (rc != HYPAD_OK) return rc;
     uint32_t* hist = (uint32_t*)fin_local_record(ctx);
-    for (int p = 0; p < hypad_stats_select_passes(0); ++p) {
+    for (int p = 0; p < hypad_stats_select_passes(keys_f32); ++p) {
         if ((rc = hypad_stats_select_hist(ctx, kmax, len, p, hist, stream)) != HYPAD_OK) return rc;
         if ((rc = hypad_stats_select_pick(ctx, hist, 1, p, stream)) != HYPAD_OK) return rc;
     }
@@ -750,6 +750,11 @@ int hypad_critic_zscore_smooth(hypad_ctx* ctx, const double* kmax, int64_t len, 
     if ((rc = hypad_stats_moments_partial(ctx, kmax, 0, len, 1, rec, stream)) != HYPAD_OK) return rc;
     if ((rc = hypad_stats_moments_final(ctx, rec, 1, len, 1, 0, stream)) != HYPAD_OK) return rc;
     return hypad_critic_smooth_shard(ctx, kmax, len, 0, len, 0, len, smooth_window, out, stream);
+}
+
+int hypad_critic_zscore_smooth(hypad_ctx* ctx, const double* kmax, int64_t len, int64_t smooth_window, double* out,
+                               void* stream) {
+    return hypad_critic_scores(ctx, kmax, len, smooth_window, 0, out, stream);  // arbitrary doubles: 64-bit keys
 }
 
 int hypad_zscore_clip_apply(hypad_ctx* ctx, const void* x, int x_is_f32, int64_t len, double* out, void* stream_) {

@@ -25,6 +25,7 @@ namespace hypad {
 
 constexpr int KDE_WARPS = 4;
 constexpr int KDE_MAXPTS = 128;
+constexpr int KDE_CTAS = 7;  // resident CTAs per SM of the screened kernel (register budget 65536 / (7 x 128) = 73)
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -242,7 +243,7 @@ __device__ __forceinline__ void screen_pairs(const float (&d)[4], const float* D
     for (int q = 0; q < Q; ++q) e32[q] = e[q];
 }
 
-__global__ void __launch_bounds__(KDE_WARPS * 32, 6) kde_screened_kernel(const KdeArgs a) {
+__global__ void __launch_bounds__(KDE_WARPS * 32, KDE_CTAS) kde_screened_kernel(const KdeArgs a) {
     __shared__ double sP[KDE_WARPS][KDE_MAXPTS];
     __shared__ float sD[KDE_WARPS][2 * KDE_MAXPTS];
     __shared__ double sScott[KDE_MAXPTS + 1];
@@ -261,31 +262,36 @@ __global__ void __launch_bounds__(KDE_WARPS * 32, 6) kde_screened_kernel(const K
         if (it0 < a.t_count) nn = fetch_points(a, a.t0 + it0, lane, nf);
     }
     for (int64_t it = (int64_t)blockIdx.x * KDE_WARPS + warp; it < a.t_count; it += stride) {
-        double v[4];
+        float cur[4];  // the raw points: what is compared and returned at the end (the float64 copies die after the set-up)
         const int n = nn;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = (double)nf[q];
+        for (int q = 0; q < 4; ++q) cur[q] = nf[q];
         if (it + stride < a.t_count) nn = fetch_points(a, a.t0 + it + stride, lane, nf);
         if (n == 1) {
-            if (lane == 0) a.out[it] = v[0];
+            if (lane == 0) a.out[it] = (double)cur[0];
             continue;
         }
-        double mean, var;
-        point_stats(v, n, lane, mean, var);
-        if (!(var > 0.0)) {
-            if (lane == 0) a.out[it] = v[0];
-            continue;
-        }
-        const double cho = sqrt(var) * sScott[n];
-        const double rcho = 1.0 / cho;
-        const double dscale = kScale * rcho;
+        double mean, var, rcho;
         float d[4];
         const float kFar = 1e18f;  // sentinel for the slots beyond n: 2^-(1e36) = 0 against every real point
+        {
+            double v[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int j = lane + 32 * q;
-            d[q] = j < n ? (float)((v[q] - mean) * dscale) : kFar;
-            if (j < n) P[j] = v[q] * rcho;  // scipy divides; a last-bit difference of the scaled points cannot change the arg-max
+            for (int q = 0; q < 4; ++q) v[q] = (double)cur[q];
+            point_stats(v, n, lane, mean, var);
+            if (!(var > 0.0)) {
+                if (lane == 0) a.out[it] = v[0];
+                continue;
+            }
+            const double cho = sqrt(var) * sScott[n];
+            rcho = 1.0 / cho;
+            const double dscale = kScale * rcho;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = lane + 32 * q;
+                d[q] = j < n ? (float)((v[q] - mean) * dscale) : kFar;
+                if (j < n) P[j] = v[q] * rcho;  // scipy divides; a last-bit difference of the scaled points cannot change the arg-max
+            }
         }
         // ---- fp32 screening: every unordered pair once, with ex2.approx ----------------------------------
         float e32[4] = {0.f, 0.f, 0.f, 0.f};
@@ -378,14 +384,14 @@ __global__ void __launch_bounds__(KDE_WARPS * 32, 6) kde_screened_kernel(const K
         {
             const int f0 = cands[0] ? __ffs(cands[0]) - 1 : cands[1] ? 31 + __ffs(cands[1]) : cands[2] ? 63 + __ffs(cands[2]) : 95 + __ffs(cands[3]);
             first_j = f0;
-            double v0 = 0.0;
+            float v0 = 0.0f;
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if ((f0 >> 5) == q) v0 = v[q];
+                if ((f0 >> 5) == q) v0 = cur[q];
             v0 = __shfl_sync(0xffffffffu, v0, f0 & 31);
             bool differs = false;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) differs |= ((cands[q] >> lane) & 1u) && v[q] != v0;
+            for (int q = 0; q < 4; ++q) differs |= ((cands[q] >> lane) & 1u) && cur[q] != v0;
             all_same = !__any_sync(0xffffffffu, differs);
         }
         if (!all_same) {
@@ -480,12 +486,12 @@ __global__ void __launch_bounds__(KDE_WARPS * 32, 6) kde_screened_kernel(const K
                 }
             }
         }
-        double val = 0.0;
+        float val = 0.0f;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            if (bj == lane + 32 * q) val = v[q];
+            if (bj == lane + 32 * q) val = cur[q];
         val = __shfl_sync(0xffffffffu, val, bj & 31);
-        if (lane == 0) a.out[it] = val;
+        if (lane == 0) a.out[it] = (double)val;
         __syncwarp();
     }
 }
@@ -516,7 +522,7 @@ static int launch_kde(K kernel, const float* critic, int64_t critic_offset, int6
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t want = ceil_div(t_count, KDE_WARPS);
-    const int64_t cap = (int64_t)sms * 6;  // 6 CTAs of 4 warps per SM (80 registers), grid-stride beyond
+    const int64_t cap = (int64_t)sms * KDE_CTAS;  // resident CTAs of 4 warps per SM, grid-stride beyond
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     kernel<<<grid, KDE_WARPS * 32, 0, stream>>>(a);
     HYPAD_LAUNCH_CHECK();

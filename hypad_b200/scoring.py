@@ -185,6 +185,11 @@ def critic_scores_staged(kmax_local, ranges, n_total, smooth_window, comm=None, 
     dev = kmax_local.device
     c = _ctx(kmax_local)
     lib, h, st = c.lib, c.handle, c.stream
+    if comm.world == 1:  # the same stages chained inside the library: one call instead of a dozen
+        out = torch.empty_like(kmax_local)
+        with torch.cuda.device(dev):
+            check(lib.hypad_critic_scores(h, ptr(kmax_local), kmax_local.shape[0], int(smooth_window), int(keys_f32), ptr(out), st()))
+        return out
     p0, ln = ranges[comm.rank]
     if kmax_local.shape[0] != ln:
         raise HypadError("hypad_b200: kmax slice has %d positions, the plan says %d" % (kmax_local.shape[0], ln))

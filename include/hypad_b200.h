@@ -282,6 +282,11 @@ int hypad_stats_moments_final(hypad_ctx* ctx, const double* records, int world, 
                               void* stream);
 /* host8[0..7] = q25, q75, mean(all), mean(in band), std(all), z-score mean, z-score std, 0 (synchronises; diagnostics). */
 int hypad_stats_read(hypad_ctx* ctx, double* host8, void* stream);
+/* _compute_critic_score (:307-333) on one GPU: the chain of the stages above with the records passed straight on.
+ * keys_f32: the values are fp32-representable (KDE selections of fp32 critics): three select passes instead of six.
+ * hypad_critic_zscore_smooth is this with keys_f32 = 0. */
+int hypad_critic_scores(hypad_ctx* ctx, const double* kmax, int64_t len, int64_t smooth_window, int keys_f32, double* out,
+                        void* stream);
 /* :322-331 on a slice: kmax_ext holds the global positions [ext0, ext0 + ext_len) of n_total; out[j] = rolling mean
  * (window smooth_window, centred, min_periods window/2) of |x - mean_band| / std + 1 at position p0 + j, j < count.  The slice
  * must hold the smoothing halo: positions p0 - window/2 .. p0 + count - 1 + (window-1)/2, clipped to [0, n_total). */
