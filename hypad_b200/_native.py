@@ -49,6 +49,10 @@ class hypad_forward_out(ctypes.Structure):
     _fields_ = [("z", _vp), ("eucl", _vp), ("hyper", _vp), ("hyper_x", _vp), ("critic", _vp), ("rec", _vp), ("unorm", _vp)]
 
 
+class hypad_signal_out(ctypes.Structure):
+    _fields_ = [("critic", _vp), ("rec", _vp), ("unorm", _vp), ("kmax", _vp), ("critic_scores", _vp), ("final", _vp), ("tw", _vp)]
+
+
 # name -> (restype, argtypes); mirrors include/hypad_b200.h one to one
 _SIGNATURES = {
     "hypad_abi_version": (_int, []),
@@ -90,6 +94,8 @@ _SIGNATURES = {
     "hypad_threshold_windows_exhaustive": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _vp, _vp, _int, _vp]),
     "hypad_tc_probe_gemm": (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _vp]),
     "hypad_tc_probe_bench": (_int, [_int, _int, _int, _vp, _vp]),
+    "hypad_score_signal_hyperbolic": (_int, [_vp, _vp, _int, _i64, _int, _i64, _i64, _i64, _int, _int, _int,
+                                             ctypes.POINTER(hypad_signal_out), _vp]),
     "hypad_critic_scores": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp]),
     "hypad_stats_select_passes": (_int, [_int]),
     "hypad_stats_select_begin": (_int, [_vp, _i64, _int, _vp]),

@@ -310,6 +310,43 @@ int hypad_forward(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n, int64_
     return launch_forward(ctx, x, x_is_f64, n, row_stride, z_in, stages, out, (cudaStream_t)stream, ctx->tc_error);
 }
 
+int hypad_score_signal_hyperbolic(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n_windows, int combine_mode,
+                                  int64_t tw_window, int64_t tw_step, int64_t tw_count, int ddof_flags, int anomaly_padding,
+                                  int max_runs, const hypad_signal_out* o, void* stream) {
+    HYPAD_REQUIRE(ctx && x && o && o->critic && o->rec && o->unorm && o->final, "hypad_score_signal_hyperbolic: NULL argument");
+    HYPAD_REQUIRE(ctx->has_weights && ctx->prog.hyperbolic, "hypad_score_signal_hyperbolic: the context holds no hyperbolic model");
+    HYPAD_REQUIRE(n_windows >= 1, "hypad_score_signal_hyperbolic: no windows to score (signal shorter than the window?)");
+    const int S = ctx->prog.S;
+    const int64_t n_pos = n_windows + S - 1;
+    hypad_forward_out fo;
+    memset(&fo, 0, sizeof(fo));
+    fo.critic = o->critic;
+    fo.rec = o->rec;
+    fo.unorm = o->unorm;
+    int rc = hypad_forward(ctx, x, x_is_f64, n_windows, 1, nullptr,
+                           HYPAD_STAGE_ENCODER | HYPAD_STAGE_DECODER | HYPAD_STAGE_CRITIC | HYPAD_STAGE_MOBIUS_X, &fo, stream);
+    if (rc != HYPAD_OK) return rc;
+    const bool need_c = combine_mode != 6 && combine_mode != 7;  // rec, rec_uncertainty: no critic scores (:356-360)
+    if (need_c) {
+        HYPAD_REQUIRE(o->kmax && o->critic_scores, "hypad_score_signal_hyperbolic: kmax / critic_scores buffers missing");
+        if ((rc = hypad_kde_argmax_overlap(o->critic, 0, n_windows, n_windows, S, 0, n_pos, o->kmax, stream)) != HYPAD_OK) return rc;
+        // final_critic_scores (:365-404): smoothing window trunc(0.01 n_windows); fp32-valued selections: 32-bit keys
+        if ((rc = hypad_critic_scores(ctx, o->kmax, n_pos, (int64_t)((double)n_windows * 0.01), 1, o->critic_scores, stream)) != HYPAD_OK)
+            return rc;
+    }
+    if ((rc = hypad_combine_scores(combine_mode, need_c ? o->critic_scores : nullptr, o->rec, 1, o->unorm, 0.5, n_windows, o->final,
+                                   stream)) != HYPAD_OK)
+        return rc;
+    if (o->tw && tw_count > 0) {
+        double* stats = o->tw;
+        double* runs = stats + tw_count * 4;
+        int32_t* n_runs = (int32_t*)(runs + tw_count * (int64_t)max_runs * 3);
+        rc = hypad_threshold_windows(ctx, o->final, n_windows, tw_window, tw_step, tw_count, ddof_flags, anomaly_padding, stats, runs,
+                                     n_runs, max_runs, stream);
+    }
+    return rc;
+}
+
 int hypad_ctx_set_strict_range(hypad_ctx* ctx, int strict) {
     HYPAD_REQUIRE(ctx != nullptr, "hypad_ctx_set_strict_range: NULL context");
     ctx->strict_range = strict != 0;

@@ -750,6 +750,44 @@ class WindowScorer:
         check(self.net.ctx.lib.hypad_ctx_set_strict_range(self.net.ctx.handle, int(bool(strict))))
 
     # -- scoring -------------------------------------------------------------------------------------------
+    def score_chain(self, x, combination, tw=None):
+        """The univariate hyperbolic path of one device-resident signal as ONE library call (hypad_score_signal_hyperbolic):
+        network, KDE aggregation, critic scores, combination and -- tw = (window, step, count, ddof flags, padding, max_runs,
+        packed buffer) -- the device part of find_anomalies, queued back to back without returning to Python in between.  All
+        results are views of one device allocation.  Same kernels, same results as the step-by-step calls."""
+        self.net.ensure(self.encoder, self.decoder, self.critic_x)
+        x, n, _ = self._input(x, True)
+        if n <= 0:
+            raise HypadError("hypad_b200: no windows to score (signal shorter than the window?)")
+        S, dev = self.S, x.device
+        npos = n + S - 1
+        need_c = combination in _NEEDS_CRITIC
+        # one allocation: final f64 (n) | kmax f64 (npos) | critic_scores f64 (npos) | critic, rec, unorm f32 (n each)
+        n64 = n + (2 * npos if need_c else 0)
+        buf = torch.empty(n64 * 8 + 3 * n * 4, dtype=torch.uint8, device=dev)
+        d64 = buf[: n64 * 8].view(torch.float64)
+        f32 = buf[n64 * 8:].view(torch.float32)
+        out = {"final": d64[:n], "critic": f32[:n], "rec": f32[n:2 * n], "unorm": f32[2 * n:3 * n]}
+        so = _native.hypad_signal_out()
+        base = buf.data_ptr()
+        so.final = base
+        if need_c:
+            out["kmax"], out["critic_scores_full"] = d64[n:n + npos], d64[n + npos:]
+            out["critic_scores"] = out["critic_scores_full"][:n]
+            so.kmax, so.critic_scores = base + 8 * n, base + 8 * (n + npos)
+        else:
+            out["critic_scores"] = None
+        so.critic, so.rec, so.unorm = base + 8 * n64, base + 8 * n64 + 4 * n, base + 8 * n64 + 8 * n
+        w = s_ = c = dd = pad = mr = 0
+        if tw is not None:
+            w, s_, c, dd, pad, mr, twbuf = tw
+            so.tw = twbuf.data_ptr()
+        ctx = self.net.ctx
+        with torch.cuda.device(dev):
+            check(ctx.lib.hypad_score_signal_hyperbolic(ctx.handle, ptr(x), int(x.dtype == torch.float64), n, _native.COMBINE_MODES[combination],
+                                                        w, s_, c, dd, pad, mr, ctypes.byref(so), ctx.stream()))
+        return out
+
     def critic_scores(self, critic, n_windows):
         """final_critic_scores (:365-404): KDE arg-max overlap aggregation + quantile-band z-score + smoothing."""
         kmax = kde_argmax_overlap(critic, self.S)
@@ -774,6 +812,30 @@ class WindowScorer:
         stats_f32 = False
         if self.hyperbolic and not multivariate:
             univariate_hyperbolic_semantics(combination)  # unknown / undefined combinations fail before any work is queued
+        if (self.hyperbolic and sliding and not multivariate and not keep and isinstance(x, torch.Tensor) and x.is_cuda
+                and x.numel() - self.S < 200000):
+            # short device-resident signals are launch- and host-bound: the whole path as one library call
+            ddof, stats_f32 = univariate_hyperbolic_semantics(combination)
+            tw = None
+            if index is not None:
+                n = x.numel() - self.S
+                wsize, step, count = analysis_windows(n, None, 0.33, None, 0.1)
+                mr = _RUNS_HINT["max"]
+                twbuf = torch.empty(threshold_buffer_len(count, mr), dtype=torch.float64, device=x.device)
+                tw = (wsize, step, count, ddof | (_native.STATS_F32 if stats_f32 else 0), 50, mr, twbuf)
+            out = self.score_chain(x, combination, tw)
+            if out_host is not None:
+                download_async(self, out["final"], out_host)
+            if index is not None:
+                stats, runs, nr = threshold_windows_parse(twbuf.cpu().numpy(), count, mr)
+                if nr.max(initial=0) > mr:  # more runs than the buffer holds: the growing one-by-one path
+                    stats, runs, nr = threshold_windows(out["final"], wsize, step, count, tw[3], 50)
+                out["intervals"] = intervals_to_index(intervals_from_runs(stats, runs, nr, step, 0.1, f32=stats_f32), index)
+            if out_host is not None:
+                self._down_stream.synchronize()
+            if poll:
+                self.poll_error()
+            return out
         need = keep if self.hyperbolic else tuple(set(keep) | {"eucl"})
         if sliding and isinstance(x, torch.Tensor) and not x.is_cuda:
             fw = self.forward_from_host(x, need)

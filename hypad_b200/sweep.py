@@ -11,6 +11,7 @@ with one `all_gather_object` at the end.  No collective on the data path.
 import numpy as np
 import torch
 
+from . import _native
 from . import scoring as _sc
 from ._native import HypadError
 
@@ -112,17 +113,27 @@ class SignalSweep:
                 sc = self.scorers(i)  # inside the lane: a scorer built on demand packs its weights on the stream that uses them
                 used[id(sc)] = sc
                 x = resident[i] if i in resident else _sc._as_dev(signals[i], torch.float64, sc.device).reshape(-1)
-                out = sc.score(x, sliding=True, combination=combination, rec_error_type=rec_error_type, index=None, poll=False)
-                final = out["final"]
-                # find_anomalies' device part queued right behind the scores: no host synchronisation per signal
-                ddof = 1 if sc.hyperbolic else 0  # torch tensor (unbiased) vs ndarray
-                wsize, step, count = _sc.analysis_windows(final.numel(), None, 0.33, None, 0.1)
                 off, room = slot[i]
-                used_len = _sc.threshold_buffer_len(count, MAX_RUNS)
-                if used_len > room:
-                    raise HypadError("hypad_b200: signal %d yields %d scores, neither T-window nor T-1" % (i, final.numel()))
-                _sc.threshold_windows_launch(final, wsize, step, count, ddof, 50, MAX_RUNS, out=dev_buf[off:off + used_len])
-            queued.append((i, final, lane, ddof, (wsize, step, count), off, used_len))
+                f32 = False
+                if sc.hyperbolic:
+                    # the whole path of the signal, find_anomalies' device part included, as one library call
+                    ddof, f32 = _sc.univariate_hyperbolic_semantics(combination)  # what find_anomalies is handed
+                    wsize, step, count = _sc.analysis_windows(x.numel() - S, None, 0.33, None, 0.1)
+                    used_len = _sc.threshold_buffer_len(count, MAX_RUNS)
+                    flags = ddof | (_native.STATS_F32 if f32 else 0)
+                    out = sc.score_chain(x, combination, (wsize, step, count, flags, 50, MAX_RUNS, dev_buf[off:off + used_len]))
+                    final = out["final"]
+                else:
+                    out = sc.score(x, sliding=True, combination=combination, rec_error_type=rec_error_type, index=None, poll=False)
+                    final = out["final"]
+                    # find_anomalies' device part queued right behind the scores: no host synchronisation per signal
+                    ddof = 0  # an ndarray on the Euclidean path
+                    wsize, step, count = _sc.analysis_windows(final.numel(), None, 0.33, None, 0.1)
+                    used_len = _sc.threshold_buffer_len(count, MAX_RUNS)
+                    if used_len > room:
+                        raise HypadError("hypad_b200: signal %d yields %d scores, neither T-window nor T-1" % (i, final.numel()))
+                    _sc.threshold_windows_launch(final, wsize, step, count, ddof, 50, MAX_RUNS, out=dev_buf[off:off + used_len])
+            queued.append((i, final, lane, ddof | (_native.STATS_F32 if f32 else 0), (wsize, step, count), off, used_len, f32))
         cur = torch.cuda.current_stream()
         if self.n_streams > 1:
             for st in lanes:
@@ -132,11 +143,11 @@ class SignalSweep:
         cur.synchronize()
         host_np = host_buf.numpy()
         res = {}
-        for i, final, lane, ddof, (wsize, step, count), off, used_len in queued:
+        for i, final, lane, ddof, (wsize, step, count), off, used_len, f32 in queued:
             stats, runs, nr = _sc.threshold_windows_parse(host_np[off:off + used_len], count, MAX_RUNS)
             if nr.max(initial=0) > MAX_RUNS:  # more runs in one analysis window than the buffer holds (never seen): the one-by-one path
                 stats, runs, nr = _sc.threshold_windows(final, wsize, step, count, ddof, 50, max_runs=int(nr.max()) + 16)
-            merged = _sc.intervals_from_runs(stats, runs, nr, step, 0.1)
+            merged = _sc.intervals_from_runs(stats, runs, nr, step, 0.1, f32=f32)
             res[i] = {"intervals": _sc.intervals_to_index(merged, np.asarray(indices[i]))}
             if keep_scores:
                 res[i]["final"] = final

@@ -250,6 +250,26 @@ int hypad_threshold_windows_exhaustive(hypad_ctx* ctx, const double* errors, int
                             int64_t n_analysis, int ddof, int anomaly_padding, double* stats, double* runs,
                             int32_t* n_runs, int max_runs, void* stream);
 
+/* One signal through the whole univariate hyperbolic path in one call (anomaly_detection.py:67-155 + univariate_anomaly_detection,
+ * utils/anomaly_detection_utils.py:21-94): fused network over the n_windows sliding windows of x (n_windows + S samples) ->
+ * KDE arg-max overlap aggregation -> critic z-score + smoothing -> combine_scores(combine_mode) -> the device part of
+ * find_anomalies.  Every buffer is the caller's (device memory); tw, when not NULL, receives the packed thresholding result
+ * stats (tw_count, 4) | runs (tw_count, max_runs, 3) | n_runs int32 (tw_count) for hypad_intervals_from_runs.  The same kernels
+ * as the step-by-step entry points, queued back to back on `stream` without a host round trip in between: short signals are
+ * launch-bound, and a chain of calls through a binding costs more than their kernels. */
+typedef struct hypad_signal_out {
+    float* critic;         /* (n_windows) */
+    float* rec;            /* (n_windows) */
+    float* unorm;          /* (n_windows) */
+    double* kmax;          /* (n_windows + S - 1); may be NULL for combine modes rec / rec_uncertainty */
+    double* critic_scores; /* (n_windows + S - 1); likewise */
+    double* final;         /* (n_windows) */
+    double* tw;            /* packed thresholding result or NULL */
+} hypad_signal_out;
+int hypad_score_signal_hyperbolic(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n_windows, int combine_mode,
+                                  int64_t tw_window, int64_t tw_step, int64_t tw_count, int ddof_flags, int anomaly_padding,
+                                  int max_runs, const hypad_signal_out* out, void* stream);
+
 /* Host tail of find_anomalies on the outputs of hypad_threshold_windows (host pointers, no device work): prune
  * (utils/anomaly_detection_utils.py:1203-1237), score (:1240-1269) and merge (:1272-1313) with numpy's / pandas' arithmetic.
  * out receives up to `cap` (start, end, score) triples in positions of the scored array, *n_out their number (call again with
