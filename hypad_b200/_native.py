@@ -96,6 +96,8 @@ _SIGNATURES = {
     "hypad_tc_probe_bench": (_int, [_int, _int, _int, _vp, _vp]),
     "hypad_score_signal_hyperbolic": (_int, [_vp, _vp, _int, _i64, _int, _i64, _i64, _i64, _int, _int, _int,
                                              ctypes.POINTER(hypad_signal_out), _vp]),
+    "hypad_critic_small_max": (_int, []),
+    "hypad_critic_combine_small": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp, _vp, _i64, _vp, _vp, _vp]),
     "hypad_critic_scores": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp]),
     "hypad_stats_select_passes": (_int, [_int]),
     "hypad_stats_select_begin": (_int, [_vp, _i64, _int, _vp]),

@@ -327,15 +327,23 @@ int hypad_score_signal_hyperbolic(hypad_ctx* ctx, const void* x, int x_is_f64, i
                            HYPAD_STAGE_ENCODER | HYPAD_STAGE_DECODER | HYPAD_STAGE_CRITIC | HYPAD_STAGE_MOBIUS_X, &fo, stream);
     if (rc != HYPAD_OK) return rc;
     const bool need_c = combine_mode != 6 && combine_mode != 7;  // rec, rec_uncertainty: no critic scores (:356-360)
+    bool combined = false;
     if (need_c) {
         HYPAD_REQUIRE(o->kmax && o->critic_scores, "hypad_score_signal_hyperbolic: kmax / critic_scores buffers missing");
         if ((rc = hypad_kde_argmax_overlap(o->critic, 0, n_windows, n_windows, S, 0, n_pos, o->kmax, stream)) != HYPAD_OK) return rc;
         // final_critic_scores (:365-404): smoothing window trunc(0.01 n_windows); fp32-valued selections: 32-bit keys
-        if ((rc = hypad_critic_scores(ctx, o->kmax, n_pos, (int64_t)((double)n_windows * 0.01), 1, o->critic_scores, stream)) != HYPAD_OK)
-            return rc;
+        const int64_t smooth = (int64_t)((double)n_windows * 0.01);
+        if (n_pos <= hypad_critic_small_max()) {  // short signal: statistics, smoothing and combination in one launch
+            rc = hypad_critic_combine_small(ctx, o->kmax, n_pos, smooth, 1, combine_mode, o->rec, o->unorm, n_windows, o->critic_scores,
+                                            o->final, stream);
+            combined = true;
+        } else {
+            rc = hypad_critic_scores(ctx, o->kmax, n_pos, smooth, 1, o->critic_scores, stream);
+        }
+        if (rc != HYPAD_OK) return rc;
     }
-    if ((rc = hypad_combine_scores(combine_mode, need_c ? o->critic_scores : nullptr, o->rec, 1, o->unorm, 0.5, n_windows, o->final,
-                                   stream)) != HYPAD_OK)
+    if (!combined && (rc = hypad_combine_scores(combine_mode, need_c ? o->critic_scores : nullptr, o->rec, 1, o->unorm, 0.5, n_windows,
+                                                o->final, stream)) != HYPAD_OK)
         return rc;
     if (o->tw && tw_count > 0) {
         double* stats = o->tw;

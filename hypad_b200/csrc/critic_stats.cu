@@ -9,6 +9,7 @@
 //   zscore + clip of the multivariate reconstruction error (:177-178, :523-524): mean and std of all rows, same sums.
 #include "common.cuh"
 #include "dd.cuh"
+#include "finish_common.cuh"
 
 namespace hypad {
 
@@ -58,7 +59,9 @@ __host__ __device__ inline void sel_digit(int key_bits, int pass, int* shift, in
     }
 }
 
-__global__ void sel_begin_kernel(FinState* st, long long n_total, int key_bits) {
+__device__ __forceinline__ void sel_begin_body(FinState* st, long long n_total, int key_bits);
+__global__ void sel_begin_kernel(FinState* st, long long n_total, int key_bits) { sel_begin_body(st, n_total, key_bits); }
+__device__ __forceinline__ void sel_begin_body(FinState* st, long long n_total, int key_bits) {
     // np.quantile(method='linear'): virtual index q (n-1); neighbours floor and floor+1 (clipped)
     const double v25 = 0.25 * (double)(n_total - 1), v75 = 0.75 * (double)(n_total - 1);
     const long long f25 = (long long)v25, f75 = (long long)v75;
@@ -133,9 +136,10 @@ __global__ void __launch_bounds__(RB) sel_hist_kernel(const double* __restrict__
 // One CTA, 256 threads per order statistic: sum the ranks' histograms (8 consecutive bins per thread), locate the digit holding
 // rank[q] with a block-wide prefix sum, extend the prefix; after the last pass turn the four order statistics into the two
 // quantiles (numpy's _lerp).
-__global__ void __launch_bounds__(NQ * 256) sel_pick_kernel(const unsigned int* __restrict__ hists, int world, int pass, FinState* st) {
-    __shared__ long long wsum[NQ][8];
-    const int q = threadIdx.x >> 8, t = threadIdx.x & 255, lane = threadIdx.x & 31, w = t >> 5;
+// (NQ * 256 threads take part; st and hists may live in shared or global memory; wsum: shared scratch)
+__device__ __forceinline__ void sel_pick_body(const unsigned int* __restrict__ hists, int world, int pass, FinState* st, long long (*wsum)[8],
+                                              int tid) {
+    const int q = tid >> 8, t = tid & 255, lane = tid & 31, w = t >> 5;
     int shift, width;
     sel_digit(st->key_bits, pass, &shift, &width);
     const int bins = 1 << width;  // 1024 or 2048
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(NQ * 256) sel_pick_kernel(const unsigned int* 
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         for (int a = 0; a < NQ; ++a) {
             int rep = a;
             for (int b = a - 1; b >= 0; --b)
@@ -193,6 +197,11 @@ __global__ void __launch_bounds__(NQ * 256) sel_pick_kernel(const unsigned int* 
             st->s[1] = g75 >= 0.5 ? v[3] - d1 * (1.0 - g75) : v[2] + d1 * g75;
         }
     }
+}
+
+__global__ void __launch_bounds__(NQ * 256) sel_pick_kernel(const unsigned int* __restrict__ hists, int world, int pass, FinState* st) {
+    __shared__ long long wsum[NQ][8];
+    sel_pick_body(hists, world, pass, st, wsum, threadIdx.x);
 }
 
 // Local partial sums: out[0..1] sum x, [2..3] sum x^2, [4..5] sum of the x inside [lo, hi], [6] their count -- (hi, lo) pairs.
@@ -253,16 +262,7 @@ __global__ void __launch_bounds__(RB) moments_partial_kernel(const T* __restrict
 
 // The ranks' records (rank order) -> mean(all), mean(in band), std(all, ddof): s[2], s[3], s[4]; for the z-score moments
 // (band == 0) s[5] = mean, s[6] = std.
-__global__ void moments_final_kernel(const double* __restrict__ parts, int world, long long n_total, int band, int ddof, FinState* st) {
-    dd s1 = dd_make(0.0), s2 = dd_make(0.0), sb = dd_make(0.0);
-    double nb = 0.0;
-    for (int r = 0; r < world; ++r) {
-        const double* p = parts + (size_t)r * 8;
-        s1 = dd_add(s1, dd_make(p[0], p[1]));
-        s2 = dd_add(s2, dd_make(p[2], p[3]));
-        sb = dd_add(sb, dd_make(p[4], p[5]));
-        nb += p[6];
-    }
+__device__ __forceinline__ void moments_finish(dd s1, dd s2, dd sb, double nb, long long n_total, int band, int ddof, FinState* st) {
     const double n = (double)n_total;
     const dd mean = dd_div(s1, n);
     // sum (x - mean)^2 = sum x^2 - (sum x)^2 / n, every term carried to ~1e-32
@@ -277,6 +277,142 @@ __global__ void moments_final_kernel(const double* __restrict__ parts, int world
     } else {
         st->s[5] = dd_value(mean);
         st->s[6] = sd;
+    }
+}
+__global__ void moments_final_kernel(const double* __restrict__ parts, int world, long long n_total, int band, int ddof, FinState* st) {
+    dd s1 = dd_make(0.0), s2 = dd_make(0.0), sb = dd_make(0.0);
+    double nb = 0.0;
+    for (int r = 0; r < world; ++r) {
+        const double* p = parts + (size_t)r * 8;
+        s1 = dd_add(s1, dd_make(p[0], p[1]));
+        s2 = dd_add(s2, dd_make(p[2], p[3]));
+        sb = dd_add(sb, dd_make(p[4], p[5]));
+        nb += p[6];
+    }
+    moments_finish(s1, s2, sb, nb, n_total, band, ddof, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Short signals: the whole critic-score step -- select, band mean / std, z-score, smoothing -- and the score combination in ONE
+// launch of one CTA.  A signal of a few thousand positions is launch-bound: the 16 launches of the staged chain above cost an
+// order of magnitude more than their arithmetic.  Same arithmetic (exact select; (hi, lo) sums, whose rounded results do not
+// depend on the order; the shared element-wise definitions), so the results are those of the staged chain bit for bit.
+// Smoothing: a thread owns a run of consecutive positions, forms the first window's sum directly and slides it -- add the
+// entering value, subtract the leaving one, both in (hi, lo) arithmetic -- and keeps the index of the last value change for
+// pandas' all-equal-window rule (finish.cu).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SMALL_THREADS = 1024;
+constexpr int SMALL_MAX = 65536;  // positions
+
+template <typename TR>
+__global__ void __launch_bounds__(SMALL_THREADS) critic_small_kernel(const double* __restrict__ x, int n_pos, int smooth_window, int keys_f32,
+                                                                     int combine_mode, const TR* __restrict__ rec, const float* __restrict__ unorm,
+                                                                     int n_windows, double* __restrict__ cs_out, double* __restrict__ final_out,
+                                                                     double* __restrict__ zbuf, FinState* gstate) {
+    __shared__ unsigned int hist[NQ][SEL_BINS];
+    __shared__ long long wsum[NQ][8];
+    __shared__ double sh[64];
+    __shared__ FinState st;
+    const int tid = threadIdx.x;
+    if (tid == 0) sel_begin_body(&st, n_pos, keys_f32 ? 32 : 64);
+    __syncthreads();
+    // ---- radix select ---------------------------------------------------------------------------------
+    const int key_bits = keys_f32 ? 32 : 64, passes = keys_f32 ? 3 : 6;
+    for (int pass = 0; pass < passes; ++pass) {
+        for (int e = tid; e < NQ * SEL_BINS; e += SMALL_THREADS) (&hist[0][0])[e] = 0u;
+        __syncthreads();
+        int shift, width;
+        sel_digit(key_bits, pass, &shift, &width);
+        const int hi_shift = shift + width;
+        const unsigned int dmask = (1u << width) - 1u;
+        for (int i = tid; i < n_pos; i += SMALL_THREADS) {
+            const unsigned long long k = key_bits == 32 ? dkey32(x[i]) : dkey64(x[i]);
+            const unsigned long long hi = hi_shift >= key_bits ? 0ull : (k >> hi_shift);
+            const unsigned int digit = (unsigned int)(k >> shift) & dmask;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                if (st.rep[q] == q && hi == st.prefix[q]) atomicAdd(&hist[q][digit], 1u);
+        }
+        __syncthreads();
+        sel_pick_body(&hist[0][0], 1, pass, &st, wsum, tid);
+        __syncthreads();
+    }
+    // ---- band mean, std ---------------------------------------------------------------------------------
+    {
+        const double lo = st.s[0], hi = st.s[1];
+        dd s1 = dd_make(0.0), s2 = dd_make(0.0), sb = dd_make(0.0);
+        double nb = 0.0;
+        for (int i = tid; i < n_pos; i += SMALL_THREADS) {
+            const double v = x[i];
+            s1 = dd_add(s1, v);
+            s2 = dd_add(s2, dd_prod(v, v));
+            if (v >= lo && v <= hi) {
+                sb = dd_add(sb, v);
+                nb += 1.0;
+            }
+        }
+        s1 = dd_block_sum(s1, sh);
+        s2 = dd_block_sum(s2, sh);
+        sb = dd_block_sum(sb, sh);
+        const dd nbs = dd_block_sum(dd_make(nb), sh);
+        if (tid == 0) moments_finish(s1, s2, sb, nbs.hi, n_pos, 1, 0, &st);
+        __syncthreads();
+    }
+    if (tid < 8 && gstate) gstate->s[tid] = st.s[tid];  // for hypad_stats_read
+    // ---- z-score, smoothing, combination ------------------------------------------------------------------
+    const double mu = st.s[3], sd = st.s[4];
+    // z once per position into scratch (a double division each): the smoothing reads every value up to `window` times
+    for (int i = tid; i < n_pos; i += SMALL_THREADS) zbuf[i] = critic_z(x[i], mu, sd);
+    __syncthreads();
+    const int window = smooth_window, back = window / 2, fwd = (window - 1) / 2;
+    const int need = window / 2 > 1 ? window / 2 : 1;  // min_periods = window // 2, at least one sample
+    const int per = (n_pos + SMALL_THREADS - 1) / SMALL_THREADS;
+    const int i0 = tid * per, i1 = i0 + per < n_pos ? i0 + per : n_pos;
+    dd S = dd_make(0.0);
+    int a = 0, b = 0;        // the current window [a, b)
+    bool have = false;       // S, a, b, zlast, last_change describe the previous position's window
+    double zlast = 0.0;      // z at b - 1
+    long long last_change = -1;
+    for (int i = i0; i < i1; ++i) {
+        double out;
+        int na = i - back, nb = i + fwd + 1;
+        if (na < 0) na = 0;
+        if (nb > n_pos) nb = n_pos;
+        if (window <= 0 || nb - na < need) {
+            out = nan("");
+            have = false;
+        } else {
+            if (!have) {  // the window's sum from scratch
+                S = dd_make(0.0);
+                last_change = -1;
+                zlast = na > 0 ? zbuf[na - 1] : 0.0;
+                for (int j = na; j < nb; ++j) {
+                    const double z = zbuf[j];
+                    S = dd_add(S, z);
+                    if (j == 0 || z != zlast) last_change = j;
+                    zlast = z;
+                }
+                a = na;
+                b = nb;
+                have = true;
+            } else {
+                for (; b < nb; ++b) {  // values entering on the right
+                    const double z = zbuf[b];
+                    S = dd_add(S, z);
+                    if (z != zlast) last_change = b;
+                    zlast = z;
+                }
+                for (; a < na; ++a) S = dd_add(S, -zbuf[a]);  // values leaving on the left
+            }
+            // x[a .. b-1] all equal: pandas returns the value, not sum / count
+            out = last_change <= a ? zlast : S.hi / (double)(b - a);
+        }
+        cs_out[i] = out;
+        if (i < n_windows) {
+            const TR rv = rec ? rec[i] : (TR)0;
+            const double uv = unorm ? (double)unorm[i] : 0.0;
+            final_out[i] = combine_value<TR>(combine_mode, out, rv, uv, 0.5);
+        }
     }
 }
 
@@ -363,6 +499,26 @@ int hypad_stats_moments_final(hypad_ctx* ctx, const double* records, int world, 
     HYPAD_REQUIRE(ctx && ctx->fin_state && records && world >= 1 && n_total >= 1, "hypad_stats_moments_final: bad argument");
     HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
     moments_final_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(records, world, (long long)n_total, band, ddof, fin_state(ctx));
+    HYPAD_LAUNCH_CHECK();
+    return HYPAD_OK;
+}
+
+int hypad_critic_small_max(void) { return SMALL_MAX; }
+
+int hypad_critic_combine_small(hypad_ctx* ctx, const double* kmax, int64_t n_pos, int64_t smooth_window, int keys_f32, int combine_mode,
+                               const float* rec, const float* unorm, int64_t n_windows, double* critic_scores, double* final,
+                               void* stream) {
+    HYPAD_REQUIRE(ctx && kmax && critic_scores && final, "hypad_critic_combine_small: NULL argument");
+    HYPAD_REQUIRE(n_pos >= 1 && n_pos <= SMALL_MAX && n_windows >= 0 && n_windows <= n_pos, "hypad_critic_combine_small: %lld positions "
+                  "outside 1..%d", (long long)n_pos, SMALL_MAX);
+    HYPAD_REQUIRE(combine_mode >= 0 && combine_mode <= 8, "hypad_critic_combine_small: unknown mode %d", combine_mode);
+    HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
+    int rc = ensure_fin_state(ctx);
+    if (rc != HYPAD_OK) return rc;
+    if ((rc = ensure_workspace(ctx, (size_t)n_pos * 8)) != HYPAD_OK) return rc;
+    critic_small_kernel<float><<<1, SMALL_THREADS, 0, (cudaStream_t)stream>>>(kmax, (int)n_pos, (int)smooth_window, keys_f32, combine_mode, rec,
+                                                                            unorm, (int)n_windows, critic_scores, final,
+                                                                            (double*)ctx->workspace, fin_state(ctx));
     HYPAD_LAUNCH_CHECK();
     return HYPAD_OK;
 }

@@ -4,6 +4,7 @@
 // (:1098-1166).  All results stay on the device; scalars travel through a small block of the workspace.
 #include "common.cuh"
 #include "dd.cuh"
+#include "finish_common.cuh"
 
 namespace hypad {
 
@@ -80,7 +81,7 @@ struct ScanBufs {
 // the scanned value: x itself, or the critic z-score |x - s[3]| / s[4] + 1 (:322-325) taken on the fly
 template <bool Z>
 __device__ __forceinline__ double scan_value(const double* __restrict__ x, int64_t i, double mu, double sd) {
-    return Z ? fabs((x[i] - mu) / sd) + 1.0 : x[i];
+    return Z ? critic_z(x[i], mu, sd) : x[i];
 }
 
 template <bool Z>
@@ -238,23 +239,9 @@ __global__ void combine_kernel(int mode, const double* __restrict__ c, const TR*
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double cv = c ? c[i] : 0.0;
-        const double rv = r ? (double)r[i] : 0.0;
+        const TR rv = r ? r[i] : (TR)0;
         const double uv = u ? (double)u[i] : 0.0;
-        double o;
-        switch (mode) {
-            case 0: o = cv * rv; break;                                  // mult
-            case 1: o = (cv * rv) * uv; break;                           // uncertainty
-            case 2: o = 0.2 * cv + 0.8 * rv; break;                      // sum
-            case 3: o = cv; break;                                       // critic
-            case 4: o = cv * uv; break;                                  // critic_uncertainty
-            case 5: o = (0.5 * cv) * uv + (0.5 * rv) * uv; break;        // sum_uncertainty
-            case 6: o = rv; break;                                       // rec
-            case 7:                                                      // rec_uncertainty: an fp32 tensor times the fp32 norms stays fp32
-                if (sizeof(TR) == 4) o = (double)__fmul_rn((float)rv, (float)uv);
-                else o = rv * uv;
-                break;
-            default: o = (1.0 - lambda_rec) * (cv - 1.0) + lambda_rec * (rv - 1.0); break;  // score_anomalies "sum"
-        }
+        const double o = combine_value<TR>(mode, cv, rv, uv, lambda_rec);
         out[i] = o;
     }
 }

@@ -612,12 +612,18 @@ class WindowScorer:
     names) whose parameters live on a CUDA device.
     """
 
-    def __init__(self, encoder, decoder, critic_x):
+    def __init__(self, encoder, decoder, critic_x, own_context=False):
+        """own_context: pack the model into a context of this scorer's own instead of the one cached for the module triple -- a
+        context (packed weights, workspace, statistics state) serves one stream at a time, so scorers of the same modules that
+        run side by side on different streams (sweep.SignalSweep) each need theirs."""
         for m in (encoder, decoder, critic_x):
             if m.training:
                 raise HypadError("hypad_b200: call .eval() on the modules first (scoring is eval-mode only)")
         self.encoder, self.decoder, self.critic_x = encoder, decoder, critic_x
-        self.net = _weights.packed_net(encoder, decoder, critic_x)
+        if own_context:
+            self.net = _weights.PackedNet(next(encoder.parameters()).device).ensure(encoder, decoder, critic_x)
+        else:
+            self.net = _weights.packed_net(encoder, decoder, critic_x)
         self.device = self.net.device
         self.S = self.net.S
         self.hyperbolic = self.net.hyperbolic
@@ -750,12 +756,15 @@ class WindowScorer:
         check(self.net.ctx.lib.hypad_ctx_set_strict_range(self.net.ctx.handle, int(bool(strict))))
 
     # -- scoring -------------------------------------------------------------------------------------------
-    def score_chain(self, x, combination, tw=None):
+    def score_chain(self, x, combination, tw=None, check_weights=True):
         """The univariate hyperbolic path of one device-resident signal as ONE library call (hypad_score_signal_hyperbolic):
         network, KDE aggregation, critic scores, combination and -- tw = (window, step, count, ddof flags, padding, max_runs,
         packed buffer) -- the device part of find_anomalies, queued back to back without returning to Python in between.  All
-        results are views of one device allocation.  Same kernels, same results as the step-by-step calls."""
-        self.net.ensure(self.encoder, self.decoder, self.critic_x)
+        results are views of one device allocation.  Same kernels, same results as the step-by-step calls.
+        check_weights=False skips the comparison of the modules' parameters with the packed copy (a sweep checks each scorer
+        once per run: the walk over 43 parameters costs as much host time as the launches of a short signal)."""
+        if check_weights:
+            self.net.ensure(self.encoder, self.decoder, self.critic_x)
         x, n, _ = self._input(x, True)
         if n <= 0:
             raise HypadError("hypad_b200: no windows to score (signal shorter than the window?)")

@@ -43,14 +43,26 @@ class SignalSweep:
     them).  With torch.distributed initialised the signals are dealt out over the ranks of `group`; otherwise this process
     scores all of them."""
 
-    def __init__(self, scorers, group=None, window=100, streams=1):
+    def __init__(self, scorers, group=None, window=100, streams=4):
         """streams > 1 deals a rank's signals out over that many CUDA streams so that the small kernels of short signals overlap
-        on the device; only with one scorer per signal (a scorer's packed weights and workspace serve one stream at a time)."""
+        on the device (a short signal's network launch occupies a dozen of the 148 SMs).  A scorer's packed weights and workspace
+        serve one stream at a time: with one shared scorer every stream gets its own copy of the packed model (same modules,
+        packed once per stream)."""
         self.shared = not callable(scorers)
-        self.scorers = scorers if callable(scorers) else (lambda _i, s=scorers: s)
+        self.n_streams = max(1, int(streams))
+        if self.shared:
+            clones = {0: scorers}
+
+            def per_lane(_i, lane=0, base=scorers):
+                if lane not in clones:
+                    clones[lane] = _sc.WindowScorer(base.encoder, base.decoder, base.critic_x, own_context=True)
+                return clones[lane]
+
+            self.scorers = per_lane
+        else:
+            self.scorers = lambda i, lane=0, f=scorers: f(i)
         self.group = group
         self.window = window
-        self.n_streams = 1 if self.shared else max(1, int(streams))
         self._streams = None
         self._host_buf = None
         if torch.distributed.is_available() and torch.distributed.is_initialized():
@@ -110,7 +122,8 @@ class SignalSweep:
         for k, i in enumerate(ids):
             lane = lanes[k % len(lanes)]
             with torch.cuda.stream(lane):
-                sc = self.scorers(i)  # inside the lane: a scorer built on demand packs its weights on the stream that uses them
+                sc = self.scorers(i, k % len(lanes))  # inside the lane: a scorer built on demand packs its weights on the stream that uses them
+                first_use = id(sc) not in used
                 used[id(sc)] = sc
                 x = resident[i] if i in resident else _sc._as_dev(signals[i], torch.float64, sc.device).reshape(-1)
                 off, room = slot[i]
@@ -121,7 +134,8 @@ class SignalSweep:
                     wsize, step, count = _sc.analysis_windows(x.numel() - S, None, 0.33, None, 0.1)
                     used_len = _sc.threshold_buffer_len(count, MAX_RUNS)
                     flags = ddof | (_native.STATS_F32 if f32 else 0)
-                    out = sc.score_chain(x, combination, (wsize, step, count, flags, 50, MAX_RUNS, dev_buf[off:off + used_len]))
+                    out = sc.score_chain(x, combination, (wsize, step, count, flags, 50, MAX_RUNS, dev_buf[off:off + used_len]),
+                                         check_weights=first_use)
                     final = out["final"]
                 else:
                     out = sc.score(x, sliding=True, combination=combination, rec_error_type=rec_error_type, index=None, poll=False)

@@ -307,6 +307,12 @@ int hypad_stats_read(hypad_ctx* ctx, double* host8, void* stream);
  * hypad_critic_zscore_smooth is this with keys_f32 = 0. */
 int hypad_critic_scores(hypad_ctx* ctx, const double* kmax, int64_t len, int64_t smooth_window, int keys_f32, double* out,
                         void* stream);
+/* Short signals (n_pos <= hypad_critic_small_max()): hypad_critic_scores and hypad_combine_scores (rec fp32) in ONE launch of one
+ * CTA -- a few thousand positions are launch-bound.  Bitwise the results of the two calls. */
+int hypad_critic_small_max(void);
+int hypad_critic_combine_small(hypad_ctx* ctx, const double* kmax, int64_t n_pos, int64_t smooth_window, int keys_f32, int combine_mode,
+                               const float* rec, const float* unorm, int64_t n_windows, double* critic_scores, double* final,
+                               void* stream);
 /* :322-331 on a slice: kmax_ext holds the global positions [ext0, ext0 + ext_len) of n_total; out[j] = rolling mean
  * (window smooth_window, centred, min_periods window/2) of |x - mean_band| / std + 1 at position p0 + j, j < count.  The slice
  * must hold the smoothing halo: positions p0 - window/2 .. p0 + count - 1 + (window-1)/2, clipped to [0, n_total). */

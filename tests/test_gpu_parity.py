@@ -338,6 +338,43 @@ def test_flat_stretches_stay_flat_and_raise_no_runs(cuda_device):
     assert iv.shape[0] == 0 and ho.find_anomalies(y, np.arange(20000), 0.33, 0.1, anomaly_padding=50, ddof=0).shape[0] == 0
 
 
+def test_single_cta_finish_equals_the_staged_chain(cuda_device):
+    """hypad_critic_combine_small (short signals: select, band statistics, z-score, smoothing and combination in one launch of one
+    CTA) against hypad_critic_scores + hypad_combine_scores, bit for bit: fp32-valued inputs as the KDE hands them over, flat
+    stretches, every combination, window lengths from 0 up, sizes up to the kernel's limit."""
+    import ctypes
+
+    from hypad_b200 import _native, scoring
+
+    lib = _native.load_library()
+    assert lib.hypad_critic_small_max() >= 65536
+    rng = np.random.default_rng(21)
+    for n_pos, S in ((1, 1), (2, 2), (101, 100), (164, 100), (1499, 100), (8639, 100), (24099, 100), (65536, 123)):
+        n = n_pos - S + 1
+        x = rng.standard_normal(n_pos).astype(np.float32).astype(np.float64) * 0.01 + 0.3
+        if n_pos > 600:
+            x[200:200 + n_pos // 4] = x[200]       # a flat stretch longer than the smoothing window
+            x[n_pos - 50:] = x[n_pos - 50]         # and one running into the right edge
+        rec = rng.uniform(0.01, 1, n).astype(np.float32)
+        un = rng.uniform(0.1, 0.9, n).astype(np.float32)
+        xd, rd, ud = (torch.from_numpy(a).to(cuda_device) for a in (x, rec, un))
+        ctx = _native.default_context(cuda_device)
+        for w in sorted({0, 1, 2, 7, int(n * 0.01), min(n_pos, 700)}):
+            want_cs = torch.empty_like(xd)
+            _native.check(lib.hypad_critic_scores(ctx.handle, _native.ptr(xd), n_pos, w, 1, _native.ptr(want_cs), ctx.stream()))
+            for comb in ("uncertainty", "mult", "critic", "sum_uncertainty", "rec_uncertainty"):
+                want = scoring.combine(comb, want_cs[:n], rd, ud, n=n)
+                cs, fin = torch.full_like(xd, -7.0), torch.full((max(n, 1),), -7.0, dtype=torch.float64, device=cuda_device)
+                _native.check(lib.hypad_critic_combine_small(ctx.handle, _native.ptr(xd), n_pos, w, 1, _native.COMBINE_MODES[comb],
+                                                             _native.ptr(rd), _native.ptr(ud), n, _native.ptr(cs), _native.ptr(fin), ctx.stream()))
+                a, b = cs.cpu().numpy(), want_cs.cpu().numpy()
+                assert np.array_equal(a, b, equal_nan=True), (n_pos, w, comb, np.nanmax(np.abs(a - b)))
+                assert np.array_equal(fin[:n].cpu().numpy(), want.cpu().numpy(), equal_nan=True), (n_pos, w, comb)
+    with pytest.raises(_native.HypadError):
+        big = torch.zeros(70000, dtype=torch.float64, device=cuda_device)
+        _native.check(lib.hypad_critic_combine_small(ctx.handle, _native.ptr(big), 70000, 5, 1, 0, None, None, 0, _native.ptr(big), _native.ptr(big), ctx.stream()))
+
+
 def test_median_overlap_exact(cuda_device):
     from hypad_b200 import scoring
 
