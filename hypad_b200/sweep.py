@@ -169,8 +169,13 @@ class SignalSweep:
             sc.poll_error()
         return res
 
-    def run(self, signals, indices, combination="uncertainty", rec_error_type="dtw"):
-        """Every rank returns the full {signal id: (K,3) intervals} map (empty (0,3) array for signals without a window)."""
+    def run(self, signals, indices, combination="uncertainty", rec_error_type="dtw", known_anomalies=None):
+        """Every rank returns the full {signal id: (K,3) intervals} map (empty (0,3) array for signals without a window).
+
+        known_anomalies: optional list (one entry per signal) of [(start, end), ...] labelled anomalies in index units.  Then the
+        return value is (intervals map, evaluation): per signal the overlap-segment confusion counts the reference records for it
+        (utils/anomaly_detection_utils.py:96-105, :579-599 -- `[tn, fp, fn, tp]`, tn is None) and, summed over the sweep, the
+        precision / recall / F1 its compute_metrics prints (:241-254)."""
         if len(signals) != len(indices):
             raise HypadError("hypad_b200: %d signals but %d index arrays" % (len(signals), len(indices)))
         plan = self.plan([_n_samples(s) for s in signals])
@@ -183,4 +188,26 @@ class SignalSweep:
         merged = {}
         for part in parts:
             merged.update(part)
-        return {i: merged.get(i, np.empty((0, 3))) for i in range(len(signals))}
+        intervals = {i: merged.get(i, np.empty((0, 3))) for i in range(len(signals))}
+        if known_anomalies is None:
+            return intervals
+        return intervals, evaluate_sweep(intervals, known_anomalies)
+
+
+def evaluate_sweep(intervals, known_anomalies):
+    """Per-signal overlap-segment confusion counts (contextual_confusion_matrix(..., weighted=False), the only variant the
+    reference's callers use) and the sweep totals with the reference's metric formulas.  Host work on a handful of intervals."""
+    from .utils.anomaly_detection_utils import _overlap_segment, _pad
+
+    per_signal = {}
+    fp = fn = tp = 0
+    for i, iv in intervals.items():
+        expected = [(float(a), float(b)) for a, b in known_anomalies[i]]
+        observed = [(float(r[0]), float(r[1])) for r in np.asarray(iv).reshape(-1, 3)]
+        _tn, f_p, f_n, t_p = _overlap_segment(_pad(expected), _pad(observed))
+        per_signal[i] = [None, f_p, f_n, t_p]
+        fp, fn, tp = fp + f_p, fn + f_n, tp + t_p
+    precision = tp / (tp + fp) if tp + fp else float("nan")
+    recall = tp / (tp + fn) if tp + fn else float("nan")
+    f1 = 2 * precision * recall / (precision + recall) if precision + recall > 0 else float("nan")
+    return {"per_signal": per_signal, "fp": fp, "fn": fn, "tp": tp, "precision": precision, "recall": recall, "f1": f1}

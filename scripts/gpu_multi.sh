@@ -12,3 +12,4 @@ P
 tail -3 gpurun_out/bench_${TAG}_n$N.err
 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29534 scripts/cfg4_multivariate_sharded.py --steps 5 > gpurun_out/cfg4_${TAG}_n$N.json 2> gpurun_out/cfg4_${TAG}_n$N.err; echo "cfg4 exit $?"; cat gpurun_out/cfg4_${TAG}_n$N.json; tail -3 gpurun_out/cfg4_${TAG}_n$N.err
 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29535 scripts/sharded_phases.py 2> gpurun_out/phases_${TAG}_n$N.err | tee gpurun_out/phases_${TAG}_n$N.json
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29536 scripts/cfg5_sweep_sharded.py 2> gpurun_out/cfg5_${TAG}_n$N.err | tee gpurun_out/cfg5_${TAG}_n$N.json; tail -2 gpurun_out/cfg5_${TAG}_n$N.err

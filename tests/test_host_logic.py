@@ -295,3 +295,31 @@ def test_library_host_tail_equals_the_python_restatement():
             assert len(a) == len(b), (trial, len(a), len(b))
             for x, y in zip(a, b):
                 assert all((p == q) or (p != p and q != q) for p, q in zip(x, map(float, y))), (trial, x, y)
+
+
+def test_sweep_evaluation_counts_follow_the_reference_rule():
+    """SignalSweep.run(..., known_anomalies=...): per signal the reference's overlap-segment confusion counts (tp = labelled
+    anomalies hit by at least one detection, fn = the others, fp = detections that hit nothing; closed intervals padded by one,
+    utils/anomaly_detection_utils.py:579-603), and the totals with its precision / recall / F1 formulas (:241-254)."""
+    from hypad_b200.sweep import evaluate_sweep
+
+    rng = np.random.default_rng(9)
+    intervals, known = {}, []
+    want_fp = want_fn = want_tp = 0
+    for i in range(40):
+        obs = sorted((int(a), int(a) + int(w)) for a, w in zip(rng.integers(0, 1000, rng.integers(0, 5)), rng.integers(0, 30, 5)))
+        exp = sorted((int(a), int(a) + int(w)) for a, w in zip(rng.integers(0, 1000, rng.integers(0, 4)), rng.integers(0, 30, 4)))
+        intervals[i] = np.asarray([[a, b, 1.0] for a, b in obs], dtype=np.float64).reshape(-1, 3)
+        known.append(exp)
+        # the nested-loop rule of the reference on half-open intervals
+        e2, o2 = [(a, b + 1) for a, b in exp], [(a, b + 1) for a, b in obs]
+        hit_e = [any((e[0] - o[1]) * (e[1] - o[0]) < 0 for o in o2) for e in e2]
+        hit_o = [any((e[0] - o[1]) * (e[1] - o[0]) < 0 for e in e2) for o in o2]
+        tp, fn, fp = sum(hit_e), len(e2) - sum(hit_e), len(o2) - sum(hit_o)
+        want_fp, want_fn, want_tp = want_fp + fp, want_fn + fn, want_tp + tp
+        got = evaluate_sweep({i: intervals[i]}, {i: exp})["per_signal"][i]
+        assert got == [None, fp, fn, tp], (i, got, (fp, fn, tp))
+    ev = evaluate_sweep(intervals, known)
+    assert (ev["fp"], ev["fn"], ev["tp"]) == (want_fp, want_fn, want_tp)
+    p, r = want_tp / (want_tp + want_fp), want_tp / (want_tp + want_fn)
+    assert ev["precision"] == p and ev["recall"] == r and ev["f1"] == 2 * p * r / (p + r)
