@@ -34,58 +34,115 @@ __global__ void true_from_signal_kernel(const T* __restrict__ x, int64_t n, int6
 }
 
 // ---- utils/anomaly_detection_utils.py:918-923: median over the anti-diagonal ---------------------------
-// One warp per timestep i: values y_hat[i-j][j], j in [max(0,i-N+1), min(i,S-1)] (n <= 128).  Ranks by counting
-// (stable on ties), np.median semantics for fp32: odd n -> middle, even n -> fp32 (a+b)/2 of the two middles.
-// A CTA handles MED_WARPS consecutive timesteps so that the 128-byte lines it touches are shared through L1.
+// Timestep i takes the median of y_hat[i-j][j], j in [max(0,i-N+1), min(i,S-1)] (n <= 128 values): np.median semantics for
+// fp32 -- odd n the middle value, even n the fp32 mean (a+b)/2 of the two middles, NaN if any value is NaN.
+// An anti-diagonal is the worst possible access pattern for the row-major reconstruction (lanes S-1 floats apart, one sector
+// per lane), and every element belongs to exactly one of them.  So a CTA takes MED_TILE consecutive timesteps, copies the
+// MED_TILE + S - 1 reconstruction rows they touch into shared memory with coalesced 16-byte loads (neighbouring CTAs re-read
+// the S - 1 rows they share from L2), and its warps cut the diagonals from there: lane k reads row (i - lo - k), column lo + k,
+// S - 1 words apart -- odd for an even pitch, no bank conflict.  The median comes from a bitonic sort of the <= 128 values
+// across the warp (4 per lane as order-preserving integer keys, padding sorts last): 28 compare-exchange stages instead of
+// the n^2 = 10^4 comparisons of ranking by counting.
 constexpr int MED_WARPS = 8;
+constexpr int MED_TILE = 128;
 
-__global__ void __launch_bounds__(MED_WARPS * 32) median_overlap_kernel(const float* __restrict__ y_hat, int64_t N, int S,
+__device__ __forceinline__ unsigned int med_key(float v) {
+    if (v != v) return 0xffffffffu;  // NaN sorts last (and makes the result NaN)
+    const unsigned int b = __float_as_uint(v);
+    return (b >> 31) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float med_unkey(unsigned int k) { return __uint_as_float((k >> 31) ? (k & 0x7fffffffu) : ~k); }
+
+__global__ void __launch_bounds__(MED_WARPS * 32) median_overlap_kernel(const float* __restrict__ y_hat, int64_t N, int S, int pitch,
                                                                        float* __restrict__ pred) {
-    __shared__ float sV[MED_WARPS][128];
-    __shared__ float sMid[MED_WARPS][2];
+    extern __shared__ __align__(16) float srows[];  // (MED_TILE + S - 1) rows x pitch
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* V = sV[warp];
     const int64_t T = N + S - 1;
-    const int64_t nblk = (T + MED_WARPS - 1) / MED_WARPS;
-    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-        const int64_t i = blk * MED_WARPS + warp;
-        if (i < T) {
+    const int64_t ntiles = (T + MED_TILE - 1) / MED_TILE;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t t0 = tile * MED_TILE;
+        const int64_t w_lo = t0 - (S - 1) > 0 ? t0 - (S - 1) : 0;
+        const int64_t w_hi = t0 + MED_TILE - 1 < N - 1 ? t0 + MED_TILE - 1 : N - 1;  // inclusive
+        const int rows = (int)(w_hi - w_lo + 1);
+        __syncthreads();  // the previous tile's diagonals have been read
+        if (rows > 0) {
+            const float* src = y_hat + w_lo * (int64_t)S;
+            const int total = rows * S;
+            if (pitch == S && (S & 3) == 0) {
+                const float4* s4 = reinterpret_cast<const float4*>(src);  // w_lo * S floats: a multiple of 4, 16-byte aligned
+                float4* d4 = reinterpret_cast<float4*>(srows);
+                for (int e = threadIdx.x; e < total / 4; e += MED_WARPS * 32) d4[e] = __ldg(s4 + e);
+            } else {
+                for (int e = threadIdx.x; e < total; e += MED_WARPS * 32) {
+                    const int w = e / S;
+                    srows[w * pitch + (e - w * S)] = __ldg(src + e);
+                }
+            }
+        }
+        __syncthreads();
+        for (int tt = warp; tt < MED_TILE; tt += MED_WARPS) {
+            const int64_t i = t0 + tt;
+            if (i >= T) break;
             const int lo = (int)(i - N + 1 > 0 ? i - N + 1 : 0);
             const int hi = (int)(i < S - 1 ? i : S - 1);
             const int n = hi - lo + 1;
-            float v[4];
+            unsigned int key[4];
+            bool has_nan = false;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int k = lane + 32 * q;
-                v[q] = 0.f;
+                key[q] = 0xffffffffu;
                 if (k < n) {
                     const int j = lo + k;
-                    v[q] = y_hat[(i - j) * (int64_t)S + j];
-                    V[k] = v[q];
+                    const float v = srows[(int)(i - j - w_lo) * pitch + j];
+                    has_nan |= v != v;
+                    key[q] = med_key(v);
                 }
             }
-            __syncwarp();
+            has_nan = __any_sync(0xffffffffu, has_nan);
+            // bitonic sort, ascending, of the 128 keys at positions p = lane + 32 q
+#pragma unroll
+            for (int k = 2; k <= 128; k <<= 1) {
+#pragma unroll
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    if (j >= 32) {  // partner in the same lane: registers q and q ^ (j / 32)
+                        const int dq = j >> 5;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (!(q & dq)) {
+                                const bool up = ((q * 32) & k) == 0;  // ascending block (lane bits are below 32 <= j < k)
+                                const unsigned int a = key[q], b = key[q | dq];
+                                const unsigned int mn = a < b ? a : b, mx = a < b ? b : a;
+                                key[q] = up ? mn : mx;
+                                key[q | dq] = up ? mx : mn;
+                            }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int p = lane + 32 * q;
+                            const unsigned int other = __shfl_xor_sync(0xffffffffu, key[q], j);
+                            const bool up = (p & k) == 0, lower = (lane & j) == 0;
+                            const unsigned int mn = key[q] < other ? key[q] : other, mx = key[q] < other ? other : key[q];
+                            key[q] = (up == lower) ? mn : mx;
+                        }
+                    }
+                }
+            }
             const int r_lo = (n - 1) >> 1, r_hi = n >> 1;
+            unsigned int ka = 0, kb = 0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int k = lane + 32 * q;
-                if (k < n) {
-                    int rank = 0;
-                    const float mine = v[q];
-                    for (int t = 0; t < n; ++t) {
-                        const float o = V[t];
-                        rank += (o < mine) || (o == mine && t < k);
-                    }
-                    if (rank == r_lo) sMid[warp][0] = mine;
-                    if (rank == r_hi) sMid[warp][1] = mine;
-                }
+                if ((r_lo >> 5) == q) ka = key[q];
+                if ((r_hi >> 5) == q) kb = key[q];
             }
-            __syncwarp();
+            ka = __shfl_sync(0xffffffffu, ka, r_lo & 31);
+            kb = __shfl_sync(0xffffffffu, kb, r_hi & 31);
             if (lane == 0) {
-                const float a = sMid[warp][0], b = sMid[warp][1];
-                pred[i] = (n & 1) ? a : __fmul_rn(__fadd_rn(a, b), 0.5f);
+                const float a = med_unkey(ka), b = med_unkey(kb);
+                float m = (n & 1) ? a : __fmul_rn(__fadd_rn(a, b), 0.5f);
+                if (has_nan) m = __uint_as_float(0x7fc00000u);
+                pred[i] = m;
             }
-            __syncwarp();
         }
     }
 }
@@ -181,8 +238,20 @@ int hypad_true_from_signal(const void* x, int x_is_f64, int64_t n, int64_t row_s
 int hypad_median_overlap(const float* y_hat, int64_t n, int S, float* pred, void* stream) {
     HYPAD_REQUIRE(y_hat && pred, "hypad_median_overlap: NULL argument");
     HYPAD_REQUIRE(n >= 1 && S >= 1 && S <= 128, "hypad_median_overlap: S=%d outside 1..128 or n<1", S);
-    const unsigned grid = grid_for(n + S - 1, MED_WARPS, 8);
-    median_overlap_kernel<<<grid, MED_WARPS * 32, 0, (cudaStream_t)stream>>>(y_hat, n, S, pred);
+    const int pitch = S + (S & 1);  // even pitch: the diagonal's lane stride pitch - 1 is odd (no shared-memory bank conflict)
+    const size_t smem = (size_t)(MED_TILE + S - 1) * pitch * sizeof(float);
+    static bool configured = false;  // idempotent, cheap: racing threads at worst set the attribute twice
+    if (!configured) {
+        HYPAD_CUDA_TRY(cudaFuncSetAttribute(median_overlap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (MED_TILE + 127) * 128 * 4));
+        configured = true;
+    }
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t ntiles = ceil_div(n + S - 1, MED_TILE);
+    const int64_t cap = (int64_t)sms * 2;  // two resident CTAs per SM (91 KB of rows each at S = 100)
+    const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
+    median_overlap_kernel<<<grid, MED_WARPS * 32, smem, (cudaStream_t)stream>>>(y_hat, n, S, pitch, pred);
     HYPAD_LAUNCH_CHECK();
     return HYPAD_OK;
 }
