@@ -107,6 +107,7 @@ _SIGNATURES = {
     "hypad_stats_moments_final": (_int, [_vp, _vp, _int, _i64, _int, _int, _vp]),
     "hypad_stats_read": (_int, [_vp, _vp, _vp]),
     "hypad_critic_smooth_shard": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "hypad_rolling_mean_shard": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
     "hypad_zscore_clip_apply": (_int, [_vp, _vp, _int, _i64, _vp, _vp]),
     "hypad_intervals_from_runs": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, ctypes.c_double, _int, _vp, _i64, ctypes.POINTER(_i64)]),
     "hypad_peak_probe": (_int, [_int, _int, _int, _vp, ctypes.POINTER(ctypes.c_longlong), _vp]),

@@ -721,6 +721,27 @@ int hypad_critic_smooth_shard(hypad_ctx* ctx, const double* kmax_ext, int64_t ex
                         (char*)ctx->workspace, (cudaStream_t)stream);
 }
 
+int hypad_rolling_mean_shard(hypad_ctx* ctx, const double* x_ext, int64_t ext_len, int64_t ext0, int64_t n_total, int64_t p0,
+                             int64_t count, int64_t window, int64_t min_periods, double* out, void* stream) {
+    HYPAD_REQUIRE(ctx && x_ext && out, "hypad_rolling_mean_shard: NULL argument");
+    HYPAD_REQUIRE(ext_len >= 1 && ext0 >= 0 && ext0 + ext_len <= n_total && p0 >= ext0 && count >= 0 && p0 + count <= ext0 + ext_len,
+                  "hypad_rolling_mean_shard: the slice [%lld, %lld) does not hold the positions [%lld, %lld)", (long long)ext0,
+                  (long long)(ext0 + ext_len), (long long)p0, (long long)(p0 + count));
+    if (count == 0) return HYPAD_OK;
+    if (window > 0) {
+        const int64_t need_lo = p0 - window / 2 > 0 ? p0 - window / 2 : 0;
+        const int64_t hi = p0 + count - 1 + (window - 1) / 2 + 1, need_hi = hi < n_total ? hi : n_total;
+        HYPAD_REQUIRE(ext0 <= need_lo && ext0 + ext_len >= need_hi, "hypad_rolling_mean_shard: the slice lacks the smoothing halo "
+                      "(needs [%lld, %lld), holds [%lld, %lld))", (long long)need_lo, (long long)need_hi, (long long)ext0,
+                      (long long)(ext0 + ext_len));
+    }
+    HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
+    int rc = ensure_workspace(ctx, rolling_ws_bytes(ext_len));
+    if (rc != HYPAD_OK) return rc;
+    return rolling_mean(ctx, x_ext, ext_len, ext0, n_total, p0, count, window, min_periods, false, out, (char*)ctx->workspace,
+                        (cudaStream_t)stream);
+}
+
 int hypad_critic_scores(hypad_ctx* ctx, const double* kmax, int64_t len, int64_t smooth_window, int keys_f32, double* out,
                         void* stream) {
     HYPAD_REQUIRE(ctx && kmax && out, "hypad_critic_scores: NULL argument");

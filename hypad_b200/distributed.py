@@ -209,6 +209,74 @@ class ShardedScorer:
         fw = sc.forward(local_rows, False)  # rows h0 .. first+count-1
         return self._score(fw, n_rows, combination, index, True, 0.2, 200, 0)
 
+    # Positions either side that the windowed reconstruction errors reach (score_window 10): the area error looks 5 either way; the
+    # DTW error of position i is the distance of the windows over [i - 10, i] (the reference stores window c of the zero-padded
+    # arrays at position c + 5, utils/anomaly_detection_utils.py:834-861) and the last 6 positions of the array are zero -- an end
+    # effect that must stay outside the owned positions wherever the slice end is not the signal's end.
+    ERR_HALO = 10
+
+    def plan_euclidean(self, n_windows):
+        """(t0, tc, w_lo, w_hi, sample_lo, sample_hi) for the Euclidean per-timestep path: the owned positions [t0, t0 + tc) of the
+        n_windows + S - 1 timesteps, the windows [w_lo, w_hi) whose reconstructions this rank computes -- every window under a
+        position it needs the prediction of, i.e. the owned positions and ERR_HALO more on either side -- and the samples
+        [sample_lo, sample_hi) of the signal to keep resident (window w reads [w, w + S))."""
+        S, H = self.scorer.S, self.ERR_HALO
+        t0, tc = self.position_ranges(n_windows)[self.rank]
+        w_lo = max(0, t0 - H - (S - 1))
+        w_hi = min(n_windows, t0 + tc + H)
+        return t0, tc, w_lo, w_hi, w_lo, w_hi + S
+
+    def score_euclidean(self, local_slice, n_windows, combination="mult", rec_error_type="dtw", index=None, lambda_rec=0.5):
+        """The per-timestep Euclidean path (score_anomalies, utils/anomaly_detection_utils.py:407-576) of a signal whose windows
+        are sharded over the ranks.  local_slice: the samples [sample_lo, sample_hi) of plan_euclidean() on this rank's GPU.
+        Halos: S - 1 windows to the left for the overlap aggregations (KDE arg-max of the critics, median of the
+        reconstructions), ERR_HALO positions either side for the windowed reconstruction error; the smoothing halo and the
+        global z-score / critic statistics travel in small all-gathers (scoring.*_staged).  Returns this rank's positions
+        (`final_local`, `rec_local`, `critic_scores_local`, `kmax_local`, `pred_local`, `t0`, `count`) and, with `index`, the
+        gathered `final` and the intervals.  Bitwise WindowScorer.score(signal, True, combination, rec_error_type)."""
+        sc, S, H = self.scorer, self.scorer.S, self.ERR_HALO
+        if sc.hyperbolic:
+            raise HypadError("hypad_b200: ShardedScorer.score_euclidean needs a Euclidean model")
+        mode = {"mult": "mult", "sum": "euclidean_sum", "rec": "rec", "critic": "critic"}.get(combination)
+        if mode is None:
+            raise ValueError('Unknown combination specified {}, use "mult", "sum", or "rec" instead.'.format(combination))
+        n = n_windows
+        n_pos = n + S - 1
+        t0, tc, w_lo, w_hi, lo, hi = self.plan_euclidean(n)
+        if local_slice.numel() != hi - lo:
+            raise ValueError("local slice has %d samples, plan_euclidean() asks for %d" % (local_slice.numel(), hi - lo))
+        ranges = self.position_ranges(n)
+        x = local_slice.reshape(-1)
+        fw = sc.forward(x, True, keep=("eucl",), count=w_hi - w_lo)  # windows w_lo .. w_hi-1
+        kmax = scoring.kde_argmax_overlap(fw["critic"], S, n_windows=n, critic_offset=w_lo, t0=t0, t_count=tc)
+        cs = scoring.critic_scores_staged(kmax, ranges, n_pos, math.trunc(n * 0.01), self.comm)
+        # prediction and truth on the positions [e_lo, e_hi): the owned ones and the error halo
+        e_lo, e_hi = max(0, t0 - H), min(n_pos, t0 + tc + H)
+        pred_all = scoring.median_overlap(fw["eucl"])  # local position k <-> global position w_lo + k; complete diagonals only
+        pred = pred_all[e_lo - w_lo: e_hi - w_lo]      # inside [w_lo + S - 1, w_hi) or at a global end, which is what is read
+        true = x[e_lo - lo: e_hi - lo].double()        # true[t] = signal[t] (:908-910 on sliding windows)
+        kind = rec_error_type.lower()
+        if kind == "dtw":
+            err = scoring.dtw_error(true, pred, 10)
+        elif kind == "point":
+            err = scoring.point_error(true, pred)
+        elif kind == "area":
+            err = scoring.area_error(true, pred, 10)
+        else:
+            raise ValueError("unknown rec_error_type %r" % (rec_error_type,))
+        err = err[t0 - e_lo: t0 - e_lo + tc]  # the slice ends' padding only reaches the halo positions
+        err = scoring.rolling_mean_staged(err, ranges, n_pos, math.trunc(n * 0.01), self.comm)
+        rec = scoring.zscore_clip_staged(err, n_pos, self.comm)
+        final = scoring.combine(mode, cs, rec, None, n=tc, lambda_rec=lambda_rec)
+        out = {"t0": t0, "count": tc, "final_local": final, "rec_local": rec, "critic_scores_local": cs, "kmax_local": kmax,
+               "pred_local": pred[t0 - e_lo: t0 - e_lo + tc], "errors_local": err}
+        if index is not None:
+            pc = [c for _, c in ranges]
+            out["final"] = _concat_rows(self.comm.all_gather(_pad_to(final, max(pc))), pc)
+            out["intervals"] = self.find_anomaly_intervals(out["final"], index, 0.33, 0.1, anomaly_padding=50, ddof=0)
+        sc.poll_error()
+        return out
+
     max_runs = 64  # room per analysis window in the gathered buffer; grown (on every rank alike) when a window holds more runs
 
     def find_anomaly_intervals(self, final, index, window_size_portion, window_step_size_portion, min_percent=0.1,

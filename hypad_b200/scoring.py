@@ -240,6 +240,39 @@ def critic_scores_staged(kmax_local, ranges, n_total, smooth_window, comm=None, 
     return out
 
 
+def rolling_mean_staged(x_local, ranges, n_total, window, comm=None, min_periods=None):
+    """rolling_mean_centered of an array sharded by contiguous range (ranges[comm.rank] = (p0, len) of n_total positions): the
+    first and last window/2 values of every rank are exchanged in one all-gather and give the neighbours their halo."""
+    comm = comm or LocalComm()
+    x_local = _native.require_cuda(x_local, "x").double().contiguous()
+    dev = x_local.device
+    c = _ctx(x_local)
+    p0, ln = ranges[comm.rank]
+    w = int(window)
+    mp = w // 2 if min_periods is None else int(min_periods)
+    back, fwd = (w // 2, (w - 1) // 2) if w > 0 else (0, 0)
+    out = torch.empty(ln, dtype=torch.float64, device=dev)
+    if ln == 0 and comm.world == 1:
+        return out
+    ext, lo, hi = x_local, p0, p0 + ln
+    if comm.world > 1 and back > 0:
+        H = back
+        strips = torch.zeros(2 * H, dtype=torch.float64, device=dev)
+        k = min(ln, H)
+        if k:
+            strips[:k] = x_local[:k]
+            strips[2 * H - k:] = x_local[ln - k:]
+        g = comm.all_gather(strips).view(comm.world, 2, H)
+        lo, hi = max(p0 - back, 0), min(p0 + ln + fwd, n_total)
+        if ln:
+            left, right = _halo_from_strips(g, ranges, comm.rank, p0 - lo, hi - (p0 + ln))
+            ext = torch.cat(left + [x_local] + right)
+    if ln:
+        with torch.cuda.device(dev):
+            check(c.lib.hypad_rolling_mean_shard(c.handle, ptr(ext), ext.shape[0], lo, int(n_total), p0, ln, w, mp, ptr(out), c.stream()))
+    return out
+
+
 def zscore_clip_staged(x_local, n_total, comm=None):
     """stats.zscore + clip(0) + 1 (:177-178, :523-524) of an array sharded over the ranks: mean / std of ALL rows from the
     ranks' partial sums, applied to the local rows."""

@@ -318,6 +318,11 @@ int hypad_critic_combine_small(hypad_ctx* ctx, const double* kmax, int64_t n_pos
  * must hold the smoothing halo: positions p0 - window/2 .. p0 + count - 1 + (window-1)/2, clipped to [0, n_total). */
 int hypad_critic_smooth_shard(hypad_ctx* ctx, const double* kmax_ext, int64_t ext_len, int64_t ext0, int64_t n_total, int64_t p0,
                               int64_t count, int64_t smooth_window, double* out, void* stream);
+/* hypad_rolling_mean_centered on a slice: x_ext holds the global positions [ext0, ext0 + ext_len) of an n_total-long array;
+ * out[j] = the centred rolling mean at position p0 + j, j < count (same halo rule as hypad_critic_smooth_shard).  The
+ * reconstruction-error smoothing (:954-961) of a signal sharded over several GPUs. */
+int hypad_rolling_mean_shard(hypad_ctx* ctx, const double* x_ext, int64_t ext_len, int64_t ext0, int64_t n_total, int64_t p0,
+                             int64_t count, int64_t window, int64_t min_periods, double* out, void* stream);
 /* out = clip((x - mean) / std, 0) + 1 with the mean / std of hypad_stats_moments_final(band = 0). */
 int hypad_zscore_clip_apply(hypad_ctx* ctx, const void* x, int x_is_f32, int64_t len, double* out, void* stream);
 

@@ -63,6 +63,23 @@ def main():
     if rank == 0:
         print("multivariate rows S=123: world=%d sharded == single-GPU: %s" % (world, bool(t.item())))
     ok = ok and bool(t.item())
+    # the per-timestep Euclidean path (BASELINE config 2's model) sharded by window range
+    enc, dec, cx, _ = build_modules("weights_eucl_s100.npz", 100, False, dev)
+    scorer = WindowScorer(enc, dec, cx)
+    g = golden("cfg2_eucl_dtw_mult.npz")
+    sig = full_signal(g)
+    n = sig.shape[0] - 100
+    sh = ShardedScorer(scorer)
+    t0, cnt, w_lo, w_hi, lo, hi = sh.plan_euclidean(n)
+    out = sh.score_euclidean(torch.from_numpy(sig[lo:hi].copy()).to(dev), n, "mult", "dtw", index=g["index"])
+    ref = scorer.score(torch.from_numpy(sig).to(dev), True, "mult", "dtw", index=g["index"])
+    same = torch.equal(out["final"], ref["final"]) and torch.equal(out["final_local"], ref["final"][t0:t0 + cnt])
+    same = same and torch.equal(out["rec_local"], ref["rec"][t0:t0 + cnt]) and np.array_equal(out["intervals"], ref["intervals"])
+    t = torch.tensor([int(same)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("euclidean dtw mult (cfg2 signal): world=%d sharded == single-GPU: %s" % (world, bool(t.item())))
+    ok = ok and bool(t.item())
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

@@ -1066,6 +1066,64 @@ def test_sharded_long_signal_staged_statistics_equal_unsharded(world, T, hyp_sco
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("world,case,kind,comb", [(2, "noisy1500_eucl_dtw_mult.npz", "dtw", "mult"), (5, "cfg2_eucl_dtw_mult.npz", "dtw", "mult"),
+                                                  (3, "cfg2_eucl_dtw_mult.npz", "area", "sum"), (8, "long60k", "dtw", "mult"),
+                                                  (4, "cfg2_eucl_dtw_mult.npz", "point", "rec")])
+def test_sharded_euclidean_equal_unsharded(world, case, kind, comb, cuda_device):
+    """The per-timestep Euclidean path sharded by window range (median halo S-1 windows, error halo 5 positions, smoothing halo
+    and global z-score through the staged exchanges): every rank replayed on this GPU, bitwise the single-GPU result."""
+    import threading
+
+    from conftest import long_signal
+    from hypad_b200.distributed import ShardedScorer
+    from hypad_b200.scoring import WindowScorer
+
+    enc, dec, cx, _ = build_modules("weights_eucl_s100.npz", 100, False, cuda_device)
+    if case == "long60k":
+        sig = long_signal(60000)
+        index = np.arange(60000)
+    else:
+        g = golden(case)
+        sig, index = full_signal(g), g["index"]
+    x = torch.from_numpy(sig).to(cuda_device)
+    n = x.shape[0] - 100
+    ref = WindowScorer(enc, dec, cx).score(x, True, comb, kind, index=index)
+    tc = ThreadComm(world)
+    shs = [ShardedScorer(WindowScorer(enc, dec, cx, own_context=True), rank=r, world=world, comm=tc.for_rank(r)) for r in range(world)]
+    torch.cuda.synchronize()
+    results, errors = [None] * world, []
+
+    def run(r):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                t0, cnt, w_lo, w_hi, lo, hi = shs[r].plan_euclidean(n)
+                results[r] = shs[r].score_euclidean(x[lo:hi].contiguous(), n, comb, kind, index=index)
+                torch.cuda.current_stream().synchronize()
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+            tc.barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    pos = 0
+    for r in range(world):
+        out = results[r]
+        assert out["t0"] == pos
+        sl = slice(pos, pos + out["count"])
+        pos += out["count"]
+        for mine, theirs in (("final_local", "final"), ("rec_local", "rec"), ("critic_scores_local", "critic_scores"), ("kmax_local", "kmax"),
+                             ("pred_local", "pred"), ("errors_local", "errors")):
+            assert torch.equal(out[mine], ref[theirs][sl]), (r, mine)
+        assert torch.equal(out["final"], ref["final"])
+        assert np.array_equal(out["intervals"], ref["intervals"])
+    assert pos == n + 99
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("T", [101, 102, 105])
 def test_signals_of_a_few_windows_vs_oracle(T, hyp_scorer, cuda_device):
     """One, two and five windows: the critic values under every timestep coincide or nearly so, the smoothing window is 0 -- the
