@@ -61,7 +61,9 @@ class PackedNet:
 
     def ensure(self, encoder, decoder, critic_x):
         params = [owner._parameters[name] for owner, name in self._param_slots((encoder, decoder, critic_x))]
-        key = tuple((p.data_ptr(), p._version, p.dtype, p.device) for p in params)
+        # identity of the packed weights: storage address and in-place version of every parameter (a dtype / device change
+        # replaces the storage); 43 parameters, checked on every forward call -- kept to two attribute reads each
+        key = tuple([(p.data_ptr(), p._version) for p in params])
         if key == self.key:
             return self
         dev = self.device

@@ -2,6 +2,8 @@
 // centred rolling mean (pandas rolling(center=True).mean(), :326-331 / :954-961), z-score + clip (:523-524),
 // score combination (:336-362, :554-570) and the per-window statistics / run extraction of find_anomalies
 // (:1098-1166).  All results stay on the device; scalars travel through a small block of the workspace.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "dd.cuh"
 #include "finish_common.cuh"
@@ -15,22 +17,25 @@ int ensure_fin_state(hypad_ctx* ctx);
 double* fin_scalars(hypad_ctx* ctx);
 double* fin_local_record(hypad_ctx* ctx);
 
+// barrier of the first RB threads of a CTA (all of a 256-thread CTA; the statistics group of the fused thresholding kernel)
+__device__ __forceinline__ void group_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 __device__ __forceinline__ double block_sum(double v, double* sh) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) sh[warp] = v;
-    __syncthreads();
+    group_sync();
     double t = 0.0;
     if (warp == 0) {
-        t = lane < (blockDim.x >> 5) ? sh[lane] : 0.0;
+        t = lane < (RB >> 5) ? sh[lane] : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
         if (lane == 0) sh[0] = t;
     }
-    __syncthreads();
+    group_sync();
     t = sh[0];
-    __syncthreads();
+    group_sync();
     return t;
 }
 
@@ -470,9 +475,8 @@ __global__ void __launch_bounds__(TW_TILE) tw_runmax_kernel(const TwArgs a) {
 // like numpy's two-pass mean / std do (a far-away centre left a residue of ~1e-16 in the mean with the variance clamped to 0,
 // i.e. a threshold below the constant and one run spanning the whole window).
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RB) tw_blocks_kernel(const TwArgs a) {
-    __shared__ double sh[32];
-    const int64_t b = blockIdx.x, i0 = b * TW_TILE, i1 = i0 + TW_TILE < a.len ? i0 + TW_TILE : a.len;
+__device__ __forceinline__ void tw_blocks_body(const TwArgs& a, int64_t b, double* sh, unsigned long long* shm) {
+    const int64_t i0 = b * TW_TILE, i1 = i0 + TW_TILE < a.len ? i0 + TW_TILE : a.len;
     const double c = a.errors[i0];
     double s1 = 0.0, s2 = 0.0;
     unsigned long long m = 0ull;
@@ -490,22 +494,26 @@ __global__ void __launch_bounds__(RB) tw_blocks_kernel(const TwArgs a) {
         const unsigned long long v = __shfl_xor_sync(0xffffffffu, m, o);
         m = v > m ? v : m;
     }
-    __shared__ unsigned long long shm[RB / 32];
     if ((threadIdx.x & 31) == 0) shm[threadIdx.x >> 5] = m;
-    __syncthreads();
+    group_sync();
     if (threadIdx.x == 0) {
         for (int w = 1; w < RB / 32; ++w) m = shm[w] > m ? shm[w] : m;
         a.bsum1[b] = s1;
         a.bsum2[b] = s2;
         a.bmax[b] = m;
     }
+    group_sync();  // shm is reused by the caller's next block
+}
+__global__ void __launch_bounds__(RB) tw_blocks_kernel(const TwArgs a) {
+    __shared__ double sh[32];
+    __shared__ unsigned long long shm[RB / 32];
+    tw_blocks_body(a, blockIdx.x, sh, shm);
 }
 
 // one CTA per window: statistics, reset of the event state, classification of the window's blocks
-__global__ void __launch_bounds__(RB) tw_window_kernel(const TwArgs a) {
-    __shared__ double sh[32];
-    __shared__ unsigned long long s_quiet;
-    const int k = blockIdx.x, tid = threadIdx.x;
+__device__ __forceinline__ void tw_window_body(const TwArgs& a, int k, double* sh, unsigned long long* s_quiet_p) {
+    unsigned long long& s_quiet = *s_quiet_p;
+    const int tid = threadIdx.x;
     const int64_t w0 = (int64_t)(a.k0 + k) * a.step, w1 = w0 + a.window_size < a.len ? w0 + a.window_size : a.len, n = w1 - w0;
     const double c0 = a.errors[w0];  // the window's own centre
     const int64_t bf0 = (w0 + TW_TILE - 1) / TW_TILE, bf1 = w1 / TW_TILE;  // blocks [bf0, bf1) lie fully inside
@@ -552,7 +560,7 @@ __global__ void __launch_bounds__(RB) tw_window_kernel(const TwArgs a) {
         s_quiet = 0ull;
     }
     for (int r = tid; r < a.max_runs; r += RB) a.rmax[(size_t)k * a.max_runs + r] = 0ull;
-    __syncthreads();
+    group_sync();
     // blocks overlapping the window: quiet ones give their maximum, the others go to the work list
     const int64_t nb = (a.len + TW_TILE - 1) / TW_TILE;
     const int64_t b_lo = w0 / TW_TILE, b_hi = (w1 - 1) / TW_TILE;
@@ -575,8 +583,14 @@ __global__ void __launch_bounds__(RB) tw_window_kernel(const TwArgs a) {
         quiet = v > quiet ? v : quiet;
     }
     if ((tid & 31) == 0 && quiet) atomicMax(&s_quiet, quiet);
-    __syncthreads();
+    group_sync();
     if (tid == 0) a.below[k] = s_quiet;
+    group_sync();  // s_quiet is reused by the caller's next window
+}
+__global__ void __launch_bounds__(RB) tw_window_kernel(const TwArgs a) {
+    __shared__ double sh[32];
+    __shared__ unsigned long long s_quiet;
+    tw_window_body(a, blockIdx.x, sh, &s_quiet);
 }
 
 // the work list's (window, block) pairs through the element-wise tile code
@@ -607,14 +621,13 @@ __global__ void __launch_bounds__(TW_TILE) tw_runmax_work_kernel(const TwArgs a)
 }
 
 // per window: order the runs by start, pair the r-th start with the r-th end, emit (start, end, max)
-__global__ void __launch_bounds__(256) tw_emit_kernel(const TwArgs a) {
-    const int k = blockIdx.x;
+__device__ __forceinline__ void tw_emit_body(const TwArgs& a, int k, int tid, int nthreads) {
     const int total = a.cnt[k * 2];
     const int R = total < a.max_runs ? total : a.max_runs;
     const long long* st = a.starts + (size_t)k * a.max_runs;
     const long long* en = a.ends + (size_t)k * a.max_runs;
     double* out = a.runs + (size_t)k * a.max_runs * 3;
-    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    for (int r = tid; r < R; r += nthreads) {
         const long long s = st[r], t = en[r];
         int rank_s = 0, rank_e = 0;
         for (int q = 0; q < R; ++q) {
@@ -625,11 +638,52 @@ __global__ void __launch_bounds__(256) tw_emit_kernel(const TwArgs a) {
         out[rank_s * 3 + 2] = dunkey(a.rmax[(size_t)k * a.max_runs + r]);
         out[rank_e * 3 + 1] = (double)t;
     }
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         a.n_runs[k] = total;
         const unsigned long long b = a.below[k];
         a.stats[k * 4 + 3] = b ? dunkey(b) : 0.0;  // `above.all()` -> max_below = 0 (:1154-1155)
     }
+}
+__global__ void __launch_bounds__(256) tw_emit_kernel(const TwArgs a) { tw_emit_body(a, blockIdx.x, threadIdx.x, blockDim.x); }
+
+// Short arrays: the five phases above in ONE cooperative launch, a grid-wide barrier between them (a signal of a few thousand
+// positions is launch-bound: five launches cost more than their work).  The same device code, phase by phase, so the results are
+// those of the separate launches.  The statistics phases use the first 256 threads of each CTA (the shape their reductions
+// were written for), the element-wise phases all 1024.
+__global__ void __launch_bounds__(TW_TILE) tw_fused_kernel(const TwArgs a, int nb) {
+    constexpr int REGION = TW_TILE + 2 * TW_MAXPAD + 2;
+    __shared__ unsigned s_bits[(REGION + 31) / 32 + 1];
+    __shared__ unsigned char s_dil[TW_TILE + 2];
+    __shared__ unsigned long long s_below, s_quiet, shm[RB / 32];
+    __shared__ double sh[32];
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int tid = threadIdx.x;
+    if (blockIdx.x == 0 && tid == 0) *a.work_cnt = 0;
+    if (tid < RB)
+        for (int64_t b = blockIdx.x; b < nb; b += gridDim.x) tw_blocks_body(a, b, sh, shm);
+    grid.sync();
+    if (tid < RB)
+        for (int k = blockIdx.x; k < a.n_analysis; k += gridDim.x) tw_window_body(a, k, sh, &s_quiet);
+    grid.sync();
+    const int total = *a.work_cnt;
+    for (int j = blockIdx.x; j < total; j += gridDim.x) {
+        const longlong2 kb = a.work[j];
+        const int k = (int)kb.x;
+        const int64_t w0 = (int64_t)(a.k0 + k) * a.step, w1 = w0 + a.window_size < a.len ? w0 + a.window_size : a.len;
+        const int64_t g0 = kb.y * TW_TILE > w0 ? kb.y * TW_TILE : w0, g1 = (kb.y + 1) * TW_TILE < w1 ? (kb.y + 1) * TW_TILE : w1;
+        tw_events_tile(a, k, g0 - w0, (int)(g1 - g0), s_bits, s_dil, &s_below);
+    }
+    grid.sync();
+    for (int j = blockIdx.x; j < total; j += gridDim.x) {
+        const longlong2 kb = a.work[j];
+        const int k = (int)kb.x;
+        const int64_t w0 = (int64_t)(a.k0 + k) * a.step, w1 = w0 + a.window_size < a.len ? w0 + a.window_size : a.len;
+        const int64_t g = kb.y * TW_TILE + tid;
+        if (g >= w0 && g < w1) tw_runmax_elem(a, k, a.errors + w0, g - w0);
+    }
+    grid.sync();
+    if (tid < RB)
+        for (int k = blockIdx.x; k < a.n_analysis; k += gridDim.x) tw_emit_body(a, k, tid, RB);
 }
 
 static unsigned red_grid(int64_t n) {
@@ -858,6 +912,15 @@ static int threshold_windows_impl(hypad_ctx* ctx, const double* errors, int64_t 
     } else {
         int sms = kNumSMs;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        if ((int64_t)nb <= 2 * (int64_t)sms) {  // short array: one cooperative launch for all five phases
+            int nbi = (int)nb;
+            int64_t want = (int64_t)nb > n_analysis ? (int64_t)nb : n_analysis;
+            const unsigned grid = (unsigned)(want < sms ? (want < 8 ? 8 : want) : sms);
+            void* args[] = {(void*)&a, (void*)&nbi};
+            HYPAD_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)tw_fused_kernel, dim3(grid), dim3(TW_TILE), args, 0, stream));
+            count_launch();
+            return HYPAD_OK;
+        }
         HYPAD_CUDA_TRY(cudaMemsetAsync(a.work_cnt, 0, sizeof(int), stream));
         tw_blocks_kernel<<<(unsigned)nb, RB, 0, stream>>>(a);
         HYPAD_LAUNCH_CHECK();
