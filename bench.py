@@ -97,6 +97,26 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa(index):
+    """Pins this process to the CPUs NVML reports as local to GPU `index` (the usual multi-GPU host set-up): the pinned staging
+    buffers are then allocated on the GPU's own NUMA node, so that eight ranks copying at once do not all cross the socket
+    interconnect.  Returns the number of CPUs bound to, or None when NVML / affinity is unavailable (nothing changes then)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (mask >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -199,6 +219,7 @@ def run_native(args):
             raise SystemExit("bench.py --gpus %d must be launched with torchrun --nproc-per-node %d" % (args.gpus, args.gpus))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    affinity = bind_to_gpu_numa(local) if world > 1 else None  # before the pinned buffers are allocated (first touch)
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -347,6 +368,7 @@ def run_native(args):
                         "h2d_bytes_per_step": int(host_slice.numel() * 8), "d2h_bytes_per_step": int(n_own * 8),
                         "bytes_are": "per rank (each rank uploads its slice of the signal and reads back its windows' scores)",
                         "ms_per_step": e2e_ms / args.steps},
+                "host_cpus_bound": affinity,
                 "gpu_launches": int(launches), "roofline": roofline, "roofline_kde": roofline_kde,
                 "kernels_ms": {"forward_tc_kernel": fw_ms, "kde_screened_kernel": kde_ms, "step_total": ms_per_step},
                 "kde": {"pair_evals_per_timestep": 4950, "timesteps_per_launch": n_local + S - 1,

@@ -110,6 +110,10 @@ _SIGNATURES = {
     "hypad_rolling_mean_shard": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
     "hypad_zscore_clip_apply": (_int, [_vp, _vp, _int, _i64, _vp, _vp]),
     "hypad_intervals_from_runs": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, ctypes.c_double, _int, _vp, _i64, ctypes.POINTER(_i64)]),
+    "hypad_tw_shard_record_doubles": (ctypes.c_size_t, [_i64, _i64, _int]),
+    "hypad_tw_shard_pack": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _int, _i64, _vp, _vp]),
+    "hypad_tw_shard_runs": (_int, [_vp, _vp, _int, _int, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _vp, _vp]),
+    "hypad_tw_shard_merge": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _i64, ctypes.POINTER(_i64), ctypes.POINTER(_int)]),
     "hypad_peak_probe": (_int, [_int, _int, _int, _vp, ctypes.POINTER(ctypes.c_longlong), _vp]),
 }
 

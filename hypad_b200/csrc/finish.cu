@@ -285,6 +285,15 @@ struct TwArgs {
     unsigned long long* bmax;   // [blocks] order-preserving key of the block maximum
     int* work_cnt;
     longlong2* work;            // (window, block) pairs that need the element-wise pass
+    // One rank's share of an array sharded by contiguous, block-aligned ranges (hypad_tw_shard_*): `errors` is then a VIRTUAL
+    // base pointer -- only the positions [lim_lo, lim_hi) (the own ones and a halo of pad + 1 either side) exist -- the
+    // statistics read block summaries, block centres and window-edge elements assembled from every rank's record, and only
+    // the own blocks [own_b0, own_b1) are classified and walked.
+    int64_t lim_lo, lim_hi;     // readable positions of `errors` (0, len when the whole array is here)
+    int64_t own_b0, own_b1;     // blocks this rank walks (0, number of blocks when the whole array is here)
+    const double* cblk;         // [blocks] first element of every block (shard view; else read from `errors`)
+    const double* edge;         // [n_analysis][2][TW_TILE] elements of every window's two ragged edges (shard view)
+    unsigned long long* lead;   // [n_analysis] maximum of the above-threshold values in front of the first own run start
 };
 
 __device__ __forceinline__ void tw_window(const TwArgs& a, int k, const double*& e, int64_t& n) {
@@ -370,7 +379,8 @@ __device__ __forceinline__ void tw_events_tile(const TwArgs& a, int k, int64_t t
     bool any_flag = false;
     for (int f = tid; f < ((region + 31) & ~31); f += TW_TILE) {
         const int64_t q = r0 + f;
-        const bool flag = f < region && q >= 0 && q < n && e[q] > thr;
+        const int64_t gq = (int64_t)(a.k0 + k) * a.step + q;  // global position: only [lim_lo, lim_hi) is readable
+        const bool flag = f < region && q >= 0 && q < n && gq >= a.lim_lo && gq < a.lim_hi && e[q] > thr;
         const unsigned word = __ballot_sync(0xffffffffu, flag);
         any_flag |= word != 0u;
         if ((tid & 31) == 0) s_bits[f >> 5] = word;
@@ -449,6 +459,7 @@ __device__ __forceinline__ void tw_runmax_elem(const TwArgs& a, int k, const dou
         }
     }
     if (arg >= 0) atomicMax(&a.rmax[(size_t)k * a.max_runs + arg], dkey(v));
+    else if (a.lead) atomicMax(&a.lead[k], dkey(v));  // its run started on an earlier rank
 }
 
 // every above-threshold value goes to the run whose start is the largest start <= its position
@@ -501,6 +512,7 @@ __device__ __forceinline__ void tw_blocks_body(const TwArgs& a, int64_t b, doubl
         a.bsum1[b] = s1;
         a.bsum2[b] = s2;
         a.bmax[b] = m;
+        if (a.cblk) const_cast<double*>(a.cblk)[b] = c;
     }
     group_sync();  // shm is reused by the caller's next block
 }
@@ -511,35 +523,40 @@ __global__ void __launch_bounds__(RB) tw_blocks_kernel(const TwArgs a) {
 }
 
 // one CTA per window: statistics, reset of the event state, classification of the window's blocks
+// SHARD: the array is not here; block centres and edge elements come from the assembled records (same values, same arithmetic)
+template <bool SHARD>
 __device__ __forceinline__ void tw_window_body(const TwArgs& a, int k, double* sh, unsigned long long* s_quiet_p) {
     unsigned long long& s_quiet = *s_quiet_p;
     const int tid = threadIdx.x;
     const int64_t w0 = (int64_t)(a.k0 + k) * a.step, w1 = w0 + a.window_size < a.len ? w0 + a.window_size : a.len, n = w1 - w0;
-    const double c0 = a.errors[w0];  // the window's own centre
     const int64_t bf0 = (w0 + TW_TILE - 1) / TW_TILE, bf1 = w1 / TW_TILE;  // blocks [bf0, bf1) lie fully inside
     const bool blocks = bf0 < bf1;
     const int64_t e0 = blocks ? bf0 * TW_TILE : w1, e1 = blocks ? bf1 * TW_TILE : w1;  // ragged edges [w0, e0) and [e1, w1)
+    const double* eL = SHARD ? a.edge + (size_t)k * 2 * TW_TILE - w0 : a.errors;             // element i of the left edge: eL[i]
+    const double* eR = SHARD ? a.edge + ((size_t)k * 2 + 1) * TW_TILE - e1 : a.errors;       // element i of the right edge: eR[i]
+    auto centre = [&](int64_t b) { return SHARD ? a.cblk[b] : a.errors[b * TW_TILE]; };
+    const double c0 = SHARD ? (w0 < e0 ? eL[w0] : a.cblk[bf0]) : a.errors[w0];  // the window's own centre: its first element
     // mean = c0 + sum(x - c0) / n, with sum over a block = TW_TILE (c_b - c0) + sum(x - c_b)
     double s1 = 0.0;
     if (blocks)
-        for (int64_t b = bf0 + tid; b < bf1; b += RB) s1 += (double)TW_TILE * (a.errors[b * TW_TILE] - c0) + a.bsum1[b];
-    for (int64_t i = w0 + tid; i < e0; i += RB) s1 += a.errors[i] - c0;
-    for (int64_t i = e1 + tid; i < w1; i += RB) s1 += a.errors[i] - c0;
+        for (int64_t b = bf0 + tid; b < bf1; b += RB) s1 += (double)TW_TILE * (centre(b) - c0) + a.bsum1[b];
+    for (int64_t i = w0 + tid; i < e0; i += RB) s1 += eL[i] - c0;
+    for (int64_t i = e1 + tid; i < w1; i += RB) s1 += eR[i] - c0;
     s1 = block_sum(s1, sh);
     const double dm = s1 / (double)n;  // mean - c0
     // sum((x - mean)^2); over a block, with e = c_b - mean: sum((x-c_b)^2) + 2 e sum(x-c_b) + TW_TILE e^2
     double s2 = 0.0;
     if (blocks)
         for (int64_t b = bf0 + tid; b < bf1; b += RB) {
-            const double e = (a.errors[b * TW_TILE] - c0) - dm;
+            const double e = (centre(b) - c0) - dm;
             s2 += a.bsum2[b] + 2.0 * e * a.bsum1[b] + (double)TW_TILE * e * e;
         }
     for (int64_t i = w0 + tid; i < e0; i += RB) {
-        const double d = (a.errors[i] - c0) - dm;
+        const double d = (eL[i] - c0) - dm;
         s2 += d * d;
     }
     for (int64_t i = e1 + tid; i < w1; i += RB) {
-        const double d = (a.errors[i] - c0) - dm;
+        const double d = (eR[i] - c0) - dm;
         s2 += d * d;
     }
     s2 = block_sum(s2, sh);
@@ -557,6 +574,7 @@ __device__ __forceinline__ void tw_window_body(const TwArgs& a, int k, double* s
         a.stats[k * 4 + 2] = thr;
         a.cnt[k * 2] = 0;
         a.cnt[k * 2 + 1] = 0;
+        if (a.lead) a.lead[k] = 0ull;
         s_quiet = 0ull;
     }
     for (int r = tid; r < a.max_runs; r += RB) a.rmax[(size_t)k * a.max_runs + r] = 0ull;
@@ -566,6 +584,7 @@ __device__ __forceinline__ void tw_window_body(const TwArgs& a, int k, double* s
     const int64_t b_lo = w0 / TW_TILE, b_hi = (w1 - 1) / TW_TILE;
     unsigned long long quiet = 0ull;
     for (int64_t b = b_lo + tid; b <= b_hi; b += RB) {
+        if (b < a.own_b0 || b >= a.own_b1) continue;  // another rank's block
         const bool inner = b >= bf0 && b < bf1;
         bool hot = !inner || a.bmax[b] > dkey(thr);
         if (b > 0) hot |= a.bmax[b - 1] > dkey(thr);
@@ -590,7 +609,7 @@ __device__ __forceinline__ void tw_window_body(const TwArgs& a, int k, double* s
 __global__ void __launch_bounds__(RB) tw_window_kernel(const TwArgs a) {
     __shared__ double sh[32];
     __shared__ unsigned long long s_quiet;
-    tw_window_body(a, blockIdx.x, sh, &s_quiet);
+    tw_window_body<false>(a, blockIdx.x, sh, &s_quiet);
 }
 
 // the work list's (window, block) pairs through the element-wise tile code
@@ -663,7 +682,7 @@ __global__ void __launch_bounds__(TW_TILE) tw_fused_kernel(const TwArgs a, int n
         for (int64_t b = blockIdx.x; b < nb; b += gridDim.x) tw_blocks_body(a, b, sh, shm);
     grid.sync();
     if (tid < RB)
-        for (int k = blockIdx.x; k < a.n_analysis; k += gridDim.x) tw_window_body(a, k, sh, &s_quiet);
+        for (int k = blockIdx.x; k < a.n_analysis; k += gridDim.x) tw_window_body<false>(a, k, sh, &s_quiet);
     grid.sync();
     const int total = *a.work_cnt;
     for (int j = blockIdx.x; j < total; j += gridDim.x) {
@@ -684,6 +703,111 @@ __global__ void __launch_bounds__(TW_TILE) tw_fused_kernel(const TwArgs a, int n
     grid.sync();
     if (tid < RB)
         for (int k = blockIdx.x; k < a.n_analysis; k += gridDim.x) tw_emit_body(a, k, tid, RB);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// find_anomalies on an array sharded over several GPUs by contiguous, block-aligned ranges (hypad_tw_shard_pack / _runs).
+// Nothing of the array's total length is gathered: a rank contributes a record -- the summaries (first element, centred sums,
+// maximum) of its blocks, the elements of the window edges that fall into its range (at most two partial blocks per analysis
+// window) and its first / last pad + 1 values for the neighbours' dilation halo -- and, with everybody's records, computes
+// every window's statistics itself (the single-GPU arithmetic on the same values, tw_window_body<true>) and extracts the run
+// fragments of ITS positions.  The fragments are gathered and joined on the host.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TW_MAXWORLD = 64;
+struct TwShardMap {
+    int world, rank;
+    long long blk_start[TW_MAXWORLD + 1];  // first block of every rank (blocks are dealt out in order)
+};
+
+// record: cblk[bmax] | s1[bmax] | s2[bmax] | maxkey[bmax] | edge[n_analysis][2][TW_TILE] | strips[2][hp]
+__global__ void __launch_bounds__(RB) tw_shard_edges_kernel(const double* __restrict__ local, int64_t first, int64_t count, int64_t n_total,
+                                                            int64_t window_size, int64_t step, int hp, double* __restrict__ edge,
+                                                            double* __restrict__ strips) {
+    const int k = blockIdx.x, side = blockIdx.y;
+    if (k == gridDim.x - 1) {  // the extra row of CTAs copies the halo strips: first hp values left-aligned, last hp right-aligned
+        const int64_t m = count < hp ? count : hp;
+        for (int j = threadIdx.x; j < m; j += RB) strips[side * hp + (side ? hp - m + j : j)] = side ? local[count - m + j] : local[j];
+        return;
+    }
+    const int64_t w0 = (int64_t)k * step, w1 = w0 + window_size < n_total ? w0 + window_size : n_total;
+    const int64_t bf0 = (w0 + TW_TILE - 1) / TW_TILE, bf1 = w1 / TW_TILE;
+    const int64_t g0 = side ? bf1 * TW_TILE : w0, g1 = side ? w1 : bf0 * TW_TILE;  // the edge [g0, g1) lies inside one block
+    if (g0 >= g1 || g0 < first || g0 >= first + count) return;                     // no edge, or another rank's
+    double* dst = edge + ((size_t)k * 2 + side) * TW_TILE;
+    for (int64_t j = threadIdx.x; j < g1 - g0; j += RB) dst[j] = local[g0 - first + j];
+}
+
+// every rank's record -> dense arrays over ALL blocks / windows (what tw_window_body<true> reads)
+__global__ void tw_shard_assemble_kernel(const double* __restrict__ records, size_t rec_len, TwShardMap map, int bmax_per_rank, int64_t nb_total,
+                                         int n_analysis, int64_t window_size, int64_t step, int64_t n_total, double* __restrict__ cblk,
+                                         double* __restrict__ bsum1, double* __restrict__ bsum2, unsigned long long* __restrict__ bmaxk,
+                                         double* __restrict__ edge) {
+    auto owner = [&](int64_t b) {
+        int r = 0;
+        while (r + 1 < map.world && b >= map.blk_start[r + 1]) ++r;
+        return r;
+    };
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t b = gid; b < nb_total; b += stride) {
+        const int r = owner(b);
+        const double* rec = records + (size_t)r * rec_len;
+        const int64_t lb = b - map.blk_start[r];
+        cblk[b] = rec[lb];
+        bsum1[b] = rec[bmax_per_rank + lb];
+        bsum2[b] = rec[2 * (size_t)bmax_per_rank + lb];
+        bmaxk[b] = (unsigned long long)__double_as_longlong(rec[3 * (size_t)bmax_per_rank + lb]);
+    }
+    const int64_t total = (int64_t)n_analysis * 2 * TW_TILE;
+    for (int64_t e = gid; e < total; e += stride) {
+        const int64_t ks = e / TW_TILE;
+        const int k = (int)(ks >> 1), side = (int)(ks & 1);
+        const int64_t w0 = (int64_t)k * step, w1 = w0 + window_size < n_total ? w0 + window_size : n_total;
+        const int64_t bf0 = (w0 + TW_TILE - 1) / TW_TILE, bf1 = w1 / TW_TILE;
+        const int64_t g0 = side ? bf1 * TW_TILE : w0, g1 = side ? w1 : bf0 * TW_TILE;
+        double v = 0.0;
+        if (g0 < g1) v = records[(size_t)owner(g0 / TW_TILE) * rec_len + 4 * (size_t)bmax_per_rank + e];
+        edge[e] = v;
+    }
+}
+
+__global__ void __launch_bounds__(RB) tw_shard_window_kernel(const TwArgs a) {
+    __shared__ double sh[32];
+    __shared__ unsigned long long s_quiet;
+    tw_window_body<true>(a, blockIdx.x, sh, &s_quiet);
+}
+
+// per window: [n_starts, n_ends, lead key, below key, mean, std, threshold, 0] | starts (ascending) | their maxima | ends (ascending)
+__global__ void __launch_bounds__(256) tw_shard_emit_kernel(const TwArgs a, double* __restrict__ out) {
+    const int k = blockIdx.x;
+    const int ns = a.cnt[k * 2], ne = a.cnt[k * 2 + 1];
+    const int Rs = ns < a.max_runs ? ns : a.max_runs, Re = ne < a.max_runs ? ne : a.max_runs;
+    const long long* st = a.starts + (size_t)k * a.max_runs;
+    const long long* en = a.ends + (size_t)k * a.max_runs;
+    double* o = out + (size_t)k * (8 + 3 * (size_t)a.max_runs);
+    for (int r = threadIdx.x; r < Rs; r += blockDim.x) {
+        const long long s = st[r];
+        int rank_s = 0;
+        for (int q = 0; q < Rs; ++q) rank_s += st[q] < s;
+        o[8 + rank_s] = (double)s;
+        const unsigned long long m = a.rmax[(size_t)k * a.max_runs + r];
+        o[8 + a.max_runs + rank_s] = m ? dunkey(m) : -1.0 / 0.0;  // a start whose flagged values all lie on the next rank: -inf
+    }
+    for (int r = threadIdx.x; r < Re; r += blockDim.x) {
+        const long long t = en[r];
+        int rank_e = 0;
+        for (int q = 0; q < Re; ++q) rank_e += en[q] < t;
+        o[8 + 2 * a.max_runs + rank_e] = (double)t;
+    }
+    if (threadIdx.x == 0) {
+        o[0] = (double)ns;
+        o[1] = (double)ne;
+        o[2] = __longlong_as_double((long long)a.lead[k]);
+        o[3] = __longlong_as_double((long long)a.below[k]);
+        o[4] = a.stats[k * 4 + 0];
+        o[5] = a.stats[k * 4 + 1];
+        o[6] = a.stats[k * 4 + 2];
+        o[7] = 0.0;
+    }
 }
 
 static unsigned red_grid(int64_t n) {
@@ -875,6 +999,7 @@ static int threshold_windows_impl(hypad_ctx* ctx, const double* errors, int64_t 
     const int64_t wlen = window_size < len ? window_size : len;
     TwArgs a;
     a.errors = errors; a.len = len; a.window_size = window_size; a.step = step;
+    a.lim_lo = 0; a.lim_hi = len; a.own_b0 = 0; a.own_b1 = ceil_div(len, TW_TILE); a.cblk = nullptr; a.edge = nullptr; a.lead = nullptr;
     a.k0 = first_window;
     a.n_analysis = (int)n_analysis; a.ddof = ddof; a.pad = anomaly_padding; a.max_runs = max_runs;
     a.stats_f32 = stats_f32;
@@ -955,6 +1080,102 @@ int hypad_threshold_windows_exhaustive(hypad_ctx* ctx, const double* errors, int
                                        int32_t* n_runs, int max_runs, void* stream_) {
     return threshold_windows_impl(ctx, errors, len, window_size, step, 0, n_analysis, ddof, anomaly_padding, stats, runs, n_runs,
                                   max_runs, (cudaStream_t)stream_, true);
+}
+
+size_t hypad_tw_shard_record_doubles(int64_t blocks_per_rank, int64_t n_analysis, int anomaly_padding) {
+    return (size_t)(4 * blocks_per_rank + n_analysis * 2 * TW_TILE + 2 * (anomaly_padding + 1));
+}
+
+int hypad_tw_shard_pack(hypad_ctx* ctx, const double* local, int64_t first, int64_t count, int64_t n_total, int64_t window_size,
+                        int64_t step, int64_t n_analysis, int anomaly_padding, int64_t blocks_per_rank, double* record, void* stream_) {
+    HYPAD_REQUIRE(ctx && record && (local || count == 0), "hypad_tw_shard_pack: NULL argument");
+    HYPAD_REQUIRE(first >= 0 && count >= 0 && first + count <= n_total && first % TW_TILE == 0, "hypad_tw_shard_pack: the range must start at "
+                  "a multiple of %d positions", TW_TILE);
+    HYPAD_REQUIRE(first + count == n_total || count % TW_TILE == 0, "hypad_tw_shard_pack: only the last range may end inside a block");
+    HYPAD_REQUIRE(window_size >= 2 * TW_TILE && step >= 1 && n_analysis >= 1 && n_analysis <= 65535, "hypad_tw_shard_pack: analysis windows of "
+                  "at least %d positions", 2 * TW_TILE);
+    HYPAD_REQUIRE(anomaly_padding >= 0 && anomaly_padding <= TW_MAXPAD && ceil_div(count, TW_TILE) <= blocks_per_rank,
+                  "hypad_tw_shard_pack: padding or block count out of range");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t rec = hypad_tw_shard_record_doubles(blocks_per_rank, n_analysis, anomaly_padding);
+    HYPAD_CUDA_TRY(cudaMemsetAsync(record, 0, rec * 8, stream));
+    if (count == 0) return HYPAD_OK;
+    TwArgs a;
+    memset(&a, 0, sizeof(a));
+    a.errors = local; a.len = count;
+    a.cblk = record; a.bsum1 = record + blocks_per_rank; a.bsum2 = record + 2 * blocks_per_rank;
+    a.bmax = (unsigned long long*)(record + 3 * blocks_per_rank);
+    tw_blocks_kernel<<<(unsigned)ceil_div(count, TW_TILE), RB, 0, stream>>>(a);
+    HYPAD_LAUNCH_CHECK();
+    const int hp = anomaly_padding + 1;
+    double* edge = record + 4 * blocks_per_rank;
+    tw_shard_edges_kernel<<<dim3((unsigned)n_analysis + 1, 2), RB, 0, stream>>>(local, first, count, n_total, window_size, step, hp, edge,
+                                                                              edge + n_analysis * 2 * TW_TILE);
+    HYPAD_LAUNCH_CHECK();
+    return HYPAD_OK;
+}
+
+int hypad_tw_shard_runs(hypad_ctx* ctx, const double* records, int world, int rank, const int64_t* block_start, int64_t blocks_per_rank,
+                        const double* ext, int64_t ext0, int64_t ext_len, int64_t n_total, int64_t window_size, int64_t step,
+                        int64_t n_analysis, int ddof, int anomaly_padding, int max_runs, double* out, void* stream_) {
+    HYPAD_REQUIRE(ctx && records && block_start && ext && out, "hypad_tw_shard_runs: NULL argument");
+    HYPAD_REQUIRE(world >= 1 && world <= TW_MAXWORLD && rank >= 0 && rank < world, "hypad_tw_shard_runs: world %d / rank %d", world, rank);
+    HYPAD_REQUIRE(window_size >= 2 * TW_TILE && step >= 1 && n_analysis >= 1 && n_analysis <= 65535 && max_runs >= 1,
+                  "hypad_tw_shard_runs: bad shape");
+    HYPAD_REQUIRE(anomaly_padding >= 0 && anomaly_padding <= TW_MAXPAD, "hypad_tw_shard_runs: padding %d outside 0..%d", anomaly_padding, TW_MAXPAD);
+    const int stats_f32 = (ddof & HYPAD_STATS_F32) ? 1 : 0;
+    ddof &= ~HYPAD_STATS_F32;
+    HYPAD_REQUIRE(ddof == 0 || ddof == 1, "hypad_tw_shard_runs: ddof must be 0 or 1 (optionally | HYPAD_STATS_F32)");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    HYPAD_CUDA_TRY(cudaSetDevice(ctx->device));
+    TwShardMap map;
+    map.world = world; map.rank = rank;
+    for (int r = 0; r <= world; ++r) map.blk_start[r] = block_start[r];
+    const int64_t nbt = ceil_div(n_total, TW_TILE);
+    HYPAD_REQUIRE(map.blk_start[0] == 0 && map.blk_start[world] == nbt, "hypad_tw_shard_runs: the block ranges do not cover the array");
+    const int64_t own0 = map.blk_start[rank] * TW_TILE, own1 = map.blk_start[rank + 1] * TW_TILE < n_total ? map.blk_start[rank + 1] * TW_TILE : n_total;
+    const int64_t hp = anomaly_padding + 1;
+    HYPAD_REQUIRE(ext0 <= (own0 - hp > 0 ? own0 - hp : 0) && ext0 + ext_len >= (own1 + hp < n_total ? own1 + hp : n_total),
+                  "hypad_tw_shard_runs: the slice [%lld, %lld) lacks the dilation halo of the own positions [%lld, %lld)", (long long)ext0,
+                  (long long)(ext0 + ext_len), (long long)own0, (long long)own1);
+    const size_t na = (size_t)n_analysis, mr = (size_t)max_runs, nb = (size_t)nbt;
+    const size_t wb = (size_t)(map.blk_start[rank + 1] - map.blk_start[rank]) + 2;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o += align256(bytes); return at; };
+    const size_t o_stats = take(na * 4 * 8), o_cnt = take(na * 2 * 4), o_below = take(na * 8), o_lead = take(na * 8);
+    const size_t o_starts = take(na * mr * 8), o_ends = take(na * mr * 8), o_rmax = take(na * mr * 8);
+    const size_t o_c = take(nb * 8), o_b1 = take(nb * 8), o_b2 = take(nb * 8), o_bm = take(nb * 8), o_edge = take(na * 2 * TW_TILE * 8);
+    const size_t o_wc = take(256), o_work = take(na * wb * 16);
+    int rc = ensure_workspace(ctx, o);
+    if (rc != HYPAD_OK) return rc;
+    char* ws = (char*)ctx->workspace;
+    TwArgs a;
+    memset(&a, 0, sizeof(a));
+    a.errors = ext - ext0;  // virtual base: only [lim_lo, lim_hi) is ever read
+    a.len = n_total; a.window_size = window_size; a.step = step; a.k0 = 0;
+    a.n_analysis = (int)n_analysis; a.ddof = ddof; a.pad = anomaly_padding; a.max_runs = max_runs; a.stats_f32 = stats_f32;
+    a.lim_lo = ext0; a.lim_hi = ext0 + ext_len; a.own_b0 = map.blk_start[rank]; a.own_b1 = map.blk_start[rank + 1];
+    a.stats = (double*)(ws + o_stats); a.cnt = (int*)(ws + o_cnt); a.below = (unsigned long long*)(ws + o_below);
+    a.lead = (unsigned long long*)(ws + o_lead); a.starts = (long long*)(ws + o_starts); a.ends = (long long*)(ws + o_ends);
+    a.rmax = (unsigned long long*)(ws + o_rmax); a.cblk = (double*)(ws + o_c); a.bsum1 = (double*)(ws + o_b1); a.bsum2 = (double*)(ws + o_b2);
+    a.bmax = (unsigned long long*)(ws + o_bm); a.edge = (double*)(ws + o_edge); a.work_cnt = (int*)(ws + o_wc); a.work = (longlong2*)(ws + o_work);
+    const size_t rec_len = hypad_tw_shard_record_doubles(blocks_per_rank, n_analysis, anomaly_padding);
+    int sms = kNumSMs;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    HYPAD_CUDA_TRY(cudaMemsetAsync(a.work_cnt, 0, sizeof(int), stream));
+    tw_shard_assemble_kernel<<<(unsigned)(2 * sms), 256, 0, stream>>>(records, rec_len, map, (int)blocks_per_rank, nbt, (int)n_analysis, window_size,
+                                                                       step, n_total, (double*)a.cblk, a.bsum1, a.bsum2, a.bmax, (double*)a.edge);
+    HYPAD_LAUNCH_CHECK();
+    tw_shard_window_kernel<<<(unsigned)n_analysis, RB, 0, stream>>>(a);
+    HYPAD_LAUNCH_CHECK();
+    tw_events_work_kernel<<<(unsigned)(2 * sms), TW_TILE, 0, stream>>>(a);
+    HYPAD_LAUNCH_CHECK();
+    tw_runmax_work_kernel<<<(unsigned)(2 * sms), TW_TILE, 0, stream>>>(a);
+    HYPAD_LAUNCH_CHECK();
+    tw_shard_emit_kernel<<<(unsigned)n_analysis, 256, 0, stream>>>(a, out);
+    HYPAD_LAUNCH_CHECK();
+    return HYPAD_OK;
 }
 
 }  // extern "C"

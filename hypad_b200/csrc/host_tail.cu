@@ -133,3 +133,74 @@ extern "C" int hypad_intervals_from_runs(const double* stats, const double* runs
     *n_out = n;
     return HYPAD_OK;
 }
+
+// Joins the run fragments of a sharded find_anomalies (hypad_tw_shard_runs records of every rank, rank order, host memory) into
+// the per-window statistics and runs hypad_intervals_from_runs takes.  Ranks own increasing position ranges, so concatenating
+// their sorted starts / ends gives the global order; the r-th start pairs with the r-th end; a rank's `lead` (the maximum of its
+// above-threshold values in front of its first start) belongs to the run that was open when its range began.
+// cap: runs per window the output has room for; *max_needed = the largest run count of a window (call again when > cap),
+// *overflow = 1 when a rank's own fragment list did not fit max_runs (redo hypad_tw_shard_runs with more room).
+extern "C" int hypad_tw_shard_merge(const double* records, int world, int64_t n_analysis, int max_runs, double* stats, double* runs,
+                                    int32_t* n_runs, int64_t cap, int64_t* max_needed, int* overflow) {
+    HYPAD_REQUIRE(records && stats && runs && n_runs && max_needed && overflow && world >= 1 && n_analysis >= 1 && max_runs >= 1 && cap >= 1,
+                  "hypad_tw_shard_merge: bad argument");
+    auto unkey = [](unsigned long long k) {
+        unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+        double d;
+        memcpy(&d, &b, 8);
+        return d;
+    };
+    const size_t per = 8 + 3 * (size_t)max_runs;
+    *max_needed = 0;
+    *overflow = 0;
+    std::vector<double> st, mx, en;
+    for (int64_t k = 0; k < n_analysis; ++k) {
+        st.clear();
+        mx.clear();
+        en.clear();
+        unsigned long long below = 0ull;
+        for (int r = 0; r < world; ++r) {
+            const double* o = records + ((size_t)r * n_analysis + k) * per;
+            const int64_t ns = (int64_t)o[0], ne = (int64_t)o[1];
+            if (ns > max_runs || ne > max_runs) {
+                *overflow = 1;
+                const int64_t m = ns > ne ? ns : ne;
+                if (m > *max_needed) *max_needed = m;
+                continue;
+            }
+            unsigned long long lead, bk;
+            memcpy(&lead, o + 2, 8);
+            memcpy(&bk, o + 3, 8);
+            if (bk > below) below = bk;
+            if (lead && !mx.empty()) {
+                const double v = unkey(lead);
+                if (v > mx.back()) mx.back() = v;
+            }
+            for (int64_t j = 0; j < ns; ++j) {
+                st.push_back(o[8 + j]);
+                mx.push_back(o[8 + max_runs + j]);
+            }
+            for (int64_t j = 0; j < ne; ++j) en.push_back(o[8 + 2 * (size_t)max_runs + j]);
+        }
+        const double* o0 = records + (size_t)k * per;  // the statistics are the same in every rank's record
+        stats[k * 4 + 0] = o0[4];
+        stats[k * 4 + 1] = o0[5];
+        stats[k * 4 + 2] = o0[6];
+        stats[k * 4 + 3] = below ? unkey(below) : 0.0;  // `above.all()` -> max_below = 0 (:1154-1155)
+        if (*overflow) continue;
+        HYPAD_REQUIRE(st.size() == en.size(), "hypad_tw_shard_merge: window %lld has %zu run starts but %zu ends", (long long)k, st.size(),
+                      en.size());
+        const int64_t nr = (int64_t)st.size();
+        if (nr > *max_needed) *max_needed = nr;
+        n_runs[k] = (int32_t)nr;
+        if (nr <= cap)
+            for (int64_t j = 0; j < nr; ++j) {
+                double* p = runs + ((size_t)k * cap + j) * 3;
+                p[0] = st[j];
+                p[1] = en[j];
+                p[2] = mx[j];
+            }
+    }
+    return HYPAD_OK;
+}
+

@@ -40,6 +40,24 @@ def shard_ranges(n_windows, world_size):
     return out
 
 
+BLOCK = 1024  # positions per block of the thresholding summaries (csrc/finish.cu: TW_TILE)
+
+
+def shard_ranges_aligned(n_windows, world_size, block=BLOCK):
+    """Contiguous ranges that start at multiples of `block`: the blocks are dealt out evenly, in order (counts differ by at most
+    one block; the last range ends with the array).  What the sharded find_anomalies needs: a block never straddles two ranks."""
+    nb = -(-n_windows // block)
+    base, extra = divmod(nb, world_size)
+    out, b = [], 0
+    for r in range(world_size):
+        cnt_b = base + (1 if r < extra else 0)
+        first = min(b * block, n_windows)
+        end = min((b + cnt_b) * block, n_windows)
+        out.append((first, end - first))
+        b += cnt_b
+    return out
+
+
 def timestep_range(first, count, n_windows, S, is_last):
     """Timesteps a rank aggregates: its window indices, plus the S-1 trailing ones on the last rank."""
     return first, count + (S - 1 if is_last else 0)
@@ -113,11 +131,18 @@ class ShardedScorer:
         self.world = dist.get_world_size(group) if world is None else world
         self.comm = comm if comm is not None else (TorchComm(group) if rank is None else None)
 
+    def ranges(self, n):
+        """[(first, count)] of every rank.  Long arrays are dealt out in whole blocks of 1024 positions (the sharded find_anomalies
+        works on block summaries); short ones are balanced to the window and thresholded from one gathered copy."""
+        if n >= self.world * 8 * BLOCK:
+            return shard_ranges_aligned(n, self.world)
+        return shard_ranges(n, self.world)
+
     def plan(self, n_windows):
         """(first, count, h0, sample_lo, sample_hi): owned windows, first halo window and the sample range
         [sample_lo, sample_hi) of the signal this rank needs resident (sliding windows)."""
         S = self.scorer.S
-        first, count = shard_ranges(n_windows, self.world)[self.rank]
+        first, count = self.ranges(n_windows)[self.rank]
         h0 = halo_first(first, S)
         # window w reads samples [w, w+S); as in the reference (utils/dataloader.py:200) a signal of L samples
         # yields L-S windows, so the slice carries one sample beyond the last window.
@@ -127,24 +152,24 @@ class ShardedScorer:
         """Multivariate rows (one row = one window, BASELINE config 4): (first, count, h0, row_lo, row_hi) -- the owned rows, the
         first halo row and the row range [row_lo, row_hi) this rank needs resident.  The S-1 halo rows in front are recomputed
         locally: the critic overlap aggregation of position i reads the critics of rows i-S+1 .. i."""
-        first, count = shard_ranges(n_rows, self.world)[self.rank]
+        first, count = self.ranges(n_rows)[self.rank]
         h0 = halo_first(first, self.scorer.S)
         return first, count, h0, h0, first + count
 
     def position_ranges(self, n_windows):
         """[(first position, count)] of every rank in the kmax array (n_windows + S - 1 positions)."""
         S = self.scorer.S
-        return [timestep_range(f, c, n_windows, S, r == self.world - 1) for r, (f, c) in enumerate(shard_ranges(n_windows, self.world))]
+        return [timestep_range(f, c, n_windows, S, r == self.world - 1) for r, (f, c) in enumerate(self.ranges(n_windows))]
 
     def _gather_windows(self, local, n_windows):
         """Per-window array of the own windows -> the full array on every rank (one all-gather)."""
-        counts = [c for _, c in shard_ranges(n_windows, self.world)]
+        counts = [c for _, c in self.ranges(n_windows)]
         g = self.comm.all_gather(_pad_to(local, max(counts)))
         return _concat_rows(g, counts)
 
-    def _score(self, fw, n, combination, index, multivariate, portion, padding, ddof, out_host=None):
+    def _score(self, fw, n, combination, index, multivariate, portion, padding, ddof, out_host=None, stats_f32=False):
         sc, S = self.scorer, self.scorer.S
-        first, count = shard_ranges(n, self.world)[self.rank]
+        first, count = self.ranges(n)[self.rank]
         lead = first - halo_first(first, S)
         ranges = self.position_ranges(n)
         t0, tc = ranges[self.rank]
@@ -159,8 +184,12 @@ class ShardedScorer:
         if out_host is not None:  # this rank's scores travel to its host while the interval extraction still runs
             scoring.download_async(sc, final, out_host)
         if index is not None:
-            out["final"] = self._gather_windows(final, n)
-            out["intervals"] = self.find_anomaly_intervals(out["final"], index, portion, 0.1, anomaly_padding=padding, ddof=ddof)
+            iv = self.find_anomaly_intervals_sharded(final, self.ranges(n), n, index, portion, 0.1, anomaly_padding=padding, ddof=ddof,
+                                                     stats_f32=stats_f32)
+            if iv is None:  # short array: one gathered copy, the analysis windows dealt out
+                out["final"] = self._gather_windows(final, n)
+                iv = self.find_anomaly_intervals(out["final"], index, portion, 0.1, anomaly_padding=padding, ddof=ddof, stats_f32=stats_f32)
+            out["intervals"] = iv
         if out_host is not None:
             sc._down_stream.synchronize()
         sc.poll_error()  # after the collectives, so that every rank still reaches them
@@ -188,12 +217,12 @@ class ShardedScorer:
         first, count, h0, lo, hi = self.plan(n_windows)
         if local_slice.numel() != hi - lo:
             raise ValueError("local slice has %d samples, plan() asks for %d" % (local_slice.numel(), hi - lo))
-        scoring.univariate_hyperbolic_semantics(combination)
+        ddof, stats_f32 = scoring.univariate_hyperbolic_semantics(combination)  # what find_anomalies is handed
         if local_slice.is_cuda:
             fw = self.scorer.forward(local_slice, True)  # windows h0 .. first+count-1
         else:
             fw = self.scorer.forward_from_host(local_slice)
-        return self._score(fw, n_windows, combination, index, False, 0.33, 50, 1, out_host=out_host)
+        return self._score(fw, n_windows, combination, index, False, 0.33, 50, ddof, out_host=out_host, stats_f32=stats_f32)
 
     def score_multivariate(self, local_rows, n_rows, combination="mult", index=None):
         """BASELINE config 4: (N, C) rows sharded by contiguous row range.  local_rows: rows [row_lo, row_hi) of plan_rows() on
@@ -277,10 +306,62 @@ class ShardedScorer:
         sc.poll_error()
         return out
 
+    def find_anomaly_intervals_sharded(self, final_local, ranges, n, index, window_size_portion, window_step_size_portion,
+                                       min_percent=0.1, anomaly_padding=50, ddof=0, stats_f32=False):
+        """find_anomalies (fixed threshold) on scores sharded over the ranks by block-aligned ranges, without gathering them:
+        every rank reduces its scores to a record (block summaries, the analysis windows' edge elements in its range, its
+        boundary values for the neighbours' dilation halo), the records are all-gathered (a few hundred KB), every rank computes
+        all windows' statistics from them and the run fragments of its own positions, the fragments are all-gathered and joined
+        on the host (csrc/finish.cu, hypad_tw_shard_*).  Same arithmetic on the same values as the single-GPU path: bitwise its
+        intervals.  Returns None when the array is too short for this path (ranges not block-aligned, windows under two blocks)."""
+        wsize, step, count = scoring.analysis_windows(n, None, window_size_portion, None, window_step_size_portion)
+        first, cnt = ranges[self.rank]
+        aligned = all(f % BLOCK == 0 and (c % BLOCK == 0 or f + c == n) for f, c in ranges)
+        if not aligned or wsize < 2 * BLOCK or anomaly_padding + 1 > min(c for _, c in ranges) or self.world > 64:
+            return None
+        final_local = final_local.double().contiguous()
+        dev = final_local.device
+        ctx = scoring._ctx(final_local)  # the stream's own workspace context, like the other finish steps
+        lib, h = ctx.lib, ctx.handle
+        bpr = max(-(-c // BLOCK) for _, c in ranges)
+        hp = anomaly_padding + 1
+        rec_len = lib.hypad_tw_shard_record_doubles(bpr, count, anomaly_padding)
+        blk = np.asarray([f // BLOCK for f, _ in ranges] + [-(-n // BLOCK)], dtype=np.int64)
+        flags = ddof | (scoring._native.STATS_F32 if stats_f32 else 0)
+        with torch.cuda.device(dev):
+            record = torch.empty(rec_len, dtype=torch.float64, device=dev)
+            scoring.check(lib.hypad_tw_shard_pack(h, scoring.ptr(final_local), first, cnt, n, wsize, step, count, anomaly_padding, bpr,
+                                                  scoring.ptr(record), ctx.stream()))
+            g = self.comm.all_gather(record).contiguous()
+            strips = g[:, rec_len - 2 * hp:].contiguous().view(self.world, 2, hp)
+            lo, hi = max(first - hp, 0), min(first + cnt + hp, n)
+            left, right = scoring._halo_from_strips(strips, ranges, self.rank, first - lo, hi - (first + cnt))
+            ext = torch.cat(left + [final_local] + right) if (left or right) else final_local
+            while True:
+                R = self.max_runs
+                per = 8 + 3 * R
+                frag = torch.empty(count * per, dtype=torch.float64, device=dev)
+                scoring.check(lib.hypad_tw_shard_runs(h, scoring.ptr(g), self.world, self.rank, blk.ctypes.data, bpr, scoring.ptr(ext), lo,
+                                                      ext.shape[0], n, wsize, step, count, flags, anomaly_padding, R, scoring.ptr(frag),
+                                                      ctx.stream()))
+                host = self.comm.all_gather(frag).cpu().numpy()
+                cap = self.world * R
+                stats = np.empty((count, 4), dtype=np.float64)
+                runs = np.empty((count, cap, 3), dtype=np.float64)
+                n_runs = np.zeros(count, dtype=np.int32)
+                need, over = scoring.ctypes.c_int64(0), scoring.ctypes.c_int(0)
+                scoring.check(lib.hypad_tw_shard_merge(host.ctypes.data, self.world, count, R, stats.ctypes.data, runs.ctypes.data,
+                                                       n_runs.ctypes.data, cap, scoring.ctypes.byref(need), scoring.ctypes.byref(over)))
+                if not over.value:
+                    break
+                self.max_runs = int(need.value) * 3 // 2 + 16  # the same decision on every rank: the gathered records are identical
+        merged = scoring.intervals_from_runs(stats, runs, n_runs, step, min_percent, f32=stats_f32)
+        return scoring.intervals_to_index(merged, index)
+
     max_runs = 64  # room per analysis window in the gathered buffer; grown (on every rank alike) when a window holds more runs
 
     def find_anomaly_intervals(self, final, index, window_size_portion, window_step_size_portion, min_percent=0.1,
-                               anomaly_padding=50, ddof=0):
+                               anomaly_padding=50, ddof=0, stats_f32=False):
         """scoring.find_anomaly_intervals with the analysis windows dealt out to the ranks: rank r thresholds windows
         [r*per, (r+1)*per) of the (identical, gathered) score array, the packed per-window results are all-gathered and the
         host tail (prune, score, merge) runs on every rank.  The kernels work on the whole array with a first-window index, so
@@ -295,7 +376,8 @@ class ShardedScorer:
             blen = scoring.threshold_buffer_len(per, R)
             local = torch.zeros(blen, dtype=torch.float64, device=final.device)
             if kc > 0:
-                sub = scoring.threshold_windows_launch(final, wsize, step, kc, ddof, anomaly_padding, R, first_window=k0)
+                sub = scoring.threshold_windows_launch(final, wsize, step, kc, ddof | (scoring._native.STATS_F32 if stats_f32 else 0),
+                                                       anomaly_padding, R, first_window=k0)
                 # re-pack the kc-window buffer into the fixed per-window layout of `per` windows
                 s_loc, r_loc, n_loc = scoring.threshold_buffer_len(kc, R), kc * 4, kc * R * 3
                 local[: kc * 4] = sub[:r_loc]
@@ -315,5 +397,5 @@ class ShardedScorer:
             if most <= R:
                 break
             self.max_runs = most * 3 // 2 + 16  # the same decision on every rank: the gathered counts are identical
-        merged = scoring.intervals_from_runs(stats, runs, n_runs, step, min_percent)
+        merged = scoring.intervals_from_runs(stats, runs, n_runs, step, min_percent, f32=stats_f32)
         return scoring.intervals_to_index(merged, index)

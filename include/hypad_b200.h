@@ -277,6 +277,25 @@ int hypad_score_signal_hyperbolic(hypad_ctx* ctx, const void* x, int x_is_f64, i
 int hypad_intervals_from_runs(const double* stats, const double* runs, const int32_t* n_runs, int64_t count, int64_t max_runs,
                               int64_t step, double min_percent, int f32, double* out, int64_t cap, int64_t* n_out);
 
+/* find_anomalies on an array sharded over several GPUs by contiguous ranges that start at multiples of 1024 positions (only the
+ * last may end inside a block): nothing of the array's total length is gathered.  hypad_tw_shard_pack reduces this rank's
+ * positions [first, first + count) to a record of hypad_tw_shard_record_doubles(...) doubles -- the summaries of its blocks, the
+ * elements of the analysis windows' ragged edges that fall into its range, and its first / last padding + 1 values; the caller
+ * all-gathers the records (rank order) and passes them, with this rank's positions plus a halo of padding + 1 either side
+ * (`ext`, global positions [ext0, ext0 + ext_len)), to hypad_tw_shard_runs, which computes every window's statistics (the
+ * arithmetic of hypad_threshold_windows on the same values) and the run fragments of the own positions: per window
+ * 8 + 3 max_runs doubles {n_starts, n_ends, lead key, below key, mean, std, threshold, 0 | starts | their maxima | ends}.
+ * The gathered fragment records are joined on the host by hypad_tw_shard_merge into the (stats, runs, n_runs) that
+ * hypad_intervals_from_runs takes.  block_start[world + 1]: first block of every rank.  All windows (first_window = 0). */
+size_t hypad_tw_shard_record_doubles(int64_t blocks_per_rank, int64_t n_analysis, int anomaly_padding);
+int hypad_tw_shard_pack(hypad_ctx* ctx, const double* local, int64_t first, int64_t count, int64_t n_total, int64_t window_size,
+                        int64_t step, int64_t n_analysis, int anomaly_padding, int64_t blocks_per_rank, double* record, void* stream);
+int hypad_tw_shard_runs(hypad_ctx* ctx, const double* records, int world, int rank, const int64_t* block_start, int64_t blocks_per_rank,
+                        const double* ext, int64_t ext0, int64_t ext_len, int64_t n_total, int64_t window_size, int64_t step,
+                        int64_t n_analysis, int ddof, int anomaly_padding, int max_runs, double* out, void* stream);
+int hypad_tw_shard_merge(const double* records, int world, int64_t n_analysis, int max_runs, double* stats, double* runs,
+                         int32_t* n_runs, int64_t cap, int64_t* max_needed, int* overflow);
+
 /* ---- staged global statistics: one GPU's slice per call, a small record exchanged between stages -------------------------
  * The reference computes its statistics on whole arrays (np.quantile / mean / std in _compute_critic_score,
  * utils/anomaly_detection_utils.py:307-333; stats.zscore at :177 and :523).  When a signal's windows are sharded over

@@ -13,7 +13,7 @@ import torch.distributed as dist
 
 from bench import S, make_signal
 from hypad_b200 import scoring
-from hypad_b200.distributed import ShardedScorer, halo_first, shard_ranges
+from hypad_b200.distributed import ShardedScorer
 from hypad_b200.models.tadgan import CriticX, Decoder, Encoder
 
 
@@ -34,7 +34,7 @@ def main():
     index = np.arange(T)
     first, count, h0, lo, hi = sh.plan(n)
     x = torch.from_numpy(sig[lo:hi].copy()).to(dev)
-    names = ["forward", "kde", "critic_staged", "combine", "gather_final", "threshold"]
+    names = ["forward", "kde", "critic_staged", "combine", "find_anomalies_sharded"]
     acc = {k: 0.0 for k in names}
     reps = 8
     for it in range(reps + 3):
@@ -53,10 +53,8 @@ def main():
         lead = first - h0
         final = scoring.combine("uncertainty", cs[:count], fw["rec"][lead:], fw["unorm"][lead:], n=count)
         ev[4].record()
-        full = sh._gather_windows(final, n)
+        iv = sh.find_anomaly_intervals_sharded(final, sh.ranges(n), n, index, 0.33, 0.1, anomaly_padding=50, ddof=1)
         ev[5].record()
-        iv = sh.find_anomaly_intervals(full, index, 0.33, 0.1, anomaly_padding=50, ddof=1)
-        ev[6].record()
         torch.cuda.synchronize()
         if it >= 3:
             for i, k in enumerate(names):

@@ -41,7 +41,12 @@ def _worker(rank, world, port, n_windows, S, q):
     fs.S = S
     sh = hd.ShardedScorer(fs)
     f2, c2, h0, lo, hi = sh.plan(n_windows)
-    ok = ok and (f2, c2) == (first, count) and h0 == max(0, first - (S - 1)) and lo == h0 and hi - lo - S == first + count - h0
+    # long arrays are dealt out in whole blocks of 1024 positions (the sharded find_anomalies), short ones balanced to the window
+    want = hd.shard_ranges_aligned(n_windows, world) if n_windows >= world * 8 * hd.BLOCK else ranges
+    ok = ok and (f2, c2) == want[rank] and h0 == max(0, f2 - (S - 1)) and lo == h0 and hi - lo - S == f2 + c2 - h0
+    al = hd.shard_ranges_aligned(n_windows, world)
+    ok = ok and sum(c for _, c in al) == n_windows and all(f % hd.BLOCK == 0 or c == 0 for f, c in al)
+    ok = ok and all(al[i][0] + al[i][1] == al[i + 1][0] for i in range(world - 1))
     q.put((rank, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()

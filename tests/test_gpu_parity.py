@@ -967,8 +967,11 @@ def replay_sharded(scorer, x, n, world, sliding, combination, multivariate, inde
     def run(r):
         try:
             with torch.cuda.stream(torch.cuda.Stream()):
+                from hypad_b200 import scoring as _scoring
+
+                ddof, f32 = (0, False) if multivariate else _scoring.univariate_hyperbolic_semantics(combination)
                 out = shs[r]._score(fws[r], n, combination, index, multivariate, 0.2 if multivariate else 0.33,
-                                    200 if multivariate else 50, 0 if multivariate else 1)
+                                    200 if multivariate else 50, ddof, stats_f32=f32)
                 results[r] = shs[r].gather_full(out, n)
                 torch.cuda.current_stream().synchronize()
         except BaseException as e:  # noqa: BLE001 -- surfaced below; the barrier must not be left waiting
@@ -1007,6 +1010,17 @@ def test_sharded_rows_multivariate_equal_unsharded(world, cuda_device):
     for k in ("final", "kmax", "rec"):
         assert torch.equal(out[k], ref[k]), k
     assert torch.equal(out["critic_scores"], ref["critic_scores"])
+    if world == 3:  # enough rows for the block-aligned path: find_anomalies (20 % windows, padding 200) without gathering the scores
+        rows = rng.uniform(-1, 1, (30000, 123))
+        rows[12000:12040] *= 3
+        rows[10200:10260] *= 2.5  # next to the first rank boundary (10240)
+        x = torch.from_numpy(rows).to(cuda_device)
+        index = 1353715200.0 + np.arange(30000)
+        ref = scorer.score(x, False, "mult", multivariate=True, index=index)
+        out = replay_sharded(scorer, x, 30000, world, False, "mult", True, index=index)
+        for k in ("final", "kmax", "rec", "critic_scores"):
+            assert torch.equal(out[k], ref[k]), k
+        assert np.array_equal(out["intervals"], ref["intervals"]) and len(ref["intervals"]) >= 1
 
 
 @pytest.mark.gpu
@@ -1042,8 +1056,9 @@ def test_host_buffer_call_equals_device_call(hyp_scorer, cuda_device):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,T", [(8, 60000), (3, 200000)])
-def test_sharded_long_signal_staged_statistics_equal_unsharded(world, T, hyp_scorer, cuda_device):
+@pytest.mark.parametrize("world,T,comb", [(8, 60000, "uncertainty"), (3, 200000, "uncertainty"), (8, 70100, "critic"), (5, 150000, "rec_uncertainty"),
+                                          (2, 40000, "mult")])
+def test_sharded_long_signal_staged_statistics_equal_unsharded(world, T, comb, hyp_scorer, cuda_device):
     """The staged statistics at a size where they matter: the smoothing window (1 % of the windows) needs a halo of hundreds of
     positions from the neighbours, the quantile ranks fall inside other ranks' slices, and the partial sums of eight ranks
     must round to the single-GPU mean / std."""
@@ -1054,11 +1069,16 @@ def test_sharded_long_signal_staged_statistics_equal_unsharded(world, T, hyp_sco
     x = torch.from_numpy(sig).to(cuda_device)
     n = T - 100
     index = np.arange(T)
-    ref = hyp_scorer.score(x, True, "uncertainty", index=index)
-    out = replay_sharded(hyp_scorer, x, n, world, True, "uncertainty", False, index=index)
-    for k in ("kmax", "rec", "unorm", "critic_scores", "final"):
+    sig[T // 2: T // 2 + 30] = 1.0  # one long burst: a run of a few hundred padded positions
+    sig[(T // world) // 1024 * 1024 + 1000: (T // world) // 1024 * 1024 + 1060] = -1.0  # and one across the first rank boundary
+    x = torch.from_numpy(sig).to(cuda_device)
+    ref = hyp_scorer.score(x, True, comb, index=index)
+    out = replay_sharded(hyp_scorer, x, n, world, True, comb, False, index=index)
+    for k in ("rec", "unorm", "final") + (() if comb.startswith("rec") else ("kmax", "critic_scores")):
         assert torch.equal(out[k], ref[k]), k
     assert np.array_equal(out["intervals"], ref["intervals"]) and len(ref["intervals"]) >= 1
+    if comb != "uncertainty":
+        return
     # and the statistics themselves against numpy on the gathered selections
     km = ref["kmax"].cpu().numpy()
     want = ho.compute_critic_score(km, math.trunc(n * 0.01))[:n]
