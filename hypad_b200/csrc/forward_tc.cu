@@ -245,14 +245,20 @@ __device__ __forceinline__ void check_range8(const float (&v)[8], float sc, int*
 // 1 / (1 + exp(-x)).  exp(-x) = 2^(-x log2 e) straight through MUFU.EX2 (relative error 2^-22, like expf's own core):
 // without expf's two-step argument reduction the exponent carries a rounding error of |x| 2^-24, which moves the result by
 // sigma (1 - sigma) |x| 6e-8 <= 1.3e-8 in absolute terms whatever x is -- below half an ulp of the gate values that matter.
-// The reciprocal is MUFU.RCP refined by one Newton step (<= 1 ulp, branch-free).  6 instructions instead of 12.
+// The reciprocal is MUFU.RCP as it comes (<= 1 ulp of sigma, i.e. <= 6e-8 absolute, next to the 6e-8 of the exponential): the
+// Newton step the first version added (HYPAD_SIGMOID_NEWTON) changed no parity count of any golden case and cost 2 of 6
+// instructions, 912 times per window.
 __device__ __forceinline__ float sigmoid_tc(float x) {
     float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(x, -1.4426950408889634f)));
     const float d = __fadd_rn(1.0f, e);
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+#ifdef HYPAD_SIGMOID_NEWTON
     return fmaf(r, fmaf(-d, r, 1.0f), r);
+#else
+    return r;
+#endif
 }
 
 // tanh(x) for |x| <= 1 (the LSTM cell value c = sigmoid(i) tanh(g)): x + x s C(s) / B(s), s = x^2, a (1,2) rational fit of
