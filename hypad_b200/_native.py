@@ -53,6 +53,11 @@ class hypad_signal_out(ctypes.Structure):
     _fields_ = [("critic", _vp), ("rec", _vp), ("unorm", _vp), ("kmax", _vp), ("critic_scores", _vp), ("final", _vp), ("tw", _vp)]
 
 
+class hypad_signal_eucl_out(ctypes.Structure):
+    _fields_ = [("critic", _vp), ("eucl", _vp), ("kmax", _vp), ("critic_scores", _vp), ("truth", _vp), ("pred", _vp), ("errors", _vp),
+                ("rec", _vp), ("final", _vp), ("tw", _vp)]
+
+
 # name -> (restype, argtypes); mirrors include/hypad_b200.h one to one
 _SIGNATURES = {
     "hypad_abi_version": (_int, []),
@@ -96,6 +101,8 @@ _SIGNATURES = {
     "hypad_tc_probe_bench": (_int, [_int, _int, _int, _vp, _vp]),
     "hypad_score_signal_hyperbolic": (_int, [_vp, _vp, _int, _i64, _int, _i64, _i64, _i64, _int, _int, _int,
                                              ctypes.POINTER(hypad_signal_out), _vp]),
+    "hypad_score_signal_euclidean": (_int, [_vp, _vp, _int, _i64, _int, _int, ctypes.c_double, _i64, _i64, _i64, _int, _int, _int,
+                                            ctypes.POINTER(hypad_signal_eucl_out), _vp]),
     "hypad_critic_small_max": (_int, []),
     "hypad_critic_combine_small": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp, _vp, _i64, _vp, _vp, _vp]),
     "hypad_critic_scores": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp]),

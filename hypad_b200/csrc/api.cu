@@ -355,6 +355,52 @@ int hypad_score_signal_hyperbolic(hypad_ctx* ctx, const void* x, int x_is_f64, i
     return rc;
 }
 
+int hypad_score_signal_euclidean(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n_windows, int combine_mode, int rec_error_kind,
+                                 double lambda_rec, int64_t tw_window, int64_t tw_step, int64_t tw_count, int ddof_flags,
+                                 int anomaly_padding, int max_runs, const hypad_signal_eucl_out* o, void* stream) {
+    HYPAD_REQUIRE(ctx && x && o && o->critic && o->eucl && o->kmax && o->critic_scores && o->truth && o->pred && o->errors && o->rec && o->final,
+                  "hypad_score_signal_euclidean: NULL argument");
+    HYPAD_REQUIRE(ctx->has_weights && !ctx->prog.hyperbolic, "hypad_score_signal_euclidean: the context holds no Euclidean model");
+    HYPAD_REQUIRE(n_windows >= 1, "hypad_score_signal_euclidean: no windows to score (signal shorter than the window?)");
+    HYPAD_REQUIRE(combine_mode == 0 || combine_mode == 3 || combine_mode == 6 || combine_mode == 8, "hypad_score_signal_euclidean: combine "
+                  "mode %d (mult 0, critic 3, rec 6, sum 8)", combine_mode);
+    HYPAD_REQUIRE(rec_error_kind >= 0 && rec_error_kind <= 2, "hypad_score_signal_euclidean: rec_error_kind %d (dtw 0, point 1, area 2)", rec_error_kind);
+    const int S = ctx->prog.S;
+    const int64_t n_pos = n_windows + S - 1;
+    const int64_t smooth = (int64_t)((double)n_windows * 0.01);
+    hypad_forward_out fo;
+    memset(&fo, 0, sizeof(fo));
+    fo.critic = o->critic;
+    fo.eucl = o->eucl;
+    int rc = hypad_forward(ctx, x, x_is_f64, n_windows, 1, nullptr, HYPAD_STAGE_ENCODER | HYPAD_STAGE_DECODER | HYPAD_STAGE_CRITIC, &fo, stream);
+    if (rc != HYPAD_OK) return rc;
+    if ((rc = hypad_kde_argmax_overlap(o->critic, 0, n_windows, n_windows, S, 0, n_pos, o->kmax, stream)) != HYPAD_OK) return rc;
+    // critic scores (:365-404); the single-CTA kernel for short signals (its combination output is not used here: 0 windows)
+    if (n_pos <= hypad_critic_small_max())
+        rc = hypad_critic_combine_small(ctx, o->kmax, n_pos, smooth, 1, 3, nullptr, nullptr, 0, o->critic_scores, o->final, stream);
+    else
+        rc = hypad_critic_scores(ctx, o->kmax, n_pos, smooth, 1, o->critic_scores, stream);
+    if (rc != HYPAD_OK) return rc;
+    // reconstruction_errors (:866-962): truth unrolled, prediction = median over the overlapping windows, error, smoothing
+    if ((rc = hypad_true_from_signal(x, x_is_f64, n_windows, 1, S, o->truth, stream)) != HYPAD_OK) return rc;
+    if ((rc = hypad_median_overlap(o->eucl, n_windows, S, o->pred, stream)) != HYPAD_OK) return rc;
+    if (rec_error_kind == 0) rc = hypad_dtw_error(o->truth, o->pred, 1, n_pos, 10, o->rec, stream);  // o->rec as scratch for the raw error
+    else if (rec_error_kind == 1) rc = hypad_point_error(o->truth, o->pred, 1, n_pos, o->rec, stream);
+    else rc = hypad_area_error(o->truth, o->pred, 1, n_pos, 10, o->rec, stream);
+    if (rc != HYPAD_OK) return rc;
+    if ((rc = hypad_rolling_mean_centered(ctx, o->rec, n_pos, smooth, smooth / 2, o->errors, stream)) != HYPAD_OK) return rc;
+    if ((rc = hypad_zscore_clip(ctx, o->errors, 0, n_pos, o->rec, stream)) != HYPAD_OK) return rc;  // :523-524
+    if ((rc = hypad_combine_scores(combine_mode, o->critic_scores, o->rec, 0, nullptr, lambda_rec, n_pos, o->final, stream)) != HYPAD_OK) return rc;
+    if (o->tw && tw_count > 0) {
+        double* stats = o->tw;
+        double* runs = stats + tw_count * 4;
+        int32_t* n_runs = (int32_t*)(runs + tw_count * (int64_t)max_runs * 3);
+        rc = hypad_threshold_windows(ctx, o->final, n_pos, tw_window, tw_step, tw_count, ddof_flags, anomaly_padding, stats, runs, n_runs,
+                                     max_runs, stream);
+    }
+    return rc;
+}
+
 int hypad_ctx_set_strict_range(hypad_ctx* ctx, int strict) {
     HYPAD_REQUIRE(ctx != nullptr, "hypad_ctx_set_strict_range: NULL context");
     ctx->strict_range = strict != 0;

@@ -830,6 +830,42 @@ class WindowScorer:
                                                         w, s_, c, dd, pad, mr, ctypes.byref(so), ctx.stream()))
         return out
 
+    def score_chain_euclidean(self, x, combination, rec_error_type="dtw", lambda_rec=0.5, tw=None, check_weights=True):
+        """The per-timestep Euclidean path of one device-resident signal as ONE library call (hypad_score_signal_euclidean);
+        same layout of the result as score(): critic, eucl, kmax, critic_scores, true, pred, errors, rec, final."""
+        if check_weights:
+            self.net.ensure(self.encoder, self.decoder, self.critic_x)
+        x, n, _ = self._input(x, True)
+        if n <= 0:
+            raise HypadError("hypad_b200: no windows to score (signal shorter than the window?)")
+        mode = {"mult": "mult", "sum": "euclidean_sum", "rec": "rec", "critic": "critic"}.get(combination)
+        if mode is None:
+            raise ValueError('Unknown combination specified {}, use "mult", "sum", or "rec" instead.'.format(combination))
+        kind = {"dtw": 0, "point": 1, "area": 2}.get(rec_error_type.lower())
+        if kind is None:
+            raise ValueError("unknown rec_error_type %r" % (rec_error_type,))
+        S, dev = self.S, x.device
+        npos = n + S - 1
+        # one allocation: six float64 arrays of npos | eucl f32 (n, S) | critic f32 (n) | pred f32 (npos)
+        buf = torch.empty(6 * npos * 8 + (n * S + n + npos) * 4, dtype=torch.uint8, device=dev)
+        d64 = buf[: 6 * npos * 8].view(torch.float64).view(6, npos)
+        f32 = buf[6 * npos * 8:].view(torch.float32)
+        out = {"final": d64[0], "kmax": d64[1], "critic_scores": d64[2], "true": d64[3], "errors": d64[4], "rec": d64[5],
+               "eucl": f32[: n * S].view(n, S), "critic": f32[n * S: n * S + n], "pred": f32[n * S + n:]}
+        so = _native.hypad_signal_eucl_out()
+        for name, key in (("final", "final"), ("kmax", "kmax"), ("critic_scores", "critic_scores"), ("truth", "true"), ("errors", "errors"),
+                          ("rec", "rec"), ("eucl", "eucl"), ("critic", "critic"), ("pred", "pred")):
+            setattr(so, name, out[key].data_ptr())
+        w = s_ = c = dd = pad = mr = 0
+        if tw is not None:
+            w, s_, c, dd, pad, mr, twbuf = tw
+            so.tw = twbuf.data_ptr()
+        ctx = self.net.ctx
+        with torch.cuda.device(dev):
+            check(ctx.lib.hypad_score_signal_euclidean(ctx.handle, ptr(x), int(x.dtype == torch.float64), n, _native.COMBINE_MODES[mode], kind,
+                                                       float(lambda_rec), w, s_, c, dd, pad, mr, ctypes.byref(so), ctx.stream()))
+        return out
+
     def critic_scores(self, critic, n_windows):
         """final_critic_scores (:365-404): KDE arg-max overlap aggregation + quantile-band z-score + smoothing."""
         kmax = kde_argmax_overlap(critic, self.S)
@@ -873,6 +909,28 @@ class WindowScorer:
                 if nr.max(initial=0) > mr:  # more runs than the buffer holds: the growing one-by-one path
                     stats, runs, nr = threshold_windows(out["final"], wsize, step, count, tw[3], 50)
                 out["intervals"] = intervals_to_index(intervals_from_runs(stats, runs, nr, step, 0.1, f32=stats_f32), index)
+            if out_host is not None:
+                self._down_stream.synchronize()
+            if poll:
+                self.poll_error()
+            return out
+        if (not self.hyperbolic and sliding and not multivariate and set(keep) <= {"eucl"} and isinstance(x, torch.Tensor) and x.is_cuda
+                and x.numel() - self.S < 200000):
+            tw = None
+            if index is not None:
+                npos = x.numel() - 1
+                wsize, step, count = analysis_windows(npos, None, 0.33, None, 0.1)
+                mr = _RUNS_HINT["max"]
+                twbuf = torch.empty(threshold_buffer_len(count, mr), dtype=torch.float64, device=x.device)
+                tw = (wsize, step, count, 0, 50, mr, twbuf)  # an ndarray on the Euclidean path: ddof 0
+            out = self.score_chain_euclidean(x, combination, rec_error_type, lambda_rec, tw)
+            if out_host is not None:
+                download_async(self, out["final"], out_host)
+            if index is not None:
+                stats, runs, nr = threshold_windows_parse(twbuf.cpu().numpy(), count, mr)
+                if nr.max(initial=0) > mr:
+                    stats, runs, nr = threshold_windows(out["final"], wsize, step, count, 0, 50)
+                out["intervals"] = intervals_to_index(intervals_from_runs(stats, runs, nr, step, 0.1), index)
             if out_host is not None:
                 self._down_stream.synchronize()
             if poll:

@@ -270,6 +270,26 @@ int hypad_score_signal_hyperbolic(hypad_ctx* ctx, const void* x, int x_is_f64, i
                                   int64_t tw_window, int64_t tw_step, int64_t tw_count, int ddof_flags, int anomaly_padding,
                                   int max_runs, const hypad_signal_out* out, void* stream);
 
+/* The per-timestep Euclidean (TadGAN) path of one signal in one call (score_anomalies, utils/anomaly_detection_utils.py:407-576):
+ * network -> KDE critic scores -> truth / median prediction -> reconstruction error (rec_error_kind 0 dtw, 1 point, 2 area) ->
+ * smoothing -> z-score + clip -> combination (combine_mode 0 mult, 3 critic, 6 rec, 8 sum with lambda_rec) -> find_anomalies'
+ * device part.  n_pos = n_windows + S - 1 positions.  Same kernels as the step-by-step entry points. */
+typedef struct hypad_signal_eucl_out {
+    float* critic;         /* (n_windows) */
+    float* eucl;           /* (n_windows, S) reconstruction */
+    double* kmax;          /* (n_pos) */
+    double* critic_scores; /* (n_pos) */
+    double* truth;         /* (n_pos) */
+    float* pred;           /* (n_pos) */
+    double* errors;        /* (n_pos) smoothed reconstruction error */
+    double* rec;           /* (n_pos) z-scored, clipped, + 1 */
+    double* final;         /* (n_pos) */
+    double* tw;            /* packed thresholding result or NULL */
+} hypad_signal_eucl_out;
+int hypad_score_signal_euclidean(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n_windows, int combine_mode, int rec_error_kind,
+                                 double lambda_rec, int64_t tw_window, int64_t tw_step, int64_t tw_count, int ddof_flags,
+                                 int anomaly_padding, int max_runs, const hypad_signal_eucl_out* out, void* stream);
+
 /* Host tail of find_anomalies on the outputs of hypad_threshold_windows (host pointers, no device work): prune
  * (utils/anomaly_detection_utils.py:1203-1237), score (:1240-1269) and merge (:1272-1313) with numpy's / pandas' arithmetic.
  * out receives up to `cap` (start, end, score) triples in positions of the scored array, *n_out their number (call again with
