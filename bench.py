@@ -369,6 +369,8 @@ def run_native(args):
                         "bytes_are": "per rank (each rank uploads its slice of the signal and reads back its windows' scores)",
                         "ms_per_step": e2e_ms / args.steps},
                 "host_cpus_bound": affinity,
+                "stage_exchange": None if not distributed else ("nvlink peer memory (hypad_peer_exchange)" if sharded.comm.peer is not None
+                                                                else "nccl all_gather"),
                 "gpu_launches": int(launches), "roofline": roofline, "roofline_kde": roofline_kde,
                 "kernels_ms": {"forward_tc_kernel": fw_ms, "kde_screened_kernel": kde_ms, "step_total": ms_per_step},
                 "kde": {"pair_evals_per_timestep": 4950, "timesteps_per_launch": n_local + S - 1,

@@ -121,6 +121,7 @@ _SIGNATURES = {
     "hypad_tw_shard_pack": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _int, _i64, _vp, _vp]),
     "hypad_tw_shard_runs": (_int, [_vp, _vp, _int, _int, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _vp, _vp]),
     "hypad_tw_shard_merge": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _i64, ctypes.POINTER(_i64), ctypes.POINTER(_int)]),
+    "hypad_peer_exchange": (_int, [_vp, _i64, _vp, _int, _int, _i64, _i64, ctypes.c_uint64, _vp, _vp]),
     "hypad_peak_probe": (_int, [_int, _int, _int, _vp, ctypes.POINTER(ctypes.c_longlong), _vp]),
 }
 

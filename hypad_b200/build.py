@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhypad_b200.so")
-SOURCES = ["api.cu", "forward.cu", "kde.cu", "aggregate.cu", "dtw.cu", "finish.cu", "critic_stats.cu", "tc_probe.cu", "forward_tc.cu", "preprocess.cu", "pairwise.cu", "peaks.cu", "host_tail.cu"]
+SOURCES = ["api.cu", "forward.cu", "kde.cu", "aggregate.cu", "dtw.cu", "finish.cu", "critic_stats.cu", "tc_probe.cu", "forward_tc.cu", "preprocess.cu", "pairwise.cu", "peaks.cu", "host_tail.cu", "peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

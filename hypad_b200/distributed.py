@@ -20,6 +20,7 @@ ranks took part: a sharded run equals the single-GPU run bit for bit (tests/test
 There is no collective inside a kernel.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -103,16 +104,84 @@ def gather_concat(local, sizes, group=None):
     return _concat_rows(out, sizes)
 
 
-class TorchComm:
-    """The stage exchange over torch.distributed: all_gather_into_tensor of one flat device buffer per rank."""
+class PeerExchange:
+    """All-gather of small records through NVLink peer memory (csrc/peer.cu): one kernel launch per exchange, no host-side
+    collective.  Owns a symmetric buffer (torch.distributed._symmetric_memory) of `slots` data areas + flag rows; exchanges are
+    numbered and rotate through the slots.  Raises at construction when symmetric memory is unavailable (the caller then stays
+    with NCCL)."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, slots=8, slot_bytes=1 << 20):
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _native
+
+        self.lib = _native.load_library()
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.slots, self.slot_bytes = slots, slot_bytes * self.world  # room for `world` records of slot_bytes each
+        self.flag_off = self.slots * self.slot_bytes
+        total = self.flag_off + self.slots * self.world * 8
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.buf = symm.empty(total, dtype=torch.uint8, device=dev)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group.group_name)
+        self.bases = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=dev)
+        self.error = torch.zeros(1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        self.handle.barrier()  # every rank's flags are zero before the first exchange
+        self.counter = 0
+
+    def fits(self, nbytes):
+        return nbytes % 8 == 0 and 0 < nbytes * self.world <= self.slot_bytes
+
+    def all_gather(self, flat_u8):
+        """flat_u8: contiguous uint8 CUDA tensor (a multiple of 8 bytes, the same size on every rank).  Returns a (world, nbytes)
+        uint8 view of the local buffer, valid until `slots` further exchanges have been issued."""
+        from ._native import check
+
+        nbytes = flat_u8.numel()
+        slot, seq = self.counter % self.slots, self.counter // self.slots + 1
+        self.counter += 1
+        data_off = slot * self.slot_bytes
+        flag_off = self.flag_off + slot * self.world * 8
+        check(self.lib.hypad_peer_exchange(flat_u8.data_ptr(), nbytes, self.bases.data_ptr(), self.rank, self.world, data_off, flag_off,
+                                           seq, self.error.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return self.buf[data_off: data_off + self.world * nbytes].view(self.world, nbytes)
+
+    def poll(self):
+        if int(self.error.item()):
+            raise HypadError("hypad_b200: a peer's record did not arrive within the exchange time-out")
+
+
+class TorchComm:
+    """The stage exchange over torch.distributed: small records through NVLink peer memory when the node offers symmetric memory
+    (PeerExchange: one kernel launch per exchange), anything else -- and everything when it does not -- through
+    all_gather_into_tensor."""
+
+    def __init__(self, group=None, peer=True):
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        self.peer = None
+        if peer and self.world > 1 and dist.get_backend(group) == "nccl" and os.environ.get("HYPAD_PEER_EXCHANGE", "1") != "0":
+            # every rank must take the same path: the outcome of the set-up is agreed on before it is used
+            ok = torch.ones(1, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+            px = None
+            try:
+                px = PeerExchange(group)
+            except Exception:  # noqa: BLE001 -- no symmetric memory on this node / build: NCCL carries the exchanges
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            self.peer = px if int(ok.item()) else None
 
     def all_gather(self, buf):
         flat = buf.reshape(-1)
+        if self.peer is not None and flat.is_cuda and flat.is_contiguous():
+            nbytes = flat.numel() * flat.element_size()
+            if self.peer.fits(nbytes):  # a function of the size alone: every rank takes the same path
+                if flat.data_ptr() % 16:
+                    flat = flat.clone()  # a view into the middle of an array: the copy kernel wants an aligned source
+                return self.peer.all_gather(flat.view(torch.uint8)).view(flat.dtype).view(self.world, -1)
         out = flat.new_empty(self.world * flat.numel())
         dist.all_gather_into_tensor(out, flat, group=self.group)
         return out.view(self.world, -1)
@@ -193,6 +262,8 @@ class ShardedScorer:
         if out_host is not None:
             sc._down_stream.synchronize()
         sc.poll_error()  # after the collectives, so that every rank still reaches them
+        if getattr(self.comm, "peer", None) is not None:
+            self.comm.peer.poll()
         return out
 
     def gather_full(self, out, n):
@@ -332,7 +403,7 @@ class ShardedScorer:
             record = torch.empty(rec_len, dtype=torch.float64, device=dev)
             scoring.check(lib.hypad_tw_shard_pack(h, scoring.ptr(final_local), first, cnt, n, wsize, step, count, anomaly_padding, bpr,
                                                   scoring.ptr(record), ctx.stream()))
-            g = self.comm.all_gather(record).contiguous()
+            g = self.comm.all_gather(record).clone()  # kept across the fragment exchanges below
             strips = g[:, rec_len - 2 * hp:].contiguous().view(self.world, 2, hp)
             lo, hi = max(first - hp, 0), min(first + cnt + hp, n)
             left, right = scoring._halo_from_strips(strips, ranges, self.rank, first - lo, hi - (first + cnt))

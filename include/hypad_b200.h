@@ -373,6 +373,15 @@ int hypad_tc_probe_gemm(const float* A, const float* B, float* D, int K, int N, 
  * until retired, h_out2[1] = cycles spent issuing.  mode 0 same accumulator, 1 rotating accumulators, 2 alternating operands. */
 int hypad_tc_probe_bench(int N, int reps, int mode, long long* h_out2, void* stream);
 
+/* All-gather of a small record through NVLink peer memory in one kernel launch (no host-side collective): CTA p copies `local`
+ * (nbytes, a multiple of 8) into peer p's symmetric buffer at data_off + rank * nbytes, raises flag [flag_off + 8 rank] there to
+ * `seq` (release, system scope) and waits until peer p's flag in the LOCAL buffer reaches `seq`.  peer_base_dev: device array of
+ * the `world` buffer addresses as mapped in THIS process (torch.distributed._symmetric_memory rendezvous).  After the kernel the
+ * records of all ranks lie back to back at data_off of the local buffer.  hypad_b200.distributed.PeerExchange numbers the
+ * exchanges and rotates the slots.  *error_flag_dev is set when a peer's record does not arrive within ~10 s. */
+int hypad_peer_exchange(const void* local, int64_t nbytes, const int64_t* peer_base_dev, int rank, int world, int64_t data_off,
+                        int64_t flag_off, uint64_t seq, int* error_flag_dev, void* stream);
+
 /* Diagnostic (not on the product path): one launch of a pipe-rate micro-benchmark filling every SM with `ctas_per_sm` CTAs
  * of 1024 threads, each running 8 independent chains of `iters` instructions.  kind 0 FP32 FFMA, 1 FP64 DFMA, 2 MUFU.EX2
  * (ex2.approx.ftz.f32), 3 MUFU.EX2 packed (ex2.approx.f16x2), 4 SHFL.IDX.  *instr_per_launch = thread-level instructions

@@ -22,6 +22,24 @@ def main():
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
+    from hypad_b200.distributed import TorchComm
+
+    comm = TorchComm()
+    if rank == 0:
+        print("stage exchanges: %s" % ("NVLink peer memory (hypad_peer_exchange)" if comm.peer is not None else "NCCL all-gather"))
+    if comm.peer is not None:  # the exchange itself: every rank's record arrives intact, in rank order, over many rounds
+        for rnd in range(40):
+            rec = torch.full((1024 + 8 * (rnd % 5),), float(rank * 1000 + rnd), dtype=torch.float64, device=dev)
+            g = comm.all_gather(rec)
+            want = torch.tensor([r * 1000.0 + rnd for r in range(world)], dtype=torch.float64, device=dev)
+            good = bool((g == want[:, None]).all().item()) and g.shape == (world, rec.numel())
+            ok = ok and good
+        comm.peer.poll()
+        t = torch.tensor([int(ok)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = bool(t.item())
+        if rank == 0:
+            print("peer exchange, 40 rounds of varying size: %s" % ok)
     for case in ("cfg1_hyp_uncertainty.npz", "noisy1500_hyp_uncertainty.npz", "edge_n300_hyp.npz", "long200k"):
         enc, dec, cx, _ = build_modules("weights_hyp_s100.npz", 100, True, dev)
         scorer = WindowScorer(enc, dec, cx)
