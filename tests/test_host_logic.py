@@ -323,3 +323,76 @@ def test_sweep_evaluation_counts_follow_the_reference_rule():
     assert (ev["fp"], ev["fn"], ev["tp"]) == (want_fp, want_fn, want_tp)
     p, r = want_tp / (want_tp + want_fp), want_tp / (want_tp + want_fn)
     assert ev["precision"] == p and ev["recall"] == r and ev["f1"] == 2 * p * r / (p + r)
+
+
+def test_shard_fragment_merge_joins_runs_across_ranks():
+    """hypad_tw_shard_merge (host code): the run fragments of a sharded find_anomalies -- every rank's sorted starts / ends of ITS
+    positions, the maximum per own start, the maximum in front of its first start (`lead`, a run begun on an earlier rank) and the
+    maximum outside runs -- joined into whole runs.  Reference: the runs of the unsharded array, cut into rank ranges here."""
+    import ctypes
+
+    from hypad_b200 import _native
+
+    lib = _native.load_library()
+
+    def key(v):  # the order-preserving integer the kernels carry maxima in
+        b = np.float64(v).view(np.uint64)
+        return np.uint64(~b) if (int(b) >> 63) else np.uint64(int(b) | (1 << 63))
+
+    rng = np.random.default_rng(17)
+    for trial in range(60):
+        world, R, count = int(rng.integers(1, 6)), 8, int(rng.integers(1, 4))
+        n = 400
+        bounds = np.sort(rng.choice(np.arange(1, n), world - 1, replace=False)).tolist() if world > 1 else []
+        edges = [0] + bounds + [n]
+        per = 8 + 3 * R
+        rec = np.zeros((world, count, per))
+        want_runs, want_below = [], []
+        for k in range(count):
+            x = rng.uniform(0, 1, n)
+            flagged = np.zeros(n, bool)
+            for _ in range(int(rng.integers(0, 4))):
+                a = int(rng.integers(0, n - 5))
+                flagged[a:a + int(rng.integers(1, 60))] = True
+            x[flagged] += 2.0
+            # runs = maximal stretches of `flagged` (the dilation is the kernels' business; here a run is a flagged stretch)
+            d = np.diff(np.concatenate([[0], flagged.astype(int), [0]]))
+            starts, ends = np.flatnonzero(d == 1), np.flatnonzero(d == -1) - 1
+            want_runs.append([(float(s), float(e), float(x[s:e + 1].max())) for s, e in zip(starts, ends)])
+            want_below.append(float(x[~flagged].max()) if (~flagged).any() else 0.0)
+            for r in range(world):
+                lo, hi = edges[r], edges[r + 1]
+                o = rec[r, k]
+                st = [s for s in starts if lo <= s < hi]
+                en = [e for e in ends if lo <= e < hi]
+                o[0], o[1] = len(st), len(en)
+                first = st[0] if st else hi
+                lead = x[lo:first][flagged[lo:first]]
+                o[2:3].view(np.uint64)[0] = key(lead.max()) if lead.size else 0
+                below = x[lo:hi][~flagged[lo:hi]]
+                o[3:4].view(np.uint64)[0] = key(below.max()) if below.size else 0
+                o[4], o[5], o[6] = 1.0 + k, 0.25, 2.0 + k
+                for j, s0 in enumerate(st):
+                    nxt = st[j + 1] if j + 1 < len(st) else hi
+                    own = x[s0:nxt][flagged[s0:nxt]]
+                    o[8 + j] = s0
+                    o[8 + R + j] = own.max() if own.size else -np.inf
+                for j, e0 in enumerate(en):
+                    o[8 + 2 * R + j] = e0
+        cap = world * R
+        stats, runs = np.empty((count, 4)), np.empty((count, cap, 3))
+        n_runs = np.zeros(count, np.int32)
+        need, over = ctypes.c_int64(0), ctypes.c_int(0)
+        _native.check(lib.hypad_tw_shard_merge(rec.ctypes.data, world, count, R, stats.ctypes.data, runs.ctypes.data, n_runs.ctypes.data, cap,
+                                               ctypes.byref(need), ctypes.byref(over)))
+        assert not over.value
+        for k in range(count):
+            assert n_runs[k] == len(want_runs[k]), (trial, k)
+            assert [tuple(r) for r in runs[k, :n_runs[k]].tolist()] == want_runs[k], (trial, k)
+            assert stats[k].tolist() == [1.0 + k, 0.25, 2.0 + k, want_below[k]]
+    # a rank whose fragment list did not fit: reported, with the room that is needed
+    rec = np.zeros((2, 1, 8 + 3 * 4))
+    rec[1, 0, 0] = rec[1, 0, 1] = 9
+    _native.check(lib.hypad_tw_shard_merge(rec.ctypes.data, 2, 1, 4, stats.ctypes.data, runs.ctypes.data, n_runs.ctypes.data, 8, ctypes.byref(need),
+                                           ctypes.byref(over)))
+    assert over.value == 1 and need.value == 9
