@@ -8,7 +8,9 @@ Layout
                              host-side mirror of the reference's modules: same names and signatures as
                              models/tadgan.py, hyperspace/hyrnn_nets.py, utils/anomaly_detection_utils.py,
                              utils/dataloader.py, anomaly_detection.py of aleflabo/HypAD
-  distributed.py             window sharding across GPUs (one process per GPU, NCCL gather at the end)
+  distributed.py             window sharding across GPUs: one process per GPU, the finish sharded, small stage exchanges through
+                             NVLink peer memory (or NCCL)
+  sweep.py                   many signals, one model each, sharded by signal
   dropin.py                  registers the mirror under the reference's import names
 
 There is no CPU fallback anywhere in this package.
