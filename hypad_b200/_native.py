@@ -101,6 +101,7 @@ _SIGNATURES = {
     "hypad_tc_probe_bench": (_int, [_int, _int, _int, _vp, _vp]),
     "hypad_score_signal_hyperbolic": (_int, [_vp, _vp, _int, _i64, _int, _i64, _i64, _i64, _int, _int, _int,
                                              ctypes.POINTER(hypad_signal_out), _vp]),
+    "hypad_score_signals_hyperbolic": (_int, [_vp, _i64, _int, _int, _int, _int, _int, _vp, _int]),
     "hypad_score_signal_euclidean": (_int, [_vp, _vp, _int, _i64, _int, _int, ctypes.c_double, _i64, _i64, _i64, _int, _int, _int,
                                             ctypes.POINTER(hypad_signal_eucl_out), _vp]),
     "hypad_critic_small_max": (_int, []),
@@ -122,6 +123,7 @@ _SIGNATURES = {
     "hypad_tw_shard_runs": (_int, [_vp, _vp, _int, _int, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _int, _int, _int, _vp, _vp]),
     "hypad_tw_shard_merge": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _i64, ctypes.POINTER(_i64), ctypes.POINTER(_int)]),
     "hypad_peer_exchange": (_int, [_vp, _i64, _vp, _int, _int, _i64, _i64, ctypes.c_uint64, _vp, _vp]),
+    "hypad_sweep_intervals": (_int, [_vp, _i64, _vp, _vp, _vp, _int, ctypes.c_double, _int, _vp, _i64, _vp, ctypes.POINTER(_i64)]),
     "hypad_peak_probe": (_int, [_int, _int, _int, _vp, ctypes.POINTER(ctypes.c_longlong), _vp]),
 }
 

@@ -355,6 +355,18 @@ int hypad_score_signal_hyperbolic(hypad_ctx* ctx, const void* x, int x_is_f64, i
     return rc;
 }
 
+int hypad_score_signals_hyperbolic(const hypad_sweep_item* items, int64_t n_items, int x_is_f64, int combine_mode, int ddof_flags,
+                                   int anomaly_padding, int max_runs, void* const* streams, int n_streams) {
+    HYPAD_REQUIRE((items || n_items == 0) && n_items >= 0 && streams && n_streams >= 1, "hypad_score_signals_hyperbolic: bad argument");
+    for (int64_t i = 0; i < n_items; ++i) {
+        const hypad_sweep_item& it = items[i];
+        const int rc = hypad_score_signal_hyperbolic(it.ctx, it.x, x_is_f64, it.n_windows, combine_mode, it.tw_window, it.tw_step, it.tw_count,
+                                                     ddof_flags, anomaly_padding, max_runs, &it.out, streams[i % n_streams]);
+        if (rc != HYPAD_OK) return rc;
+    }
+    return HYPAD_OK;
+}
+
 int hypad_score_signal_euclidean(hypad_ctx* ctx, const void* x, int x_is_f64, int64_t n_windows, int combine_mode, int rec_error_kind,
                                  double lambda_rec, int64_t tw_window, int64_t tw_step, int64_t tw_count, int ddof_flags,
                                  int anomaly_padding, int max_runs, const hypad_signal_eucl_out* o, void* stream) {

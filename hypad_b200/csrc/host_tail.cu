@@ -46,10 +46,9 @@ struct Seq {
 
 using namespace hypad;
 
-extern "C" int hypad_intervals_from_runs(const double* stats, const double* runs, const int32_t* n_runs, int64_t count,
-                                         int64_t max_runs, int64_t step, double min_percent, int f32, double* out, int64_t cap,
-                                         int64_t* n_out) {
-    HYPAD_REQUIRE(stats && runs && n_runs && n_out && count >= 0 && max_runs >= 1 && (out || cap == 0), "hypad_intervals_from_runs: bad argument");
+// prune + score + merge of one array's windows; appends (start, end, score) triples to `merged`
+static int intervals_core(const double* stats, const double* runs, const int32_t* n_runs, int64_t count, int64_t max_runs, int64_t step,
+                          double min_percent, int f32, std::vector<double>& merged) {
     std::vector<Seq> seqs;
     std::vector<Row> rows;
     for (int64_t k = 0; k < count; ++k) {
@@ -81,14 +80,10 @@ extern "C" int hypad_intervals_from_runs(const double* stats, const double* runs
             seqs.push_back({rows[i].s + shift, rows[i].e + shift, score});
         }
     }
-    int64_t n = 0;
     auto emit = [&](double s, double e, double sc) {
-        if (n < cap) {
-            out[n * 3 + 0] = s;
-            out[n * 3 + 1] = e;
-            out[n * 3 + 2] = sc;
-        }
-        ++n;
+        merged.push_back(s);
+        merged.push_back(e);
+        merged.push_back(sc);
     };
     if (!seqs.empty()) {
         std::stable_sort(seqs.begin(), seqs.end(), [](const Seq& a, const Seq& b) { return a.s < b.s; });
@@ -130,7 +125,59 @@ extern "C" int hypad_intervals_from_runs(const double* stats, const double* runs
         const int rc = close();
         if (rc != HYPAD_OK) return rc;
     }
+    return HYPAD_OK;
+}
+
+extern "C" int hypad_intervals_from_runs(const double* stats, const double* runs, const int32_t* n_runs, int64_t count,
+                                         int64_t max_runs, int64_t step, double min_percent, int f32, double* out, int64_t cap,
+                                         int64_t* n_out) {
+    HYPAD_REQUIRE(stats && runs && n_runs && n_out && count >= 0 && max_runs >= 1 && (out || cap == 0), "hypad_intervals_from_runs: bad argument");
+    std::vector<double> merged;
+    const int rc = intervals_core(stats, runs, n_runs, count, max_runs, step, min_percent, f32, merged);
+    if (rc != HYPAD_OK) return rc;
+    const int64_t n = (int64_t)merged.size() / 3;
+    for (int64_t i = 0; i < n && i < cap; ++i)
+        for (int j = 0; j < 3; ++j) out[i * 3 + j] = merged[(size_t)i * 3 + j];
     *n_out = n;
+    return HYPAD_OK;
+}
+
+// The host tails of a whole sweep in one call: item i's packed thresholding result (stats | runs | n_runs, the layout of
+// hypad_score_signal_hyperbolic's `tw`) starts at host_buf + offsets[i] doubles and holds counts[i] analysis windows of step
+// steps[i].  out receives the items' (start, end, score) triples back to back, n_out[i] their number per item -- or -1 for an item
+// one of whose windows holds more runs than max_runs (the caller redoes that signal with more room) and -2 for an item whose
+// merge hits numpy's "Weights sum to zero" (the caller raises for it).  *total = triples written; more than cap: call again.
+extern "C" int hypad_sweep_intervals(const double* host_buf, int64_t n_items, const int64_t* offsets, const int64_t* counts,
+                                     const int64_t* steps, int max_runs, double min_percent, int f32, double* out, int64_t cap,
+                                     int64_t* n_out, int64_t* total) {
+    HYPAD_REQUIRE(host_buf && offsets && counts && steps && n_out && total && n_items >= 0 && max_runs >= 1 && (out || cap == 0),
+                  "hypad_sweep_intervals: bad argument");
+    std::vector<double> merged;
+    int64_t written = 0;
+    for (int64_t i = 0; i < n_items; ++i) {
+        const double* stats = host_buf + offsets[i];
+        const double* runs = stats + counts[i] * 4;
+        const int32_t* n_runs = reinterpret_cast<const int32_t*>(runs + counts[i] * (int64_t)max_runs * 3);
+        bool over = false;
+        for (int64_t k = 0; k < counts[i]; ++k) over |= n_runs[k] > max_runs;
+        if (over) {
+            n_out[i] = -1;
+            continue;
+        }
+        merged.clear();
+        const int rc = intervals_core(stats, runs, n_runs, counts[i], max_runs, steps[i], min_percent, f32, merged);
+        if (rc == HYPAD_EZERODIV) {
+            n_out[i] = -2;
+            continue;
+        }
+        if (rc != HYPAD_OK) return rc;
+        const int64_t n = (int64_t)merged.size() / 3;
+        n_out[i] = n;
+        for (int64_t j = 0; j < n * 3; ++j)
+            if (written * 3 + j < cap * 3) out[written * 3 + j] = merged[(size_t)j];
+        written += n;
+    }
+    *total = written;
     return HYPAD_OK;
 }
 

@@ -270,6 +270,20 @@ int hypad_score_signal_hyperbolic(hypad_ctx* ctx, const void* x, int x_is_f64, i
                                   int64_t tw_window, int64_t tw_step, int64_t tw_count, int ddof_flags, int anomaly_padding,
                                   int max_runs, const hypad_signal_out* out, void* stream);
 
+/* A sweep over many short signals, one (hyperbolic) model each, in one call: item i is scored by hypad_score_signal_hyperbolic on
+ * streams[i % n_streams] (the reference runs `python anomaly_detection.py` once per signal; BASELINE config 5).  A context serves
+ * one stream at a time: items that share a context must land on the same stream.  Short signals are bound by what the host
+ * spends per signal; this loop leaves a dozen launches per signal and nothing else. */
+typedef struct hypad_sweep_item {
+    hypad_ctx* ctx;      /* the signal's packed model */
+    const void* x;       /* device pointer: the scaled signal, n_windows + S samples */
+    int64_t n_windows;
+    int64_t tw_window, tw_step, tw_count; /* find_anomalies' analysis windows (tw_count = 0: none) */
+    hypad_signal_out out;
+} hypad_sweep_item;
+int hypad_score_signals_hyperbolic(const hypad_sweep_item* items, int64_t n_items, int x_is_f64, int combine_mode, int ddof_flags,
+                                   int anomaly_padding, int max_runs, void* const* streams, int n_streams);
+
 /* The per-timestep Euclidean (TadGAN) path of one signal in one call (score_anomalies, utils/anomaly_detection_utils.py:407-576):
  * network -> KDE critic scores -> truth / median prediction -> reconstruction error (rec_error_kind 0 dtw, 1 point, 2 area) ->
  * smoothing -> z-score + clip -> combination (combine_mode 0 mult, 3 critic, 6 rec, 8 sum with lambda_rec) -> find_anomalies'
@@ -315,6 +329,14 @@ int hypad_tw_shard_runs(hypad_ctx* ctx, const double* records, int world, int ra
                         int64_t n_analysis, int ddof, int anomaly_padding, int max_runs, double* out, void* stream);
 int hypad_tw_shard_merge(const double* records, int world, int64_t n_analysis, int max_runs, double* stats, double* runs,
                          int32_t* n_runs, int64_t cap, int64_t* max_needed, int* overflow);
+
+/* The host tails of a whole sweep in one call: item i's packed thresholding result (the `tw` layout of hypad_score_signal_hyperbolic)
+ * starts at host_buf + offsets[i] doubles and holds counts[i] analysis windows of step steps[i].  out receives the items'
+ * (start, end, score) triples back to back, n_out[i] their number -- -1 for an item one of whose windows holds more runs than
+ * max_runs (redo that signal with more room), -2 where numpy's "Weights sum to zero" would be raised.  *total = triples produced
+ * (more than cap: call again with more room). */
+int hypad_sweep_intervals(const double* host_buf, int64_t n_items, const int64_t* offsets, const int64_t* counts, const int64_t* steps,
+                          int max_runs, double min_percent, int f32, double* out, int64_t cap, int64_t* n_out, int64_t* total);
 
 /* ---- staged global statistics: one GPU's slice per call, a small record exchanged between stages -------------------------
  * The reference computes its statistics on whole arrays (np.quantile / mean / std in _compute_critic_score,
