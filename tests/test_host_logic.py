@@ -396,3 +396,54 @@ def test_shard_fragment_merge_joins_runs_across_ranks():
     _native.check(lib.hypad_tw_shard_merge(rec.ctypes.data, 2, 1, 4, stats.ctypes.data, runs.ctypes.data, n_runs.ctypes.data, 8, ctypes.byref(need),
                                            ctypes.byref(over)))
     assert over.value == 1 and need.value == 9
+
+
+def test_sweep_host_tails_equal_the_per_signal_tail():
+    """hypad_sweep_intervals (the host tails of a whole sweep in one call) against hypad_intervals_from_runs per signal, on packed
+    thresholding results laid out the way the device writes them (stats | runs | n_runs as int32 pairs); a signal one of whose
+    windows overflows its run room is reported (-1), not mis-parsed."""
+    import ctypes
+
+    from hypad_b200 import _native, scoring
+
+    lib = _native.load_library()
+    rng = np.random.default_rng(23)
+    R = 16
+    bufs, metas = [], []
+    off = 0
+    for item in range(25):
+        count, step = int(rng.integers(1, 9)), int(rng.integers(1, 40))
+        stats = np.c_[rng.normal(1, .1, count), rng.uniform(0.1, 1, count), rng.normal(3, .2, count), rng.normal(2.5, .3, count)]
+        nr = rng.integers(0, R + 1, count).astype(np.int32)
+        if item == 7:
+            nr[0] = R + 3  # overflow
+        runs = np.zeros((count, R, 3))
+        for k in range(count):
+            m = min(int(nr[k]), R)
+            st = np.sort(rng.integers(0, 300, m))
+            runs[k, :m, 0], runs[k, :m, 1], runs[k, :m, 2] = st, st + rng.integers(1, 20, m), np.round(rng.normal(3.5, .5, m), 1)
+        tail = np.zeros((count + 1) // 2, dtype=np.float64)
+        tail.view(np.int32)[:count] = nr
+        bufs.append(np.concatenate([stats.ravel(), runs.ravel(), tail]))
+        metas.append((off, count, step, stats, runs, nr))
+        off += bufs[-1].shape[0]
+    host = np.concatenate(bufs)
+    offs = np.asarray([m[0] for m in metas], dtype=np.int64)
+    counts = np.asarray([m[1] for m in metas], dtype=np.int64)
+    steps = np.asarray([m[2] for m in metas], dtype=np.int64)
+    for f32 in (0, 1):
+        n_out = np.zeros(len(metas), dtype=np.int64)
+        out = np.empty((4096, 3))
+        tot = ctypes.c_int64(0)
+        _native.check(lib.hypad_sweep_intervals(host.ctypes.data, len(metas), offs.ctypes.data, counts.ctypes.data, steps.ctypes.data, R, 0.1, f32,
+                                                out.ctypes.data, 4096, n_out.ctypes.data, ctypes.byref(tot)))
+        pos = 0
+        for k, (_o, count, step, stats, runs, nr) in enumerate(metas):
+            if k == 7:
+                assert n_out[k] == -1
+                continue
+            want = scoring.intervals_from_runs(stats, runs, nr, step, 0.1, f32=bool(f32))
+            got = out[pos:pos + n_out[k]].tolist()
+            pos += int(n_out[k])
+            assert len(got) == len(want) and all((a == b) or (a != a and b != b) for x, y in zip(got, want) for a, b in zip(x, y)), k
+        assert pos == tot.value
